@@ -1,0 +1,216 @@
+/*
+ * vosd_b200.h -- C ABI of libvosd_b200.so: the B200 (sm_100a) region pipeline of
+ * VOSDetectron-style Mask R-CNN (proposals -> NMS -> FPN level assignment ->
+ * multi-level RoIAlign fwd/bwd -> mask paste-back).
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer unless the parameter is documented "host";
+ *   - plain pointers + explicit sizes + cudaStream_t, no framework types;
+ *   - the caller allocates outputs and the opaque workspace (size from the matching
+ *     *_workspace_bytes()); no hidden cudaMalloc, no hidden synchronisation, no global
+ *     mutable state: calls are re-entrant and only enqueue work on `stream`;
+ *   - return value: VOSD_OK (0) or a negative vosd_status -- never exit()
+ *     (the reference launchers print and exit(-1), roi_align_kernel.cu:135-139,283-287);
+ *   - there is no CPU implementation behind any entry point.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference repository root).
+ */
+#ifndef VOSD_B200_H_
+#define VOSD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VOSD_API __attribute__((visibility("default")))
+#else
+#define VOSD_API
+#endif
+
+#ifndef __DRIVER_TYPES_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+typedef enum vosd_status {
+    VOSD_OK = 0,
+    VOSD_ERR_BAD_SHAPE = -1,     /* negative / zero / inconsistent extents                 */
+    VOSD_ERR_BAD_ARG = -2,       /* NULL pointer, misaligned pointer, bad enum             */
+    VOSD_ERR_UNSUPPORTED = -3,   /* legal in the reference but beyond a compiled-in limit  */
+    VOSD_ERR_WORKSPACE = -4,     /* workspace NULL or smaller than *_workspace_bytes()     */
+    VOSD_ERR_LAUNCH = -5         /* cudaGetLastError() != cudaSuccess after a launch       */
+} vosd_status;
+
+#define VOSD_MAX_LEVELS 8        /* FPN levels in one multi-level call                     */
+#define VOSD_MAX_ANCHORS 16      /* anchors per location (A); FPN uses 3                    */
+#define VOSD_MAX_TOPK 16384      /* pre-NMS top-k / NMS segment length handled in one CTA  */
+
+VOSD_API const char* vosd_version(void);
+VOSD_API const char* vosd_status_string(int status);
+/* Number of kernels this library has enqueued since load (diagnostic counter). */
+VOSD_API unsigned long long vosd_launch_count(void);
+/* Binds the library's CUDA runtime to `device` for the calling thread (cudaSetDevice). */
+VOSD_API int vosd_set_device(int device);
+
+/* ------------------------------------------------------------------------------------ */
+/* RoIAlign, single feature level.                                                        */
+/* Replaces ROIAlignForwardLaucher / ROIAlignBackwardLaucher                              */
+/* (lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.h:13-27; kernels               */
+/* roi_align_kernel.cu:65-121 and :195-270) with the SAME argument order, so the          */
+/* reference launcher can be swapped in for an A/B comparison.  Results are bit-identical */
+/* to the reference kernel built for sm_100a (forward) / identical addends summed in a    */
+/* different order (backward).                                                            */
+/*   bottom_data (N,C,H,W) fp32; bottom_rois (R,5) fp32 [batch,x1,y1,x2,y2] in input-     */
+/*   image pixels; top_data (R,C,ph,pw) fp32.  sampling_ratio <= 0: adaptive grid.        */
+/* ------------------------------------------------------------------------------------ */
+VOSD_API int vosd_roialign_fwd(const float* bottom_data, float spatial_scale, int num_rois,
+                      int height, int width, int channels,
+                      int aligned_height, int aligned_width, int sampling_ratio,
+                      const float* bottom_rois, float* top_data, cudaStream_t stream);
+
+/* bottom_diff (N,C,H,W) is ACCUMULATED into: the caller zero-fills it, exactly as
+ * RoIAlignFunction.backward does (functions/roi_align.py:39-40).  Pass zero_init != 0 to
+ * have the library clear it on `stream` first (no pre-zeroed buffer needed). */
+VOSD_API int vosd_roialign_bwd(const float* top_diff, float spatial_scale, int batch_size, int num_rois,
+                      int height, int width, int channels,
+                      int aligned_height, int aligned_width, int sampling_ratio,
+                      const float* bottom_rois, float* bottom_diff, int zero_init,
+                      cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* RoIAlign over all FPN levels in ONE launch.                                            */
+/* Replaces the per-level loop + torch.cat + xform_shuffled[restore] of                   */
+/* Generalized_RCNN.roi_feature_transform (lib/modeling/model_builder.py:262-303; mirrors */
+/* lib_vos/vos_modeling/vos_model_builder.py:449-521).                                    */
+/*   level_data/level_h/level_w/level_scale : HOST arrays of num_levels entries           */
+/*       (device pointer of the (N,C,H_l,W_l) map, its extents, its spatial scale);       */
+/*   rois (R,5) device; roi_level (R) device int32, index into the level arrays;          */
+/*   out_index (R) device int32 or NULL: row of top_data that RoI i is written to         */
+/*       (NULL = i).  With rois = concat(rois_fpn2..5) and out_index = the inverse of     */
+/*       rois_idx_restore_int32 the result equals the reference's un-shuffled blob.       */
+/* ------------------------------------------------------------------------------------ */
+VOSD_API int vosd_roialign_ml_fwd(const float* const* level_data, const int* level_h, const int* level_w,
+                         const float* level_scale, int num_levels, int channels,
+                         int aligned_height, int aligned_width, int sampling_ratio,
+                         int num_rois, const float* rois, const int* roi_level,
+                         const int* out_index, float* top_data, cudaStream_t stream);
+
+/* level_diff[l] (N,C,H_l,W_l) accumulated into (zero_init as above, needs batch_size). */
+VOSD_API int vosd_roialign_ml_bwd(const float* top_diff, float* const* level_diff, const int* level_h,
+                         const int* level_w, const float* level_scale, int num_levels,
+                         int batch_size, int channels,
+                         int aligned_height, int aligned_width, int sampling_ratio,
+                         int num_rois, const float* rois, const int* roi_level,
+                         const int* out_index, int zero_init, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* RPN proposal generation for all (level, image) segments in one call.                   */
+/* Replaces GenerateProposalsOp.forward + proposals_for_one_image                         */
+/* (lib/modeling/generate_proposals.py:20-168): per-segment top-k by score (:131-139),    */
+/* bbox_transform (lib/utils/boxes.py:156-205), clip_tiled_boxes (:138-153),              */
+/* _filter_boxes (generate_proposals.py:171-182), cython_nms.nms                          */
+/* (lib/utils/cython_nms.pyx:37-87) and keep[:post_nms_topN] (:163-166).                  */
+/* ------------------------------------------------------------------------------------ */
+typedef struct vosd_rpn_level {
+    const float* scores;      /* (N, A, H, W) fp32, rpn_cls_prob                         */
+    const float* deltas;      /* (N, 4A, H, W) fp32, rpn_bbox_pred                       */
+    int height, width;        /* H, W of this level                                       */
+    int num_anchors;          /* A <= VOSD_MAX_ANCHORS                                    */
+    double feat_stride;       /* 1 / spatial_scale (generate_proposals.py:18)             */
+    double anchors[4 * VOSD_MAX_ANCHORS]; /* (A,4) fp64 base anchors of generate_anchors.py;*/
+                                          /* shifted in fp64, rounded to fp32 (boxes.py:164)*/
+} vosd_rpn_level;
+
+/* Row capacity of every segment in the outputs below:
+ *   cap = post_nms_topN > 0 ? min(post_nms_topN, m) : m,  m = min(pre_nms_topN>0 ? pre : inf, max_l A*H_l*W_l) */
+VOSD_API int vosd_proposals_capacity(const vosd_rpn_level* levels /*host*/, int num_levels,
+                            int pre_nms_topN, int post_nms_topN);
+VOSD_API size_t vosd_generate_proposals_workspace_bytes(const vosd_rpn_level* levels /*host*/, int num_levels,
+                                               int num_images, int pre_nms_topN, int post_nms_topN);
+/*   levels: HOST array; im_info (N,3) device fp32 [height, width, scale];
+ *   out_rois  (num_levels, N, cap, 5) fp32 [image, x1,y1,x2,y2] (rows >= count untouched = caller's fill);
+ *   out_probs (num_levels, N, cap) fp32; out_count (num_levels, N) int32.
+ *   nms_thresh <= 0 skips NMS (generate_proposals.py:159).  Ties between equal scores are
+ *   ordered by lower flat (h,w,a) index first (the reference's order is unspecified).      */
+VOSD_API int vosd_generate_proposals(const vosd_rpn_level* levels, int num_levels, int num_images,
+                            const float* im_info, int pre_nms_topN, int post_nms_topN,
+                            float nms_thresh, float min_size,
+                            float* out_rois, float* out_probs, int* out_count,
+                            void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* Streaming decode of EVERY anchor of one level (the `pre_nms_topN <= 0 or >= len(scores)`
+ * branch, generate_proposals.py:131-132, and a standalone bbox_transform+clip):
+ *   deltas (N,4A,H,W) -> boxes (N, H*W*A, 4) fp32 in (H,W,A) order, clipped to im_info.   */
+VOSD_API int vosd_decode_anchors(const vosd_rpn_level* level /*host, scores unused*/, int num_images,
+                        const float* im_info, float* boxes, cudaStream_t stream);
+
+/* Optional NaN guard of GenerateProposalsOp (generate_proposals.py:62-63):
+ * sets *flag (device int32, caller-zeroed) to 1 if any of the n floats is NaN.             */
+VOSD_API int vosd_any_nan(const float* data, size_t n, int* flag, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* Greedy box NMS.  Replaces box_utils.nms -> cython_nms.nms                              */
+/* (lib/utils/boxes.py:329-333, lib/utils/cython_nms.pyx:37-87): fp32 IEEE arithmetic,    */
+/* +1 widths, `>=` threshold, dets in any order.                                          */
+/*   dets (n,5) fp32 [x1,y1,x2,y2,score]; keep (n) int64 ascending INDEX order (np.where  */
+/*   semantics, :87); num_keep device int32.  n <= VOSD_MAX_TOPK.                         */
+/* ------------------------------------------------------------------------------------ */
+VOSD_API size_t vosd_nms_workspace_bytes(int n);
+VOSD_API int vosd_nms(const float* dets, int n, float thresh, int64_t* keep, int* num_keep,
+             void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* collect + distribute.  Replaces collect(), map_rois_to_fpn_levels() and distribute()   */
+/* (lib/modeling/collect_and_distribute_fpn_rpn_proposals.py:91-138, lib/utils/fpn.py:    */
+/* 11-28) on the outputs of vosd_generate_proposals.                                      */
+/*   Groups: images are collected `images_per_group` at a time (the reference collects    */
+/*   over its whole minibatch, :102-105; per-frame inference = 1).  G = N/images_per_group*/
+/*   out_rois (G, post, 5)   top-`post` RoIs of the group by score, best first;           */
+/*   out_count (G)           rows valid in each group;                                     */
+/*   out_level (G, post)     int32 FPN level of each RoI in [k_min, k_max];                */
+/*   level_count (G, k_max-k_min+1)                                                        */
+/*   order (G, post)         concat over levels of the indices assigned to each level      */
+/*                           (rois_fpnL = out_rois[order[level segment]]);                 */
+/*   restore (G, post)       rois_idx_restore_int32 = inverse permutation of order.        */
+/* ------------------------------------------------------------------------------------ */
+VOSD_API size_t vosd_collect_distribute_workspace_bytes(int num_levels, int num_images, int cap,
+                                               int images_per_group, int post_nms_topN);
+VOSD_API int vosd_collect_distribute(const float* rois, const float* probs, const int* count,
+                            int num_levels, int num_images, int cap, int images_per_group,
+                            int post_nms_topN, int k_min, int k_max,
+                            float canonical_scale, int canonical_level,
+                            float* out_rois, int* out_count, int* out_level, int* level_count,
+                            int* order, int* restore,
+                            void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* Level assignment + per-level split only (distribute() on caller-supplied rois; also the
+ * test-time twin _add_multilevel_rois_for_test, lib/core/test.py:909-927).
+ *   rois (R,5); outputs as above with G = 1, post = R.                                    */
+VOSD_API int vosd_distribute(const float* rois, int num_rois, int k_min, int k_max,
+                    float canonical_scale, int canonical_level,
+                    int* out_level, int* level_count, int* order, int* restore,
+                    cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* Mask paste-back.  Replaces the per-detection body of segm_results                      */
+/* (lib/core/test.py:801-855; copy lib_vos/tools/vos_test.py:867-921) up to, not          */
+/* including, the RLE encode: expand_boxes (lib/utils/boxes.py:242-258) -> int32          */
+/* truncation -> cv2.resize(INTER_LINEAR) of the zero-padded (M+2)^2 mask -> > thresh ->  */
+/* paste into a zero (im_h, im_w) uint8 canvas per detection.                             */
+/*   masks (R,K,M,M) fp32; cls (R) int32 mask channel per detection or NULL (channel 0,   */
+/*   CLS_SPECIFIC_MASK False); ref_boxes (R,4) fp32 original-image coords;                 */
+/*   out (R, im_h, im_w) uint8 (every byte written); out_prob optional (R,im_h,im_w) fp32  */
+/*   = the resized probabilities before thresholding (0 outside the box), may be NULL.    */
+/* ------------------------------------------------------------------------------------ */
+VOSD_API int vosd_paste_masks(const float* masks, const int* cls, const float* ref_boxes,
+                     int num_dets, int num_classes, int mask_size, int im_h, int im_w,
+                     float thresh, uint8_t* out, float* out_prob, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOSD_B200_H_ */

@@ -1,0 +1,340 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the per-frame region pipeline.
+
+NumPy restatement of the reference's Python/NumPy hot path plus ctypes bindings
+to ``oracle/oracle.c`` (NMS, RoIAlign fwd/bwd, cv2-style resize).  Only tests/,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs may import this module; ``vosdetectron_b200`` never does.
+
+Parity status: the reference has no tests / golden vectors for this path
+("parity unpinned by upstream tests"), so the oracle is
+pinned against *outputs of the reference itself run in the build container*:
+``tests/golden/*.npz`` (made by ``tests/golden/make_golden.py``) and the live
+comparison in ``tests/test_oracle_vs_reference.py``.  The one embedded
+known-answer of the reference (the 9 stride-16 anchors quoted in
+lib/modeling/generate_anchors.py:26-51) is checked in tests/test_oracle.py.
+
+Every function cites the reference file:line it follows.  dtypes follow the
+reference exactly (float64 anchors, float32 everything downstream, int64 index
+arrays) because the rounding points are part of the contract.
+"""
+import ctypes
+import math
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+# lib/core/config.py:1009 -- an np.float64 *scalar*, not a Python float.  That matters:
+# under NumPy >= 2 (NEP 50) ``np.minimum(float32_array, np.float64_scalar)`` is float64, so
+# the reference as run in this image carries dw/dh, exp() and pred_w/pred_h in float64 and
+# rounds to float32 only when storing into pred_boxes (boxes.py:195-203); under NumPy 1.x
+# they stay float32.  The oracle reproduces whichever NumPy it runs under, like the reference.
+BBOX_XFORM_CLIP = np.log(1000. / 16.)
+
+
+def build_c(force=False):
+    """gcc-compile oracle.c -> oracle/liboracle.so (git-ignored, travels with gpurun)."""
+    so = os.path.join(HERE, "liboracle.so")
+    src = os.path.join(HERE, "oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-mfma",
+                               "-ffp-contract=off", src, "-o", so, "-lm"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(build_c())
+        fp = ctypes.POINTER(ctypes.c_float)
+        L.orc_nms.restype = ctypes.c_int64
+        L.orc_nms.argtypes = [fp, ctypes.c_int64, ctypes.c_float, ctypes.POINTER(ctypes.c_int64)]
+        sig = [fp] + [ctypes.c_int] * 4 + [fp] + [ctypes.c_int] * 3 + [ctypes.c_float, ctypes.c_int, fp, ctypes.c_int]
+        L.orc_roialign_fwd.argtypes = sig
+        L.orc_roialign_bwd.argtypes = sig
+        L.orc_resize_linear.argtypes = [fp, ctypes.c_int, ctypes.c_int, fp, ctypes.c_int, ctypes.c_int]
+        L.orc_num_threads.restype = ctypes.c_int
+        _LIB = L
+    return _LIB
+
+
+def _fp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+# --------------------------------------------------------------------------- #
+# (a1) anchors -- lib/modeling/generate_anchors.py:54-123
+# --------------------------------------------------------------------------- #
+def generate_anchors(stride=16, sizes=(32, 64, 128, 256, 512), aspect_ratios=(0.5, 1, 2)):
+    """(A,4) float64 anchors: ratio enumeration (rounded w/h) about the centre of
+    the [0, stride-1] window, then scale enumeration (generate_anchors.py:66-123)."""
+    scales = np.asarray(sizes, dtype=np.float64) / stride
+    ratios = np.asarray(aspect_ratios, dtype=np.float64)
+    base = float(stride)                       # window (0,0,stride-1,stride-1): w = h = stride
+    ctr = 0.5 * (base - 1.0)
+    rows = []
+    for r in ratios:
+        w_r = np.round(np.sqrt(base * base / r))
+        h_r = np.round(w_r * r)
+        for s in scales:
+            ws, hs = w_r * s, h_r * s
+            rows.append([ctr - 0.5 * (ws - 1), ctr - 0.5 * (hs - 1),
+                         ctr + 0.5 * (ws - 1), ctr + 0.5 * (hs - 1)])
+    return np.asarray(rows, dtype=np.float64)
+
+
+def fpn_anchors(level, start_size=32, aspect_ratios=(0.5, 1, 2), k_min=2):
+    """Per-level anchors as built at lib/modeling/FPN.py:343-350."""
+    return generate_anchors(2.0 ** level, (start_size * 2.0 ** (level - k_min),), aspect_ratios)
+
+
+# --------------------------------------------------------------------------- #
+# (a4) bbox_transform -- lib/utils/boxes.py:156-205
+# --------------------------------------------------------------------------- #
+def bbox_transform(boxes, deltas, weights=(1.0, 1.0, 1.0, 1.0), clip=BBOX_XFORM_CLIP):
+    if boxes.shape[0] == 0:
+        return np.zeros((0, deltas.shape[1]), dtype=deltas.dtype)
+    b = boxes.astype(deltas.dtype, copy=False)               # :164 fp64 anchors -> fp32
+    w = b[:, 2] - b[:, 0] + 1.0
+    h = b[:, 3] - b[:, 1] + 1.0
+    cx = b[:, 0] + 0.5 * w
+    cy = b[:, 1] + 0.5 * h
+    wx, wy, ww, wh = weights
+    dx = deltas[:, 0::4] / wx
+    dy = deltas[:, 1::4] / wy
+    dw = np.minimum(deltas[:, 2::4] / ww, clip)               # :180-181
+    dh = np.minimum(deltas[:, 3::4] / wh, clip)
+    pcx = dx * w[:, None] + cx[:, None]                       # separate mul, add (no FMA)
+    pcy = dy * h[:, None] + cy[:, None]
+    pw = np.maximum(np.exp(dw) * w[:, None], 1.0)             # :188-193
+    ph = np.maximum(np.exp(dh) * h[:, None], 1.0)
+    out = np.zeros(deltas.shape, dtype=deltas.dtype)
+    out[:, 0::4] = pcx - 0.5 * pw
+    out[:, 1::4] = pcy - 0.5 * ph
+    out[:, 2::4] = pcx + 0.5 * pw - 1
+    out[:, 3::4] = pcy + 0.5 * ph - 1
+    return out
+
+
+# (a5) clip_tiled_boxes -- lib/utils/boxes.py:138-153 (im_shape = [h, w], fp32)
+def clip_tiled_boxes(boxes, im_shape):
+    boxes[:, 0::4] = np.maximum(np.minimum(boxes[:, 0::4], im_shape[1] - 1), 0)
+    boxes[:, 1::4] = np.maximum(np.minimum(boxes[:, 1::4], im_shape[0] - 1), 0)
+    boxes[:, 2::4] = np.maximum(np.minimum(boxes[:, 2::4], im_shape[1] - 1), 0)
+    boxes[:, 3::4] = np.maximum(np.minimum(boxes[:, 3::4], im_shape[0] - 1), 0)
+    return boxes
+
+
+# (a6) _filter_boxes -- lib/modeling/generate_proposals.py:171-182
+def filter_boxes(boxes, min_size, im_info):
+    min_size = min_size * im_info[2]
+    ws = boxes[:, 2] - boxes[:, 0] + 1
+    hs = boxes[:, 3] - boxes[:, 1] + 1
+    xc = boxes[:, 0] + ws / 2.
+    yc = boxes[:, 1] + hs / 2.
+    return np.where((ws >= min_size) & (hs >= min_size) & (xc < im_info[1]) & (yc < im_info[0]))[0]
+
+
+# (a7) nms -- lib/utils/boxes.py:329-333 -> lib/utils/cython_nms.pyx:37-87
+def nms(dets, thresh):
+    if dets.shape[0] == 0:
+        return []
+    d = np.ascontiguousarray(dets, dtype=np.float32)
+    keep = np.empty(d.shape[0], dtype=np.int64)
+    n = lib().orc_nms(_fp(d), d.shape[0], np.float32(thresh), keep.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
+    return keep[:n].copy()
+
+
+def topk_order(scores, k):
+    """Indices of the k largest scores, best first (generate_proposals.py:131-139).
+    Ties: the reference's argpartition/argsort are unstable; the oracle and the
+    CUDA path both define ties as lower flat index first."""
+    s = scores.ravel()
+    order = np.argsort(-s, kind='stable')
+    if k <= 0 or k >= s.size:
+        return order
+    return order[:k]
+
+
+# (a3) proposals_for_one_image -- lib/modeling/generate_proposals.py:104-168
+def proposals_for_one_image(im_info, all_anchors, bbox_deltas, scores,
+                            pre_nms_topN, post_nms_topN, nms_thresh, min_size):
+    deltas = bbox_deltas.transpose((1, 2, 0)).reshape((-1, 4))      # (4A,H,W)->(H*W*A,4)
+    sc = scores.transpose((1, 2, 0)).reshape((-1, 1))
+    order = topk_order(sc, pre_nms_topN)
+    deltas, anchors, sc = deltas[order, :], all_anchors[order, :], sc[order]
+    props = bbox_transform(anchors, deltas, (1.0, 1.0, 1.0, 1.0))
+    props = clip_tiled_boxes(props, im_info[:2])
+    keep = filter_boxes(props, min_size, im_info)
+    props, sc = props[keep, :], sc[keep]
+    if nms_thresh > 0:
+        keep = nms(np.hstack((props, sc)), nms_thresh)
+        if post_nms_topN > 0:
+            keep = keep[:post_nms_topN]
+        props, sc = props[keep, :], sc[keep]
+    return props, sc
+
+
+def all_anchors_for_level(anchors, H, W, feat_stride):
+    """(H*W*A, 4) float64 shifted anchors in (H, W, A) order (generate_proposals.py:69-89)."""
+    sx = np.arange(0, W) * feat_stride
+    sy = np.arange(0, H) * feat_stride
+    sx, sy = np.meshgrid(sx, sy, copy=False)
+    shifts = np.vstack((sx.ravel(), sy.ravel(), sx.ravel(), sy.ravel())).transpose()
+    A, K = anchors.shape[0], shifts.shape[0]
+    return (anchors[np.newaxis, :, :] + shifts[:, np.newaxis, :]).reshape((K * A, 4))
+
+
+# (a2) GenerateProposalsOp.forward -- lib/modeling/generate_proposals.py:20-102
+def generate_proposals(rpn_cls_prob, rpn_bbox_pred, im_info, anchors, spatial_scale,
+                       pre_nms_topN, post_nms_topN, nms_thresh, min_size):
+    scores = np.asarray(rpn_cls_prob, dtype=np.float32)
+    deltas = np.asarray(rpn_bbox_pred, dtype=np.float32)
+    if np.any(np.isnan(deltas)):
+        raise ValueError('bbox_deltas nan')                         # :62-63
+    im_info = np.asarray(im_info, dtype=np.float32)
+    H, W = scores.shape[-2:]
+    all_anchors = all_anchors_for_level(anchors, H, W, 1. / spatial_scale)
+    rois = np.empty((0, 5), dtype=np.float32)
+    probs = np.empty((0, 1), dtype=np.float32)
+    for i in range(scores.shape[0]):
+        b, p = proposals_for_one_image(im_info[i], all_anchors, deltas[i], scores[i],
+                                       pre_nms_topN, post_nms_topN, nms_thresh, min_size)
+        bi = i * np.ones((b.shape[0], 1), dtype=np.float32)
+        rois = np.append(rois, np.hstack((bi, b)), axis=0)
+        probs = np.append(probs, p, axis=0)
+    return rois, probs
+
+
+# (a8) collect -- lib/modeling/collect_and_distribute_fpn_rpn_proposals.py:91-106
+def collect(roi_inputs, score_inputs, post_nms_topN):
+    rois = np.concatenate(roi_inputs)
+    scores = np.concatenate(score_inputs).reshape(-1)
+    inds = np.argsort(-scores, kind='stable')[:post_nms_topN]
+    return rois[inds, :]
+
+
+# (a9) map_rois_to_fpn_levels -- lib/utils/fpn.py:11-28 (+ boxes_area, boxes.py:58-69)
+def map_rois_to_fpn_levels(rois, k_min=2, k_max=5, s0=224, lvl0=4):
+    w = rois[:, 2] - rois[:, 0] + 1
+    h = rois[:, 3] - rois[:, 1] + 1
+    areas = w * h
+    areas[areas < 0] = 0
+    s = np.sqrt(areas)
+    lv = np.floor(lvl0 + np.log2(s / s0 + 1e-6))
+    return np.clip(lv, k_min, k_max)
+
+
+# (a10) distribute -- collect_and_distribute_fpn_rpn_proposals.py:109-138
+def distribute(rois, k_min=2, k_max=5, prefix='rois'):
+    lvls = map_rois_to_fpn_levels(rois[:, 1:5], k_min, k_max)
+    out = {prefix: rois}
+    order = np.empty((0,))
+    for lvl in range(k_min, k_max + 1):
+        idx = np.where(lvls == lvl)[0]
+        out['%s_fpn%d' % (prefix, lvl)] = rois[idx, :]
+        order = np.concatenate((order, idx))
+    out[prefix + '_idx_restore_int32'] = np.argsort(order).astype(np.int32)
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# (a14/a15) RoIAlign -- roi_xfrom/roi_align/src/roi_align_kernel.cu:16-121,150-270
+# --------------------------------------------------------------------------- #
+def roi_align_forward(features, rois, ph, pw, spatial_scale, sampling_ratio, nthreads=0):
+    f = np.ascontiguousarray(features, dtype=np.float32)
+    r = np.ascontiguousarray(rois, dtype=np.float32)
+    N, C, H, W = f.shape
+    out = np.zeros((r.shape[0], C, ph, pw), dtype=np.float32)
+    if r.shape[0]:
+        lib().orc_roialign_fwd(_fp(f), N, C, H, W, _fp(r), r.shape[0], ph, pw,
+                               np.float32(spatial_scale), sampling_ratio, _fp(out), nthreads)
+    return out
+
+
+def roi_align_backward(top_grad, rois, feat_shape, ph, pw, spatial_scale, sampling_ratio, nthreads=0):
+    t = np.ascontiguousarray(top_grad, dtype=np.float32)
+    r = np.ascontiguousarray(rois, dtype=np.float32)
+    N, C, H, W = feat_shape
+    g = np.zeros((N, C, H, W), dtype=np.float32)
+    if r.shape[0]:
+        lib().orc_roialign_bwd(_fp(t), N, C, H, W, _fp(r), r.shape[0], ph, pw,
+                               np.float32(spatial_scale), sampling_ratio, _fp(g), nthreads)
+    return g
+
+
+def roi_feature_transform(blobs_in, rpn_ret, blob_rois, resolution, spatial_scales, sampling_ratio,
+                          k_min=2, k_max=5, nthreads=0):
+    """lib/modeling/model_builder.py:252-303 (FPN branch, method='RoIAlign');
+    ``blobs_in`` / ``spatial_scales`` are coarsest-first like the reference."""
+    outs = []
+    for lvl in range(k_min, k_max + 1):
+        r = rpn_ret['%s_fpn%d' % (blob_rois, lvl)]
+        if len(r):
+            outs.append(roi_align_forward(blobs_in[k_max - lvl], r, resolution, resolution,
+                                          spatial_scales[k_max - lvl], sampling_ratio, nthreads))
+    shuffled = np.concatenate(outs, axis=0)
+    return shuffled[rpn_ret[blob_rois + '_idx_restore_int32'].astype(np.int64)]
+
+
+# --------------------------------------------------------------------------- #
+# (a17/a18) mask paste -- lib/core/test.py:801-855, lib/utils/boxes.py:242-258
+# --------------------------------------------------------------------------- #
+def expand_boxes(boxes, scale):
+    """fp32 arithmetic, stored to a float64 array (boxes.py:242-258)."""
+    w_half = (boxes[:, 2] - boxes[:, 0]) * .5
+    h_half = (boxes[:, 3] - boxes[:, 1]) * .5
+    x_c = (boxes[:, 2] + boxes[:, 0]) * .5
+    y_c = (boxes[:, 3] + boxes[:, 1]) * .5
+    w_half *= scale
+    h_half *= scale
+    out = np.zeros(boxes.shape)
+    out[:, 0] = x_c - w_half
+    out[:, 2] = x_c + w_half
+    out[:, 1] = y_c - h_half
+    out[:, 3] = y_c + h_half
+    return out
+
+
+def resize_linear(src, dw, dh):
+    s = np.ascontiguousarray(src, dtype=np.float32)
+    dst = np.empty((dh, dw), dtype=np.float32)
+    lib().orc_resize_linear(_fp(s), s.shape[0], s.shape[1], _fp(dst), dh, dw)
+    return dst
+
+
+def paste_masks(masks, cls, ref_boxes, im_h, im_w, thresh=0.5, cls_specific=True,
+                want_prob=False, resize=None):
+    """Device-layout restatement of segm_results (test.py:801-855) without the RLE
+    step: ``masks`` (R,K,M,M) fp32, ``cls`` (R,) class of each detection in the
+    reference's class-major running order, ``ref_boxes`` (R,4) fp32.
+    Returns (R, im_h, im_w) uint8 [and the fp32 probabilities the reference
+    thresholds at :832, pasted the same way, when ``want_prob``]."""
+    resize = resize or resize_linear
+    R, K, M, _ = masks.shape
+    scale = (M + 2.0) / M
+    boxes = expand_boxes(ref_boxes, scale).astype(np.int32)           # truncation toward zero
+    out = np.zeros((R, im_h, im_w), dtype=np.uint8)
+    prob = np.zeros((R, im_h, im_w), dtype=np.float32) if want_prob else None
+    padded = np.zeros((M + 2, M + 2), dtype=np.float32)
+    for i in range(R):
+        padded[1:-1, 1:-1] = masks[i, int(cls[i]) if cls_specific else 0]
+        x0b, y0b, x1b, y1b = (int(v) for v in boxes[i])
+        w = max(x1b - x0b + 1, 1)
+        h = max(y1b - y0b + 1, 1)
+        m = resize(padded, w, h)
+        x_0, x_1 = max(x0b, 0), min(x1b + 1, im_w)
+        y_0, y_1 = max(y0b, 0), min(y1b + 1, im_h)
+        if x_1 <= x_0 or y_1 <= y_0:
+            continue
+        sub = m[(y_0 - y0b):(y_1 - y0b), (x_0 - x0b):(x_1 - x0b)]
+        out[i, y_0:y_1, x_0:x_1] = (sub > thresh).astype(np.uint8)
+        if want_prob:
+            prob[i, y_0:y_1, x_0:x_1] = sub
+    return (out, prob) if want_prob else out
+
+
+def num_threads():
+    return lib().orc_num_threads()

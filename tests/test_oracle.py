@@ -1,0 +1,132 @@
+"""CPU: the oracle restatement against the golden vectors produced by the reference itself
+(tests/golden/make_golden.py) and against the third-party functions it restates."""
+import numpy as np
+import pytest
+
+
+def test_anchor_known_answer(orc, golden):
+    # the 9 stride-16 anchors quoted in lib/modeling/generate_anchors.py:26-51
+    kat = np.array([[-84, -40, 99, 55], [-176, -88, 191, 103], [-360, -184, 375, 199],
+                    [-56, -56, 71, 71], [-120, -120, 135, 135], [-248, -248, 263, 263],
+                    [-36, -80, 51, 95], [-80, -168, 95, 183], [-168, -344, 183, 359]], dtype=np.float64)
+    a = orc.generate_anchors(16, (128, 256, 512), (0.5, 1, 2))
+    assert a.dtype == np.float64 and np.array_equal(a, kat)
+    g = golden("anchors")
+    assert np.array_equal(g["kat_stride16"], kat)
+    for lvl in range(2, 7):
+        assert np.array_equal(orc.fpn_anchors(lvl), g["fpn%d" % lvl])
+
+
+def test_generate_proposals_golden(orc, golden):
+    g = golden("proposals")
+    for lvl in range(2, 7):
+        rois, probs = orc.generate_proposals(g["scores%d" % lvl], g["deltas%d" % lvl], g["im_info"],
+                                             orc.fpn_anchors(lvl), 1. / 2 ** lvl, int(g["pre"]), int(g["post"]),
+                                             float(g["thresh"]), float(g["min_size"]))
+        assert rois.dtype == np.float32 and probs.dtype == np.float32
+        assert np.array_equal(rois, g["rois%d" % lvl]), lvl
+        assert np.array_equal(probs, g["probs%d" % lvl]), lvl
+    rois, probs = orc.generate_proposals(g["scores3"], g["deltas3"], g["im_info"], orc.fpn_anchors(3), 1. / 8,
+                                         int(g["pre"]), int(g["post"]), float(g["thresh"]), 16)
+    assert np.array_equal(rois, g["rois3_min16"]) and np.array_equal(probs, g["probs3_min16"])
+    assert not np.array_equal(rois, g["rois3"])      # the filter really removed boxes
+
+
+def test_nms_golden(orc, golden):
+    g = golden("nms")
+    for t in (0.3, 0.5, 0.7):
+        for kind in ("unsorted", "sorted"):
+            keep = orc.nms(g["dets_" + kind], t)
+            ref = g["keep_%s_%02d" % (kind, int(t * 10))]
+            assert keep.dtype == np.int64 and np.array_equal(keep, ref), (t, kind)
+    assert orc.nms(np.zeros((0, 5), np.float32), 0.5) == []
+
+
+def test_collect_distribute_golden(orc, golden):
+    g = golden("collect_distribute")
+    rois = orc.collect([g["in_rois%d" % l] for l in range(2, 7)], [g["in_probs%d" % l] for l in range(2, 7)],
+                       int(g["post"]))
+    assert np.array_equal(rois, g["rois"])
+    assert np.array_equal(orc.map_rois_to_fpn_levels(rois[:, 1:5]), g["levels"])
+    d = orc.distribute(rois)
+    for k in ("rois_fpn2", "rois_fpn3", "rois_fpn4", "rois_fpn5", "rois_idx_restore_int32"):
+        assert d[k].dtype == g[k].dtype and np.array_equal(d[k], g[k]), k
+    wide = g["wide_rois"]
+    assert np.array_equal(orc.map_rois_to_fpn_levels(wide[:, 1:5]), g["wide_levels"])
+    d = orc.distribute(wide)
+    for k in ("rois_fpn2", "rois_fpn3", "rois_fpn4", "rois_fpn5", "rois_idx_restore_int32"):
+        assert np.array_equal(d[k], g["wide_" + k]), k
+    assert {int(v) for v in g["wide_levels"]} == {2, 3, 4, 5}
+
+
+def test_box_helpers_golden(orc, golden):
+    g = golden("boxes")
+    xf = orc.bbox_transform(g["boxes"], g["deltas"], (10., 10., 5., 5.))
+    assert np.array_equal(xf, g["transformed"])
+    cl = orc.clip_tiled_boxes(xf.copy(), np.array([192, 256], dtype=np.float32))
+    assert np.array_equal(cl, g["clipped"])
+    ex = orc.expand_boxes(g["boxes"], 30.0 / 28.0)
+    assert ex.dtype == np.float64 and np.array_equal(ex, g["expanded"])
+
+
+def test_paste_golden(orc, golden):
+    g = golden("paste")
+    fh, fw = (int(v) for v in g["frame_hw"])
+    ref = np.unpackbits(g["packed"], axis=-1)[..., :fw]
+    out, prob = orc.paste_masks(g["masks"], g["cls"], g["boxes"], fh, fw, want_prob=True)
+    # the C restatement of cv2.resize is within 4e-6 of cv2, so a pixel may only flip when the
+    # probability sits on the 0.5 threshold
+    diff = out != ref
+    assert np.all(np.abs(prob[diff] - 0.5) < 1e-5)
+    assert diff.sum() <= 2
+    assert ref.sum() > 1000
+
+
+def test_resize_restatement_vs_cv2(orc):
+    cv2 = pytest.importorskip("cv2")
+    rs = np.random.RandomState(3)
+    worst = 0.0
+    for _ in range(150):
+        M = rs.choice([14, 28, 56])
+        src = np.zeros((M + 2, M + 2), np.float32)
+        src[1:-1, 1:-1] = rs.uniform(size=(M, M)).astype(np.float32)
+        w, h = int(rs.randint(1, 300)), int(rs.randint(1, 300))
+        a = orc.resize_linear(src, w, h)
+        b = cv2.resize(src, (w, h))
+        worst = max(worst, float(np.abs(a - b).max()))
+    a = orc.resize_linear(src, (M + 2) // 2, (M + 2) // 2)        # the INTER_AREA special case
+    worst = max(worst, float(np.abs(a - cv2.resize(src, ((M + 2) // 2, (M + 2) // 2))).max()))
+    assert worst <= 4e-6, worst
+
+
+def test_roialign_forward_vs_torchvision_golden(orc, golden):
+    g = golden("roialign_tv")
+    for lvl in (2, 3, 4, 5):
+        for res in (7, 14):
+            out = orc.roi_align_forward(g["feat%d" % lvl], g["rois"], res, res, 1. / 2 ** lvl, 2)
+            ref = g["tv_fwd_l%d_r%d" % (lvl, res)]
+            # two fp32 evaluations of the same formula that round the sample coordinates
+            # differently: loose anchor only
+            assert np.abs(out - ref).max() < 1e-4, (lvl, res, np.abs(out - ref).max())
+
+
+def test_roialign_backward_is_adjoint_of_forward(orc, synth):
+    rs = np.random.RandomState(9)
+    feats = rs.standard_normal((2, 3, 20, 24)).astype(np.float32)
+    rois = synth.random_rois(10, 12, (160, 192), num_images=2, smin=8, smax=150)
+    rois = np.concatenate([rois, synth.edge_rois((160, 192))])
+    for sr in (2, 0):
+        out = orc.roi_align_forward(feats, rois, 7, 7, 0.125, sr)
+        gout = rs.standard_normal(out.shape).astype(np.float32)
+        gin = orc.roi_align_backward(gout, rois, feats.shape, 7, 7, 0.125, sr)
+        lhs = float((out.astype(np.float64) * gout).sum())
+        rhs = float((feats.astype(np.float64) * gin).sum())
+        assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs)), (sr, lhs, rhs)
+
+
+def test_roialign_oracle_threads_agree(orc, synth):
+    feats = np.random.RandomState(1).standard_normal((1, 4, 30, 40)).astype(np.float32)
+    rois = synth.random_rois(2, 20, (240, 320))
+    a = orc.roi_align_forward(feats, rois, 7, 7, 0.125, 2, nthreads=1)
+    b = orc.roi_align_forward(feats, rois, 7, 7, 0.125, 2, nthreads=4)
+    assert np.array_equal(a, b)

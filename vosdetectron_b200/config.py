@@ -1,0 +1,89 @@
+"""The ~20 configuration keys the region pipeline reads.
+
+The reference reads them from a global mutable ``cfg`` AttrDict
+(lib/core/config.py:22); here they are an explicit object.  ``RegionConfig.from_cfg``
+adapts a reference-style ``cfg`` (anything with attribute access) so the shims
+can be dropped into the unmodified model builders, and ``set_cfg`` / ``get_cfg``
+hold the process-wide default the reference-signature shims consult.
+"""
+import copy
+import math
+from dataclasses import dataclass, field
+
+
+@dataclass
+class RpnMode:
+    pre_nms_topN: int
+    post_nms_topN: int
+    nms_thresh: float = 0.7
+    min_size: float = 0.0
+
+
+@dataclass
+class RegionConfig:
+    # {TRAIN,TEST}.RPN_* (lib/core/config.py:132-149, 202-215; yaml e2e_mask_rcnn_R-50-FPN_1x.yaml:37-43)
+    train: RpnMode = field(default_factory=lambda: RpnMode(2000, 2000))
+    test: RpnMode = field(default_factory=lambda: RpnMode(1000, 1000))
+    # FPN.* (config.py:679-722)
+    rpn_min_level: int = 2
+    rpn_max_level: int = 6
+    roi_min_level: int = 2
+    roi_max_level: int = 5
+    roi_canonical_scale: float = 224.0
+    roi_canonical_level: int = 4
+    rpn_collect_scale: float = 1.0
+    rpn_anchor_start_size: int = 32
+    rpn_aspect_ratios: tuple = (0.5, 1, 2)
+    # BBOX_XFORM_CLIP (config.py:1009)
+    bbox_xform_clip: float = math.log(1000.0 / 16.0)
+    # MODEL / MRCNN (config.py:740-775)
+    num_classes: int = 81
+    mrcnn_resolution: int = 28
+    mrcnn_thresh_binarize: float = 0.5
+    mrcnn_cls_specific_mask: bool = True
+
+    def mode(self, training):
+        return self.train if training else self.test
+
+    def collect_post_topN(self, training):
+        # int(POST_NMS_TOP_N * RPN_COLLECT_SCALE + 0.5), collect_and_distribute...py:93
+        return int(self.mode(training).post_nms_topN * self.rpn_collect_scale + 0.5)
+
+    @classmethod
+    def from_cfg(cls, cfg):
+        def mode(m):
+            return RpnMode(int(m.RPN_PRE_NMS_TOP_N), int(m.RPN_POST_NMS_TOP_N), float(m.RPN_NMS_THRESH),
+                           float(m.RPN_MIN_SIZE))
+        return cls(
+            train=mode(cfg.TRAIN), test=mode(cfg.TEST),
+            rpn_min_level=int(cfg.FPN.RPN_MIN_LEVEL), rpn_max_level=int(cfg.FPN.RPN_MAX_LEVEL),
+            roi_min_level=int(cfg.FPN.ROI_MIN_LEVEL), roi_max_level=int(cfg.FPN.ROI_MAX_LEVEL),
+            roi_canonical_scale=float(cfg.FPN.ROI_CANONICAL_SCALE),
+            roi_canonical_level=int(cfg.FPN.ROI_CANONICAL_LEVEL),
+            rpn_collect_scale=float(cfg.FPN.RPN_COLLECT_SCALE),
+            rpn_anchor_start_size=int(cfg.FPN.RPN_ANCHOR_START_SIZE),
+            rpn_aspect_ratios=tuple(cfg.FPN.RPN_ASPECT_RATIOS),
+            bbox_xform_clip=float(cfg.BBOX_XFORM_CLIP),
+            num_classes=int(cfg.MODEL.NUM_CLASSES),
+            mrcnn_resolution=int(cfg.MRCNN.RESOLUTION),
+            mrcnn_thresh_binarize=float(cfg.MRCNN.THRESH_BINARIZE),
+            mrcnn_cls_specific_mask=bool(cfg.MRCNN.CLS_SPECIFIC_MASK),
+        )
+
+
+_default = RegionConfig()
+
+
+def get_cfg():
+    return _default
+
+
+def set_cfg(cfg):
+    """Install the process-wide default (a RegionConfig, or a reference-style cfg)."""
+    global _default
+    _default = cfg if isinstance(cfg, RegionConfig) else RegionConfig.from_cfg(cfg)
+    return _default
+
+
+def clone_cfg():
+    return copy.deepcopy(_default)

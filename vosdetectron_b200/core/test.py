@@ -1,0 +1,86 @@
+"""Drop-in for segm_results (lib/core/test.py:801-855; identical copy in
+lib_vos/tools/vos_test.py:867-921).
+
+``segm_results(cls_boxes, masks, ref_boxes, im_h, im_w)`` keeps the reference signature and
+returns ``cls_segms``: per class a list of COCO RLE dicts.  The expand / resize / threshold /
+paste work is ONE kernel over all detections (csrc/paste.cu); the RLE step stays on the host
+(pycocotools when present, else the equivalent NumPy encoder below).
+``paste_masks`` returns the dense (R, im_h, im_w) uint8 masks without the RLE step.
+"""
+import numpy as np
+import torch
+
+from .. import ops
+from ..config import get_cfg
+
+try:                                     # pragma: no cover - optional dependency of the reference
+    import pycocotools.mask as mask_util
+except Exception:                        # noqa: BLE001
+    mask_util = None
+
+
+def rle_encode(mask):
+    """COCO compressed RLE of a (H,W) uint8 mask (column-major runs, LEB128-like string) --
+    what pycocotools.mask.encode returns for one mask, with 'counts' as ascii str."""
+    h, w = mask.shape
+    flat = np.asarray(mask, dtype=np.uint8).ravel(order='F')
+    change = np.flatnonzero(flat[1:] != flat[:-1]) + 1
+    bounds = np.concatenate(([0], change, [flat.size]))
+    counts = np.diff(bounds).tolist()
+    if flat.size and flat[0] == 1:
+        counts = [0] + counts
+    out = []
+    for i, x in enumerate(counts):
+        if i > 2:
+            x -= counts[i - 2]
+        more = True
+        while more:
+            c = x & 0x1f
+            x >>= 5
+            more = (x != -1) if (c & 0x10) else (x != 0)
+            if more:
+                c |= 0x20
+            out.append(chr(c + 48))
+    return {'size': [int(h), int(w)], 'counts': ''.join(out)}
+
+
+def _class_order(cls_boxes, num_classes):
+    """Mask channel of every detection in the reference's class-major running order (:816-850)."""
+    cls = []
+    for j in range(1, num_classes):
+        cls += [j] * int(len(cls_boxes[j]))
+    return np.asarray(cls, dtype=np.int32)
+
+
+def paste_masks(cls_boxes, masks, ref_boxes, im_h, im_w, cfg=None):
+    cfg = cfg or get_cfg()
+    cls = _class_order(cls_boxes, cfg.num_classes)
+    R = cls.shape[0]
+    assert R == masks.shape[0]                                    # test.py:854
+    if R == 0:
+        return np.zeros((0, im_h, im_w), dtype=np.uint8), cls
+    if isinstance(masks, torch.Tensor) and masks.is_cuda:
+        m = masks
+        c = torch.from_numpy(cls if cfg.mrcnn_cls_specific_mask else np.zeros_like(cls)).to(m.device)
+    else:
+        masks = np.asarray(masks, dtype=np.float32)
+        sel = masks[np.arange(R), cls if cfg.mrcnn_cls_specific_mask else 0]      # (R,M,M): upload only what is read
+        m = torch.from_numpy(np.ascontiguousarray(sel[:, None])).cuda()
+        c = None
+    b = torch.from_numpy(np.ascontiguousarray(ref_boxes, dtype=np.float32)).to(m.device)
+    out = ops.paste_masks_cuda(m, c, b, int(im_h), int(im_w), cfg.mrcnn_thresh_binarize)
+    return out.cpu().numpy(), cls
+
+
+def segm_results(cls_boxes, masks, ref_boxes, im_h, im_w, cfg=None):
+    cfg = cfg or get_cfg()
+    im_masks, cls = paste_masks(cls_boxes, masks, ref_boxes, im_h, im_w, cfg)
+    cls_segms = [[] for _ in range(cfg.num_classes)]
+    for i, j in enumerate(cls):
+        if mask_util is not None:
+            rle = mask_util.encode(np.array(im_masks[i][:, :, np.newaxis], order='F'))[0]
+            rle['counts'] = rle['counts'].decode('ascii')
+        else:
+            rle = rle_encode(im_masks[i])
+        cls_segms[int(j)].append(rle)
+    return cls_segms

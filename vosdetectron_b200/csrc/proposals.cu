@@ -1,0 +1,552 @@
+// RPN proposal generation + greedy NMS for sm_100a.
+// Reference: lib/modeling/generate_proposals.py:20-182, lib/utils/boxes.py:138-205,
+// lib/utils/cython_nms.pyx:37-87.
+//
+// One call covers every (level, image) segment:
+//   K1 topk_decode_kernel : 1 CTA / segment -- radix-select the pre_nms_topN best scores,
+//                           bitonic-sort them, decode + clip + filter the survivors.
+//   K2 nms_mask_kernel    : 64x64 IoU tiles -> suppression bitmask (upper triangle only).
+//   K3 nms_reduce_kernel  : 1 warp / segment -- ordered greedy reduce over 64-box chunks,
+//                           writes the first post_nms_topN kept boxes.
+#include <math.h>
+#include "common.cuh"
+#include "select_sort.cuh"
+
+namespace vosd {
+
+// ------------------------------------------------------------------------------------
+// Box arithmetic, operation for operation as NumPy evaluates it (no FMA contraction).
+// ------------------------------------------------------------------------------------
+// bbox_transform (boxes.py:156-205) for one anchor/delta pair.  BBOX_XFORM_CLIP is an
+// np.float64 scalar (core/config.py:1009), so under NumPy >= 2 the dw/dh branch --
+// np.minimum, np.exp, * widths, np.maximum(.,1), 0.5 * pred_w -- is carried in float64 and
+// rounded once when stored into the float32 pred_boxes; the centre branch stays float32.
+__device__ __forceinline__ float4 decode_box(float ax1, float ay1, float ax2, float ay2,
+                                             float d0, float d1, float d2, float d3,
+                                             float wx, float wy, float ww, float wh, double clip) {
+    const float bw = __fadd_rn(__fsub_rn(ax2, ax1), 1.0f);
+    const float bh = __fadd_rn(__fsub_rn(ay2, ay1), 1.0f);
+    const float cx = __fadd_rn(ax1, __fmul_rn(0.5f, bw));
+    const float cy = __fadd_rn(ay1, __fmul_rn(0.5f, bh));
+    const float dx = __fdiv_rn(d0, wx), dy = __fdiv_rn(d1, wy);
+    const double dw = fmin((double)__fdiv_rn(d2, ww), clip);
+    const double dh = fmin((double)__fdiv_rn(d3, wh), clip);
+    const float pcx = __fadd_rn(__fmul_rn(dx, bw), cx);
+    const float pcy = __fadd_rn(__fmul_rn(dy, bh), cy);
+    const double pw = fmax(__dmul_rn(exp(dw), (double)bw), 1.0);
+    const double ph = fmax(__dmul_rn(exp(dh), (double)bh), 1.0);
+    const double hw = __dmul_rn(0.5, pw), hh = __dmul_rn(0.5, ph);
+    float4 o;
+    o.x = (float)__dsub_rn((double)pcx, hw);
+    o.y = (float)__dsub_rn((double)pcy, hh);
+    o.z = (float)__dsub_rn(__dadd_rn((double)pcx, hw), 1.0);
+    o.w = (float)__dsub_rn(__dadd_rn((double)pcy, hh), 1.0);
+    return o;
+}
+
+// clip_tiled_boxes (boxes.py:138-153): max(min(v, size - 1), 0) in fp32.
+__device__ __forceinline__ float4 clip_box(float4 b, float im_h, float im_w) {
+    const float mx = __fsub_rn(im_w, 1.f), my = __fsub_rn(im_h, 1.f);
+    b.x = fmaxf(fminf(b.x, mx), 0.f);
+    b.y = fmaxf(fminf(b.y, my), 0.f);
+    b.z = fmaxf(fminf(b.z, mx), 0.f);
+    b.w = fmaxf(fminf(b.w, my), 0.f);
+    return b;
+}
+
+// _filter_boxes (generate_proposals.py:171-182).
+__device__ __forceinline__ bool keep_box(float4 b, float min_size, float im_h, float im_w) {
+    const float ws = __fadd_rn(__fsub_rn(b.z, b.x), 1.f);
+    const float hs = __fadd_rn(__fsub_rn(b.w, b.y), 1.f);
+    const float xc = __fadd_rn(b.x, __fdiv_rn(ws, 2.f));
+    const float yc = __fadd_rn(b.y, __fdiv_rn(hs, 2.f));
+    return ws >= min_size && hs >= min_size && xc < im_w && yc < im_h;
+}
+
+// IoU test of cython_nms.pyx:70-85 in IEEE fp32, +1 widths, `>=`.
+__device__ __forceinline__ float box_area(float4 b) {
+    return __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+}
+__device__ __forceinline__ bool suppresses(float4 a, float area_a, float4 b, float area_b, float thresh) {
+    const float xx1 = a.x >= b.x ? a.x : b.x;
+    const float yy1 = a.y >= b.y ? a.y : b.y;
+    const float xx2 = a.z <= b.z ? a.z : b.z;
+    const float yy2 = a.w <= b.w ? a.w : b.w;
+    float w = __fadd_rn(__fsub_rn(xx2, xx1), 1.f);
+    float h = __fadd_rn(__fsub_rn(yy2, yy1), 1.f);
+    w = 0.f >= w ? 0.f : w;
+    h = 0.f >= h ? 0.f : h;
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+    return ovr >= thresh;
+}
+
+// ------------------------------------------------------------------------------------
+struct RpnLevelDev {
+    const float* scores;
+    const float* deltas;
+    int H, W, A;
+    int n;            // A*H*W
+    int take;         // boxes entering NMS for this level: min(pre_nms_topN or n, n)
+    double stride;
+    double anchors[4 * VOSD_MAX_ANCHORS];
+};
+struct RpnParams {
+    RpnLevelDev lv[VOSD_MAX_LEVELS];
+    int num_levels, num_images;
+    int seg_stride;   // M: rows reserved per segment in the workspace
+    int sort_cap;     // power of two >= M
+    float min_size;
+    double xform_clip;
+};
+
+struct RpnKeys {
+    const float* s;   // scores of one image at one level, (A, H*W)
+    int A, HW;
+    __device__ __forceinline__ uint64_t operator()(int j) const {
+        const int a = j / HW;
+        const uint32_t flat = (uint32_t)(j - a * HW) * (uint32_t)A + (uint32_t)a;   // (h, w, a) order
+        return ((uint64_t)float_to_ordered(__ldg(s + j)) << 32) | (uint64_t)(0xffffffffu - flat);
+    }
+};
+
+// K1.  grid = num_levels * num_images, block = 1024, dyn smem = sort_cap * 8.
+__global__ void __launch_bounds__(kSelThreads, 1)
+topk_decode_kernel(const __grid_constant__ RpnParams p, const float* __restrict__ im_info,
+                   float4* __restrict__ ws_boxes, float* __restrict__ ws_scores,
+                   int* __restrict__ ws_count) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(dyn);
+    __shared__ SelectShared sh;
+
+    const int seg = blockIdx.x;
+    const int l = seg / p.num_images, img = seg - l * p.num_images;
+    const RpnLevelDev& L = p.lv[l];
+    const int HW = L.H * L.W;
+    RpnKeys kf{L.scores + (size_t)img * L.n, L.A, HW};
+    const int P = next_pow2(L.take);
+    const int m = select_and_sort(kf, L.n, L.n, L.take, keys, P, sh);
+
+    const float im_h = im_info[img * 3 + 0], im_w = im_info[img * 3 + 1], im_s = im_info[img * 3 + 2];
+    const float min_size = __fmul_rn(p.min_size, im_s);
+    const float* __restrict__ dl = L.deltas + (size_t)img * 4 * L.n;
+    float4* ob = ws_boxes + (size_t)seg * p.seg_stride;
+    float* os = ws_scores + (size_t)seg * p.seg_stride;
+
+    // decode + clip + filter, then a stable compaction in rank order
+    int base = 0;
+    for (int t0 = 0; t0 < m; t0 += kSelThreads) {
+        const int t = t0 + threadIdx.x;
+        bool keep = false;
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        float score = 0.f;
+        if (t < m) {
+            const uint64_t k = keys[t];
+            score = ordered_to_float((uint32_t)(k >> 32));
+            const uint32_t flat = 0xffffffffu - (uint32_t)k;
+            const int a = (int)(flat % (uint32_t)L.A);
+            const int pos = (int)(flat / (uint32_t)L.A);
+            const int h = pos / L.W, w = pos - h * L.W;
+            const double sx = __dmul_rn((double)w, L.stride), sy = __dmul_rn((double)h, L.stride);
+            const float ax1 = (float)__dadd_rn(L.anchors[4 * a + 0], sx), ay1 = (float)__dadd_rn(L.anchors[4 * a + 1], sy);
+            const float ax2 = (float)__dadd_rn(L.anchors[4 * a + 2], sx), ay2 = (float)__dadd_rn(L.anchors[4 * a + 3], sy);
+            const float* d = dl + (size_t)(4 * a) * HW + pos;
+            box = decode_box(ax1, ay1, ax2, ay2, __ldg(d), __ldg(d + HW), __ldg(d + 2 * HW), __ldg(d + 3 * HW),
+                             1.f, 1.f, 1.f, 1.f, p.xform_clip);
+            box = clip_box(box, im_h, im_w);
+            keep = keep_box(box, min_size, im_h, im_w);
+        }
+        int total;
+        const int off = block_exclusive_scan(keep ? 1 : 0, sh.warp_sums, total);
+        if (keep) { ob[base + off] = box; os[base + off] = score; }
+        base += total;
+    }
+    if (threadIdx.x == 0) ws_count[seg] = base;
+}
+
+// K2.  grid = (col blocks, row blocks, segments), block = 64.  Bit j of mask[i][c] is set
+// when sorted box i suppresses sorted box 64c+j (only j-global > i is ever computed).
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ count, int seg_stride,
+                int words_per_row, float thresh, unsigned long long* __restrict__ mask) {
+    const int seg = blockIdx.z;
+    const int n = count[seg];
+    const int rb = blockIdx.y, cb = blockIdx.x;
+    if (cb < rb || rb * 64 >= n || cb * 64 >= n) return;
+    const float4* b = boxes + (size_t)seg * seg_stride;
+    __shared__ float4 cbox[64];
+    __shared__ float carea[64];
+    const int cj = cb * 64 + threadIdx.x;
+    if (cj < n) {
+        const float4 v = b[cj];
+        cbox[threadIdx.x] = v;
+        carea[threadIdx.x] = box_area(v);
+    }
+    __syncthreads();
+    const int i = rb * 64 + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = b[i];
+    const float area = box_area(a);
+    const int ncol = min(64, n - cb * 64);
+    unsigned long long bits = 0;
+    const int start = (cb == rb) ? threadIdx.x + 1 : 0;
+    for (int j = start; j < ncol; j++)
+        if (suppresses(a, area, cbox[j], carea[j], thresh)) bits |= 1ull << j;
+    mask[((size_t)seg * seg_stride + i) * words_per_row + cb] = bits;
+}
+
+// K3.  grid = segments, block = 32 (one warp).  Greedy reduce in sorted order, 64 boxes at
+// a time: resolve the chunk against itself sequentially, then OR the rows of its survivors
+// into the running `removed` bitmap.
+//   mode 0: write [img, box] / score of the first `post` kept boxes (proposal path);
+//   mode 1: set keep_flag[orig_index[pos]] for every kept box (standalone nms).
+constexpr int kMaxWords = VOSD_MAX_TOPK / 64;
+__global__ void __launch_bounds__(32)
+nms_reduce_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                  const int* __restrict__ count, int seg_stride, int words_per_row,
+                  const unsigned long long* __restrict__ mask, int use_mask, int post, int mode,
+                  int num_images, int cap, float* __restrict__ out_rois, float* __restrict__ out_probs,
+                  int* __restrict__ out_count, const int* __restrict__ orig_index,
+                  int* __restrict__ keep_flag) {
+    __shared__ unsigned long long removed[kMaxWords];
+    __shared__ unsigned long long diag[64];
+    const int seg = blockIdx.x, lane = threadIdx.x;
+    const int n = count[seg];
+    const int nblk = (n + 63) / 64;
+    const float4* b = boxes + (size_t)seg * seg_stride;
+    const float* sc = scores ? scores + (size_t)seg * seg_stride : nullptr;
+    const unsigned long long* mrow = mask + (size_t)seg * seg_stride * words_per_row;
+    const int limit = post > 0 ? post : n;
+    const float img = (float)(seg % num_images);
+    for (int w = lane; w < nblk; w += 32) removed[w] = 0;
+    __syncwarp();
+    int kept_total = 0;
+    for (int c = 0; c < nblk && kept_total < limit; c++) {
+        const int i0 = c * 64;
+        const int nin = min(64, n - i0);
+        unsigned long long kept;
+        if (use_mask) {
+            for (int t = lane; t < 64; t += 32)
+                diag[t] = t < nin ? mrow[(size_t)(i0 + t) * words_per_row + c] : 0ull;
+            __syncwarp();
+            unsigned long long alive = ~removed[c];
+            if (nin < 64) alive &= (1ull << nin) - 1ull;
+            kept = 0;
+#pragma unroll 8
+            for (int t = 0; t < 64; t++) {
+                const unsigned long long d = diag[t];
+                if ((alive >> t) & 1ull) { kept |= 1ull << t; alive &= ~d; }
+            }
+            // OR the rows of the survivors into the words of the following chunks
+            for (int w = c + 1 + lane; w < nblk; w += 32) {
+                unsigned long long acc = removed[w];
+                unsigned long long kk = kept;
+                while (kk) {
+                    const int t = __ffsll((long long)kk) - 1;
+                    kk &= kk - 1;
+                    acc |= mrow[(size_t)(i0 + t) * words_per_row + w];
+                }
+                removed[w] = acc;
+            }
+            __syncwarp();
+        } else {
+            kept = nin < 64 ? (1ull << nin) - 1ull : ~0ull;
+        }
+        // emit survivors of this chunk in order
+        for (int t = lane; t < 64; t += 32) {
+            if ((kept >> t) & 1ull) {
+                const int pos = kept_total + __popcll(kept & ((1ull << t) - 1ull));
+                if (pos < limit) {
+                    if (mode == 0) {
+                        const float4 v = b[i0 + t];
+                        float* r = out_rois + ((size_t)seg * cap + pos) * 5;
+                        r[0] = img; r[1] = v.x; r[2] = v.y; r[3] = v.z; r[4] = v.w;
+                        out_probs[(size_t)seg * cap + pos] = sc[i0 + t];
+                    } else {
+                        keep_flag[orig_index[i0 + t]] = 1;
+                    }
+                }
+            }
+        }
+        kept_total += __popcll(kept);
+    }
+    if (lane == 0 && out_count) out_count[seg] = min(kept_total, limit);
+}
+
+// ------------------------------------------------------------------------------------
+// Streaming decode of every anchor of a level (coalesced plane reads, 16-byte stores).
+// grid-stride over (image, position); each thread handles all A anchors of one position.
+// ------------------------------------------------------------------------------------
+struct DecodeAllParams {
+    const float* deltas;
+    int H, W, A, N;
+    double stride, clip;
+    double anchors[4 * VOSD_MAX_ANCHORS];
+};
+__global__ void __launch_bounds__(256)
+decode_all_kernel(const __grid_constant__ DecodeAllParams p, const float* __restrict__ im_info, float4* __restrict__ out) {
+    const int HW = p.H * p.W;
+    const long long total = (long long)p.N * HW;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int img = (int)(idx / HW);
+        const int pos = (int)(idx - (long long)img * HW);
+        const int h = pos / p.W, w = pos - h * p.W;
+        const float im_h = __ldg(im_info + img * 3), im_w = __ldg(im_info + img * 3 + 1);
+        const double sx = __dmul_rn((double)w, p.stride), sy = __dmul_rn((double)h, p.stride);
+        const float* d = p.deltas + (size_t)img * 4 * p.A * HW + pos;
+        float4* o = out + ((size_t)img * HW + pos) * p.A;
+        for (int a = 0; a < p.A; a++) {
+            const float ax1 = (float)__dadd_rn(p.anchors[4 * a + 0], sx), ay1 = (float)__dadd_rn(p.anchors[4 * a + 1], sy);
+            const float ax2 = (float)__dadd_rn(p.anchors[4 * a + 2], sx), ay2 = (float)__dadd_rn(p.anchors[4 * a + 3], sy);
+            const float* da = d + (size_t)(4 * a) * HW;
+            float4 box = decode_box(ax1, ay1, ax2, ay2, __ldg(da), __ldg(da + HW), __ldg(da + 2 * HW),
+                                    __ldg(da + 3 * HW), 1.f, 1.f, 1.f, 1.f, p.clip);
+            box = clip_box(box, im_h, im_w);
+            st_stream_f4(o + a, box);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+any_nan_kernel(const float* __restrict__ x, size_t n, int* flag) {
+    bool bad = false;
+    const size_t n4 = n / 4;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = ld_stream_f4(x4 + i);
+        bad |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float v = x[n4 * 4 + threadIdx.x]; bad |= v != v; }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+// ------------------------------------------------------------------------------------
+// Standalone NMS helpers: sort (n,5) dets by score, then reuse K2/K3.
+// ------------------------------------------------------------------------------------
+struct DetKeys {
+    const float* d;
+    __device__ __forceinline__ uint64_t operator()(int j) const {
+        return ((uint64_t)float_to_ordered(__ldg(d + 5 * (size_t)j + 4)) << 32) | (uint64_t)(0xffffffffu - (uint32_t)j);
+    }
+};
+__global__ void __launch_bounds__(kSelThreads, 1)
+nms_sort_kernel(const float* __restrict__ dets, int n, int P, float4* __restrict__ boxes,
+                int* __restrict__ orig, int* __restrict__ count, int* __restrict__ keep_flag) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(dyn);
+    __shared__ SelectShared sh;
+    DetKeys kf{dets};
+    select_and_sort(kf, n, n, n, keys, P, sh);
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int j = (int)(0xffffffffu - (uint32_t)keys[t]);
+        const float* r = dets + 5 * (size_t)j;
+        boxes[t] = make_float4(r[0], r[1], r[2], r[3]);
+        orig[t] = j;
+        keep_flag[t] = 0;
+    }
+    if (threadIdx.x == 0) *count = n;
+}
+
+// keep = np.where(flag)[0] as int64 (ascending index), 1 CTA.
+__global__ void __launch_bounds__(kSelThreads, 1)
+compact_flags_kernel(const int* __restrict__ flag, int n, long long* __restrict__ keep, int* __restrict__ num_keep) {
+    __shared__ int warp_sums[32];
+    int base = 0;
+    for (int t0 = 0; t0 < n; t0 += kSelThreads) {
+        const int t = t0 + threadIdx.x;
+        const int f = (t < n && flag[t]) ? 1 : 0;
+        int total;
+        const int off = block_exclusive_scan(f, warp_sums, total);
+        if (f) keep[base + off] = t;
+        base += total;
+    }
+    if (threadIdx.x == 0) *num_keep = base;
+}
+
+static int seg_take(const vosd_rpn_level& L, int pre) {
+    const long long n = (long long)L.num_anchors * L.height * L.width;
+    return (int)((pre <= 0 || pre >= n) ? n : pre);
+}
+
+struct PropLayout {
+    int M, words, cap, S;
+    size_t off_boxes, off_scores, off_count, off_mask, total;
+};
+static int prop_layout(const vosd_rpn_level* levels, int num_levels, int num_images, int pre, int post,
+                       PropLayout& lay) {
+    if (!levels) return VOSD_ERR_BAD_ARG;
+    if (num_levels < 1 || num_levels > VOSD_MAX_LEVELS || num_images < 1) return VOSD_ERR_BAD_SHAPE;
+    int M = 0;
+    for (int l = 0; l < num_levels; l++) {
+        const vosd_rpn_level& L = levels[l];
+        if (L.height <= 0 || L.width <= 0 || L.num_anchors <= 0) return VOSD_ERR_BAD_SHAPE;
+        if (L.num_anchors > VOSD_MAX_ANCHORS) return VOSD_ERR_UNSUPPORTED;
+        if ((long long)L.num_anchors * L.height * L.width > 0x7fffffffLL / 8) return VOSD_ERR_UNSUPPORTED;
+        const int t = seg_take(L, pre);
+        if (t > VOSD_MAX_TOPK) return VOSD_ERR_UNSUPPORTED;
+        M = t > M ? t : M;
+    }
+    lay.M = M;
+    lay.words = (M + 63) / 64;
+    lay.cap = post > 0 && post < M ? post : M;
+    lay.S = num_levels * num_images;
+    size_t o = 0;
+    lay.off_boxes = o;  o = align_up(o + (size_t)lay.S * M * sizeof(float4), 256);
+    lay.off_scores = o; o = align_up(o + (size_t)lay.S * M * sizeof(float), 256);
+    lay.off_count = o;  o = align_up(o + (size_t)lay.S * sizeof(int), 256);
+    lay.off_mask = o;   o = align_up(o + (size_t)lay.S * M * lay.words * sizeof(unsigned long long), 256);
+    lay.total = o;
+    return VOSD_OK;
+}
+
+}  // namespace vosd
+
+using namespace vosd;
+
+extern "C" int vosd_proposals_capacity(const vosd_rpn_level* levels, int num_levels,
+                                       int pre_nms_topN, int post_nms_topN) {
+    PropLayout lay;
+    const int rc = prop_layout(levels, num_levels, 1, pre_nms_topN, post_nms_topN, lay);
+    return rc ? rc : lay.cap;
+}
+
+extern "C" size_t vosd_generate_proposals_workspace_bytes(const vosd_rpn_level* levels, int num_levels,
+                                                          int num_images, int pre_nms_topN,
+                                                          int post_nms_topN) {
+    PropLayout lay;
+    if (prop_layout(levels, num_levels, num_images, pre_nms_topN, post_nms_topN, lay)) return 0;
+    return lay.total;
+}
+
+extern "C" int vosd_generate_proposals(const vosd_rpn_level* levels, int num_levels, int num_images,
+                                       const float* im_info, int pre_nms_topN, int post_nms_topN,
+                                       float nms_thresh, float min_size,
+                                       float* out_rois, float* out_probs, int* out_count,
+                                       void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    PropLayout lay;
+    int rc = prop_layout(levels, num_levels, num_images, pre_nms_topN, post_nms_topN, lay);
+    if (rc) return rc;
+    if (!im_info || !out_rois || !out_probs || !out_count) return VOSD_ERR_BAD_ARG;
+    if (!workspace || workspace_bytes < lay.total || !aligned16(workspace)) return VOSD_ERR_WORKSPACE;
+    RpnParams p;
+    for (int l = 0; l < num_levels; l++) {
+        const vosd_rpn_level& L = levels[l];
+        if (!L.scores || !L.deltas) return VOSD_ERR_BAD_ARG;
+        RpnLevelDev& D = p.lv[l];
+        D.scores = L.scores; D.deltas = L.deltas;
+        D.H = L.height; D.W = L.width; D.A = L.num_anchors;
+        D.n = L.num_anchors * L.height * L.width;
+        D.take = seg_take(L, pre_nms_topN);
+        D.stride = L.feat_stride;
+        for (int k = 0; k < 4 * L.num_anchors; k++) D.anchors[k] = L.anchors[k];
+    }
+    p.num_levels = num_levels; p.num_images = num_images;
+    p.seg_stride = lay.M; p.sort_cap = next_pow2(lay.M);
+    p.min_size = min_size;
+    p.xform_clip = log(1000.0 / 16.0);      // cfg.BBOX_XFORM_CLIP, core/config.py:1009
+    char* ws = static_cast<char*>(workspace);
+    float4* ws_boxes = reinterpret_cast<float4*>(ws + lay.off_boxes);
+    float* ws_scores = reinterpret_cast<float*>(ws + lay.off_scores);
+    int* ws_count = reinterpret_cast<int*>(ws + lay.off_count);
+    unsigned long long* ws_mask = reinterpret_cast<unsigned long long*>(ws + lay.off_mask);
+
+    // without NMS the reference keeps every filtered box (generate_proposals.py:159-166):
+    // the caller must size the outputs with post_nms_topN = 0 in that case
+    if (!(nms_thresh > 0.f) && lay.cap != lay.M) return VOSD_ERR_BAD_ARG;
+    const size_t dyn = (size_t)p.sort_cap * sizeof(uint64_t);
+    if (cudaFuncSetAttribute(topk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
+        return VOSD_ERR_LAUNCH;
+    topk_decode_kernel<<<lay.S, kSelThreads, dyn, stream>>>(p, im_info, ws_boxes, ws_scores, ws_count);
+    count_launch();
+    const int use_mask = nms_thresh > 0.f;
+    if (use_mask) {
+        dim3 grid(lay.words, lay.words, lay.S);
+        nms_mask_kernel<<<grid, 64, 0, stream>>>(ws_boxes, ws_count, lay.M, lay.words, nms_thresh, ws_mask);
+        count_launch();
+    }
+    nms_reduce_kernel<<<lay.S, 32, 0, stream>>>(ws_boxes, ws_scores, ws_count, lay.M, lay.words, ws_mask,
+                                                use_mask, use_mask ? post_nms_topN : 0, 0, num_images, lay.cap,
+                                                out_rois, out_probs, out_count, nullptr, nullptr);
+    count_launch();
+    return check_launch();
+}
+
+extern "C" int vosd_decode_anchors(const vosd_rpn_level* level, int num_images, const float* im_info,
+                                   float* boxes, cudaStream_t stream) {
+    if (!level || !level->deltas || !im_info || !boxes) return VOSD_ERR_BAD_ARG;
+    if (level->height <= 0 || level->width <= 0 || level->num_anchors <= 0 || num_images <= 0) return VOSD_ERR_BAD_SHAPE;
+    if (level->num_anchors > VOSD_MAX_ANCHORS) return VOSD_ERR_UNSUPPORTED;
+    if (!aligned16(boxes)) return VOSD_ERR_BAD_ARG;
+    DecodeAllParams p;
+    p.deltas = level->deltas; p.H = level->height; p.W = level->width; p.A = level->num_anchors; p.N = num_images;
+    p.stride = level->feat_stride; p.clip = log(1000.0 / 16.0);
+    for (int k = 0; k < 4 * p.A; k++) p.anchors[k] = level->anchors[k];
+    const long long total = (long long)num_images * p.H * p.W;
+    long long blocks = (total + 255) / 256;
+    if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
+    decode_all_kernel<<<(int)blocks, 256, 0, stream>>>(p, im_info, reinterpret_cast<float4*>(boxes));
+    count_launch();
+    return check_launch();
+}
+
+extern "C" int vosd_any_nan(const float* data, size_t n, int* flag, cudaStream_t stream) {
+    if (!data || !flag) return VOSD_ERR_BAD_ARG;
+    if (!aligned16(data)) return VOSD_ERR_BAD_ARG;
+    if (n == 0) return VOSD_OK;
+    size_t blocks = (n / 4 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
+    any_nan_kernel<<<(int)blocks, 256, 0, stream>>>(data, n, flag);
+    count_launch();
+    return check_launch();
+}
+
+// workspace: boxes[n] float4 | orig[n] int | flag[n] int | count int | mask n*words u64
+struct NmsLayout { size_t off_boxes, off_orig, off_flag, off_count, off_mask, total; int words; };
+static NmsLayout nms_layout(int n) {
+    NmsLayout L;
+    L.words = (n + 63) / 64;
+    size_t o = 0;
+    L.off_boxes = o; o = align_up(o + (size_t)n * sizeof(float4), 256);
+    L.off_orig = o;  o = align_up(o + (size_t)n * sizeof(int), 256);
+    L.off_flag = o;  o = align_up(o + (size_t)n * sizeof(int), 256);
+    L.off_count = o; o = align_up(o + sizeof(int), 256);
+    L.off_mask = o;  o = align_up(o + (size_t)n * L.words * sizeof(unsigned long long), 256);
+    L.total = o;
+    return L;
+}
+
+extern "C" size_t vosd_nms_workspace_bytes(int n) {
+    if (n <= 0) return 256;
+    return nms_layout(n).total;
+}
+
+extern "C" int vosd_nms(const float* dets, int n, float thresh, int64_t* keep, int* num_keep,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (n < 0) return VOSD_ERR_BAD_SHAPE;
+    if (!num_keep) return VOSD_ERR_BAD_ARG;
+    if (n == 0) return cudaMemsetAsync(num_keep, 0, sizeof(int), stream) == cudaSuccess ? VOSD_OK : VOSD_ERR_LAUNCH;
+    if (n > VOSD_MAX_TOPK) return VOSD_ERR_UNSUPPORTED;
+    if (!dets || !keep) return VOSD_ERR_BAD_ARG;
+    const NmsLayout L = nms_layout(n);
+    if (!workspace || workspace_bytes < L.total || !aligned16(workspace)) return VOSD_ERR_WORKSPACE;
+    char* ws = static_cast<char*>(workspace);
+    float4* boxes = reinterpret_cast<float4*>(ws + L.off_boxes);
+    int* orig = reinterpret_cast<int*>(ws + L.off_orig);
+    int* flag = reinterpret_cast<int*>(ws + L.off_flag);
+    int* count = reinterpret_cast<int*>(ws + L.off_count);
+    unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws + L.off_mask);
+    const int P = next_pow2(n);
+    const size_t dyn = (size_t)P * sizeof(uint64_t);
+    if (cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
+        return VOSD_ERR_LAUNCH;
+    nms_sort_kernel<<<1, kSelThreads, dyn, stream>>>(dets, n, P, boxes, orig, count, flag);
+    dim3 grid(L.words, L.words, 1);
+    nms_mask_kernel<<<grid, 64, 0, stream>>>(boxes, count, n, L.words, thresh, mask);
+    nms_reduce_kernel<<<1, 32, 0, stream>>>(boxes, nullptr, count, n, L.words, mask, 1, 0, 1, 1, n,
+                                            nullptr, nullptr, nullptr, orig, flag);
+    compact_flags_kernel<<<1, kSelThreads, 0, stream>>>(flag, n, reinterpret_cast<long long*>(keep), num_keep);
+    count_launch(4);
+    return check_launch();
+}

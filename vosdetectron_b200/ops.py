@@ -1,0 +1,265 @@
+"""Tensor-in / tensor-out host wrappers over the C ABI (the ``*_cuda`` fast variants of
+SURVEY.md section 8b).  Everything stays on the device; nothing here synchronises.
+
+PyTorch is used for device memory (caching allocator) and the current stream only.
+CPU tensors raise NotImplementedError, like the reference's RoIAlignFunction
+(lib/modeling/roi_xfrom/roi_align/functions/roi_align.py:29-30): there is no CPU path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import RpnLevel, c_float_p, c_int_p, vp
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise NotImplementedError("%s is a CPU tensor: vosdetectron_b200 has no CPU path" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+def _bind(t):
+    _lib.call("vosd_set_device", t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+# ----------------------------------------------------------------------------- RoIAlign
+def roi_align_forward(features, rois, aligned_height, aligned_width, spatial_scale, sampling_ratio):
+    """(N,C,H,W) x (R,5) -> (R,C,ph,pw); roi_align_kernel.cu:65-121 semantics."""
+    f = _need_cuda(features, "features")
+    r = _need_cuda(rois, "rois")
+    if r.dim() != 2 or r.size(1) != 5:
+        raise ValueError("rois must be (R,5)")          # reference shim returns 0 here (roi_align_cuda.c:15-18)
+    N, C, H, W = f.shape
+    out = torch.empty((r.size(0), C, aligned_height, aligned_width), dtype=torch.float32, device=f.device)
+    _bind(f)
+    _lib.call("vosd_roialign_fwd", _ptr(f), float(spatial_scale), r.size(0), H, W, C,
+              int(aligned_height), int(aligned_width), int(sampling_ratio), _ptr(r), _ptr(out), _stream())
+    return out
+
+
+def roi_align_backward(grad_output, rois, feature_size, aligned_height, aligned_width, spatial_scale,
+                       sampling_ratio):
+    """grad (R,C,ph,pw) -> (N,C,H,W); roi_align_kernel.cu:195-270 semantics.  The gradient map
+    is cleared on the stream by the library (zero_init=1), no separate fill kernel."""
+    g = _need_cuda(grad_output, "grad_output")
+    r = _need_cuda(rois, "rois")
+    N, C, H, W = (int(v) for v in feature_size)
+    gi = torch.empty((N, C, H, W), dtype=torch.float32, device=g.device)
+    _bind(g)
+    _lib.call("vosd_roialign_bwd", _ptr(g), float(spatial_scale), N, r.size(0), H, W, C,
+              int(aligned_height), int(aligned_width), int(sampling_ratio), _ptr(r), _ptr(gi), 1, _stream())
+    return gi
+
+
+def _level_arrays(tensors, scales):
+    L = len(tensors)
+    ptrs = (vp * L)(*[t.data_ptr() for t in tensors])
+    hs = (ctypes.c_int * L)(*[int(t.shape[2]) for t in tensors])
+    ws = (ctypes.c_int * L)(*[int(t.shape[3]) for t in tensors])
+    sc = (ctypes.c_float * L)(*[float(s) for s in scales])
+    return ptrs, hs, ws, sc
+
+
+def roi_align_ml_forward(level_features, level_scales, rois, roi_level, aligned_height, aligned_width,
+                         sampling_ratio, out_index=None):
+    """All FPN levels in one launch.  ``level_features[k]`` is the map ``roi_level == k`` reads."""
+    feats = [_need_cuda(f, "level_features[%d]" % i) for i, f in enumerate(level_features)]
+    r = _need_cuda(rois, "rois")
+    lv = _need_cuda(roi_level, "roi_level", torch.int32)
+    oi = None if out_index is None else _need_cuda(out_index, "out_index", torch.int32)
+    C = feats[0].shape[1]
+    R = r.size(0)
+    out = torch.empty((R, C, aligned_height, aligned_width), dtype=torch.float32, device=r.device)
+    ptrs, hs, ws, sc = _level_arrays(feats, level_scales)
+    _bind(r)
+    _lib.call("vosd_roialign_ml_fwd", ptrs, hs, ws, sc, len(feats), C, int(aligned_height), int(aligned_width),
+              int(sampling_ratio), R, _ptr(r), _ptr(lv), _ptr(oi), _ptr(out), _stream())
+    return out
+
+
+def roi_align_ml_backward(grad_output, level_shapes, level_scales, rois, roi_level, aligned_height,
+                          aligned_width, sampling_ratio, out_index=None):
+    g = _need_cuda(grad_output, "grad_output")
+    r = _need_cuda(rois, "rois")
+    lv = _need_cuda(roi_level, "roi_level", torch.int32)
+    oi = None if out_index is None else _need_cuda(out_index, "out_index", torch.int32)
+    grads = [torch.empty(tuple(int(v) for v in s), dtype=torch.float32, device=g.device) for s in level_shapes]
+    N, C = grads[0].shape[:2]
+    ptrs, hs, ws, sc = _level_arrays(grads, level_scales)
+    _bind(g)
+    _lib.call("vosd_roialign_ml_bwd", _ptr(g), ptrs, hs, ws, sc, len(grads), N, C, int(aligned_height),
+              int(aligned_width), int(sampling_ratio), r.size(0), _ptr(r), _ptr(lv), _ptr(oi), 1, _stream())
+    return grads
+
+
+# ----------------------------------------------------------------------------- proposals
+def make_rpn_levels(level_inputs):
+    """level_inputs: list of (scores (N,A,H,W), deltas (N,4A,H,W), anchors ndarray (A,4) float64,
+    feat_stride).  Returns (ctypes array of vosd_rpn_level, list keeping the tensors alive)."""
+    L = len(level_inputs)
+    arr = (RpnLevel * L)()
+    keep = []
+    for i, (sc, dl, anchors, stride) in enumerate(level_inputs):
+        sc = _need_cuda(sc, "scores")
+        dl = _need_cuda(dl, "deltas")
+        a = np.ascontiguousarray(anchors, dtype=np.float64)
+        N, A, H, W = sc.shape
+        if a.shape != (A, 4) or tuple(dl.shape) != (N, 4 * A, H, W):
+            raise ValueError("level %d: scores %s, deltas %s, anchors %s are inconsistent"
+                             % (i, tuple(sc.shape), tuple(dl.shape), a.shape))
+        arr[i].scores = sc.data_ptr()
+        arr[i].deltas = dl.data_ptr()
+        arr[i].height, arr[i].width, arr[i].num_anchors = H, W, A
+        arr[i].feat_stride = float(stride)
+        for k, v in enumerate(a.ravel()):
+            arr[i].anchors[k] = v
+        keep += [sc, dl]
+    return arr, keep
+
+
+def generate_proposals_cuda(level_inputs, im_info, pre_nms_topN, post_nms_topN, nms_thresh, min_size,
+                            workspace=None):
+    """All (level, image) segments in 3 launches.  Returns device tensors
+    rois (L,N,cap,5) [image,x1,y1,x2,y2], probs (L,N,cap), count (L,N) int32 (rows >= count are 0)."""
+    arr, keep = make_rpn_levels(level_inputs)
+    L = len(level_inputs)
+    N = keep[0].shape[0]
+    info = _need_cuda(im_info, "im_info")
+    if nms_thresh <= 0:
+        post_nms_topN = 0
+    lib = _lib.load()
+    cap = lib.vosd_proposals_capacity(arr, L, int(pre_nms_topN), int(post_nms_topN))
+    if cap < 0:
+        _lib.check("vosd_proposals_capacity", cap)
+    nbytes = lib.vosd_generate_proposals_workspace_bytes(arr, L, N, int(pre_nms_topN), int(post_nms_topN))
+    dev = info.device
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    rois = torch.zeros((L, N, cap, 5), dtype=torch.float32, device=dev)
+    probs = torch.zeros((L, N, cap), dtype=torch.float32, device=dev)
+    count = torch.empty((L, N), dtype=torch.int32, device=dev)
+    _bind(info)
+    _lib.call("vosd_generate_proposals", arr, L, N, _ptr(info), int(pre_nms_topN), int(post_nms_topN),
+              float(nms_thresh), float(min_size), _ptr(rois), _ptr(probs), _ptr(count),
+              _ptr(workspace), workspace.numel(), _stream())
+    return rois, probs, count
+
+
+def decode_anchors_cuda(deltas, anchors, feat_stride, im_info):
+    """Streaming decode+clip of every anchor: (N,4A,H,W) -> (N, H*W*A, 4)."""
+    dl = _need_cuda(deltas, "deltas")
+    info = _need_cuda(im_info, "im_info")
+    N, A4, H, W = dl.shape
+    A = A4 // 4
+    lvl = (RpnLevel * 1)()
+    lvl[0].scores = None
+    lvl[0].deltas = dl.data_ptr()
+    lvl[0].height, lvl[0].width, lvl[0].num_anchors = H, W, A
+    lvl[0].feat_stride = float(feat_stride)
+    for k, v in enumerate(np.ascontiguousarray(anchors, dtype=np.float64).ravel()):
+        lvl[0].anchors[k] = v
+    out = torch.empty((N, H * W * A, 4), dtype=torch.float32, device=dl.device)
+    _bind(dl)
+    _lib.call("vosd_decode_anchors", lvl, N, _ptr(info), _ptr(out), _stream())
+    return out
+
+
+def any_nan_cuda(t):
+    """Device int32 flag tensor (1 element): 1 if any NaN (generate_proposals.py:62-63)."""
+    x = _need_cuda(t, "tensor")
+    flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+    _bind(x)
+    _lib.call("vosd_any_nan", _ptr(x), x.numel(), _ptr(flag), _stream())
+    return flag
+
+
+# ----------------------------------------------------------------------------- NMS
+def nms_cuda(dets, thresh):
+    """dets (n,5) [x1,y1,x2,y2,score] any order -> (keep int64 (n), num_keep int32 (1)) device
+    tensors; keep[:num_keep] are ascending indices (cython_nms.pyx:87)."""
+    d = _need_cuda(dets, "dets")
+    if d.dim() != 2 or d.size(1) != 5:
+        raise ValueError("dets must be (n,5)")
+    n = d.size(0)
+    keep = torch.empty(max(n, 1), dtype=torch.int64, device=d.device)
+    num = torch.empty(1, dtype=torch.int32, device=d.device)
+    nbytes = _lib.load().vosd_nms_workspace_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=d.device)
+    _bind(d)
+    _lib.call("vosd_nms", _ptr(d), n, float(np.float32(thresh)), _ptr(keep), _ptr(num), _ptr(ws), nbytes, _stream())
+    return keep, num
+
+
+# ----------------------------------------------------------------------------- collect / distribute
+def collect_distribute_cuda(rois, probs, count, post_nms_topN, images_per_group=1, k_min=2, k_max=5,
+                            canonical_scale=224.0, canonical_level=4):
+    """Outputs of generate_proposals_cuda -> dict of device tensors (G = N / images_per_group):
+    rois (G,post,5), count (G), level (G,post), level_count (G,nl), order (G,post), restore (G,post)."""
+    r = _need_cuda(rois, "rois")
+    p = _need_cuda(probs, "probs")
+    c = _need_cuda(count, "count", torch.int32)
+    L, N, cap, _ = r.shape
+    G = N // images_per_group
+    dev = r.device
+    post = int(post_nms_topN)
+    out = {
+        "rois": torch.zeros((G, post, 5), dtype=torch.float32, device=dev),
+        "count": torch.empty((G,), dtype=torch.int32, device=dev),
+        "level": torch.zeros((G, post), dtype=torch.int32, device=dev),
+        "level_count": torch.empty((G, k_max - k_min + 1), dtype=torch.int32, device=dev),
+        "order": torch.zeros((G, post), dtype=torch.int32, device=dev),
+        "restore": torch.zeros((G, post), dtype=torch.int32, device=dev),
+    }
+    _bind(r)
+    _lib.call("vosd_collect_distribute", _ptr(r), _ptr(p), _ptr(c), L, N, cap, int(images_per_group), post,
+              int(k_min), int(k_max), float(canonical_scale), int(canonical_level),
+              _ptr(out["rois"]), _ptr(out["count"]), _ptr(out["level"]), _ptr(out["level_count"]),
+              _ptr(out["order"]), _ptr(out["restore"]), None, 0, _stream())
+    return out
+
+
+def distribute_cuda(rois, k_min=2, k_max=5, canonical_scale=224.0, canonical_level=4):
+    """rois (R,5) -> (level (R), level_count (nl), order (R), restore (R)) int32 device tensors."""
+    r = _need_cuda(rois, "rois")
+    R = r.size(0)
+    dev = r.device
+    level = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
+    lc = torch.empty(k_max - k_min + 1, dtype=torch.int32, device=dev)
+    order = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
+    restore = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
+    _bind(r)
+    _lib.call("vosd_distribute", _ptr(r), R, int(k_min), int(k_max), float(canonical_scale), int(canonical_level),
+              _ptr(level), _ptr(lc), _ptr(order), _ptr(restore), _stream())
+    return level[:R], lc, order[:R], restore[:R]
+
+
+# ----------------------------------------------------------------------------- paste
+def paste_masks_cuda(masks, cls, ref_boxes, im_h, im_w, thresh=0.5, want_prob=False):
+    """masks (R,K,M,M), cls (R) int32 or None, ref_boxes (R,4) -> uint8 (R,im_h,im_w)
+    [, fp32 probabilities (R,im_h,im_w)]."""
+    m = _need_cuda(masks, "masks")
+    b = _need_cuda(ref_boxes, "ref_boxes")
+    c = None if cls is None else _need_cuda(cls, "cls", torch.int32)
+    R, K, M, M2 = m.shape
+    if M != M2 or b.shape != (R, 4):
+        raise ValueError("masks must be (R,K,M,M) and ref_boxes (R,4)")
+    out = torch.empty((R, im_h, im_w), dtype=torch.uint8, device=m.device)
+    prob = torch.empty((R, im_h, im_w), dtype=torch.float32, device=m.device) if want_prob else None
+    _bind(m)
+    _lib.call("vosd_paste_masks", _ptr(m), _ptr(c), _ptr(b), R, K, M, int(im_h), int(im_w), float(thresh),
+              _ptr(out), _ptr(prob), _stream())
+    return (out, prob) if want_prob else out

@@ -1,0 +1,129 @@
+"""Frame-batched, device-resident region pipeline and the frame-sharded clip driver.
+
+The reference runs the path once per frame with three host round trips
+(lib/core/test.py:50-120 -> model_builder.py:146-250).  Here a batch of frames goes through
+
+    generate_proposals (all levels x frames, 3 launches)  -> collect+distribute (1 launch)
+    -> box RoIAlign over all levels (1 launch)  ...box head (not part of this library)...
+    -> distribute(detections) (1 launch) -> mask RoIAlign (1 launch) ...mask head...
+    -> paste (1 launch)
+
+without leaving the GPU.  Frames are independent units, so a clip is
+split frame-wise over ranks exactly like the reference's multi-GPU test splits its dataset
+(np.array_split, lib/utils/subprocess.py:56), and the only collective is the final all-gather
+of per-frame detections and (bit-packed) masks.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .config import RegionConfig
+from .modeling.generate_anchors import fpn_level_anchors
+
+
+class RegionPipeline:
+    def __init__(self, cfg=None, training=False, box_resolution=7, mask_resolution=14, sampling_ratio=2):
+        self.cfg = cfg or RegionConfig()
+        self.training = training
+        self.box_resolution = box_resolution
+        self.mask_resolution = mask_resolution
+        self.sampling_ratio = sampling_ratio
+        c = self.cfg
+        self.rpn_levels = list(range(c.rpn_min_level, c.rpn_max_level + 1))
+        self.roi_levels = list(range(c.roi_min_level, c.roi_max_level + 1))
+        self.anchors = {l: fpn_level_anchors(l, c.rpn_anchor_start_size, c.rpn_aspect_ratios, c.rpn_min_level)
+                        for l in self.rpn_levels}
+        self._ws = None
+
+    # ---- stage 1: proposals -> top RoIs + FPN levels (rows of frame f are in group f) ----------
+    def proposals(self, rpn, im_info, images_per_group=1):
+        """rpn: {lvl: (scores (B,A,H,W), deltas (B,4A,H,W))} CUDA tensors; im_info (B,3) CUDA."""
+        m = self.cfg.mode(self.training)
+        inputs = [(rpn[l][0], rpn[l][1], self.anchors[l], float(2 ** l)) for l in self.rpn_levels]
+        rois, probs, count = ops.generate_proposals_cuda(inputs, im_info, m.pre_nms_topN, m.post_nms_topN,
+                                                         m.nms_thresh, m.min_size)
+        c = self.cfg
+        return ops.collect_distribute_cuda(rois, probs, count, c.collect_post_topN(self.training),
+                                           images_per_group, c.roi_min_level, c.roi_max_level,
+                                           c.roi_canonical_scale, c.roi_canonical_level)
+
+    # ---- stage 2: multi-level RoIAlign on device-resident rois --------------------------------
+    def roi_features(self, feats, rois, level, resolution):
+        """feats: {lvl: (B,C,H,W)}; rois (R,5) with column 0 = frame index in the batch;
+        level (R) int32 FPN level in [roi_min_level, roi_max_level]."""
+        k_min = self.cfg.roi_min_level
+        fl = [feats[l] for l in self.roi_levels]
+        sc = [1.0 / 2 ** l for l in self.roi_levels]
+        return ops.roi_align_ml_forward(fl, sc, rois, (level - k_min).to(torch.int32), resolution, resolution,
+                                        self.sampling_ratio)
+
+    # ---- whole step on device-resident inputs -------------------------------------------------
+    def step(self, rpn, im_info, feats, det_boxes, det_cls, det_masks, frame_hw, im_scale):
+        """One batch of B frames.
+        det_boxes (B,D,4) original-frame coords, det_cls (B,D) int32, det_masks (B,D,K,M,M):
+        the box-head / mask-head outputs the pipeline sits between (synthetic in the benchmark).
+        Returns dict of device tensors."""
+        c = self.cfg
+        B, D = det_boxes.shape[:2]
+        prop = self.proposals(rpn, im_info)
+        post = prop["rois"].shape[1]
+        rois = prop["rois"].view(B * post, 5)
+        # rows beyond count[g] are zero boxes on frame 0 level k_min: harmless filler, masked by count
+        box_feats = self.roi_features(feats, rois, prop["level"].view(-1).clamp_(c.roi_min_level, c.roi_max_level),
+                                      self.box_resolution)
+        # mask branch: detections -> blob coords -> level -> RoIAlign (im_detect_mask, test.py:366-402)
+        frame_idx = torch.arange(B, device=det_boxes.device, dtype=torch.float32).view(B, 1, 1).expand(B, D, 1)
+        mask_rois = torch.cat([frame_idx, det_boxes * im_scale], dim=2).view(B * D, 5).contiguous()
+        mlevel, _, _, _ = ops.distribute_cuda(mask_rois, c.roi_min_level, c.roi_max_level,
+                                              c.roi_canonical_scale, c.roi_canonical_level)
+        mask_feats = self.roi_features(feats, mask_rois, mlevel, self.mask_resolution)
+        K, M = det_masks.shape[2], det_masks.shape[3]
+        pasted = ops.paste_masks_cuda(det_masks.view(B * D, K, M, M),
+                                      det_cls.view(-1) if c.mrcnn_cls_specific_mask else None,
+                                      det_boxes.view(B * D, 4), frame_hw[0], frame_hw[1], c.mrcnn_thresh_binarize)
+        return {"rois": prop["rois"], "roi_count": prop["count"], "roi_level": prop["level"],
+                "box_feats": box_feats, "mask_feats": mask_feats,
+                "masks": pasted.view(B, D, frame_hw[0], frame_hw[1])}
+
+
+# Number of library kernels one RegionPipeline.step enqueues (counted, see bench.py):
+#   topk_decode + nms_mask + nms_reduce + collect_distribute + roialign(box) + distribute +
+#   roialign(mask) + paste
+STEP_LAUNCHES = 8
+
+
+def shard_frames(num_frames, world_size, rank):
+    """Frames of rank `rank`: contiguous np.array_split, the reference's convention
+    (lib/utils/subprocess.py:56)."""
+    return np.array_split(np.arange(num_frames), world_size)[rank]
+
+
+def pack_mask_bits(masks_u8):
+    """(…,H,W) uint8 {0,1} -> (…, ceil(H*W/8)) uint8, 8 pixels per byte (lossless; the payload
+    of the all-gather)."""
+    flat = masks_u8.reshape(*masks_u8.shape[:-2], -1)
+    n = flat.shape[-1]
+    pad = (-n) % 8
+    if pad:
+        flat = torch.nn.functional.pad(flat, (0, pad))
+    w = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.uint8, device=flat.device)
+    return (flat.view(*flat.shape[:-1], -1, 8) * w).sum(dim=-1, dtype=torch.uint8)
+
+
+def unpack_mask_bits(packed, h, w):
+    sh = torch.arange(8, dtype=torch.uint8, device=packed.device)
+    bits = (packed.unsqueeze(-1) >> sh) & 1
+    return bits.reshape(*packed.shape[:-1], -1)[..., :h * w].reshape(*packed.shape[:-1], h, w)
+
+
+def all_gather_frames(dets, masks, group=None):
+    """All-gather per-frame detection records (F_r, D, 6) fp32 and masks (F_r, D, …) uint8 over the
+    ranks of `group` (NCCL on GPUs, gloo on CPU in the tests).  Every rank must hold the same
+    number of frames (pad the clip); returns tensors with F = F_r * world frames in rank order."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    d_out = torch.empty((world,) + tuple(dets.shape), dtype=dets.dtype, device=dets.device)
+    m_out = torch.empty((world,) + tuple(masks.shape), dtype=masks.dtype, device=masks.device)
+    dist.all_gather_into_tensor(d_out, dets.contiguous(), group=group)
+    dist.all_gather_into_tensor(m_out, masks.contiguous(), group=group)
+    return d_out.flatten(0, 1), m_out.flatten(0, 1)

@@ -1,0 +1,37 @@
+"""CUDA-backed subset of lib/utils/boxes.py with the reference's ndarray signatures.
+
+``nms(dets, thresh)`` replaces boxes.py:329-333 -> cython_nms.pyx:37-87: ndarray (n,5) float32
+in, int64 ndarray of kept indices (ascending) out, ``[]`` for empty input.  One H2D copy in,
+one D2H copy out; the work is done by the bitmask kernels of csrc/proposals.cu.
+``nms_cuda`` is the tensor-in / tensor-out variant that stays on the device.
+"""
+import numpy as np
+import torch
+
+from .. import ops
+
+nms_cuda = ops.nms_cuda
+
+
+def nms(dets, thresh):
+    if dets.shape[0] == 0:
+        return []
+    d = torch.from_numpy(np.ascontiguousarray(dets, dtype=np.float32)).cuda()
+    keep, num = ops.nms_cuda(d, thresh)
+    n = int(num.item())
+    return keep[:n].cpu().numpy()
+
+
+def expand_boxes(boxes, scale):
+    """boxes.py:242-258 (host helper kept for callers that need the expanded reference boxes;
+    the paste kernel applies the same arithmetic on the device)."""
+    w_half = (boxes[:, 2] - boxes[:, 0]) * .5
+    h_half = (boxes[:, 3] - boxes[:, 1]) * .5
+    x_c = (boxes[:, 2] + boxes[:, 0]) * .5
+    y_c = (boxes[:, 3] + boxes[:, 1]) * .5
+    w_half *= scale
+    h_half *= scale
+    out = np.zeros(boxes.shape)
+    out[:, 0], out[:, 2] = x_c - w_half, x_c + w_half
+    out[:, 1], out[:, 3] = y_c - h_half, y_c + h_half
+    return out

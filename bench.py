@@ -1,0 +1,487 @@
+#!/usr/bin/env python
+"""Benchmark of the per-frame region pipeline (BASELINE.json metric: frames/s at 1/2/4/8 B200;
+RoIAlign achieved HBM GB/s vs peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path over one batch of --frames-per-gpu synthetic frames per GPU
+(BASELINE config 3: 480x854 frame -> 768x1344 blob, R-50-FPN RPN outputs for 5 levels, TEST
+1000/1000 proposals, box RoIAlign 1000x256x7x7, mask RoIAlign 100x256x14x14, paste of 100
+detections).  With 10 frames per GPU, 8 GPUs process the 80-frame DAVIS-shaped clip of config 5
+per step; frames are sharded with no data-path collective, only the final all-gather of
+detections + bit-packed masks ("scaling": "weak").
+
+  value : frames/s, inputs resident in HBM, CUDA events around exactly K steps, max over ranks.
+  e2e   : same metric through the host-buffer API: per step H2D of every input from pinned host
+          memory and D2H of the step's results (rois, counts, pasted masks), copies in the timed region.
+  roofline : the dominant kernel of the step, algorithmic bytes / its mean launch duration
+          (CUDA events recorded on the launching stream inside the timed region).
+  cpu_baseline : the oracle port of the reference's CPU path on this box's host cores (N=1 only).
+`--impl reference` times that CPU path alone (the reference has no CPU RoIAlign at all --
+functions/roi_align.py:29-30 raises -- so its RoIAlign leg is the oracle's C restatement).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "region_pipeline_frames_per_sec"
+UNIT = "frames/s"
+POST = 1000
+DETS = 100
+K_CLASSES = 81
+MASK_M = 28
+C_FPN = 256
+
+
+def workload_name(frames):
+    return ("cfg3 per-frame region pipeline: 480x854 frame (blob 768x1344), 5-level RPN top-k/decode/NMS "
+            "1000/1000 + collect/distribute, box RoIAlign 1000x256x7x7, mask RoIAlign 100x256x14x14, "
+            "paste 100 dets; %d frames/GPU/step" % frames)
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic inputs (host)
+# ------------------------------------------------------------------------------------------
+def make_host_inputs(frames, seed0, full=True):
+    """Per-rank batch of `frames` frames.  RPN outputs from the seeded generator of SURVEY 8d
+    (clustered, tie-free); FPN features N(0,1); detections + sigmoid masks."""
+    import torch
+    from vosdetectron_b200 import synth
+    blob = synth.DAVIS_BLOB
+    rpn = {l: [[], []] for l in synth.FPN_LEVELS}
+    for f in range(frames):
+        r = synth.rpn_outputs(seed0 + f, blob, 1)
+        for l in synth.FPN_LEVELS:
+            rpn[l][0].append(r[l][0])
+            rpn[l][1].append(r[l][1])
+    rpn = {l: (np.concatenate(v[0]), np.concatenate(v[1])) for l, v in rpn.items()}
+    gen = torch.Generator().manual_seed(seed0)
+    feats = {l: torch.randn((frames, C_FPN) + synth.level_shape(blob, l), generator=gen).numpy()
+             for l in synth.ROI_LEVELS} if full else None
+    im_info = np.tile(np.array([[blob[0], blob[1], synth.DAVIS_SCALE]], np.float32), (frames, 1))
+    det = [synth.detections(seed0 + 500 + f, DETS, synth.DAVIS_FRAME, MASK_M, K_CLASSES) for f in range(frames)]
+    return {"rpn": rpn, "feats": feats, "im_info": im_info,
+            "det_boxes": np.stack([d[0] for d in det]), "det_cls": np.stack([d[1] for d in det]),
+            "det_masks": np.stack([d[2] for d in det])}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU path (oracle port) -- cpu_baseline leg and --impl reference
+# ------------------------------------------------------------------------------------------
+_CPU_CACHE = {}
+
+
+def _cpu_inputs(seed):
+    if seed not in _CPU_CACHE:
+        import torch
+        from vosdetectron_b200 import synth
+        blob = synth.DAVIS_BLOB
+        gen = torch.Generator().manual_seed(seed)
+        _CPU_CACHE.clear()
+        _CPU_CACHE[seed] = (
+            synth.rpn_outputs(seed, blob, 1),
+            {l: torch.randn((1, C_FPN) + synth.level_shape(blob, l), generator=gen).numpy() for l in synth.ROI_LEVELS},
+            synth.detections(seed + 500, DETS, synth.DAVIS_FRAME, MASK_M, K_CLASSES))
+    return _CPU_CACHE[seed]
+
+
+def _cpu_one_frame(seed):
+    """The reference's per-frame CPU work on one synthetic frame, single thread:
+    GenerateProposalsOp x5 levels (NumPy + C NMS), collect, distribute, RoIAlign box + mask
+    (C restatement of the CUDA kernel), paste (cv2.resize when present, else its C restatement).
+    Returns the seconds spent per stage (input synthesis excluded)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import region_oracle as orc
+    from vosdetectron_b200 import synth
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        resize = lambda p, w, h: cv2.resize(p, (w, h))
+    except Exception:  # noqa: BLE001
+        resize = None
+    blob = synth.DAVIS_BLOB
+    rpn, feats, (boxes, cls, masks) = _cpu_inputs(seed)
+    im_info = np.array([[blob[0], blob[1], synth.DAVIS_SCALE]], np.float32)
+    t0 = time.perf_counter()
+    rl, pl = [], []
+    for l in synth.FPN_LEVELS:
+        r, p = orc.generate_proposals(rpn[l][0], rpn[l][1], im_info, orc.fpn_anchors(l), 1. / 2 ** l, 1000, 1000, 0.7, 0)
+        rl.append(r)
+        pl.append(p)
+    rois = orc.collect(rl, pl, POST)
+    blobs = orc.distribute(rois)
+    t1 = time.perf_counter()
+    fl = [feats[l] for l in (5, 4, 3, 2)]
+    sc = [1. / 32, 1. / 16, 1. / 8, 1. / 4]
+    orc.roi_feature_transform(fl, blobs, 'rois', 7, sc, 2, nthreads=1)
+    t2 = time.perf_counter()
+    mr = np.concatenate([np.zeros((DETS, 1), np.float32), boxes * np.float32(synth.DAVIS_SCALE)], axis=1)
+    orc.roi_feature_transform(fl, orc.distribute(mr), 'rois', 14, sc, 2, nthreads=1)
+    t3 = time.perf_counter()
+    orc.paste_masks(masks, cls, boxes, synth.DAVIS_FRAME[0], synth.DAVIS_FRAME[1], resize=resize)
+    t4 = time.perf_counter()
+    return [t1 - t0, t2 - t1, t3 - t2, t4 - t3]
+
+
+def cpu_path_run(steps, warmup, workers):
+    """`steps` timed rounds of `workers` frames, one frame per single-threaded worker process (the
+    reference's own sharding model: one process per range of frames, lib/utils/subprocess.py:41-113).
+    A round costs the slowest worker's compute time.  Returns (frames/s, ms per round, per-stage
+    seconds per frame)."""
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import region_oracle as orc
+    orc.build_c()
+    seeds = list(range(9000, 9000 + workers))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        for _ in range(max(1, warmup)):
+            pool.map(_cpu_one_frame, seeds, chunksize=1)
+        wall, stages = 0.0, []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            st = pool.map(_cpu_one_frame, seeds, chunksize=1)
+            wall += time.perf_counter() - t0
+            stages += st
+    st = np.mean(np.asarray(stages), axis=0)
+    return steps * workers / wall, 1000.0 * wall / steps, {
+        "proposals_collect_s": float(st[0]), "roialign_box_s": float(st[1]),
+        "roialign_mask_s": float(st[2]), "paste_s": float(st[3])}
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    workers = os.cpu_count() or 1
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
+    fps, ms_step, stages = cpu_path_run(steps, warmup, workers)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(workers) + " [CPU: one frame per host process per step]"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": "%d steps x %d frames (one per worker process, 1 thread each); "
+                                   "NumPy proposal path + C NMS/RoIAlign restatement + cv2.resize paste" % (steps, workers),
+                         "stages_per_frame": stages},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# helpers for the GPU arm
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def touched_texel_bytes(rois, levels, res, sr, shapes, channels):
+    """Exact algorithmic input bytes of a multi-level RoIAlign: 4*C*|unique (frame,level,y,x) texels
+    read|, from the RoIs (host replay of the sampling geometry, fp32 like the kernel)."""
+    total = 0
+    rois = np.asarray(rois, np.float32)
+    for li, lvl in enumerate(sorted(shapes)):
+        H, W = shapes[lvl]
+        sel = np.where(levels == lvl)[0]
+        if not len(sel):
+            continue
+        r = rois[sel]
+        scale = np.float32(1.0 / 2 ** lvl)
+        frames = r[:, 0].astype(np.int64)
+        nf = int(frames.max()) + 1
+        touched = np.zeros((nf, H, W), dtype=bool)
+        x1, y1 = r[:, 1] * scale, r[:, 2] * scale
+        rw = np.maximum(r[:, 3] * scale - x1, 1).astype(np.float32)
+        rh = np.maximum(r[:, 4] * scale - y1, 1).astype(np.float32)
+        g = np.arange(res * sr, dtype=np.float32)
+        p, i = np.floor(g / sr), g % sr
+
+        def taps(start, ext, size):
+            b = (ext / np.float32(res))[:, None]
+            v = start[:, None] + p[None] * b + (i[None] + np.float32(.5)) * b / np.float32(sr)
+            ok = ~((v < -1) | (v > size))
+            v = np.maximum(v, 0)
+            lo = np.minimum(v.astype(np.int64), size - 1)
+            hi = np.minimum(lo + 1, size - 1)
+            return lo, hi, ok
+        ylo, yhi, yok = taps(y1, rh, H)
+        xlo, xhi, xok = taps(x1, rw, W)
+        for k in range(len(r)):
+            ys = np.unique(np.concatenate([ylo[k][yok[k]], yhi[k][yok[k]]]))
+            xs = np.unique(np.concatenate([xlo[k][xok[k]], xhi[k][xok[k]]]))
+            if len(ys) and len(xs):
+                touched[frames[k]][np.ix_(ys, xs)] = True
+        total += int(touched.sum()) * 4 * channels
+    return total
+
+
+def gpu_arm(args, rank, world, local_rank):
+    # CPU baseline first (fork-based pool before any CUDA context exists in this process)
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        workers = os.cpu_count() or 1
+        fps, _, stages = cpu_path_run(3, 1, workers)
+        cpu_baseline = {"value": fps, "unit": UNIT, "cores": workers, "kind": "port",
+                        "sample": "3 rounds x %d frames of the same workload, one per worker process (1 thread each)" % workers,
+                        "stages_per_frame": stages}
+
+    import torch
+    import torch.distributed as dist
+    from vosdetectron_b200 import _lib, synth
+    from vosdetectron_b200.config import RegionConfig
+    from vosdetectron_b200.pipeline import RegionPipeline, STEP_LAUNCHES, all_gather_frames, pack_mask_bits
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.frames_per_gpu
+    host = make_host_inputs(B, 3000 + 100 * rank)
+    pipe = RegionPipeline(RegionConfig())
+    frame_hw, im_scale = synth.DAVIS_FRAME, synth.DAVIS_SCALE
+
+    # pinned host buffers (e2e) and device-resident copies (value)
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.pin_memory()
+    h_rpn = {l: (pin(s), pin(d)) for l, (s, d) in host["rpn"].items()}
+    h_feats = {l: pin(f) for l, f in host["feats"].items()}
+    h_info, h_boxes, h_cls = pin(host["im_info"]), pin(host["det_boxes"]), pin(host["det_cls"])
+    # the mask head output the reference moves is (D,81,28,28); the API uploads what paste reads
+    h_masks = pin(host["det_masks"])
+    h2d_tensors = [t for p in h_rpn.values() for t in p] + list(h_feats.values()) + [h_info, h_boxes, h_cls, h_masks]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in h2d_tensors)
+
+    def upload():
+        return ({l: (s.to(dev, non_blocking=True), d.to(dev, non_blocking=True)) for l, (s, d) in h_rpn.items()},
+                h_info.to(dev, non_blocking=True), {l: f.to(dev, non_blocking=True) for l, f in h_feats.items()},
+                h_boxes.to(dev, non_blocking=True), h_cls.to(dev, non_blocking=True), h_masks.to(dev, non_blocking=True))
+
+    d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks = upload()
+    torch.cuda.synchronize()
+
+    stage_names = ["proposals", "collect_distribute", "roialign_box", "mask_rois", "roialign_mask", "paste", "end"]
+    events = []
+
+    def run_step(mark=None):
+        out = pipe.step(d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks, frame_hw, im_scale, mark=mark)
+        if world > 1:
+            dets = torch.cat([d_boxes, d_cls.unsqueeze(-1).float(), torch.ones_like(d_cls).unsqueeze(-1).float()], dim=2)
+            all_gather_frames(dets, pack_mask_bits(out["masks"]))
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = run_step()
+    barrier()
+
+    # ---- value: K steps, device-resident inputs ------------------------------------------
+    def mark(name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        events[-1].append((name, e))
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        events.append([])
+        out = run_step(mark)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms / 1000.0)
+
+    stage_ms = {n: 0.0 for n in stage_names[:-1]}
+    for ev in events:
+        for (n0, a), (_, b) in zip(ev[:-1], ev[1:]):
+            stage_ms[n0] += a.elapsed_time(b)
+    stage_ms = {n: v / args.steps for n, v in stage_ms.items()}
+
+    # ---- e2e: host buffers, copies inside the timed region --------------------------------
+    post = out["rois"].shape[1]
+    o_rois = torch.empty((B, post, 5), dtype=torch.float32).pin_memory()
+    o_cnt = torch.empty((B,), dtype=torch.int32).pin_memory()
+    o_masks = torch.empty((B, DETS) + tuple(frame_hw), dtype=torch.uint8).pin_memory()
+    d2h_bytes = sum(t.numel() * t.element_size() for t in (o_rois, o_cnt, o_masks))
+
+    def e2e_step():
+        nonlocal d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks
+        d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks = upload()
+        o = run_step()
+        o_rois.copy_(o["rois"], non_blocking=True)
+        o_cnt.copy_(o["roi_count"], non_blocking=True)
+        o_masks.copy_(o["masks"], non_blocking=True)
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * B * e2e_steps / (e2e_ms / 1000.0)
+    clocks = sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    shapes = {l: synth.level_shape(synth.DAVIS_BLOB, l) for l in synth.ROI_LEVELS}
+    cnt = out["roi_count"].cpu().numpy()
+    rois_h = out["rois"].cpu().numpy()
+    lvl_h = out["roi_level"].cpu().numpy()
+    box_rois = np.concatenate([rois_h[b, :cnt[b]] for b in range(B)])
+    box_lvls = np.concatenate([lvl_h[b, :cnt[b]] for b in range(B)])
+    bytes_box = (len(box_rois) * C_FPN * 49 * 4 + 20 * len(box_rois)
+                 + touched_texel_bytes(box_rois, box_lvls, 7, 2, shapes, C_FPN))
+    m_rois, m_lvl = out["mask_rois"].cpu().numpy(), out["mask_level"].cpu().numpy()
+    bytes_mask = (len(m_rois) * C_FPN * 196 * 4 + 20 * len(m_rois)
+                  + touched_texel_bytes(m_rois, m_lvl, 14, 2, shapes, C_FPN))
+    bytes_paste = B * DETS * (frame_hw[0] * frame_hw[1] + MASK_M * MASK_M * 4 + 16)
+    n_anchor = sum(3 * h * w for h, w in (synth.level_shape(synth.DAVIS_BLOB, l) for l in synth.FPN_LEVELS))
+    bytes_prop = B * (4 * n_anchor + 5 * 1000 * 40)
+    alg = {"roialign_box": bytes_box, "roialign_mask": bytes_mask, "paste": bytes_paste, "proposals": bytes_prop}
+    dom = max(alg, key=lambda k: stage_ms[k])
+    ach = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": stage_ms[dom],
+                "peak_source": peak_src,
+                "stages": {k: {"ms": stage_ms[k], "algorithmic_bytes": alg.get(k),
+                               "gbs": (alg[k] / (stage_ms[k] * 1e-3) / 1e9) if k in alg and stage_ms[k] > 0 else None}
+                           for k in stage_ms}}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(B), "frames_per_gpu": B, "global_frames_per_step": B * world,
+                   "l2": "inputs larger than L2 (%.2f GB touched per step)" % (h2d_bytes / 1e9),
+                   "parallelism": "frame-sharded x%d%s" % (world, ", all-gather of dets + bit-packed masks per step" if world > 1 else "")},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+        "gpu_launches": int(launches),
+        "launches_per_step_expected": STEP_LAUNCHES,
+        "roofline": roofline,
+    }
+    if cpu_baseline is not None:
+        line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames-per-gpu", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,212 @@
+"""GPU parity: RoIAlign forward / backward through the C ABI against
+  (i)   the reference kernel itself (oracle/_ref/libref_roialign.so = the unmodified
+        roi_align_kernel.cu built for sm_100a) run on the same GPU -- forward must be bit-identical;
+  (ii)  the CPU oracle (oracle/oracle.c);
+  (iii) the torchvision golden (loose anchor).
+Tolerances: forward rtol 1e-5 of max|out| is the pass bar (target 0 ulp); backward
+rtol 1e-5 + atol 1e-6*max|grad| (atomics reorder the fp32 sum, also in the reference)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_roialign.so")
+
+
+@pytest.fixture(scope="module")
+def refk():
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref/libref_roialign.so not built")
+    lib = ctypes.CDLL(REF_SO)
+    vp = ctypes.c_void_p
+    lib.ROIAlignForwardLaucher.argtypes = [vp, ctypes.c_float] + [ctypes.c_int] * 7 + [vp, vp, vp]
+    lib.ROIAlignBackwardLaucher.argtypes = [vp, ctypes.c_float] + [ctypes.c_int] * 8 + [vp, vp, vp]
+
+    class R:
+        @staticmethod
+        def fwd(f, rois, ph, pw, scale, sr):
+            N, C, H, W = f.shape
+            out = torch.zeros((rois.shape[0], C, ph, pw), device=f.device)
+            if rois.shape[0]:
+                lib.ROIAlignForwardLaucher(f.data_ptr(), scale, rois.shape[0], H, W, C, ph, pw, sr, rois.data_ptr(),
+                                           out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            return out
+
+        @staticmethod
+        def bwd(g, rois, shape, ph, pw, scale, sr):
+            N, C, H, W = shape
+            out = torch.zeros(shape, device=g.device)
+            if rois.shape[0]:
+                lib.ROIAlignBackwardLaucher(g.data_ptr(), scale, N, rois.shape[0], H, W, C, ph, pw, sr,
+                                            rois.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            return out
+    return R
+
+
+def ulp_diff(a, b):
+    ia = a.view(torch.int32).long()
+    ib = b.view(torch.int32).long()
+    ia = torch.where(ia < 0, -(ia & 0x7fffffff), ia)
+    ib = torch.where(ib < 0, -(ib & 0x7fffffff), ib)
+    return (ia - ib).abs()
+
+
+def _case(synth, lvl, R=150, C=16, N=2, seed=0, blob=None):
+    blob = blob or synth.COCO_BLOB
+    feats = synth.fpn_features(100 + seed, blob, N, (lvl,), C)[lvl]
+    rois = synth.random_rois(200 + seed, R, blob, N)
+    return torch.from_numpy(feats).cuda(), torch.from_numpy(rois).cuda()
+
+
+@pytest.mark.parametrize("lvl", [2, 3, 4, 5])
+@pytest.mark.parametrize("res,sr", [(7, 2), (14, 2), (7, 0), (3, 1)])
+def test_forward_bit_exact_vs_reference_kernel(refk, synth, orc, lvl, res, sr):
+    from vosdetectron_b200 import ops
+    f, rois = _case(synth, lvl, seed=lvl)
+    scale = 1.0 / 2 ** lvl
+    out = ops.roi_align_forward(f, rois, res, res, scale, sr)
+    ref = refk.fwd(f, rois, res, res, scale, sr)
+    torch.cuda.synchronize()
+    d = ulp_diff(out, ref)
+    assert int(d.max()) == 0, "ulp histogram: %s" % torch.bincount(d.flatten().clamp(max=8)).tolist()
+    o = orc.roi_align_forward(f.cpu().numpy(), rois.cpu().numpy(), res, res, scale, sr)
+    err = np.abs(out.cpu().numpy() - o).max()
+    assert err <= 1e-5 * np.abs(o).max(), err
+
+
+def test_forward_edge_rois_vs_reference_kernel(refk, synth, orc):
+    from vosdetectron_b200 import ops
+    for lvl in (2, 5):
+        f = torch.from_numpy(synth.fpn_features(7, synth.COCO_BLOB, 1, (lvl,), 8)[lvl]).cuda()
+        rois = torch.from_numpy(synth.edge_rois()).cuda()
+        for res, sr in ((7, 2), (14, 2), (7, 0)):
+            out = ops.roi_align_forward(f, rois, res, res, 1.0 / 2 ** lvl, sr)
+            ref = refk.fwd(f, rois, res, res, 1.0 / 2 ** lvl, sr)
+            assert torch.equal(out, ref), (lvl, res, sr)
+            o = orc.roi_align_forward(f.cpu().numpy(), rois.cpu().numpy(), res, res, 1.0 / 2 ** lvl, sr)
+            assert np.array_equal(out.cpu().numpy(), o), (lvl, res, sr)
+
+
+def test_forward_vs_torchvision_golden(golden):
+    from vosdetectron_b200 import ops
+    g = golden("roialign_tv")
+    rois = torch.from_numpy(g["rois"]).cuda()
+    for lvl in (2, 3, 4, 5):
+        f = torch.from_numpy(g["feat%d" % lvl]).cuda()
+        for res in (7, 14):
+            out = ops.roi_align_forward(f, rois, res, res, 1.0 / 2 ** lvl, 2).cpu().numpy()
+            assert np.abs(out - g["tv_fwd_l%d_r%d" % (lvl, res)]).max() < 1e-4
+
+
+def test_empty_and_cpu_inputs(synth):
+    from vosdetectron_b200 import ops
+    from vosdetectron_b200.modeling.roi_xfrom.roi_align.functions.roi_align import RoIAlignFunction
+    f = torch.randn(1, 4, 10, 12, device="cuda")
+    out = ops.roi_align_forward(f, torch.zeros((0, 5), device="cuda"), 7, 7, 0.25, 2)
+    assert out.shape == (0, 4, 7, 7)
+    with pytest.raises(NotImplementedError):
+        RoIAlignFunction(7, 7, 0.25, 2)(f.cpu(), torch.zeros((1, 5)))
+    with pytest.raises(ValueError):
+        ops.roi_align_forward(f, torch.zeros((3, 4), device="cuda"), 7, 7, 0.25, 2)
+
+
+@pytest.mark.parametrize("lvl,res,sr", [(2, 7, 2), (3, 14, 2), (4, 7, 0), (5, 14, 2)])
+def test_backward_vs_reference_kernel_and_oracle(refk, synth, orc, lvl, res, sr):
+    from vosdetectron_b200 import ops
+    f, rois = _case(synth, lvl, R=120, C=8, seed=10 + lvl)
+    scale = 1.0 / 2 ** lvl
+    g = torch.from_numpy(np.random.RandomState(lvl).standard_normal((rois.shape[0], 8, res, res)).astype(np.float32)).cuda()
+    mine = ops.roi_align_backward(g, rois, f.shape, res, res, scale, sr)
+    ref = refk.bwd(g, rois, tuple(f.shape), res, res, scale, sr)
+    tol = 1e-5 * ref.abs() + 1e-6 * float(ref.abs().max())
+    assert bool(((mine - ref).abs() <= tol).all()), float((mine - ref).abs().max())
+    o = orc.roi_align_backward(g.cpu().numpy(), rois.cpu().numpy(), tuple(f.shape), res, res, scale, sr)
+    o = torch.from_numpy(o).cuda()
+    tol = 1e-5 * o.abs() + 1e-6 * float(o.abs().max())
+    assert bool(((mine - o).abs() <= tol).all())
+
+
+def test_autograd_function_and_modules(synth):
+    from vosdetectron_b200.modeling.roi_xfrom.roi_align.functions.roi_align import RoIAlignFunction
+    from vosdetectron_b200.modeling.roi_xfrom.roi_align.modules.roi_align import RoIAlign, RoIAlignAvg, RoIAlignMax
+    torchvision = pytest.importorskip("torchvision")
+    f, rois = _case(synth, 3, R=40, C=4, seed=3)
+    f.requires_grad_(True)
+    out = RoIAlignFunction(7, 7, 0.125, 2)(f, rois)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    g_mine = f.grad.clone()
+    f2 = f.detach().clone().requires_grad_(True)
+    out2 = torchvision.ops.roi_align(f2, rois, (7, 7), 0.125, sampling_ratio=2, aligned=False)
+    (out2 * w).sum().backward()
+    assert (out - out2).abs().max() < 1e-4
+    assert (g_mine - f2.grad).abs().max() < 1e-4 * max(1.0, float(f2.grad.abs().max()))
+    assert RoIAlign(7, 7, 0.125, 2)(f, rois).shape == (40, 4, 7, 7)
+    assert RoIAlignAvg(7, 7, 0.125, 2)(f, rois).shape == (40, 4, 7, 7)
+    assert RoIAlignMax(7, 7, 0.125, 2)(f, rois).shape == (40, 4, 7, 7)
+
+
+def test_multilevel_matches_reference_loop(refk, synth, orc):
+    """roi_feature_transform: one launch == per-level launches + cat + restore (model_builder.py:271-303)."""
+    from vosdetectron_b200.modeling.model_builder import roi_feature_transform
+    N, C = 2, 8
+    feats = synth.fpn_features(55, synth.COCO_BLOB, N, synth.ROI_LEVELS, C)
+    rois = synth.random_rois(56, 400, synth.COCO_BLOB, N)
+    blobs = orc.distribute(rois)                       # reference-format rpn_ret (ndarrays)
+    blobs_in = [torch.from_numpy(feats[l]).cuda() for l in (5, 4, 3, 2)]      # coarsest first
+    scales = [1. / 32, 1. / 16, 1. / 8, 1. / 4]
+    for res in (7, 14):
+        out = roi_feature_transform(blobs_in, blobs, 'rois', 'RoIAlign', res, scales, 2)
+        parts = []
+        for lvl in (2, 3, 4, 5):
+            r = blobs['rois_fpn%d' % lvl]
+            if len(r):
+                parts.append(refk.fwd(blobs_in[5 - lvl], torch.from_numpy(r).cuda(), res, res, scales[5 - lvl], 2))
+        ref = torch.cat(parts)[torch.from_numpy(blobs['rois_idx_restore_int32'].astype(np.int64)).cuda()]
+        assert torch.equal(out, ref)
+    # tensors in rpn_ret work too, and gradients flow to every level
+    t_blobs = {k: torch.from_numpy(v).cuda() for k, v in blobs.items()}
+    leaf = [b.clone().requires_grad_(True) for b in blobs_in]
+    out = roi_feature_transform(leaf, t_blobs, 'rois', 'RoIAlign', 7, scales, 2)
+    assert torch.equal(out, roi_feature_transform(blobs_in, blobs, 'rois', 'RoIAlign', 7, scales, 2))
+    gout = torch.randn_like(out)
+    out.backward(gout)
+    order = np.concatenate([np.where(orc.map_rois_to_fpn_levels(rois[:, 1:5]) == l)[0] for l in (2, 3, 4, 5)])
+    for lvl in (2, 3, 4, 5):
+        idx = np.where(orc.map_rois_to_fpn_levels(rois[:, 1:5]) == lvl)[0]
+        ref = refk.bwd(gout[torch.from_numpy(idx).cuda()].contiguous(), torch.from_numpy(rois[idx]).cuda(),
+                       tuple(blobs_in[5 - lvl].shape), 7, 7, scales[5 - lvl], 2)
+        got = leaf[5 - lvl].grad
+        tol = 1e-5 * ref.abs() + 1e-6 * float(ref.abs().max())
+        assert bool(((got - ref).abs() <= tol).all()), lvl
+    assert len(order) == len(rois)
+
+
+def test_full_size_properties(synth):
+    """BASELINE config 2 sizes: 1000 RoIs x 256 ch over P2-P5 -- size-independent checks."""
+    from vosdetectron_b200 import ops
+    feats = synth.fpn_features(2000, synth.COCO_BLOB, 1, synth.ROI_LEVELS, 256)
+    rois = torch.from_numpy(synth.random_rois(2001, 1000, synth.COCO_BLOB, 1)).cuda()
+    fl = [torch.from_numpy(feats[l]).cuda() for l in synth.ROI_LEVELS]
+    sc = [1.0 / 2 ** l for l in synth.ROI_LEVELS]
+    level, _, order, restore = ops.distribute_cuda(rois)
+    assert torch.equal(order[restore.long()].long(), torch.arange(1000, device="cuda"))
+    lv = (level - 2).to(torch.int32)
+    for res in (7, 14):
+        a = ops.roi_align_ml_forward(fl, sc, rois, lv, res, res, 2)
+        # linearity in the features
+        b = ops.roi_align_ml_forward([2.0 * f for f in fl], sc, rois, lv, res, res, 2)
+        assert torch.equal(b, 2.0 * a)
+        # constant features -> constant output for RoIs inside the map
+        ones = ops.roi_align_ml_forward([torch.ones_like(f) for f in fl], sc, rois, lv, res, res, 2)
+        assert float((ones - 1).abs().max()) < 1e-6
+        # adjoint identity <A f, g> == <f, A^T g>
+        g = torch.randn_like(a)
+        grads = ops.roi_align_ml_backward(g, [f.shape for f in fl], sc, rois, lv, res, res, 2)
+        lhs = float((a.double() * g.double()).sum())
+        rhs = float(sum((f.double() * gr.double()).sum() for f, gr in zip(fl, grads)))
+        assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs)), (lhs, rhs)

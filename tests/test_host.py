@@ -1,0 +1,162 @@
+"""CPU: the C-ABI library loads and exports every symbol include/vosd_b200.h declares, argument
+validation returns status codes without touching a GPU, and the host-side logic (config adapter,
+anchors, RLE, frame sharding, bit packing) behaves."""
+import ctypes
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vosdetectron_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_every_header_symbol_is_exported(lib):
+    from vosdetectron_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "vosd_b200.h")).read()
+    declared = set(re.findall(r"VOSD_API [\w \*]+?(vosd_\w+)\(", header))
+    assert len(declared) >= 19
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert b"sm_100a" in lib.vosd_version()
+    assert lib.vosd_status_string(-3) == b"unsupported size (compiled-in limit)"
+
+
+def test_argument_validation_without_gpu(lib):
+    from vosdetectron_b200._lib import RpnLevel
+    assert lib.vosd_nms(None, -1, 0.5, None, None, None, 0, None) == -1            # bad shape
+    assert lib.vosd_nms(None, 5, 0.5, None, None, None, 0, None) == -2             # null num_keep
+    assert lib.vosd_nms_workspace_bytes(2000) >= 2000 * 32 * 8
+    assert lib.vosd_paste_masks(None, None, None, 3, 1, 28, 0, 10, 0.5, None, None, None) == -1
+    assert lib.vosd_paste_masks(None, None, None, 3, 1, 28, 10, 10, 0.5, None, None, None) == -2
+    assert lib.vosd_roialign_fwd(None, 0.25, 4, 10, 10, 8, 7, 7, 2, None, None, None) == -2
+    assert lib.vosd_roialign_fwd(ctypes.c_void_p(256), 0.25, 4, 0, 10, 8, 7, 7, 2, None, None, None) == -1
+    assert lib.vosd_collect_distribute(None, None, None, 5, 4, 100, 3, 100, 2, 5, 224.0, 4,
+                                       None, None, None, None, None, None, None, 0, None) == -1   # 4 % 3 != 0
+    lv = (RpnLevel * 2)()
+    for i, (h, w) in enumerate(((200, 336), (13, 21))):
+        lv[i].height, lv[i].width, lv[i].num_anchors = h, w, 3
+    assert lib.vosd_proposals_capacity(lv, 2, 2000, 1000) == 1000
+    assert lib.vosd_proposals_capacity(lv, 2, 2000, 0) == 2000
+    one = ctypes.cast(ctypes.byref(lv[1]), ctypes.POINTER(RpnLevel))
+    assert lib.vosd_proposals_capacity(one, 1, 2000, 1000) == 819                  # 13*21*3 < pre
+    assert lib.vosd_proposals_capacity(lv, 2, 0, 1000) == -3                       # full sort of P2 > MAX_TOPK
+    lv[0].num_anchors = 17
+    assert lib.vosd_proposals_capacity(lv, 2, 2000, 1000) == -3
+    assert lib.vosd_generate_proposals_workspace_bytes(one, 1, 10, 2000, 1000) > 0
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from vosdetectron_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libvosd_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_cpu_tensors_are_rejected():
+    from vosdetectron_b200 import ops
+    from vosdetectron_b200.modeling.roi_xfrom.roi_align.functions.roi_align import RoIAlignFunction
+    with pytest.raises(NotImplementedError):
+        RoIAlignFunction(7, 7, 0.25, 2)(torch.zeros(1, 2, 8, 8), torch.zeros(1, 5))
+    with pytest.raises(NotImplementedError):
+        ops.nms_cuda(torch.zeros(4, 5), 0.5)
+    with pytest.raises(NotImplementedError):
+        ops.paste_masks_cuda(torch.zeros(1, 1, 28, 28), None, torch.zeros(1, 4), 10, 10)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "vosdetectron_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(d, f)).read()
+                assert "region_oracle" not in src and "liboracle" not in src and "ref_harness" not in src, f
+
+
+def test_anchors_match_golden(golden):
+    from vosdetectron_b200.modeling.generate_anchors import generate_anchors, fpn_level_anchors
+    g = golden("anchors")
+    assert np.array_equal(generate_anchors(16, (128, 256, 512), (0.5, 1, 2)), g["kat_stride16"])
+    for lvl in range(2, 7):
+        a = fpn_level_anchors(lvl)
+        assert a.dtype == np.float64 and np.array_equal(a, g["fpn%d" % lvl])
+
+
+def test_config_adapter():
+    from vosdetectron_b200.config import RegionConfig, set_cfg, get_cfg
+    ns = types.SimpleNamespace
+    rpn = lambda pre, post: ns(RPN_PRE_NMS_TOP_N=pre, RPN_POST_NMS_TOP_N=post, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=0)
+    cfg = ns(TRAIN=rpn(2000, 2000), TEST=rpn(1000, 1000),
+             FPN=ns(RPN_MIN_LEVEL=2, RPN_MAX_LEVEL=6, ROI_MIN_LEVEL=2, ROI_MAX_LEVEL=5, ROI_CANONICAL_SCALE=224,
+                    ROI_CANONICAL_LEVEL=4, RPN_COLLECT_SCALE=1, RPN_ANCHOR_START_SIZE=32, RPN_ASPECT_RATIOS=(0.5, 1, 2)),
+             BBOX_XFORM_CLIP=np.log(1000. / 16.), MODEL=ns(NUM_CLASSES=81),
+             MRCNN=ns(RESOLUTION=28, THRESH_BINARIZE=0.5, CLS_SPECIFIC_MASK=True))
+    rc = RegionConfig.from_cfg(cfg)
+    assert rc.mode(True).pre_nms_topN == 2000 and rc.mode(False).post_nms_topN == 1000
+    assert rc.collect_post_topN(False) == 1000 and rc.num_classes == 81
+    old = get_cfg()
+    try:
+        assert set_cfg(cfg).train.post_nms_topN == 2000 and get_cfg().test.pre_nms_topN == 1000
+    finally:
+        set_cfg(old)
+
+
+def test_rle_encoder_round_trip():
+    from vosdetectron_b200.core.test import rle_encode
+    rs = np.random.RandomState(0)
+    for shape in ((5, 7), (48, 85), (1, 1)):
+        m = (rs.uniform(size=shape) > 0.6).astype(np.uint8)
+        m[1:3] = 1 if shape[0] > 3 else m[1:3]
+        rle = rle_encode(m)
+        # decode (pycocotools rleFrString + rleDecode)
+        cnts, p, s = [], 0, rle["counts"]
+        while p < len(s):
+            x, k, more = 0, 0, True
+            while more:
+                c = ord(s[p]) - 48
+                x |= (c & 0x1f) << (5 * k)
+                more = bool(c & 0x20)
+                p += 1
+                k += 1
+                if not more and (c & 0x10):
+                    x |= -1 << (5 * k)
+            if len(cnts) > 2:
+                x += cnts[-2]
+            cnts.append(x)
+        flat = np.concatenate([np.full(c, i & 1, np.uint8) for i, c in enumerate(cnts)]) if cnts else np.zeros(0, np.uint8)
+        assert np.array_equal(flat.reshape(shape[::-1]).T, m)
+    assert rle_encode(np.zeros((5, 7), np.uint8))["counts"] == "S1"      # 35 zeros, pycocotools' string
+
+
+def test_frame_sharding_and_bit_packing():
+    from vosdetectron_b200.pipeline import shard_frames, pack_mask_bits, unpack_mask_bits
+    parts = [shard_frames(80, 8, r) for r in range(8)]
+    assert all(len(p) == 10 for p in parts) and np.array_equal(np.concatenate(parts), np.arange(80))
+    parts = [shard_frames(82, 4, r) for r in range(4)]
+    assert [len(p) for p in parts] == [21, 21, 20, 20]                   # np.array_split convention
+    m = (torch.rand(3, 2, 37, 53) > 0.5).to(torch.uint8)
+    p = pack_mask_bits(m)
+    assert p.shape == (3, 2, (37 * 53 + 7) // 8)
+    assert torch.equal(unpack_mask_bits(p, 37, 53), m)
+
+
+def test_reference_aliases_install():
+    import sys
+    import vosdetectron_b200 as v
+    names = v.install_reference_aliases()
+    assert 'modeling.roi_xfrom.roi_align.functions.roi_align' in names
+    mod = sys.modules['modeling.roi_xfrom.roi_align.functions.roi_align']
+    assert hasattr(mod, 'RoIAlignFunction')
+    for n in names:
+        sys.modules.pop(n, None)

@@ -36,12 +36,14 @@ class RegionPipeline:
         self._ws = None
 
     # ---- stage 1: proposals -> top RoIs + FPN levels (rows of frame f are in group f) ----------
-    def proposals(self, rpn, im_info, images_per_group=1):
+    def proposals(self, rpn, im_info, images_per_group=1, mark=None):
         """rpn: {lvl: (scores (B,A,H,W), deltas (B,4A,H,W))} CUDA tensors; im_info (B,3) CUDA."""
         m = self.cfg.mode(self.training)
         inputs = [(rpn[l][0], rpn[l][1], self.anchors[l], float(2 ** l)) for l in self.rpn_levels]
         rois, probs, count = ops.generate_proposals_cuda(inputs, im_info, m.pre_nms_topN, m.post_nms_topN,
                                                          m.nms_thresh, m.min_size)
+        if mark:
+            mark("collect_distribute")
         c = self.cfg
         return ops.collect_distribute_cuda(rois, probs, count, c.collect_post_topN(self.training),
                                            images_per_group, c.roi_min_level, c.roi_max_level,
@@ -58,31 +60,39 @@ class RegionPipeline:
                                         self.sampling_ratio)
 
     # ---- whole step on device-resident inputs -------------------------------------------------
-    def step(self, rpn, im_info, feats, det_boxes, det_cls, det_masks, frame_hw, im_scale):
+    def step(self, rpn, im_info, feats, det_boxes, det_cls, det_masks, frame_hw, im_scale, mark=None):
         """One batch of B frames.
         det_boxes (B,D,4) original-frame coords, det_cls (B,D) int32, det_masks (B,D,K,M,M):
         the box-head / mask-head outputs the pipeline sits between (synthetic in the benchmark).
-        Returns dict of device tensors."""
+        ``mark(name)`` (optional) is called on the launching stream right before each stage
+        (bench.py records CUDA events there).  Returns dict of device tensors."""
         c = self.cfg
+        mark = mark or (lambda name: None)
         B, D = det_boxes.shape[:2]
-        prop = self.proposals(rpn, im_info)
+        mark("proposals")
+        prop = self.proposals(rpn, im_info, mark=mark)
         post = prop["rois"].shape[1]
         rois = prop["rois"].view(B * post, 5)
+        mark("roialign_box")
         # rows beyond count[g] are zero boxes on frame 0 level k_min: harmless filler, masked by count
         box_feats = self.roi_features(feats, rois, prop["level"].view(-1).clamp_(c.roi_min_level, c.roi_max_level),
                                       self.box_resolution)
         # mask branch: detections -> blob coords -> level -> RoIAlign (im_detect_mask, test.py:366-402)
+        mark("mask_rois")
         frame_idx = torch.arange(B, device=det_boxes.device, dtype=torch.float32).view(B, 1, 1).expand(B, D, 1)
         mask_rois = torch.cat([frame_idx, det_boxes * im_scale], dim=2).view(B * D, 5).contiguous()
         mlevel, _, _, _ = ops.distribute_cuda(mask_rois, c.roi_min_level, c.roi_max_level,
                                               c.roi_canonical_scale, c.roi_canonical_level)
+        mark("roialign_mask")
         mask_feats = self.roi_features(feats, mask_rois, mlevel, self.mask_resolution)
+        mark("paste")
         K, M = det_masks.shape[2], det_masks.shape[3]
         pasted = ops.paste_masks_cuda(det_masks.view(B * D, K, M, M),
                                       det_cls.view(-1) if c.mrcnn_cls_specific_mask else None,
                                       det_boxes.view(B * D, 4), frame_hw[0], frame_hw[1], c.mrcnn_thresh_binarize)
+        mark("end")
         return {"rois": prop["rois"], "roi_count": prop["count"], "roi_level": prop["level"],
-                "box_feats": box_feats, "mask_feats": mask_feats,
+                "box_feats": box_feats, "mask_feats": mask_feats, "mask_rois": mask_rois, "mask_level": mlevel,
                 "masks": pasted.view(B, D, frame_hw[0], frame_hw[1])}
 
 
@@ -122,8 +132,8 @@ def all_gather_frames(dets, masks, group=None):
     number of frames (pad the clip); returns tensors with F = F_r * world frames in rank order."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    d_out = torch.empty((world,) + tuple(dets.shape), dtype=dets.dtype, device=dets.device)
-    m_out = torch.empty((world,) + tuple(masks.shape), dtype=masks.dtype, device=masks.device)
+    d_out = torch.empty((world * dets.shape[0],) + tuple(dets.shape[1:]), dtype=dets.dtype, device=dets.device)
+    m_out = torch.empty((world * masks.shape[0],) + tuple(masks.shape[1:]), dtype=masks.dtype, device=masks.device)
     dist.all_gather_into_tensor(d_out, dets.contiguous(), group=group)
     dist.all_gather_into_tensor(m_out, masks.contiguous(), group=group)
-    return d_out.flatten(0, 1), m_out.flatten(0, 1)
+    return d_out, m_out

@@ -99,6 +99,11 @@ VOSD_API int vosd_roialign_ml_fwd(const float* const* level_data, const int* lev
                          int num_rois, const float* rois, const int* roi_level,
                          const int* out_index, float* top_data, cudaStream_t stream);
 
+/* Test hook: non-zero routes RoIAlign through the generic un-staged kernels (the in-kernel
+ * fallback for RoIs that exceed the shared-memory tile budget), so both paths stay covered by
+ * the parity tests.  Returns the previous setting.  Process-wide; not for production use. */
+VOSD_API int vosd_debug_force_generic(int on);
+
 /* level_diff[l] (N,C,H_l,W_l) accumulated into (zero_init as above, needs batch_size). */
 VOSD_API int vosd_roialign_ml_bwd(const float* top_diff, float* const* level_diff, const int* level_h,
                          const int* level_w, const float* level_scale, int num_levels,

@@ -47,6 +47,15 @@ def refk():
     return R
 
 
+@pytest.fixture(params=["staged", "generic"])
+def path(request):
+    """Run a test through the shared-memory staged kernels and through the generic fallback."""
+    from vosdetectron_b200 import _lib
+    old = _lib.load().vosd_debug_force_generic(1 if request.param == "generic" else 0)
+    yield request.param
+    _lib.load().vosd_debug_force_generic(old)
+
+
 def ulp_diff(a, b):
     ia = a.view(torch.int32).long()
     ib = b.view(torch.int32).long()
@@ -64,7 +73,7 @@ def _case(synth, lvl, R=150, C=16, N=2, seed=0, blob=None):
 
 @pytest.mark.parametrize("lvl", [2, 3, 4, 5])
 @pytest.mark.parametrize("res,sr", [(7, 2), (14, 2), (7, 0), (3, 1)])
-def test_forward_bit_exact_vs_reference_kernel(refk, synth, orc, lvl, res, sr):
+def test_forward_bit_exact_vs_reference_kernel(refk, synth, orc, path, lvl, res, sr):
     from vosdetectron_b200 import ops
     f, rois = _case(synth, lvl, seed=lvl)
     scale = 1.0 / 2 ** lvl
@@ -78,7 +87,7 @@ def test_forward_bit_exact_vs_reference_kernel(refk, synth, orc, lvl, res, sr):
     assert err <= 1e-5 * np.abs(o).max(), err
 
 
-def test_forward_edge_rois_vs_reference_kernel(refk, synth, orc):
+def test_forward_edge_rois_vs_reference_kernel(refk, synth, orc, path):
     from vosdetectron_b200 import ops
     for lvl in (2, 5):
         f = torch.from_numpy(synth.fpn_features(7, synth.COCO_BLOB, 1, (lvl,), 8)[lvl]).cuda()
@@ -89,6 +98,19 @@ def test_forward_edge_rois_vs_reference_kernel(refk, synth, orc):
             assert torch.equal(out, ref), (lvl, res, sr)
             o = orc.roi_align_forward(f.cpu().numpy(), rois.cpu().numpy(), res, res, 1.0 / 2 ** lvl, sr)
             assert np.array_equal(out.cpu().numpy(), o), (lvl, res, sr)
+
+
+def test_forward_oversize_rois_and_odd_channels(refk, synth):
+    """RoIs far larger than the staged tile (banding + in-kernel fallback), C not a multiple of 32,
+    a non-square pooled size and a large fixed sampling grid."""
+    from vosdetectron_b200 import ops
+    f = torch.from_numpy(synth.fpn_features(77, synth.COCO_BLOB, 2, (2,), 40)[2]).cuda()     # 200x336, C=40
+    rois = torch.tensor([[0, 0, 0, 1343, 799], [1, 10, 20, 1300, 90], [0, 5, 5, 90, 790], [1, 300, 300, 340, 330],
+                         [0, 100, 100, 900, 700]], dtype=torch.float32, device="cuda")
+    for (ph, pw, sr) in ((7, 7, 2), (14, 14, 2), (7, 7, 0), (5, 9, 3), (2, 2, 20)):
+        out = ops.roi_align_forward(f, rois, ph, pw, 0.25, sr)
+        ref = refk.fwd(f, rois, ph, pw, 0.25, sr)
+        assert torch.equal(out, ref), (ph, pw, sr, float((out - ref).abs().max()))
 
 
 def test_forward_vs_torchvision_golden(golden):
@@ -115,7 +137,7 @@ def test_empty_and_cpu_inputs(synth):
 
 
 @pytest.mark.parametrize("lvl,res,sr", [(2, 7, 2), (3, 14, 2), (4, 7, 0), (5, 14, 2)])
-def test_backward_vs_reference_kernel_and_oracle(refk, synth, orc, lvl, res, sr):
+def test_backward_vs_reference_kernel_and_oracle(refk, synth, orc, path, lvl, res, sr):
     from vosdetectron_b200 import ops
     f, rois = _case(synth, lvl, R=120, C=8, seed=10 + lvl)
     scale = 1.0 / 2 ** lvl
@@ -150,7 +172,7 @@ def test_autograd_function_and_modules(synth):
     assert RoIAlignMax(7, 7, 0.125, 2)(f, rois).shape == (40, 4, 7, 7)
 
 
-def test_multilevel_matches_reference_loop(refk, synth, orc):
+def test_multilevel_matches_reference_loop(refk, synth, orc, path):
     """roi_feature_transform: one launch == per-level launches + cat + restore (model_builder.py:271-303)."""
     from vosdetectron_b200.modeling.model_builder import roi_feature_transform
     N, C = 2, 8

@@ -33,6 +33,7 @@ SIGNATURES = {
     "vosd_status_string": (ctypes.c_char_p, [ctypes.c_int]),
     "vosd_launch_count": (ctypes.c_ulonglong, []),
     "vosd_set_device": (ctypes.c_int, [ctypes.c_int]),
+    "vosd_debug_force_generic": (ctypes.c_int, [ctypes.c_int]),
     "vosd_roialign_fwd": (ctypes.c_int, [vp, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp]),
     "vosd_roialign_bwd": (ctypes.c_int, [vp, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -73,7 +73,83 @@ __device__ __forceinline__ float resized_at(const float* __restrict__ m, int M, 
     return __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, b1));
 }
 
-// Each thread produces 16 consecutive bytes of the flat (R*im_h*im_w) output.
+// 16 consecutive output bytes starting at pixel (y, x) of detection r; runs are split at row ends
+// (and detection ends when the flat variant walks across frames).
+template <bool kProb>
+__device__ __forceinline__ void paste_chunk(const float* __restrict__ masks, const int* __restrict__ cls,
+                                            const float* __restrict__ ref_boxes, int r, int y, int x, int nbytes,
+                                            int K, int M, int im_h, int im_w, float thresh,
+                                            uint32_t (&packed)[4], float (&pv)[16]) {
+    int done = 0;
+    while (done < nbytes) {
+        const int run = min(nbytes - done, im_w - x);
+        DetGeom g = det_geometry(ref_boxes + 4 * (size_t)r, M);
+        const int xa = max(max(g.x0, 0), x), xb = min(min(g.x1 + 1, im_w), x + run);
+        if (y >= max(g.y0, 0) && y < min(g.y1 + 1, im_h) && xa < xb) {
+            det_scales(g, M);
+            const int c = cls ? cls[r] : 0;
+            const float* m = masks + ((size_t)r * K + c) * M * M;
+            for (int xx = xa; xx < xb; xx++) {
+                const float v = resized_at(m, M, g, y - g.y0, xx - g.x0);
+                const int i = done + (xx - x);
+                if (v > thresh) packed[i >> 2] |= 1u << (8 * (i & 3));
+                if (kProb) pv[i] = v;
+            }
+        }
+        done += run;
+        x += run;
+        if (x >= im_w) { x = 0; if (++y >= im_h) { y = 0; ++r; } }
+    }
+}
+
+template <bool kProb>
+__device__ __forceinline__ void store_chunk(uint8_t* __restrict__ out, float* __restrict__ out_prob, long long f0,
+                                            int nbytes, const uint32_t (&packed)[4], const float (&pv)[16]) {
+    if (nbytes == 16) {
+        st_stream_u4(out + f0, make_uint4(packed[0], packed[1], packed[2], packed[3]));
+        if (kProb) {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                st_stream_f4(out_prob + f0 + 4 * q, make_float4(pv[4 * q], pv[4 * q + 1], pv[4 * q + 2], pv[4 * q + 3]));
+        }
+    } else {
+        for (int i = 0; i < nbytes; i++) {
+            out[f0 + i] = (uint8_t)((packed[i >> 2] >> (8 * (i & 3))) & 0xffu);
+            if (kProb) out_prob[f0 + i] = pv[i];
+        }
+    }
+}
+
+// Fast variant (im_h*im_w % 16 == 0): grid = (chunks per frame / 256, detections).  The detection is
+// fixed per CTA, so a chunk that misses the box rows/columns costs one 32-bit division, a few
+// compares and one 128-bit store.
+template <bool kProb>
+__global__ void __launch_bounds__(256)
+paste_det_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
+                 const float* __restrict__ ref_boxes, int K, int M, int im_h, int im_w,
+                 float thresh, uint8_t* __restrict__ out, float* __restrict__ out_prob) {
+    const int r = blockIdx.y;
+    const unsigned frame = (unsigned)im_h * (unsigned)im_w;
+    const unsigned f0 = (blockIdx.x * 256u + threadIdx.x) * 16u;
+    if (f0 >= frame) return;
+    const DetGeom g = det_geometry(ref_boxes + 4 * (size_t)r, M);
+    const int ya = max(g.y0, 0), yb = min(g.y1 + 1, im_h), xa = max(g.x0, 0), xb = min(g.x1 + 1, im_w);
+    const int y = (int)(f0 / (unsigned)im_w), x = (int)(f0 - (unsigned)y * (unsigned)im_w);
+    const int y_last = (int)((f0 + 15u) / (unsigned)im_w);
+    uint32_t packed[4] = {0u, 0u, 0u, 0u};
+    float pv[16];
+    if (kProb) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) pv[i] = 0.f;
+    }
+    const bool rows_hit = y_last >= ya && y < yb && xa < xb;
+    const bool cols_hit = (y_last > y) || (x < xb && x + 16 > xa);
+    if (rows_hit && cols_hit)
+        paste_chunk<kProb>(masks, cls, ref_boxes, r, y, x, 16, K, M, im_h, im_w, thresh, packed, pv);
+    store_chunk<kProb>(out, out_prob, (long long)r * frame + f0, 16, packed, pv);
+}
+
+// Generic flat variant: each thread produces 16 consecutive bytes of the (R*im_h*im_w) output.
 template <bool kProb>
 __global__ void __launch_bounds__(256)
 paste_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
@@ -84,9 +160,9 @@ paste_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
     for (long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x; ch < chunks;
          ch += (long long)gridDim.x * blockDim.x) {
         const long long f0 = ch * 16;
-        int r = (int)(f0 / frame);
+        const int r = (int)(f0 / frame);
         const int rem = (int)(f0 - (long long)r * frame);
-        int y = rem / im_w, x = rem - y * im_w;
+        const int y = rem / im_w, x = rem - y * im_w;
         const int nbytes = (int)min(16LL, total - f0);
         uint32_t packed[4] = {0u, 0u, 0u, 0u};
         float pv[16];
@@ -94,40 +170,8 @@ paste_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
 #pragma unroll
             for (int i = 0; i < 16; i++) pv[i] = 0.f;
         }
-        int done = 0;
-        while (done < nbytes) {
-            // bytes [done, done+run) share one (detection, row)
-            const int run = min(nbytes - done, im_w - x);
-            DetGeom g = det_geometry(ref_boxes + 4 * (size_t)r, M);
-            const int xa = max(max(g.x0, 0), x), xb = min(min(g.x1 + 1, im_w), x + run);
-            if (y >= max(g.y0, 0) && y < min(g.y1 + 1, im_h) && xa < xb) {
-                det_scales(g, M);
-                const int c = cls ? cls[r] : 0;
-                const float* m = masks + ((size_t)r * K + c) * M * M;
-                for (int xx = xa; xx < xb; xx++) {
-                    const float v = resized_at(m, M, g, y - g.y0, xx - g.x0);
-                    const int i = done + (xx - x);
-                    if (v > thresh) packed[i >> 2] |= 1u << (8 * (i & 3));
-                    if (kProb) pv[i] = v;
-                }
-            }
-            done += run;
-            x += run;
-            if (x >= im_w) { x = 0; if (++y >= im_h) { y = 0; ++r; } }
-        }
-        if (nbytes == 16) {
-            st_stream_u4(out + f0, make_uint4(packed[0], packed[1], packed[2], packed[3]));
-            if (kProb) {
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    st_stream_f4(out_prob + f0 + 4 * q, make_float4(pv[4 * q], pv[4 * q + 1], pv[4 * q + 2], pv[4 * q + 3]));
-            }
-        } else {
-            for (int i = 0; i < nbytes; i++) {
-                out[f0 + i] = (uint8_t)((packed[i >> 2] >> (8 * (i & 3))) & 0xffu);
-                if (kProb) out_prob[f0 + i] = pv[i];
-            }
-        }
+        paste_chunk<kProb>(masks, cls, ref_boxes, r, y, x, nbytes, K, M, im_h, im_w, thresh, packed, pv);
+        store_chunk<kProb>(out, out_prob, f0, nbytes, packed, pv);
     }
 }
 
@@ -146,12 +190,22 @@ extern "C" int vosd_paste_masks(const float* masks, const int* cls, const float*
     const long long chunks = (total + 15) / 16;
     long long blocks = (chunks + 255) / 256;
     if (blocks > (long long)kNumSMs * 32) blocks = (long long)kNumSMs * 32;
-    if (out_prob)
+    const long long frame = (long long)im_h * im_w;
+    if (frame % 16 == 0 && frame < (1LL << 31) && num_dets <= 65535) {
+        dim3 grid((unsigned)((frame / 16 + 255) / 256), (unsigned)num_dets);
+        if (out_prob)
+            paste_det_kernel<true><<<grid, 256, 0, stream>>>(masks, cls, ref_boxes, num_classes, mask_size, im_h, im_w,
+                                                             thresh, out, out_prob);
+        else
+            paste_det_kernel<false><<<grid, 256, 0, stream>>>(masks, cls, ref_boxes, num_classes, mask_size, im_h, im_w,
+                                                              thresh, out, out_prob);
+    } else if (out_prob) {
         paste_kernel<true><<<(int)blocks, 256, 0, stream>>>(masks, cls, ref_boxes, total, num_classes, mask_size,
                                                             im_h, im_w, thresh, out, out_prob);
-    else
+    } else {
         paste_kernel<false><<<(int)blocks, 256, 0, stream>>>(masks, cls, ref_boxes, total, num_classes, mask_size,
                                                              im_h, im_w, thresh, out, out_prob);
+    }
     count_launch();
     return check_launch();
 }

@@ -94,7 +94,7 @@ def main():
     timer = Timer(args.iters)
     ref = load_ref()
     out = []
-    want = lambda k: not args.only or args.only in k
+    want = lambda k: not args.only or k in args.only
     stream = lambda: torch.cuda.current_stream().cuda_stream
     lvls = synth.ROI_LEVELS
     scales = [1.0 / 2 ** l for l in lvls]

@@ -130,23 +130,25 @@ paste_det_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
                  float thresh, uint8_t* __restrict__ out, float* __restrict__ out_prob) {
     const int r = blockIdx.y;
     const unsigned frame = (unsigned)im_h * (unsigned)im_w;
-    const unsigned f0 = (blockIdx.x * 256u + threadIdx.x) * 16u;
-    if (f0 >= frame) return;
     const DetGeom g = det_geometry(ref_boxes + 4 * (size_t)r, M);
     const int ya = max(g.y0, 0), yb = min(g.y1 + 1, im_h), xa = max(g.x0, 0), xb = min(g.x1 + 1, im_w);
-    const int y = (int)(f0 / (unsigned)im_w), x = (int)(f0 - (unsigned)y * (unsigned)im_w);
-    const int y_last = (int)((f0 + 15u) / (unsigned)im_w);
-    uint32_t packed[4] = {0u, 0u, 0u, 0u};
-    float pv[16];
-    if (kProb) {
+    uint8_t* __restrict__ o = out + (size_t)r * frame;
+    float* __restrict__ op = kProb ? out_prob + (size_t)r * frame : nullptr;
+    for (unsigned f0 = (blockIdx.x * 256u + threadIdx.x) * 16u; f0 < frame; f0 += gridDim.x * 256u * 16u) {
+        const int y = (int)(f0 / (unsigned)im_w), x = (int)(f0 - (unsigned)y * (unsigned)im_w);
+        const int y_last = (int)((f0 + 15u) / (unsigned)im_w);
+        uint32_t packed[4] = {0u, 0u, 0u, 0u};
+        float pv[16];
+        if (kProb) {
 #pragma unroll
-        for (int i = 0; i < 16; i++) pv[i] = 0.f;
+            for (int i = 0; i < 16; i++) pv[i] = 0.f;
+        }
+        const bool rows_hit = y_last >= ya && y < yb && xa < xb;
+        const bool cols_hit = (y_last > y) || (x < xb && x + 16 > xa);
+        if (rows_hit && cols_hit)
+            paste_chunk<kProb>(masks, cls, ref_boxes, r, y, x, 16, K, M, im_h, im_w, thresh, packed, pv);
+        store_chunk<kProb>(o, op, (long long)f0, 16, packed, pv);
     }
-    const bool rows_hit = y_last >= ya && y < yb && xa < xb;
-    const bool cols_hit = (y_last > y) || (x < xb && x + 16 > xa);
-    if (rows_hit && cols_hit)
-        paste_chunk<kProb>(masks, cls, ref_boxes, r, y, x, 16, K, M, im_h, im_w, thresh, packed, pv);
-    store_chunk<kProb>(out, out_prob, (long long)r * frame + f0, 16, packed, pv);
 }
 
 // Generic flat variant: each thread produces 16 consecutive bytes of the (R*im_h*im_w) output.
@@ -192,7 +194,9 @@ extern "C" int vosd_paste_masks(const float* masks, const int* cls, const float*
     if (blocks > (long long)kNumSMs * 32) blocks = (long long)kNumSMs * 32;
     const long long frame = (long long)im_h * im_w;
     if (frame % 16 == 0 && frame < (1LL << 31) && num_dets <= 65535) {
-        dim3 grid((unsigned)((frame / 16 + 255) / 256), (unsigned)num_dets);
+        // ~8 chunks (128 B) per thread: few, fat CTAs instead of one 4 KB CTA per 256 chunks
+        unsigned bx = (unsigned)((frame / 16 + 256 * 8 - 1) / (256 * 8));
+        dim3 grid(bx < 1 ? 1 : bx, (unsigned)num_dets);
         if (out_prob)
             paste_det_kernel<true><<<grid, 256, 0, stream>>>(masks, cls, ref_boxes, num_classes, mask_size, im_h, im_w,
                                                              thresh, out, out_prob);

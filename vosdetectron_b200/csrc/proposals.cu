@@ -110,22 +110,28 @@ struct RpnKeys {
     }
 };
 
-// K1.  grid = num_levels * num_images, block = 1024, dyn smem = sort_cap * 8.
-__global__ void __launch_bounds__(kSelThreads, 1)
+// K1.  One thread-block CLUSTER of kTopkCluster CTAs per (level, image) segment: the score
+// planes are streamed by 8 SMs at once, histograms meet in distributed shared memory, rank 0
+// sorts the survivors and decodes them.  grid = segments * kTopkCluster, block = 1024,
+// dyn smem = sort_cap * 8.
+constexpr int kTopkCluster = 8;
+__global__ void __cluster_dims__(kTopkCluster, 1, 1) __launch_bounds__(kSelThreads, 1)
 topk_decode_kernel(const __grid_constant__ RpnParams p, const float* __restrict__ im_info,
                    float4* __restrict__ ws_boxes, float* __restrict__ ws_scores,
                    int* __restrict__ ws_count) {
     extern __shared__ __align__(16) unsigned char dyn[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(dyn);
-    __shared__ SelectShared sh;
+    __shared__ ClusterSelectShared sh;
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
 
-    const int seg = blockIdx.x;
+    const int seg = blockIdx.x / kTopkCluster;
     const int l = seg / p.num_images, img = seg - l * p.num_images;
     const RpnLevelDev& L = p.lv[l];
     const int HW = L.H * L.W;
     RpnKeys kf{L.scores + (size_t)img * L.n, L.A, HW};
     const int P = next_pow2(L.take);
-    const int m = select_and_sort(kf, L.n, L.n, L.take, keys, P, sh);
+    const int m = select_and_sort_cluster(cluster, kf, L.n, L.take, keys, P, sh);
+    if (cluster.block_rank() != 0) return;
 
     const float im_h = im_info[img * 3 + 0], im_w = im_info[img * 3 + 1], im_s = im_info[img * 3 + 2];
     const float min_size = __fmul_rn(p.min_size, im_s);
@@ -261,6 +267,81 @@ nms_reduce_kernel(const float4* __restrict__ boxes, const float* __restrict__ sc
                         const float4 v = b[i0 + t];
                         float* r = out_rois + ((size_t)seg * cap + pos) * 5;
                         r[0] = img; r[1] = v.x; r[2] = v.y; r[3] = v.z; r[4] = v.w;
+                        out_probs[(size_t)seg * cap + pos] = sc[i0 + t];
+                    } else {
+                        keep_flag[orig_index[i0 + t]] = 1;
+                    }
+                }
+            }
+        }
+        kept_total += __popcll(kept);
+    }
+    if (lane == 0 && out_count) out_count[seg] = min(kept_total, limit);
+}
+
+// K3, fast path for segments of <= 2048 boxes (<= 32 mask words per row): lane w keeps word w of the
+// running `removed` bitmap in a register.  Per 64-box chunk the warp issues ALL its global loads up
+// front -- the 64 diagonal words and, for every later word, the 64 row words of the chunk -- so the
+// chunk costs one memory round trip instead of one per surviving box; the diagonal is then resolved
+// sequentially from shared memory (warp-uniform), and the survivors' rows are OR-ed from registers.
+__global__ void __launch_bounds__(32)
+nms_reduce_warp_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                       const int* __restrict__ count, int seg_stride, int words_per_row,
+                       const unsigned long long* __restrict__ mask, int use_mask, int post, int mode,
+                       int num_images, int cap, float* __restrict__ out_rois, float* __restrict__ out_probs,
+                       int* __restrict__ out_count, const int* __restrict__ orig_index,
+                       int* __restrict__ keep_flag) {
+    __shared__ unsigned long long diag[64];
+    const int seg = blockIdx.x, lane = threadIdx.x;
+    const int n = count[seg];
+    const int nblk = (n + 63) / 64;
+    const float4* b = boxes + (size_t)seg * seg_stride;
+    const float* sc = scores ? scores + (size_t)seg * seg_stride : nullptr;
+    const unsigned long long* mrow = mask + (size_t)seg * seg_stride * words_per_row;
+    const int limit = post > 0 ? post : n;
+    const float img = (float)(seg % num_images);
+    unsigned long long rem = 0;          // removed bits of word `lane`
+    int kept_total = 0;
+    for (int c = 0; c < nblk && kept_total < limit; c++) {
+        const int i0 = c * 64;
+        const int nin = min(64, n - i0);
+        unsigned long long kept;
+        if (use_mask) {
+            // all loads of the chunk in flight together
+            unsigned long long d0 = 0, d1 = 0;
+            if (lane < nin) d0 = mrow[(size_t)(i0 + lane) * words_per_row + c];
+            if (lane + 32 < nin) d1 = mrow[(size_t)(i0 + lane + 32) * words_per_row + c];
+            unsigned long long r[64];
+            const bool mine = lane > c && lane < nblk;
+#pragma unroll
+            for (int t = 0; t < 64; t++)
+                r[t] = (mine && t < nin) ? mrow[(size_t)(i0 + t) * words_per_row + lane] : 0ull;
+            diag[lane] = d0;
+            diag[lane + 32] = d1;
+            __syncwarp();
+            unsigned long long alive = ~__shfl_sync(0xffffffffu, rem, c);
+            if (nin < 64) alive &= (1ull << nin) - 1ull;
+            kept = 0;
+#pragma unroll 16
+            for (int t = 0; t < 64; t++) {
+                const unsigned long long d = diag[t];
+                if ((alive >> t) & 1ull) { kept |= 1ull << t; alive &= ~d; }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 64; t++)
+                if ((kept >> t) & 1ull) rem |= r[t];
+        } else {
+            kept = nin < 64 ? (1ull << nin) - 1ull : ~0ull;
+        }
+        for (int t = lane; t < 64; t += 32) {
+            if ((kept >> t) & 1ull) {
+                const int pos = kept_total + __popcll(kept & ((1ull << t) - 1ull));
+                if (pos < limit) {
+                    if (mode == 0) {
+                        const float4 v = b[i0 + t];
+                        float* o = out_rois + ((size_t)seg * cap + pos) * 5;
+                        o[0] = img; o[1] = v.x; o[2] = v.y; o[3] = v.z; o[4] = v.w;
                         out_probs[(size_t)seg * cap + pos] = sc[i0 + t];
                     } else {
                         keep_flag[orig_index[i0 + t]] = 1;
@@ -457,7 +538,7 @@ extern "C" int vosd_generate_proposals(const vosd_rpn_level* levels, int num_lev
     const size_t dyn = (size_t)p.sort_cap * sizeof(uint64_t);
     if (cudaFuncSetAttribute(topk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
         return VOSD_ERR_LAUNCH;
-    topk_decode_kernel<<<lay.S, kSelThreads, dyn, stream>>>(p, im_info, ws_boxes, ws_scores, ws_count);
+    topk_decode_kernel<<<lay.S * kTopkCluster, kSelThreads, dyn, stream>>>(p, im_info, ws_boxes, ws_scores, ws_count);
     count_launch();
     const int use_mask = nms_thresh > 0.f;
     if (use_mask) {
@@ -465,9 +546,14 @@ extern "C" int vosd_generate_proposals(const vosd_rpn_level* levels, int num_lev
         nms_mask_kernel<<<grid, 64, 0, stream>>>(ws_boxes, ws_count, lay.M, lay.words, nms_thresh, ws_mask);
         count_launch();
     }
-    nms_reduce_kernel<<<lay.S, 32, 0, stream>>>(ws_boxes, ws_scores, ws_count, lay.M, lay.words, ws_mask,
-                                                use_mask, use_mask ? post_nms_topN : 0, 0, num_images, lay.cap,
-                                                out_rois, out_probs, out_count, nullptr, nullptr);
+    if (lay.words <= 32)
+        nms_reduce_warp_kernel<<<lay.S, 32, 0, stream>>>(ws_boxes, ws_scores, ws_count, lay.M, lay.words, ws_mask,
+                                                         use_mask, use_mask ? post_nms_topN : 0, 0, num_images, lay.cap,
+                                                         out_rois, out_probs, out_count, nullptr, nullptr);
+    else
+        nms_reduce_kernel<<<lay.S, 32, 0, stream>>>(ws_boxes, ws_scores, ws_count, lay.M, lay.words, ws_mask,
+                                                    use_mask, use_mask ? post_nms_topN : 0, 0, num_images, lay.cap,
+                                                    out_rois, out_probs, out_count, nullptr, nullptr);
     count_launch();
     return check_launch();
 }
@@ -544,8 +630,12 @@ extern "C" int vosd_nms(const float* dets, int n, float thresh, int64_t* keep, i
     nms_sort_kernel<<<1, kSelThreads, dyn, stream>>>(dets, n, P, boxes, orig, count, flag);
     dim3 grid(L.words, L.words, 1);
     nms_mask_kernel<<<grid, 64, 0, stream>>>(boxes, count, n, L.words, thresh, mask);
-    nms_reduce_kernel<<<1, 32, 0, stream>>>(boxes, nullptr, count, n, L.words, mask, 1, 0, 1, 1, n,
-                                            nullptr, nullptr, nullptr, orig, flag);
+    if (L.words <= 32)
+        nms_reduce_warp_kernel<<<1, 32, 0, stream>>>(boxes, nullptr, count, n, L.words, mask, 1, 0, 1, 1, n,
+                                                     nullptr, nullptr, nullptr, orig, flag);
+    else
+        nms_reduce_kernel<<<1, 32, 0, stream>>>(boxes, nullptr, count, n, L.words, mask, 1, 0, 1, 1, n,
+                                                nullptr, nullptr, nullptr, orig, flag);
     compact_flags_kernel<<<1, kSelThreads, 0, stream>>>(flag, n, reinterpret_cast<long long*>(keep), num_keep);
     count_launch(4);
     return check_launch();

@@ -88,53 +88,486 @@ roialign_bwd_generic(LevelTable lv, int channels, int pooled_h, int pooled_w, in
 
 
 // ---------------------------------------------------------------------------------------
-// Staged forward path.  One CTA = one RoI x one slab of 32 channels.
-//   1. the first threads build per-axis tap tables (low/high texel, weights, validity) for the
-//      PH*grid_h sample rows and PW*grid_w sample columns -- computed once per CTA instead of
-//      once per output element;
-//   2. the RoI's bounding tile of the feature map (rows y_lo..y_hi, columns x_lo..x_hi of the
-//      32 channel planes) is staged in shared memory as tile[c][row*tw + col] with an ODD
-//      per-channel stride, in bands of output rows when the whole tile does not fit;
-//   3. lanes own channels, warps own output bins: every tap is one shared-memory wavefront
-//      (bank = (c*stride + texel) mod 32, stride odd -> conflict-free), the weights are
-//      warp-uniform, and the per-element arithmetic is the reference's (roialign_math.cuh);
-//   4. results go through obuf[c][bin] (odd stride) so the slab leaves as ONE contiguous
-//      32*PH*PW*4-byte streaming write (evict-first: keeps the feature maps in L2).
-// RoIs whose tables or single-row tile exceed the budgets fall back to direct global gathers
-// inside the same kernel (no CPU path).
+// Staged forward path.  One CTA = one RoI x one group of output rows x several 32-channel slabs.
+//   1. Per-axis tap tables (low/high texel, weights, validity) for the sample rows / columns are
+//      built once per CTA, and from them one SAMPLE RECORD per bilinear sample: the four tile
+//      offsets (bytes) and the four corner weights hy*hx, hy*lx, ly*hx, ly*lx.  They are shared by
+//      every channel of the RoI, so the gather loop carries no coordinate arithmetic at all.
+//   2. For each slab, the bounding tile of the feature map (rows y_lo..y_hi x columns x_lo..x_hi
+//      of 32 channel planes) is staged in shared memory with 128-bit loads when rows are 16-byte
+//      aligned (W % 4 == 0; scalar otherwise), in bands of output rows if it exceeds 512 texels.
+//      Layout: word (t ^ c) of a 512-word row per channel c -- an XOR swizzle that keeps 16-byte
+//      vectors intact (the 4 texels are permuted inside their vector) and makes the gather
+//      bank-conflict-free: lanes = channels read the same texel t at banks (t ^ c) mod 32, all
+//      distinct.  Address of a tap = K_lane ^ byte_offset: one LOP3 per shared-memory load.
+//   3. Lanes own channels, warps own output bins; per-element arithmetic is the reference's
+//      (roialign_math.cuh), so staging cannot change a bit of the result.
+//   4. Results leave through obuf[c][bin] (odd stride) as contiguous streaming stores
+//      (evict-first: the feature maps stay L2-resident for the RoIs that overlap them).
+// RoIs whose tables / records exceed the budgets use direct global gathers inside the same kernel.
 // ---------------------------------------------------------------------------------------
 constexpr int kSlab = 32;
-constexpr int kFwdThreads = 256;
+constexpr int kFwdThreads = 256;             // 8 warps x 128 registers, 2 CTAs / SM; each warp stages 4 channels
 constexpr int kFwdWarps = kFwdThreads / 32;
-constexpr int kMaxTaps = 64;                 // per-axis table capacity (PH*grid_h, PW*grid_w)
+constexpr int kMaxTaps = 64;                 // per-axis table capacity (rows*grid_h, PW*grid_w)
+constexpr int kMaxRecords = 1024;            // sample records per CTA
+constexpr int kTileWords = 512;              // per channel; power of two (XOR addressing)
 
 struct __align__(16) Tap { int low, high; float l, h; };   // low < 0: sample outside the map
+struct __align__(16) SampleRec { int o1, o2, o3, o4; float w1, w2, w3, w4; };   // o1 < 0: contributes 0
 
 struct FwdShared {
     Tap ytab[kMaxTaps];
     Tap xtab[kMaxTaps];
     RoiGeom g;
     int level, H, W;
-    int x_lo, tw;            // tile columns
-    int ok;                  // 0 -> generic fallback for this RoI
+    int x_lo, tw;            // tile columns (x_lo / tw aligned to 4 when vec)
+    int vec;                 // 128-bit staging possible
+    int ok;                  // 0 -> direct-gather fallback for this RoI
+    int nbands;              // bands of output rows, each fitting the 512-texel tile
+    short band_p1[kMaxTaps]; // end row (exclusive, relative to the row group) of band b
+    short band_ylo[kMaxTaps];
+    short band_rows[kMaxTaps];
+    unsigned char band_tall[kMaxTaps];   // single output row taller than the tile: staged per sample row
 };
 
-__device__ __forceinline__ float ld_feat(const float* p) { return __ldg(p); }
+// Texel j of an aligned 4-vector of channel c lives at position j ^ (c & 3) of that vector.
+__device__ __forceinline__ float4 swizzle4(float4 v, int p) {
+    switch (p) {
+        case 0: return v;
+        case 1: return make_float4(v.y, v.x, v.w, v.z);
+        case 2: return make_float4(v.z, v.w, v.x, v.y);
+        default: return make_float4(v.w, v.z, v.y, v.x);
+    }
+}
 
-__global__ void __launch_bounds__(kFwdThreads)
+struct FwdCtx {
+    const float* feat0;      // first channel of this CTA's first slab, image g.batch
+    float* out0;             // first output of this CTA (row, first slab, first row of the group)
+    float* tile; SampleRec* rec; float* obuf; int* binrec;
+    int channels, pooled_w, bins, obuf_stride, slab0, nslab, H, W, gh, gw, nx;
+    float count;
+};
+
+// Bands x slabs main loop.  kFast = 2x2 sampling grid, 128-bit staging, no tall rows: the common
+// FPN case gets its own tightly register-allocated instance; everything else takes kFast = false.
+template <bool kFast>
+__device__ __noinline__ void run_bands(const FwdCtx cx, FwdShared& sh) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* tile = cx.tile; SampleRec* rec = cx.rec; float* obuf = cx.obuf; int* binrec = cx.binrec;
+    const int channels = cx.channels, pooled_w = cx.pooled_w, bins = cx.bins, obuf_stride = cx.obuf_stride;
+    const int H = cx.H, W = cx.W, nx = cx.nx, slab0 = cx.slab0, nslab = cx.nslab;
+    const int gh = kFast ? 2 : cx.gh, gw = kFast ? 2 : cx.gw;
+    const int x_lo = sh.x_lo, tw = sh.tw;
+    const bool vec = kFast ? true : (sh.vec != 0);
+    const unsigned klane = (unsigned)(lane * kTileWords * 4) ^ (unsigned)(lane * 4);   // swizzled lane base (bytes)
+    const char* tb = reinterpret_cast<const char*>(tile);
+    const size_t plane = (size_t)H * W;
+    const float* __restrict__ feat0 = cx.feat0;
+    float* __restrict__ out0 = cx.out0;
+    const int icount = gh * gw;
+    const bool pow2 = (icount & (icount - 1)) == 0;       // x / 2^k == x * 2^-k exactly
+    const float inv_count = 1.0f / cx.count;
+    const int nbands = sh.nbands;
+
+    int p0 = 0;                                            // rows are relative to ph_begin from here on
+    for (int band = 0; band < nbands; band++) {
+        const int p1 = sh.band_p1[band], y_lo = sh.band_ylo[band], rows_total = sh.band_rows[band];
+        const bool tall = kFast ? false : (sh.band_tall[band] != 0);
+        const int nsub = tall ? gh : 1;                    // tall row: one sample row (<= 2 texel rows) per pass
+        const int band_bins = (p1 - p0) * pooled_w;
+        // ---- once per band: sample records (tile byte offsets + corner weights), bin -> record base ----
+        const int rec_n = (p1 - p0) * gh * nx;
+        for (int s2 = tid; s2 < rec_n; s2 += kFwdThreads) {
+            const int sy = s2 / nx, sx = s2 - sy * nx;
+            const Tap ty = sh.ytab[p0 * gh + sy], tx = sh.xtab[sx];
+            SampleRec r;
+            if (ty.low >= 0 && tx.low >= 0) {
+                const int base_y = tall ? ty.low : y_lo;            // tall: origin = the sample's own low row
+                const int r0 = (ty.low - base_y) * tw - x_lo, r1 = (ty.high - base_y) * tw - x_lo;
+                r.o1 = 4 * (r0 + tx.low); r.o2 = 4 * (r0 + tx.high);
+                r.o3 = 4 * (r1 + tx.low); r.o4 = 4 * (r1 + tx.high);
+                r.w1 = __fmul_rn(ty.h, tx.h); r.w2 = __fmul_rn(ty.h, tx.l);
+                r.w3 = __fmul_rn(ty.l, tx.h); r.w4 = __fmul_rn(ty.l, tx.l);
+            } else {
+                r.o1 = -1; r.o2 = r.o3 = r.o4 = 0; r.w1 = r.w2 = r.w3 = r.w4 = 0.f;
+            }
+            rec[s2] = r;
+        }
+        for (int q = tid; q < band_bins; q += kFwdThreads) {
+            const int pr = q / pooled_w;
+            binrec[q] = pr * gh * nx + (q - pr * pooled_w) * gw;
+        }
+        // ---- once per band: what this thread stages (same for every slab) ----
+        int goff[4], toff[4];
+        if (!tall) {
+            const int tws = vec ? (tw >> 2) : tw;                   // row length in staging units
+            const int nunit = rows_total * tws;
+            const float inv = 1.0f / (float)max(tws, 1);
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const int i = lane + 32 * m;
+                const int ry = (int)(((float)i + 0.5f) * inv);
+                const int rx = vec ? ((i - ry * tws) << 2) : (i - ry * tws);
+                goff[m] = i < nunit ? (y_lo + ry) * W + (x_lo + rx) : -1;
+                toff[m] = ry * tw + rx;
+            }
+        }
+        __syncthreads();
+
+        for (int k = 0; k < nslab; k++) {
+            const int nch = min(kSlab, channels - (slab0 + k) * kSlab);
+            const float* __restrict__ feat = feat0 + (size_t)k * kSlab * plane;
+            for (int sub = 0; sub < nsub; sub++) {
+                int elems = rows_total * tw, sy_lo = y_lo;
+                if (tall) {                                         // texel rows of sample row `sub` only
+                    const Tap t = sh.ytab[p0 * gh + sub];
+                    sy_lo = t.low >= 0 ? t.low : 0;
+                    const int rows = (t.low >= 0 && tw > 0) ? t.high - t.low + 1 : 0;
+                    elems = rows * tw;
+                    const int tws = vec ? (tw >> 2) : tw;
+                    const float inv = 1.0f / (float)max(tws, 1);
+#pragma unroll
+                    for (int m = 0; m < 4; m++) {
+                        const int i = lane + 32 * m;
+                        const int ry = (int)(((float)i + 0.5f) * inv);
+                        const int rx = vec ? ((i - ry * tws) << 2) : (i - ry * tws);
+                        goff[m] = i < rows * tws ? (sy_lo + ry) * W + (x_lo + rx) : -1;
+                        toff[m] = ry * tw + rx;
+                    }
+                }
+                // ---- stage: all of a thread's loads (2 channels x <= 4 units) are issued before any store ----
+                if (vec) {
+                    // one channel at a time: its <= 4 vectors are loaded before any is stored
+                    for (int c = warp; c < nch; c += kFwdWarps) {
+                        const float* pc = feat + c * plane;
+                        float4 v[4];
+#pragma unroll
+                        for (int m = 0; m < 4; m++)
+                            if (goff[m] >= 0) v[m] = __ldg(reinterpret_cast<const float4*>(pc + goff[m]));
+                        float* tc = tile + c * kTileWords;
+                        const int cx4 = c & ~3;
+#pragma unroll
+                        for (int m = 0; m < 4; m++)
+                            if (goff[m] >= 0) *reinterpret_cast<float4*>(tc + (toff[m] ^ cx4)) = swizzle4(v[m], c & 3);
+                    }
+                } else {
+                    // scalar rows (W % 4 != 0): 128 texels per pass, up to 4 passes
+                    for (int i0 = 0; i0 < elems; i0 += 128) {
+                        int go[4];
+                        if (i0 == 0) {
+#pragma unroll
+                            for (int m = 0; m < 4; m++) go[m] = goff[m];
+                        } else {
+                            const float inv = 1.0f / (float)max(tw, 1);
+#pragma unroll
+                            for (int m = 0; m < 4; m++) {
+                                const int i = i0 + lane + 32 * m;
+                                const int ry = (int)(((float)i + 0.5f) * inv);
+                                go[m] = i < elems ? (sy_lo + ry) * W + (x_lo + i - ry * tw) : -1;
+                            }
+                        }
+                        for (int c = warp; c < nch; c += kFwdWarps) {
+                            float va[4];
+#pragma unroll
+                            for (int m = 0; m < 4; m++)
+                                if (go[m] >= 0) va[m] = __ldg(feat + c * plane + go[m]);
+#pragma unroll
+                            for (int m = 0; m < 4; m++)
+                                if (go[m] >= 0) tile[c * kTileWords + ((i0 + lane + 32 * m) ^ c)] = va[m];
+                        }
+                    }
+                }
+                __syncthreads();
+                // ---- gather: lanes = channels, warps = bins of the band ----
+                if (kFast) {
+                    for (int q = warp; q < band_bins; q += kFwdWarps) {
+                        const SampleRec* rr = rec + binrec[q];
+                        float acc = 0.f;
+#pragma unroll
+                        for (int iy = 0; iy < 2; iy++) {
+#pragma unroll
+                            for (int ix = 0; ix < 2; ix++) {
+                                const SampleRec r = rr[iy * nx + ix];
+                                float val = 0.f;
+                                if (r.o1 >= 0) {
+                                    const float v1 = *reinterpret_cast<const float*>(tb + (klane ^ (unsigned)r.o1));
+                                    const float v2 = *reinterpret_cast<const float*>(tb + (klane ^ (unsigned)r.o2));
+                                    const float v3 = *reinterpret_cast<const float*>(tb + (klane ^ (unsigned)r.o3));
+                                    const float v4 = *reinterpret_cast<const float*>(tb + (klane ^ (unsigned)r.o4));
+                                    val = __fmaf_rn(r.w4, v4, __fmaf_rn(r.w3, v3, __fmaf_rn(r.w1, v1, __fmul_rn(r.w2, v2))));
+                                }
+                                acc = __fadd_rn(acc, val);
+                            }
+                        }
+                        obuf[lane * obuf_stride + q] = __fmul_rn(acc, 0.25f);          // count == 4: exact
+                    }
+                } else {
+                    const int iy0 = tall ? sub : 0, iy1 = tall ? sub + 1 : gh;
+                    for (int q = warp; q < band_bins; q += kFwdWarps) {
+                        const SampleRec* rr0 = rec + binrec[q];
+                        float* slot = obuf + lane * obuf_stride + q;
+                        float acc = (tall && sub > 0) ? *slot : 0.f;     // tall rows carry the running sum in obuf
+                        for (int iy = iy0; iy < iy1; iy++) {
+                            const SampleRec* rr = rr0 + iy * nx;
+                            for (int ix = 0; ix < gw; ix++) {
+                                const SampleRec r = rr[ix];
+                                float val = 0.f;
+                                if (r.o1 >= 0) {
+                                    const float v1 = *reinterpret_cast<const float*>(tb + (klane ^ (unsigned)r.o1));
+                                    const float v2 = *reinterpret_cast<const float*>(tb + (klane ^ (unsigned)r.o2));
+                                    const float v3 = *reinterpret_cast<const float*>(tb + (klane ^ (unsigned)r.o3));
+                                    const float v4 = *reinterpret_cast<const float*>(tb + (klane ^ (unsigned)r.o4));
+                                    val = __fmaf_rn(r.w4, v4, __fmaf_rn(r.w3, v3, __fmaf_rn(r.w1, v1, __fmul_rn(r.w2, v2))));
+                                }
+                                acc = __fadd_rn(acc, val);
+                            }
+                        }
+                        *slot = (sub == nsub - 1) ? (pow2 ? __fmul_rn(acc, inv_count) : __fdiv_rn(acc, cx.count)) : acc;
+                    }
+                }
+                __syncthreads();
+            }
+            // ---- contiguous streaming write of this band of the slab: warp -> its two channels ----
+            float* __restrict__ out = out0 + (size_t)k * kSlab * bins + p0 * pooled_w;
+            for (int c = warp; c < nch; c += kFwdWarps)
+                for (int bq = lane; bq < band_bins; bq += 32)
+                    __stcs(out + (size_t)c * bins + bq, obuf[c * obuf_stride + bq]);
+        }
+        __syncthreads();
+        p0 = p1;
+    }
+}
+
+// ---- shared-memory access by 32-bit shared-window address (keeps the XOR-swizzled address
+//      arithmetic to a single LOP3 per tap and stops the compiler re-deriving generic pointers) ----
+__device__ __forceinline__ float lds_f32(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_v4(unsigned a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void lds_rec(unsigned a, int& o1, int& o2, int& o3, int& o4, float& w1, float& w2, float& w3, float& w4) {
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o1), "=r"(o2), "=r"(o3), "=r"(o4) : "r"(a));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(w1), "=f"(w2), "=f"(w3), "=f"(w4) : "r"(a));
+}
+
+// Ordered (volatile) read-only 128-bit global load: keeps channel a's loads/stores ahead of channel b's,
+// i.e. 4 (not 8) vectors live per thread -- the kernel is capped at 64 registers for 2 CTAs / SM.
+__device__ __forceinline__ float4 ldg_v4_ordered(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ void sts_v2(unsigned a, float x, float y) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(a), "f"(x), "f"(y) : "memory");
+}
+
+// Stores vector v of a channel with c & 3 == p to its swizzled slot: texel j goes to position j ^ p.
+// Bit 1 of p swaps the two 8-byte halves (done in the address: a_lo = slot ^ ((p & 2) * 4)), bit 0 swaps
+// inside each half (2 x 2 selects on a warp-uniform predicate).  One code instance for all warps.
+__device__ __forceinline__ void sts_swizzled(unsigned a_lo, bool swap, float4 v) {
+    sts_v2(a_lo, swap ? v.y : v.x, swap ? v.x : v.y);
+    sts_v2(a_lo ^ 8u, swap ? v.w : v.z, swap ? v.z : v.w);
+}
+
+// Fast path of the bands x slabs loop: 2x2 sampling grid, 16-byte aligned rows, no tall rows.
+//
+// Software pipeline over the slabs of the CTA: the 16 vectors a thread stages for slab k+1
+// (4 channels x <= 4 vectors, 64 registers) are requested from L2/HBM BEFORE the gather of slab k and
+// written to the tile after it, so the global-load latency hides behind the gather instead of
+// stalling all warps at a barrier.  8 warps x 128 registers, 2 CTAs per SM.
+//
+// P = warp & 3 is the swizzle phase of the channels warp, warp+8, warp+16, warp+24 a warp stages; as a
+// template parameter the in-vector permutation is pure register renaming.  Warps of one CTA run
+// different instances and meet at the same hardware barrier.
+constexpr int kChPerWarp = kSlab / kFwdWarps;      // 4
+
+__device__ __forceinline__ void prefetch_slab(float4 (&v)[kChPerWarp][4], const float* __restrict__ p0,
+                                              size_t cstride, int nch, int warp, const int (&goff)[4]) {
+#pragma unroll
+    for (int h = 0; h < kChPerWarp; h++) {
+        const float* pc = p0 + (size_t)h * cstride;
+        const bool has = warp + h * kFwdWarps < nch;
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+            if (goff[m] >= 0 && has) v[h][m] = ldg_v4_ordered(pc + goff[m]);
+    }
+}
+
+__device__ __forceinline__ void commit_slab(const float4 (&v)[kChPerWarp][4], int nch, int warp, bool swap,
+                                            const int (&goff)[4], const unsigned (&ts0)[4]) {
+#pragma unroll
+    for (int h = 0; h < kChPerWarp; h++) {
+        const bool has = warp + h * kFwdWarps < nch;
+#pragma unroll
+        for (int m = 0; m < 4; m++)    // channel warp + 8h: row + 16 KB * h, XOR phase differs in word bits 3-4
+            if (goff[m] >= 0 && has)
+                sts_swizzled((ts0[m] ^ (unsigned)(h * kFwdWarps * 4)) + (unsigned)(h * kFwdWarps * kTileWords * 4), swap, v[h][m]);
+    }
+}
+
+// Fast path of the bands x slabs loop: 2x2 sampling grid, 16-byte aligned rows, no tall rows.
+//
+// Software pipeline over the slabs of the CTA: the 16 vectors a thread stages for slab k+1
+// (4 channels x <= 4 vectors, 64 registers) are requested from L2/HBM BEFORE the gather of slab k and
+// written to the tile after it, so the global-load latency hides behind the gather instead of
+// stalling all warps at a barrier.  8 warps x 128 registers, 2 CTAs per SM.
+__device__ __noinline__ void run_bands_fast(const FwdCtx cx, FwdShared& sh) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int channels = cx.channels, pooled_w = cx.pooled_w, bins = cx.bins, obuf_stride = cx.obuf_stride;
+    const int W = cx.W, nx = cx.nx, slab0 = cx.slab0, nslab = cx.nslab;
+    const int x_lo = sh.x_lo, tw = sh.tw;
+    const size_t plane = (size_t)cx.H * W;
+    const size_t cstride = (size_t)kFwdWarps * plane;                          // between a warp's channels
+    const unsigned tile_s = (unsigned)__cvta_generic_to_shared(cx.tile);      // 2 KB aligned
+    const unsigned rec_s = (unsigned)__cvta_generic_to_shared(cx.rec);
+    const unsigned obuf_s = (unsigned)__cvta_generic_to_shared(cx.obuf);
+    const unsigned klane = (tile_s + (unsigned)lane * (kTileWords * 4)) ^ ((unsigned)lane * 4u);
+    const bool swap = (warp & 1) != 0;                      // swizzle phase of this warp's channels: warp & 3
+    const unsigned half = (unsigned)(warp & 2) * 4u;
+    const int nbands = sh.nbands;
+    const int tw4 = tw >> 2;
+    const unsigned nxb = (unsigned)nx * 32u;                // bytes between the two sample rows of a bin
+
+    int p0 = 0;
+    for (int band = 0; band < nbands; band++) {
+        const int p1 = sh.band_p1[band], y_lo = sh.band_ylo[band], rows_total = sh.band_rows[band];
+        const int band_bins = (p1 - p0) * pooled_w;
+        // ---- what this thread stages for every slab of the band ----
+        int goff[4];
+        unsigned ts0[4];
+        {
+            const int nvec = rows_total * tw4;
+            const float inv = 1.0f / (float)max(tw4, 1);
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const int i = lane + 32 * m;
+                const int ry = (int)(((float)i + 0.5f) * inv);
+                const int rx = (i - ry * tw4) << 2;
+                goff[m] = i < nvec ? (y_lo + ry) * W + (x_lo + rx) : -1;
+                ts0[m] = (tile_s + 4u * (unsigned)(warp * kTileWords + ((ry * tw + rx) ^ (warp & ~3)))) ^ half;
+            }
+        }
+        const float* pw0 = cx.feat0 + (size_t)warp * plane;       // channel `warp` of the current slab
+        float4 v[kChPerWarp][4];
+        prefetch_slab(v, pw0, cstride, min(kSlab, channels - slab0 * kSlab), warp, goff);   // slab 0 in flight
+        // ---- once per band: sample records, bin -> first record (sign bit: some sample is outside) ----
+        const int rec_n = (p1 - p0) * 2 * nx;
+        for (int s2 = tid; s2 < rec_n; s2 += kFwdThreads) {
+            const int sy = s2 / nx, sx = s2 - sy * nx;
+            const Tap ty = sh.ytab[p0 * 2 + sy], tx = sh.xtab[sx];
+            SampleRec r;
+            if (ty.low >= 0 && tx.low >= 0) {
+                const int r0 = (ty.low - y_lo) * tw - x_lo, r1 = (ty.high - y_lo) * tw - x_lo;
+                r.o1 = 4 * (r0 + tx.low); r.o2 = 4 * (r0 + tx.high);
+                r.o3 = 4 * (r1 + tx.low); r.o4 = 4 * (r1 + tx.high);
+                r.w1 = __fmul_rn(ty.h, tx.h); r.w2 = __fmul_rn(ty.h, tx.l);
+                r.w3 = __fmul_rn(ty.l, tx.h); r.w4 = __fmul_rn(ty.l, tx.l);
+            } else {
+                r.o1 = -1; r.o2 = r.o3 = r.o4 = 0; r.w1 = r.w2 = r.w3 = r.w4 = 0.f;
+            }
+            cx.rec[s2] = r;
+        }
+        for (int q = tid; q < band_bins; q += kFwdThreads) {
+            const int pr = q / pooled_w, pw = q - pr * pooled_w;
+            const bool all_in = sh.ytab[(p0 + pr) * 2].low >= 0 && sh.ytab[(p0 + pr) * 2 + 1].low >= 0 &&
+                                sh.xtab[pw * 2].low >= 0 && sh.xtab[pw * 2 + 1].low >= 0;
+            const int first = pr * 2 * nx + pw * 2;
+            cx.binrec[q] = all_in ? first : (first | (int)0x80000000);
+        }
+        commit_slab(v, min(kSlab, channels - slab0 * kSlab), warp, swap, goff, ts0);
+        __syncthreads();                                            // tile(slab 0), records, binrec visible
+
+        float* out = cx.out0 + p0 * pooled_w;
+        for (int k = 0; k < nslab; k++) {
+            const int nch = min(kSlab, channels - (slab0 + k) * kSlab);
+            const int nch_next = k + 1 < nslab ? min(kSlab, channels - (slab0 + k + 1) * kSlab) : 0;
+            pw0 += (size_t)kSlab * plane;
+            prefetch_slab(v, pw0, cstride, nch_next, warp, goff);              // slab k+1 -> registers
+            // ---- gather slab k: lanes = channels, warps = bins ----
+            for (int q = warp; q < band_bins; q += kFwdWarps) {
+                const int br = cx.binrec[q];
+                const unsigned ra = rec_s + (unsigned)(br & 0x7fffffff) * 32u;
+                float acc = 0.f;
+                if (br >= 0) {
+                    // all four samples inside the map.  Two samples at a time: both records, then the 8 taps,
+                    // then the arithmetic, so shared-memory latencies overlap instead of chaining per sample.
+#pragma unroll
+                    for (int iy = 0; iy < 2; iy++) {
+                        int o[2][4]; float w[2][4], t[2][4];
+#pragma unroll
+                        for (int ix = 0; ix < 2; ix++)
+                            lds_rec(ra + (unsigned)iy * nxb + (unsigned)ix * 32u, o[ix][0], o[ix][1], o[ix][2], o[ix][3],
+                                    w[ix][0], w[ix][1], w[ix][2], w[ix][3]);
+#pragma unroll
+                        for (int ix = 0; ix < 2; ix++)
+#pragma unroll
+                            for (int c4 = 0; c4 < 4; c4++) t[ix][c4] = lds_f32(klane ^ (unsigned)o[ix][c4]);
+#pragma unroll
+                        for (int ix = 0; ix < 2; ix++)
+                            acc = __fadd_rn(acc, __fmaf_rn(w[ix][3], t[ix][3], __fmaf_rn(w[ix][2], t[ix][2],
+                                                           __fmaf_rn(w[ix][0], t[ix][0], __fmul_rn(w[ix][1], t[ix][1])))));
+                    }
+                } else {
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; s4++) {
+                        int o1, o2, o3, o4; float w1, w2, w3, w4;
+                        lds_rec(ra + (unsigned)(s4 >> 1) * nxb + (unsigned)(s4 & 1) * 32u, o1, o2, o3, o4, w1, w2, w3, w4);
+                        float val = 0.f;
+                        if (o1 >= 0) {
+                            const float v1 = lds_f32(klane ^ (unsigned)o1), v2 = lds_f32(klane ^ (unsigned)o2);
+                            const float v3 = lds_f32(klane ^ (unsigned)o3), v4 = lds_f32(klane ^ (unsigned)o4);
+                            val = __fmaf_rn(w4, v4, __fmaf_rn(w3, v3, __fmaf_rn(w1, v1, __fmul_rn(w2, v2))));
+                        }
+                        acc = __fadd_rn(acc, val);
+                    }
+                }
+                sts_f32(obuf_s + 4u * (unsigned)(lane * obuf_stride + q), __fmul_rn(acc, 0.25f));   // count == 4: exact
+            }
+            __syncthreads();                                        // every warp is done reading the tile
+            commit_slab(v, nch_next, warp, swap, goff, ts0);        // slab k+1 -> tile
+            // ---- contiguous streaming write of slab k: warp -> its 4 channels ----
+#pragma unroll
+            for (int h = 0; h < kChPerWarp; h++) {
+                const int c = warp + h * kFwdWarps;
+                if (c < nch) {
+                    float* oc = out + (size_t)c * bins;
+                    const float* ob = cx.obuf + c * obuf_stride;
+                    for (int bq = lane; bq < band_bins; bq += 32) __stcs(oc + bq, ob[bq]);
+                }
+            }
+            out += (size_t)kSlab * bins;
+            __syncthreads();                                        // tile(slab k+1) visible, obuf free
+        }
+        p0 = p1;
+    }
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 2)
 roialign_fwd_staged(const __grid_constant__ LevelTable lv, int channels, int pooled_h, int pooled_w,
-                    int sampling_ratio, int tile_cap /* odd, words per channel */, int obuf_stride /* odd */,
+                    int sampling_ratio, int rows_per_group, int slabs_per_cta, int rec_cap, int obuf_stride,
                     const float* __restrict__ rois, const int* __restrict__ roi_level,
                     const int* __restrict__ out_index, float* __restrict__ top) {
-    extern __shared__ __align__(16) float dyn[];
-    float* tile = dyn;                                   // [kSlab][tile_cap]
-    float* obuf = dyn + (size_t)kSlab * tile_cap;        // [kSlab][obuf_stride]
+    extern __shared__ __align__(16) unsigned char dyn_raw[];
+    // the tile starts on a 2 KB boundary of the shared window: tap address = K_lane ^ offset (one LOP3)
+    unsigned char* dyn = dyn_raw + ((2048u - ((unsigned)__cvta_generic_to_shared(dyn_raw) & 2047u)) & 2047u);
+    float* tile = reinterpret_cast<float*>(dyn);                                        // [32][512] swizzled
+    SampleRec* rec = reinterpret_cast<SampleRec*>(dyn + kSlab * kTileWords * 4);       // [rec_cap]
+    float* obuf = reinterpret_cast<float*>(dyn + kSlab * kTileWords * 4 + (size_t)rec_cap * sizeof(SampleRec));
+    int* binrec = reinterpret_cast<int*>(obuf + kSlab * obuf_stride);                   // [rows_per_group * pooled_w]
     __shared__ FwdShared sh;
 
     const int n = blockIdx.x;
-    const int c0 = blockIdx.y * kSlab;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nch = min(kSlab, channels - c0);
+    const int ph_begin = blockIdx.z * rows_per_group;
+    const int ph_end = min(pooled_h, ph_begin + rows_per_group);
     const int bins = pooled_h * pooled_w;
 
     if (tid == 0) {
@@ -145,55 +578,86 @@ roialign_fwd_staged(const __grid_constant__ LevelTable lv, int channels, int poo
     __syncthreads();
     const RoiGeom g = sh.g;
     const int H = sh.H, W = sh.W;
-    const int ny = pooled_h * g.grid_h, nx = pooled_w * g.grid_w;
-    const bool tables_fit = ny <= kMaxTaps && nx <= kMaxTaps;
-    if (tables_fit) {
+    const int gh = g.grid_h, gw = g.grid_w;
+    const int ny = (ph_end - ph_begin) * gh, nx = pooled_w * gw;      // sample rows of this group / columns
+    const bool fits = ny <= kMaxTaps && nx <= kMaxTaps && ny * nx <= rec_cap;
+    if (fits) {
         if (tid < ny) {
-            const AxisTap t = axis_tap(sample_coord(g.start_h, g.bin_h, tid / g.grid_h, tid % g.grid_h, g.grid_h), H);
+            const int sy = ph_begin * gh + tid;
+            const AxisTap t = axis_tap(sample_coord(g.start_h, g.bin_h, sy / gh, sy % gh, gh), H);
             sh.ytab[tid] = Tap{t.valid ? t.low : -1, t.high, t.l, t.h};
         } else if (tid >= 64 && tid < 64 + nx) {
             const int k = tid - 64;
-            const AxisTap t = axis_tap(sample_coord(g.start_w, g.bin_w, k / g.grid_w, k % g.grid_w, g.grid_w), W);
+            const AxisTap t = axis_tap(sample_coord(g.start_w, g.bin_w, k / gw, k % gw, gw), W);
             sh.xtab[k] = Tap{t.valid ? t.low : -1, t.high, t.l, t.h};
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        int x_lo = 1 << 30, x_hi = -1;
-        if (tables_fit)
-            for (int k = 0; k < nx; k++)
-                if (sh.xtab[k].low >= 0) { x_lo = min(x_lo, sh.xtab[k].low); x_hi = max(x_hi, sh.xtab[k].high); }
-        sh.x_lo = x_lo; sh.tw = x_hi - x_lo + 1;          // tw <= 0: no valid column at all
-        // every single output row must fit the tile on its own
-        int ok = tables_fit;
-        if (ok && sh.tw > 0) {
-            for (int ph = 0; ph < pooled_h && ok; ph++) {
-                int lo = 1 << 30, hi = -1;
-                for (int i = 0; i < g.grid_h; i++) {
-                    const Tap t = sh.ytab[ph * g.grid_h + i];
-                    if (t.low >= 0) { lo = min(lo, t.low); hi = max(hi, t.high); }
-                }
-                if (hi >= lo && (hi - lo + 1) * sh.tw > tile_cap) ok = 0;
-            }
+    if (warp == 0) {
+        // column extent of the tile (warp reduction over the x taps)
+        int lo = 1 << 30, hi = -1;
+        if (fits)
+            for (int k = lane; k < nx; k += 32)
+                if (sh.xtab[k].low >= 0) { lo = min(lo, sh.xtab[k].low); hi = max(hi, sh.xtab[k].high); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
         }
-        sh.ok = ok;
+        const int l = sh.level;
+        const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(lv.data[l]) & 15) == 0;
+        if (vec && hi >= lo) { lo &= ~3; hi |= 3; }
+        const int tw = hi - lo + 1;                                  // <= 0: no valid column
+        // every sample row must fit the tile on its own (2 texel rows)
+        int ok = fits && (tw <= 0 || 2 * tw <= kTileWords);
+        if (lane == 0) {
+            sh.x_lo = lo; sh.tw = tw; sh.vec = vec; sh.ok = ok;
+            int nb = 0;
+            if (ok) {
+                const int nrows = ph_end - ph_begin;
+                int p0 = 0;
+                while (p0 < nrows) {
+                    int p1 = p0, y_lo = 1 << 30, y_hi = -1, tall = 0;
+                    while (p1 < nrows) {
+                        int l2 = y_lo, h2 = y_hi;
+                        for (int i = 0; i < gh; i++) {
+                            const Tap t = sh.ytab[p1 * gh + i];
+                            if (t.low >= 0) { l2 = min(l2, t.low); h2 = max(h2, t.high); }
+                        }
+                        const bool over = h2 >= l2 && tw > 0 && (h2 - l2 + 1) * tw > kTileWords;
+                        if (over && p1 > p0) break;
+                        y_lo = l2; y_hi = h2; p1++;
+                        if (over) { tall = 1; break; }
+                    }
+                    sh.band_p1[nb] = (short)p1;
+                    sh.band_ylo[nb] = (short)(y_hi >= y_lo ? y_lo : 0);
+                    sh.band_rows[nb] = (short)((y_hi >= y_lo && tw > 0) ? y_hi - y_lo + 1 : 0);
+                    sh.band_tall[nb] = (unsigned char)tall;
+                    nb++;
+                    p0 = p1;
+                }
+            }
+            sh.nbands = nb;
+        }
     }
     __syncthreads();
-    const float* __restrict__ feat = lv.data[sh.level] + ((size_t)g.batch * channels + c0) * H * W;
     const int row = out_index ? out_index[n] : n;
-    float* __restrict__ out = top + ((size_t)row * channels + c0) * bins;
+    const int group_bins = (ph_end - ph_begin) * pooled_w;
 
     if (!sh.ok) {
-        // direct-gather fallback: thread per (channel, bin) of this slab
-        for (int e = tid; e < nch * bins; e += kFwdThreads) {
-            const int c = e / bins, b = e - c * bins;
-            const int ph = b / pooled_w, pw = b - ph * pooled_w;
-            const float* d = feat + (size_t)c * H * W;
+        // direct-gather fallback: thread per (channel, bin) of this row group, all slabs of this CTA
+        const int c_begin = blockIdx.y * slabs_per_cta * kSlab;
+        const int c_end = min(channels, c_begin + slabs_per_cta * kSlab);
+        const float* fbase = lv.data[sh.level] + (size_t)g.batch * channels * H * W;
+        for (int e = tid; e < (c_end - c_begin) * group_bins; e += kFwdThreads) {
+            const int c = c_begin + e / group_bins, b = e % group_bins;
+            const int ph = ph_begin + b / pooled_w, pw = b % pooled_w;
+            const float* d = fbase + (size_t)c * H * W;
             float acc = 0.f;
-            for (int iy = 0; iy < g.grid_h; iy++) {
-                const AxisTap ty = axis_tap(sample_coord(g.start_h, g.bin_h, ph, iy, g.grid_h), H);
-                for (int ix = 0; ix < g.grid_w; ix++) {
-                    const AxisTap tx = axis_tap(sample_coord(g.start_w, g.bin_w, pw, ix, g.grid_w), W);
+            for (int iy = 0; iy < gh; iy++) {
+                const AxisTap ty = axis_tap(sample_coord(g.start_h, g.bin_h, ph, iy, gh), H);
+                for (int ix = 0; ix < gw; ix++) {
+                    const AxisTap tx = axis_tap(sample_coord(g.start_w, g.bin_w, pw, ix, gw), W);
                     float val = 0.f;
                     if (ty.valid && tx.valid)
                         val = bilinear_value(ty.h, ty.l, tx.h, tx.l, __ldg(d + ty.low * W + tx.low),
@@ -202,71 +666,26 @@ roialign_fwd_staged(const __grid_constant__ LevelTable lv, int channels, int poo
                     acc = __fadd_rn(acc, val);
                 }
             }
-            out[e] = __fdiv_rn(acc, g.count);
+            top[((size_t)row * channels + c) * bins + ph * pooled_w + pw] = __fdiv_rn(acc, g.count);
         }
         return;
     }
 
-    const int x_lo = sh.x_lo, tw = sh.tw;
-    const float inv_tw = tw > 0 ? 1.0f / (float)tw : 0.f;
-    int p0 = 0;
-    while (p0 < pooled_h) {
-        // ---- band [p0, p1): as many output rows as fit the tile (uniform across the CTA) ----
-        int p1 = p0, y_lo = 1 << 30, y_hi = -1;
-        while (p1 < pooled_h) {
-            int lo = y_lo, hi = y_hi;
-            for (int i = 0; i < g.grid_h; i++) {
-                const Tap t = sh.ytab[p1 * g.grid_h + i];
-                if (t.low >= 0) { lo = min(lo, t.low); hi = max(hi, t.high); }
-            }
-            if (hi >= lo && tw > 0 && (hi - lo + 1) * tw > tile_cap) break;
-            y_lo = lo; y_hi = hi; p1++;
-        }
-        const int rows = (y_hi >= y_lo && tw > 0) ? y_hi - y_lo + 1 : 0;
-        const int elems = rows * tw;
-        // ---- stage: warp w copies channels w, w+8, ... ; lanes run over the flattened tile ----
-        for (int i0 = 0; i0 < elems; i0 += 32) {
-            const int i = i0 + lane;
-            if (i < elems) {
-                const int ry = (int)(((float)i + 0.5f) * inv_tw);
-                const int rx = i - ry * tw;
-                const float* src = feat + (size_t)(y_lo + ry) * W + (x_lo + rx);
-#pragma unroll
-                for (int k = 0; k < kSlab / kFwdWarps; k++) {
-                    const int c = warp + k * kFwdWarps;
-                    if (c < nch) tile[c * tile_cap + i] = ld_feat(src + (size_t)c * H * W);
-                }
-            }
-        }
-        __syncthreads();
-        // ---- gather: lanes = channels, warps = bins ----
-        const int nb = (p1 - p0) * pooled_w;
-        const float* tl = tile + lane * tile_cap;
-        for (int q = warp; q < nb; q += kFwdWarps) {
-            const int pr = q / pooled_w;
-            const int ph = p0 + pr, pw = q - pr * pooled_w;
-            float acc = 0.f;
-            for (int iy = 0; iy < g.grid_h; iy++) {
-                const Tap ty = sh.ytab[ph * g.grid_h + iy];
-                const int r0 = (ty.low - y_lo) * tw - x_lo, r1 = (ty.high - y_lo) * tw - x_lo;
-                for (int ix = 0; ix < g.grid_w; ix++) {
-                    const Tap tx = sh.xtab[pw * g.grid_w + ix];
-                    float val = 0.f;
-                    if (ty.low >= 0 && tx.low >= 0)
-                        val = bilinear_value(ty.h, ty.l, tx.h, tx.l, tl[r0 + tx.low], tl[r0 + tx.high],
-                                             tl[r1 + tx.low], tl[r1 + tx.high]);
-                    acc = __fadd_rn(acc, val);
-                }
-            }
-            obuf[lane * obuf_stride + ph * pooled_w + pw] = __fdiv_rn(acc, g.count);
-        }
-        __syncthreads();
-        p0 = p1;
-    }
-    // ---- one contiguous streaming write of the slab ----
-    for (int e = tid; e < nch * bins; e += kFwdThreads) {
-        const int c = e / bins, b = e - c * bins;
-        __stcs(out + e, obuf[c * obuf_stride + b]);
+    FwdCtx cx;
+    cx.tile = tile; cx.rec = rec; cx.obuf = obuf; cx.binrec = binrec;
+    cx.channels = channels; cx.pooled_w = pooled_w; cx.bins = bins; cx.obuf_stride = obuf_stride;
+    cx.slab0 = blockIdx.y * slabs_per_cta;
+    cx.nslab = min(slabs_per_cta, (channels + kSlab - 1) / kSlab - cx.slab0);
+    cx.H = H; cx.W = W; cx.gh = gh; cx.gw = gw; cx.nx = nx; cx.count = g.count;
+    cx.feat0 = lv.data[sh.level] + ((size_t)g.batch * channels + (size_t)cx.slab0 * kSlab) * H * W;
+    cx.out0 = top + ((size_t)row * channels + (size_t)cx.slab0 * kSlab) * bins + ph_begin * pooled_w;
+    // fast path: 2x2 sampling grid, 16-byte aligned rows, no output row taller than the tile
+    bool fast = gh == 2 && gw == 2 && sh.vec != 0;
+    for (int bnd = 0; bnd < sh.nbands; bnd++) fast = fast && sh.band_tall[bnd] == 0;
+    if (fast) {
+        run_bands_fast(cx, sh);
+    } else {
+        run_bands<false>(cx, sh);
     }
 }
 
@@ -297,19 +716,29 @@ static int ml_fwd(const LevelTable& t, int channels, int ph, int pw, int sr, int
     if (channels <= 0 || ph <= 0 || pw <= 0 || num_rois < 0) return VOSD_ERR_BAD_SHAPE;
     if (num_rois == 0) return VOSD_OK;
     if (!rois || !top) return VOSD_ERR_BAD_ARG;
-    // staged path: shared-memory budget per CTA chosen so that 3 (small outputs) or 2 CTAs fit an SM
-    const int bins = ph * pw;
-    const int obuf_stride = bins | 1;
-    const int budget = (bins <= 64 ? 74 : 112) * 1024 - (int)sizeof(FwdShared) - 64;
-    int tile_cap = (budget - kSlab * obuf_stride * (int)sizeof(float)) / (kSlab * (int)sizeof(float));
-    tile_cap = (tile_cap - 1) | 1;
-    if (tile_cap >= 65 && !g_force_generic) {
-        const size_t dyn = (size_t)kSlab * (tile_cap + obuf_stride) * sizeof(float);
+    // staged path: row groups of <= ~112 bins, sample records <= kMaxRecords, >= ~8 waves of CTAs
+    const int slabs = ceil_div(channels, kSlab);
+    int groups = ceil_div(ph * pw, 112);
+    if (groups > ph) groups = ph;
+    int rpg = ceil_div(ph, groups);
+    const int gs = sr > 0 ? sr : 1;
+    while (rpg > 1 && ((long long)rpg * gs * pw * gs > kMaxRecords || rpg * gs > kMaxTaps)) rpg--;
+    groups = ceil_div(ph, rpg);
+    const bool staged_ok = !g_force_generic && pw * gs <= kMaxTaps && rpg * gs <= kMaxTaps &&
+                           (long long)rpg * gs * pw * gs <= kMaxRecords && groups <= 65535;
+    if (staged_ok) {
+        const int rec_cap = sr > 0 ? rpg * sr * pw * sr : kMaxRecords;
+        const int obuf_stride = (rpg * pw) | 1;
+        long long spc = (long long)slabs * num_rois * groups / (6LL * 2 * kNumSMs);
+        if (spc < 1) spc = 1;
+        if (spc > slabs) spc = slabs;
+        const size_t dyn = (size_t)kSlab * kTileWords * 4 + (size_t)rec_cap * sizeof(SampleRec) +
+                           (size_t)kSlab * obuf_stride * sizeof(float) + (size_t)rpg * pw * sizeof(int) + 2048;
         if (cudaFuncSetAttribute(roialign_fwd_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
             return VOSD_ERR_LAUNCH;
-        dim3 grid(num_rois, ceil_div(channels, kSlab));
-        roialign_fwd_staged<<<grid, kFwdThreads, dyn, stream>>>(t, channels, ph, pw, sr, tile_cap, obuf_stride,
-                                                                rois, roi_level, out_index, top);
+        dim3 grid(num_rois, ceil_div(slabs, (int)spc), groups);
+        roialign_fwd_staged<<<grid, kFwdThreads, dyn, stream>>>(t, channels, ph, pw, sr, rpg, (int)spc, rec_cap,
+                                                                obuf_stride, rois, roi_level, out_index, top);
     } else {
         const long long total = (long long)num_rois * channels * ph * pw;
         roialign_fwd_generic<<<grid_for(total, 256), 256, 0, stream>>>(

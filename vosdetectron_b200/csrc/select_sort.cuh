@@ -6,6 +6,7 @@
 // and np.argsort(-scores) (collect_and_distribute_fpn_rpn_proposals.py:104), both unstable:
 // on tie-free inputs the orders coincide bit for bit.
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace vosd {
@@ -132,6 +133,107 @@ __device__ int select_and_sort(const KeyFn& key_at, int n, int n_valid, int m, u
     }
     __syncthreads();
     bitonic_sort_desc(keys_out, P);
+    return take;
+}
+
+// ------------------------------------------------------------------------------------
+// Cluster variant: the n keys of ONE segment are split over the CTAs of a thread-block cluster.
+// Every pass each CTA histograms its slice into its own shared memory; after one cluster
+// barrier all CTAs read the peer histograms through distributed shared memory (DSMEM) and
+// derive the same threshold bin redundantly, so nothing has to be broadcast.  Histograms are
+// double-buffered: one cluster barrier per pass.
+// ------------------------------------------------------------------------------------
+struct ClusterSelectShared {
+    int hist[2][kBins];
+    int warp_sums[32];
+    int found_bin;
+    int found_above;
+    int found_count;
+    int counter;          // keys this CTA selected from its slice
+};
+
+template <class KeyFn>
+__device__ void radix_select_cluster(cooperative_groups::cluster_group& cluster, const KeyFn& key_at,
+                                     int j0, int j1, int m, ClusterSelectShared& sh,
+                                     uint64_t& out_mask, uint64_t& out_prefix) {
+    uint64_t mask = 0, prefix = 0;
+    int need = m, shift = 64, buf = 0;
+    const unsigned nranks = cluster.num_blocks();
+    while (shift > 0) {
+        const int bits = shift >= kRadixBits ? kRadixBits : shift;
+        shift -= bits;
+        const uint32_t dmask = (1u << bits) - 1u;
+        int* h = sh.hist[buf];
+        for (int b = threadIdx.x; b < kBins; b += kSelThreads) h[b] = 0;
+        __syncthreads();
+        for (int j = j0 + threadIdx.x; j < j1; j += kSelThreads) {
+            const uint64_t k = key_at(j);
+            if (k != 0 && (k & mask) == prefix) atomicAdd(&h[(uint32_t)(k >> shift) & dmask], 1);
+        }
+        cluster.sync();
+        const int b0 = kBins - 1 - 2 * threadIdx.x, b1 = b0 - 1;
+        int h0 = 0, h1 = 0;
+        for (unsigned r = 0; r < nranks; r++) {
+            const int* rh = cluster.map_shared_rank(h, r);
+            h0 += rh[b0];
+            h1 += rh[b1];
+        }
+        int total;
+        const int above0 = block_exclusive_scan(h0 + h1, sh.warp_sums, total);
+        const int above1 = above0 + h0;
+        if (above0 < need && need <= above0 + h0) { sh.found_bin = b0; sh.found_above = above0; sh.found_count = h0; }
+        if (above1 < need && need <= above1 + h1) { sh.found_bin = b1; sh.found_above = above1; sh.found_count = h1; }
+        __syncthreads();
+        need -= sh.found_above;
+        prefix |= (uint64_t)sh.found_bin << shift;
+        mask |= (uint64_t)dmask << shift;
+        const bool done = sh.found_count == need;
+        __syncthreads();
+        buf ^= 1;
+        if (done) break;
+    }
+    out_mask = mask;
+    out_prefix = prefix;
+}
+
+// Cluster-wide select + sort.  On return rank 0 holds the `take` largest keys sorted descending in
+// its keys_out[0..take) (padded with 0 to P); the other ranks may exit.  All threads of all CTAs of
+// the cluster must call it.
+template <class KeyFn>
+__device__ int select_and_sort_cluster(cooperative_groups::cluster_group& cluster, const KeyFn& key_at,
+                                       int n, int m, uint64_t* keys_out, int P, ClusterSelectShared& sh) {
+    const unsigned rank = cluster.block_rank(), nranks = cluster.num_blocks();
+    const int take = m < n ? m : n;
+    const int chunk = (n + (int)nranks - 1) / (int)nranks;
+    const int j0 = min(n, (int)rank * chunk), j1 = min(n, j0 + chunk);
+    if (threadIdx.x == 0) sh.counter = 0;
+    __syncthreads();
+    uint64_t mask = 0, prefix = 0;
+    if (take < n) radix_select_cluster(cluster, key_at, j0, j1, take, sh, mask, prefix);
+    for (int j = j0 + threadIdx.x; j < j1; j += kSelThreads) {
+        const uint64_t k = key_at(j);
+        if (k != 0 && (k & mask) >= prefix) {
+            const int pos = atomicAdd(&sh.counter, 1);
+            if (pos < P) keys_out[pos] = k;
+        }
+    }
+    cluster.sync();                                   // every slice collected, counters final
+    if (rank == 0) {
+        int off = sh.counter;
+        for (unsigned r = 1; r < nranks; r++) {
+            const int cnt = *cluster.map_shared_rank(&sh.counter, r);
+            const uint64_t* rk = cluster.map_shared_rank(keys_out, r);
+            for (int i = threadIdx.x; i < cnt; i += kSelThreads)
+                if (off + i < P) keys_out[off + i] = rk[i];
+            off += cnt;
+        }
+        for (int i = off + threadIdx.x; i < P; i += kSelThreads) keys_out[i] = 0;
+    }
+    cluster.sync();                                   // peers may leave once rank 0 has copied
+    if (rank == 0) {
+        __syncthreads();
+        bitonic_sort_desc(keys_out, P);
+    }
     return take;
 }
 

@@ -99,9 +99,11 @@ VOSD_API int vosd_roialign_ml_fwd(const float* const* level_data, const int* lev
                          int num_rois, const float* rois, const int* roi_level,
                          const int* out_index, float* top_data, cudaStream_t stream);
 
-/* Test hook: non-zero routes RoIAlign through the generic un-staged kernels (the in-kernel
- * fallback for RoIs that exceed the shared-memory tile budget), so both paths stay covered by
- * the parity tests.  Returns the previous setting.  Process-wide; not for production use. */
+/* Test hook selecting the RoIAlign kernel family, so every path stays covered by the parity tests:
+ *   0 = default (shared-memory staged forward, atomic-scatter backward),
+ *   1 = generic un-staged kernels everywhere (also the in-kernel fallback for oversize RoIs),
+ *   2 = staged kernels everywhere (adds the staged backward).
+ * Returns the previous setting.  Process-wide; not for production use. */
 VOSD_API int vosd_debug_force_generic(int on);
 
 /* level_diff[l] (N,C,H_l,W_l) accumulated into (zero_init as above, needs batch_size). */

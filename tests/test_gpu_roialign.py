@@ -47,11 +47,12 @@ def refk():
     return R
 
 
-@pytest.fixture(params=["staged", "generic"])
+@pytest.fixture(params=["default", "generic", "staged"])
 def path(request):
-    """Run a test through the shared-memory staged kernels and through the generic fallback."""
+    """Run a test through every RoIAlign kernel family: default (staged forward + atomic backward),
+    generic un-staged kernels, and staged forward + staged backward."""
     from vosdetectron_b200 import _lib
-    old = _lib.load().vosd_debug_force_generic(1 if request.param == "generic" else 0)
+    old = _lib.load().vosd_debug_force_generic({"default": 0, "generic": 1, "staged": 2}[request.param])
     yield request.param
     _lib.load().vosd_debug_force_generic(old)
 

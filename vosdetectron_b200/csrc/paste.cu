@@ -120,33 +120,111 @@ __device__ __forceinline__ void store_chunk(uint8_t* __restrict__ out, float* __
     }
 }
 
-// Fast variant (im_h*im_w % 16 == 0): grid = (chunks per frame / 256, detections).  The detection is
-// fixed per CTA, so a chunk that misses the box rows/columns costs one 32-bit division, a few
-// compares and one 128-bit store.
+// Fast variant (im_h*im_w % 16 == 0): grid = (chunk ranges, detections); a CTA owns a contiguous range of
+// 16-byte chunks of ONE detection's frame.  If the range misses the box it is a pure zero fill.  Otherwise the
+// CTA first builds, in shared memory, the zero-padded (M+2)^2 source mask and cv2's per-column / per-row
+// interpolation tables (source index pair + the two fp32 coefficients, with cv2's border rules) for the
+// visible part of the box, so the per-pixel work is 2 table loads, 4 mask loads and 6 flops -- no double
+// precision and no bounds checks in the pixel loop.
+struct __align__(16) AxisCoef { int i0, i1; float c0, c1; };      // value = S[i0]*c0 + S[i1]*c1
+
+// cv2 column table entry for destination x-offset dx (zeroes the far tap at the border)
+__device__ __forceinline__ AxisCoef cv2_x_coef(int dx, double scale, int S) {
+    float fx = (float)__dsub_rn(__dmul_rn((double)dx + 0.5, scale), 0.5);
+    int sx = (int)floorf(fx);
+    fx = __fsub_rn(fx, (float)sx);
+    if (sx < 0) { fx = 0.f; sx = 0; }
+    if (sx >= S - 1) { fx = 0.f; sx = S - 1; }
+    return AxisCoef{sx, min(sx + 1, S - 1), __fsub_rn(1.f, fx), fx};
+}
+// cv2 row table entry (rows are replicate-clamped, weights kept)
+__device__ __forceinline__ AxisCoef cv2_y_coef(int dy, double scale, int S) {
+    float fy = (float)__dsub_rn(__dmul_rn((double)dy + 0.5, scale), 0.5);
+    const int sy = (int)floorf(fy);
+    fy = __fsub_rn(fy, (float)sy);
+    return AxisCoef{min(max(sy, 0), S - 1) * S, min(max(sy + 1, 0), S - 1) * S, __fsub_rn(1.f, fy), fy};
+}
+
 template <bool kProb>
 __global__ void __launch_bounds__(256)
 paste_det_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
-                 const float* __restrict__ ref_boxes, int K, int M, int im_h, int im_w,
+                 const float* __restrict__ ref_boxes, int K, int M, int im_h, int im_w, int chunks_per_cta,
                  float thresh, uint8_t* __restrict__ out, float* __restrict__ out_prob) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int S = M + 2;
+    float* smask = reinterpret_cast<float*>(smem);                                   // [S*S]
+    AxisCoef* xt = reinterpret_cast<AxisCoef*>(smem + (((size_t)S * S * 4 + 15) & ~(size_t)15));   // [<= im_w]
+    AxisCoef* yt = xt + im_w;                                                         // [rows of this CTA]
+
     const int r = blockIdx.y;
     const unsigned frame = (unsigned)im_h * (unsigned)im_w;
-    const DetGeom g = det_geometry(ref_boxes + 4 * (size_t)r, M);
+    const unsigned f_begin = blockIdx.x * (unsigned)chunks_per_cta * 16u;
+    const unsigned f_end = min(frame, f_begin + (unsigned)chunks_per_cta * 16u);
+    DetGeom g = det_geometry(ref_boxes + 4 * (size_t)r, M);
     const int ya = max(g.y0, 0), yb = min(g.y1 + 1, im_h), xa = max(g.x0, 0), xb = min(g.x1 + 1, im_w);
+    const int row_first = (int)(f_begin / (unsigned)im_w), row_last = (int)((f_end - 1u) / (unsigned)im_w);
+    const int ra = max(ya, row_first), rb = min(yb, row_last + 1);     // box rows this CTA touches
+    const bool hit = ra < rb && xa < xb;                              // uniform across the CTA
     uint8_t* __restrict__ o = out + (size_t)r * frame;
     float* __restrict__ op = kProb ? out_prob + (size_t)r * frame : nullptr;
-    for (unsigned f0 = (blockIdx.x * 256u + threadIdx.x) * 16u; f0 < frame; f0 += gridDim.x * 256u * 16u) {
-        const int y = (int)(f0 / (unsigned)im_w), x = (int)(f0 - (unsigned)y * (unsigned)im_w);
-        const int y_last = (int)((f0 + 15u) / (unsigned)im_w);
-        uint32_t packed[4] = {0u, 0u, 0u, 0u};
+
+    if (hit) {
+        det_scales(g, M);
+        const int c = cls ? cls[r] : 0;
+        const float* m = masks + ((size_t)r * K + c) * M * M;
+        for (int i = threadIdx.x; i < S * S; i += 256) {
+            const int y = i / S, x = i - y * S;
+            smask[i] = (y >= 1 && y <= M && x >= 1 && x <= M) ? __ldg(m + (y - 1) * M + (x - 1)) : 0.f;   // test.py:820-823
+        }
+        for (int x = xa + threadIdx.x; x < xb; x += 256) {
+            AxisCoef e = cv2_x_coef(x - g.x0, g.sx, S);
+            if (g.area2x) e = AxisCoef{2 * (x - g.x0), 2 * (x - g.x0) + 1, 0.5f, 0.5f};       // exact 2x shrink: INTER_AREA
+            xt[x - xa] = e;
+        }
+        for (int y = ra + threadIdx.x; y < rb; y += 256) {
+            AxisCoef e = cv2_y_coef(y - g.y0, g.sy, S);
+            if (g.area2x) e = AxisCoef{2 * (y - g.y0) * S, (2 * (y - g.y0) + 1) * S, 0.5f, 0.5f};
+            yt[y - ra] = e;
+        }
+        __syncthreads();
+    }
+
+    for (unsigned f0 = f_begin + threadIdx.x * 16u; f0 < f_end; f0 += 256u * 16u) {
+        unsigned long long lo = 0ull, hi = 0ull;          // bytes 0-7 / 8-15 of the chunk (no local-memory array)
         float pv[16];
         if (kProb) {
 #pragma unroll
             for (int i = 0; i < 16; i++) pv[i] = 0.f;
         }
-        const bool rows_hit = y_last >= ya && y < yb && xa < xb;
-        const bool cols_hit = (y_last > y) || (x < xb && x + 16 > xa);
-        if (rows_hit && cols_hit)
-            paste_chunk<kProb>(masks, cls, ref_boxes, r, y, x, 16, K, M, im_h, im_w, thresh, packed, pv);
+        if (hit) {
+            int y = (int)(f0 / (unsigned)im_w), x = (int)(f0 - (unsigned)y * (unsigned)im_w);
+            int done = 0;
+            while (done < 16) {                                       // runs never leave this detection's frame
+                const int run = min(16 - done, im_w - x);
+                const int x0r = max(xa, x), x1r = min(xb, x + run);
+                if (y >= ra && y < rb && x0r < x1r) {
+                    const AxisCoef ey = yt[y - ra];
+                    const float* s0 = smask + ey.i0;
+                    const float* s1 = smask + ey.i1;
+                    for (int xx = x0r; xx < x1r; xx++) {
+                        const AxisCoef ex = xt[xx - xa];
+                        const float r0 = __fadd_rn(__fmul_rn(s0[ex.i0], ex.c0), __fmul_rn(s0[ex.i1], ex.c1));
+                        const float r1 = __fadd_rn(__fmul_rn(s1[ex.i0], ex.c0), __fmul_rn(s1[ex.i1], ex.c1));
+                        const float v = __fadd_rn(__fmul_rn(r0, ey.c0), __fmul_rn(r1, ey.c1));
+                        const int i = done + (xx - x);
+                        if (v > thresh) {
+                            const unsigned long long bit = 1ull << (8 * (i & 7));
+                            if (i < 8) lo |= bit; else hi |= bit;
+                        }
+                        if (kProb) pv[i] = v;
+                    }
+                }
+                done += run;
+                x += run;
+                if (x >= im_w) { x = 0; ++y; }
+            }
+        }
+        const uint32_t packed[4] = {(uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)};
         store_chunk<kProb>(o, op, (long long)f0, 16, packed, pv);
     }
 }
@@ -194,15 +272,25 @@ extern "C" int vosd_paste_masks(const float* masks, const int* cls, const float*
     if (blocks > (long long)kNumSMs * 32) blocks = (long long)kNumSMs * 32;
     const long long frame = (long long)im_h * im_w;
     if (frame % 16 == 0 && frame < (1LL << 31) && num_dets <= 65535) {
-        // ~8 chunks (128 B) per thread: few, fat CTAs instead of one 4 KB CTA per 256 chunks
-        unsigned bx = (unsigned)((frame / 16 + 256 * 8 - 1) / (256 * 8));
-        dim3 grid(bx < 1 ? 1 : bx, (unsigned)num_dets);
-        if (out_prob)
-            paste_det_kernel<true><<<grid, 256, 0, stream>>>(masks, cls, ref_boxes, num_classes, mask_size, im_h, im_w,
-                                                             thresh, out, out_prob);
-        else
-            paste_det_kernel<false><<<grid, 256, 0, stream>>>(masks, cls, ref_boxes, num_classes, mask_size, im_h, im_w,
-                                                              thresh, out, out_prob);
+        // 2048 chunks (32 KB of output) per CTA: few, fat CTAs; tables cover at most the rows a CTA spans
+        const int chunks_per_cta = 2048;
+        const unsigned bx = (unsigned)((frame / 16 + chunks_per_cta - 1) / chunks_per_cta);
+        const int rows_per_cta = (chunks_per_cta * 16 + im_w - 1) / im_w + 2;
+        const int S = mask_size + 2;
+        const size_t smem = (((size_t)S * S * 4 + 15) & ~(size_t)15) + (size_t)(im_w + rows_per_cta) * 16;
+        if (smem > 200 * 1024) return VOSD_ERR_UNSUPPORTED;
+        dim3 grid(bx, (unsigned)num_dets);
+        if (out_prob) {
+            if (cudaFuncSetAttribute(paste_det_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return VOSD_ERR_LAUNCH;
+            paste_det_kernel<true><<<grid, 256, smem, stream>>>(masks, cls, ref_boxes, num_classes, mask_size, im_h, im_w,
+                                                                chunks_per_cta, thresh, out, out_prob);
+        } else {
+            if (cudaFuncSetAttribute(paste_det_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return VOSD_ERR_LAUNCH;
+            paste_det_kernel<false><<<grid, 256, smem, stream>>>(masks, cls, ref_boxes, num_classes, mask_size, im_h, im_w,
+                                                                 chunks_per_cta, thresh, out, out_prob);
+        }
     } else if (out_prob) {
         paste_kernel<true><<<(int)blocks, 256, 0, stream>>>(masks, cls, ref_boxes, total, num_classes, mask_size,
                                                             im_h, im_w, thresh, out, out_prob);

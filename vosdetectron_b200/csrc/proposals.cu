@@ -76,6 +76,9 @@ __device__ __forceinline__ bool suppresses(float4 a, float area_a, float4 b, flo
     float h = __fadd_rn(__fsub_rn(yy2, yy1), 1.f);
     w = 0.f >= w ? 0.f : w;
     h = 0.f >= h ? 0.f : h;
+    // disjoint boxes: inter = 0 and the union of two boxes (areas >= 1 by the +1 convention) is positive, so
+    // ovr = +0 < thresh for every thresh > 0 -- same decision as the division, without the division
+    if ((w == 0.f || h == 0.f) && thresh > 0.f && area_a > 0.f && area_b > 0.f) return false;
     const float inter = __fmul_rn(w, h);
     const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
     return ovr >= thresh;

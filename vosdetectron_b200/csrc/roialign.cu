@@ -550,26 +550,14 @@ __device__ __noinline__ void run_bands_fast(const FwdCtx cx, FwdShared& sh) {
     }
 }
 
-__global__ void __launch_bounds__(kFwdThreads, 2)
-roialign_fwd_staged(const __grid_constant__ LevelTable lv, int channels, int pooled_h, int pooled_w,
-                    int sampling_ratio, int rows_per_group, int slabs_per_cta, int rec_cap, int obuf_stride,
-                    const float* __restrict__ rois, const int* __restrict__ roi_level,
-                    const int* __restrict__ out_index, float* __restrict__ top) {
-    extern __shared__ __align__(16) unsigned char dyn_raw[];
-    // the tile starts on a 2 KB boundary of the shared window: tap address = K_lane ^ offset (one LOP3)
-    unsigned char* dyn = dyn_raw + ((2048u - ((unsigned)__cvta_generic_to_shared(dyn_raw) & 2047u)) & 2047u);
-    float* tile = reinterpret_cast<float*>(dyn);                                        // [32][512] swizzled
-    SampleRec* rec = reinterpret_cast<SampleRec*>(dyn + kSlab * kTileWords * 4);       // [rec_cap]
-    float* obuf = reinterpret_cast<float*>(dyn + kSlab * kTileWords * 4 + (size_t)rec_cap * sizeof(SampleRec));
-    int* binrec = reinterpret_cast<int*>(obuf + kSlab * obuf_stride);                   // [rows_per_group * pooled_w]
-    __shared__ FwdShared sh;
-
-    const int n = blockIdx.x;
+// Per-CTA setup shared by the staged forward and backward kernels: RoI geometry, per-axis tap tables for
+// the sample rows of [ph_begin, ph_end) and all sample columns, the column extent of the tile (aligned to
+// 4 texels when rows are 16-byte aligned), and the list of bands of output rows that fit the tile.
+// Ends with a barrier; afterwards sh.* is read-only.
+__device__ __forceinline__ void roi_setup(FwdShared& sh, const LevelTable& lv, const float* __restrict__ rois,
+                                          const int* __restrict__ roi_level, int n, int pooled_h, int pooled_w,
+                                          int sampling_ratio, int ph_begin, int ph_end, int rec_cap) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ph_begin = blockIdx.z * rows_per_group;
-    const int ph_end = min(pooled_h, ph_begin + rows_per_group);
-    const int bins = pooled_h * pooled_w;
-
     if (tid == 0) {
         const int l = roi_level ? roi_level[n] : 0;
         sh.level = l; sh.H = lv.h[l]; sh.W = lv.w[l];
@@ -641,6 +629,33 @@ roialign_fwd_staged(const __grid_constant__ LevelTable lv, int channels, int poo
         }
     }
     __syncthreads();
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 2)
+roialign_fwd_staged(const __grid_constant__ LevelTable lv, int channels, int pooled_h, int pooled_w,
+                    int sampling_ratio, int rows_per_group, int slabs_per_cta, int rec_cap, int obuf_stride,
+                    const float* __restrict__ rois, const int* __restrict__ roi_level,
+                    const int* __restrict__ out_index, float* __restrict__ top) {
+    extern __shared__ __align__(16) unsigned char dyn_raw[];
+    // the tile starts on a 2 KB boundary of the shared window: tap address = K_lane ^ offset (one LOP3)
+    unsigned char* dyn = dyn_raw + ((2048u - ((unsigned)__cvta_generic_to_shared(dyn_raw) & 2047u)) & 2047u);
+    float* tile = reinterpret_cast<float*>(dyn);                                        // [32][512] swizzled
+    SampleRec* rec = reinterpret_cast<SampleRec*>(dyn + kSlab * kTileWords * 4);       // [rec_cap]
+    float* obuf = reinterpret_cast<float*>(dyn + kSlab * kTileWords * 4 + (size_t)rec_cap * sizeof(SampleRec));
+    int* binrec = reinterpret_cast<int*>(obuf + kSlab * obuf_stride);                   // [rows_per_group * pooled_w]
+    __shared__ FwdShared sh;
+
+    const int n = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int ph_begin = blockIdx.z * rows_per_group;
+    const int ph_end = min(pooled_h, ph_begin + rows_per_group);
+    const int bins = pooled_h * pooled_w;
+
+    roi_setup(sh, lv, rois, roi_level, n, pooled_h, pooled_w, sampling_ratio, ph_begin, ph_end, rec_cap);
+    const RoiGeom g = sh.g;
+    const int H = sh.H, W = sh.W;
+    const int gh = g.grid_h, gw = g.grid_w;
+    const int nx = pooled_w * gw;
     const int row = out_index ? out_index[n] : n;
     const int group_bins = (ph_end - ph_begin) * pooled_w;
 
@@ -689,7 +704,183 @@ roialign_fwd_staged(const __grid_constant__ LevelTable lv, int channels, int poo
     }
 }
 
-static int g_force_generic = 0;   // test hook (vosd_debug_force_generic)
+// ---------------------------------------------------------------------------------------
+// Staged backward path: the mirror image of the forward kernel.  Float atomicAdd on shared memory is a
+// CAS loop on sm_100a, so the scatter is organised to need no shared-memory atomics at all:
+//   * same per-CTA setup (tap tables, tile extent, bands);
+//   * per band a CSR list: for every tile row the (sample row, corner) pairs that touch it with their y
+//     weight (built in ascending sample order, so the summation order is deterministic);
+//   * per slab: top_diff of the band -> gbuf[c][bin]; then lanes = channels and every warp OWNS whole tile
+//     rows: it zeroes its rows and adds (top * (wy * wx)) / count for each entry x sample column x corner
+//     with plain read-modify-writes -- every addend is computed exactly like the reference's
+//     (roi_align_kernel.cu:186-190,252-255), only the order of the sum differs;
+//   * the finished tile is written to the gradient map with lanes along x: one 128-bit vector reduction
+//     (red.global.add.v4.f32) per 4 texels instead of 16 scalar atomics per output element.
+// RoIs that need a tall band, or exceed the table budgets, use direct atomics inside the same kernel.
+// ---------------------------------------------------------------------------------------
+struct __align__(8) ListEnt { int bin; float w; };     // bin part (row: pr*PW, column: pw) and axis weight
+
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 2)
+roialign_bwd_staged(const __grid_constant__ LevelTable lv, int channels, int pooled_h, int pooled_w,
+                    int sampling_ratio, int rows_per_group, int slabs_per_cta, int gbuf_stride,
+                    const float* __restrict__ rois, const int* __restrict__ roi_level,
+                    const int* __restrict__ out_index, const float* __restrict__ top_diff) {
+    extern __shared__ __align__(16) unsigned char dyn_raw[];
+    unsigned char* dyn = dyn_raw + ((2048u - ((unsigned)__cvta_generic_to_shared(dyn_raw) & 2047u)) & 2047u);
+    float* tile = reinterpret_cast<float*>(dyn);                                        // [32][512] swizzled
+    float* gbuf = reinterpret_cast<float*>(dyn + kSlab * kTileWords * 4);              // [32][gbuf_stride]
+    ListEnt* rlist = reinterpret_cast<ListEnt*>(gbuf + kSlab * gbuf_stride);            // [2*kMaxTaps]
+    ListEnt* clist = rlist + 2 * kMaxTaps;                                              // [2*kMaxTaps]
+    int* rptr = reinterpret_cast<int*>(clist + 2 * kMaxTaps);                           // [kTileWords + 2]
+    int* cptr = rptr + (kTileWords + 2);                                                // [kTileWords + 2]
+    __shared__ FwdShared sh;
+
+    const int n = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ph_begin = blockIdx.z * rows_per_group;
+    const int ph_end = min(pooled_h, ph_begin + rows_per_group);
+    const int bins = pooled_h * pooled_w;
+
+    roi_setup(sh, lv, rois, roi_level, n, pooled_h, pooled_w, sampling_ratio, ph_begin, ph_end, kMaxRecords);
+    const RoiGeom g = sh.g;
+    const int H = sh.H, W = sh.W;
+    const int gh = g.grid_h, gw = g.grid_w;
+    const int nx = pooled_w * gw;
+    const int row = out_index ? out_index[n] : n;
+    const int icount = gh * gw;
+    const bool pow2 = (icount & (icount - 1)) == 0;
+    const float inv_count = 1.0f / g.count;
+    const int c_begin = blockIdx.y * slabs_per_cta * kSlab;
+    const int c_end = min(channels, c_begin + slabs_per_cta * kSlab);
+    float* gbase = lv.data[sh.level] + (size_t)g.batch * channels * H * W;
+    const size_t plane = (size_t)H * W;
+
+    bool staged = sh.ok != 0 && sh.tw > 0;
+    for (int b = 0; b < sh.nbands; b++) staged = staged && sh.band_tall[b] == 0;
+    if (!staged) {
+        if (sh.ok != 0 && sh.tw <= 0) return;                       // no valid column: nothing to add
+        // direct atomics: thread per (channel, bin) of this row group
+        const int group_bins = (ph_end - ph_begin) * pooled_w;
+        for (int e = tid; e < (c_end - c_begin) * group_bins; e += kFwdThreads) {
+            const int c = c_begin + e / group_bins, b = e % group_bins;
+            const int ph = ph_begin + b / pooled_w, pw = b % pooled_w;
+            float* d = gbase + (size_t)c * plane;
+            const float t = top_diff[((size_t)row * channels + c) * bins + ph * pooled_w + pw];
+            for (int iy = 0; iy < gh; iy++) {
+                const AxisTap ty = axis_tap(sample_coord(g.start_h, g.bin_h, ph, iy, gh), H);
+                for (int ix = 0; ix < gw; ix++) {
+                    const AxisTap tx = axis_tap(sample_coord(g.start_w, g.bin_w, pw, ix, gw), W);
+                    if (!(ty.valid && tx.valid)) continue;
+                    atomicAdd(d + ty.low * W + tx.low, __fdiv_rn(__fmul_rn(t, __fmul_rn(ty.h, tx.h)), g.count));
+                    atomicAdd(d + ty.low * W + tx.high, __fdiv_rn(__fmul_rn(t, __fmul_rn(ty.h, tx.l)), g.count));
+                    atomicAdd(d + ty.high * W + tx.low, __fdiv_rn(__fmul_rn(t, __fmul_rn(ty.l, tx.h)), g.count));
+                    atomicAdd(d + ty.high * W + tx.high, __fdiv_rn(__fmul_rn(t, __fmul_rn(ty.l, tx.l)), g.count));
+                }
+            }
+        }
+        return;
+    }
+
+    const int x_lo = sh.x_lo, tw = sh.tw;
+    const bool vec = sh.vec != 0;
+    // ---- per sample column: output column (bin) it belongs to ----
+    for (int sx = tid; sx < nx; sx += kFwdThreads) cptr[sx] = sx / gw;
+    int p0 = 0;
+    for (int band = 0; band < sh.nbands; band++) {
+        const int p1 = sh.band_p1[band], y_lo = sh.band_ylo[band], rows = sh.band_rows[band];
+        const int band_bins = (p1 - p0) * pooled_w;
+        const int ny_b = (p1 - p0) * gh;
+        __syncthreads();                                            // previous band done with rlist / rptr
+        // ---- row list of the band ----
+        if (tid == 0) rptr[0] = 0;
+        for (int r = tid; r < rows; r += kFwdThreads) {
+            int cnt = 0;
+            for (int sy = 0; sy < ny_b; sy++) {
+                const Tap t = sh.ytab[p0 * gh + sy];
+                if (t.low >= 0) cnt += (t.low - y_lo == r) + (t.high - y_lo == r);
+            }
+            rptr[r + 1] = cnt;
+        }
+        __syncthreads();
+        if (tid == 0) for (int r = 0; r < rows; r++) rptr[r + 1] += rptr[r];
+        __syncthreads();
+        for (int r = tid; r < rows; r += kFwdThreads) {
+            int pos = rptr[r];
+            for (int sy = 0; sy < ny_b; sy++) {
+                const Tap t = sh.ytab[p0 * gh + sy];
+                if (t.low < 0) continue;
+                if (t.low - y_lo == r) rlist[pos++] = ListEnt{(sy / gh) * pooled_w, t.h};
+                if (t.high - y_lo == r) rlist[pos++] = ListEnt{(sy / gh) * pooled_w, t.l};
+            }
+        }
+        // ---- what this thread flushes for every slab (mirror of the forward staging) ----
+        const int tws = vec ? (tw >> 2) : tw;
+        const int nunit = rows * tws;
+        const float inv = 1.0f / (float)max(tws, 1);
+
+        for (int c0 = c_begin; c0 < c_end; c0 += kSlab) {
+            const int nch = min(kSlab, channels - c0);
+            __syncthreads();                                        // lists ready / previous slab flushed
+            // ---- top_diff of the band for this slab -> gbuf[c][bin] ----
+            const float* tsrc = top_diff + ((size_t)row * channels + c0) * bins + (ph_begin + p0) * pooled_w;
+            for (int c = warp; c < nch; c += kFwdWarps)
+                for (int bq = lane; bq < band_bins; bq += 32)
+                    gbuf[c * gbuf_stride + bq] = __ldg(tsrc + (size_t)c * bins + bq);
+            __syncthreads();
+            // ---- scatter in tile space: lanes = channels, each warp OWNS whole tile rows, so the
+            //      read-modify-writes below never race and need no atomics ----
+            const float* gl = gbuf + lane * gbuf_stride;
+            float* trow = tile + lane * kTileWords;
+            for (int r = warp; r < rows; r += kFwdWarps) {
+                for (int x = 0; x < tw; x++) trow[(r * tw + x) ^ lane] = 0.f;
+                const int r0 = rptr[r], r1 = rptr[r + 1];
+                for (int a = r0; a < r1; a++) {
+                    const ListEnt ey = rlist[a];               // (sample row, corner): bin row + y weight
+                    for (int sx = 0; sx < nx; sx++) {
+                        const Tap tx = sh.xtab[sx];
+                        if (tx.low < 0) continue;              // uniform
+                        const float tv = gl[ey.bin + cptr[sx]];
+                        const float g_lo = __fmul_rn(tv, __fmul_rn(ey.w, tx.h));
+                        const float g_hi = __fmul_rn(tv, __fmul_rn(ey.w, tx.l));
+                        const int i_lo = (r * tw + tx.low - x_lo) ^ lane, i_hi = (r * tw + tx.high - x_lo) ^ lane;
+                        trow[i_lo] = __fadd_rn(trow[i_lo], pow2 ? __fmul_rn(g_lo, inv_count) : __fdiv_rn(g_lo, g.count));
+                        trow[i_hi] = __fadd_rn(trow[i_hi], pow2 ? __fmul_rn(g_hi, inv_count) : __fdiv_rn(g_hi, g.count));
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- flush: lanes along x, one vector reduction per 4 texels ----
+            float* gdst = gbase + (size_t)c0 * plane;
+            for (int i = lane; i < nunit; i += 32) {
+                const int ry = (int)(((float)i + 0.5f) * inv);
+                const int rx = vec ? ((i - ry * tws) << 2) : (i - ry * tws);
+                const size_t goff = (size_t)(y_lo + ry) * W + (x_lo + rx);
+                const int t = ry * tw + rx;
+                for (int c = warp; c < nch; c += kFwdWarps) {
+                    if (vec) {
+                        const float4 s4 = *reinterpret_cast<const float4*>(tile + c * kTileWords + (t ^ (c & ~3)));
+                        const float4 v = swizzle4(s4, c & 3);          // the permutation is an involution
+                        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
+                            red_add_v4(gdst + (size_t)c * plane + goff, v);
+                    } else {
+                        const float v = tile[c * kTileWords + (t ^ c)];
+                        if (v != 0.f) atomicAdd(gdst + (size_t)c * plane + goff, v);
+                    }
+                }
+            }
+        }
+        p0 = p1;
+    }
+}
+
+// test hook (vosd_debug_force_generic): 0 = default (staged forward, atomic backward), 1 = generic kernels
+// everywhere, 2 = staged kernels everywhere (the staged backward is parity-tested but not yet faster than
+// the atomic scatter -- profiles/r01_roialign_bwd_staged_*_ncu.txt -- so it is not the default)
+static int g_force_generic = 0;
 
 static int fill_table(LevelTable& t, const float* const* data, const int* h, const int* w,
                       const float* scale, int num_levels) {
@@ -724,7 +915,7 @@ static int ml_fwd(const LevelTable& t, int channels, int ph, int pw, int sr, int
     const int gs = sr > 0 ? sr : 1;
     while (rpg > 1 && ((long long)rpg * gs * pw * gs > kMaxRecords || rpg * gs > kMaxTaps)) rpg--;
     groups = ceil_div(ph, rpg);
-    const bool staged_ok = !g_force_generic && pw * gs <= kMaxTaps && rpg * gs <= kMaxTaps &&
+    const bool staged_ok = g_force_generic != 1 && pw * gs <= kMaxTaps && rpg * gs <= kMaxTaps &&
                            (long long)rpg * gs * pw * gs <= kMaxRecords && groups <= 65535;
     if (staged_ok) {
         const int rec_cap = sr > 0 ? rpg * sr * pw * sr : kMaxRecords;
@@ -759,9 +950,31 @@ static int ml_bwd(const LevelTable& t, int num_levels, int batch, int channels, 
     }
     if (num_rois == 0) return VOSD_OK;
     if (!rois || !top_diff) return VOSD_ERR_BAD_ARG;
-    const long long total = (long long)num_rois * channels * ph * pw;
-    roialign_bwd_generic<<<grid_for(total, 256), 256, 0, stream>>>(
-        t, channels, ph, pw, sr, total, rois, roi_level, out_index, top_diff);
+    const int slabs = ceil_div(channels, kSlab);
+    int groups = ceil_div(ph * pw, 112);
+    if (groups > ph) groups = ph;
+    int rpg = ceil_div(ph, groups);
+    const int gs = sr > 0 ? sr : 1;
+    while (rpg > 1 && rpg * gs > kMaxTaps) rpg--;
+    groups = ceil_div(ph, rpg);
+    const bool staged_ok = g_force_generic == 2 && pw * gs <= kMaxTaps && rpg * gs <= kMaxTaps && groups <= 65535;
+    if (staged_ok) {
+        const int gbuf_stride = (rpg * pw) | 1;
+        long long spc = (long long)slabs * num_rois * groups / (6LL * 2 * kNumSMs);
+        if (spc < 1) spc = 1;
+        if (spc > slabs) spc = slabs;
+        const size_t dyn = (size_t)kSlab * kTileWords * 4 + (size_t)kSlab * gbuf_stride * sizeof(float) +
+                           4 * kMaxTaps * sizeof(ListEnt) + (size_t)(2 * kTileWords + 4) * sizeof(int) + 2048;
+        if (cudaFuncSetAttribute(roialign_bwd_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
+            return VOSD_ERR_LAUNCH;
+        dim3 grid(num_rois, ceil_div(slabs, (int)spc), groups);
+        roialign_bwd_staged<<<grid, kFwdThreads, dyn, stream>>>(t, channels, ph, pw, sr, rpg, (int)spc, gbuf_stride,
+                                                                rois, roi_level, out_index, top_diff);
+    } else {
+        const long long total = (long long)num_rois * channels * ph * pw;
+        roialign_bwd_generic<<<grid_for(total, 256), 256, 0, stream>>>(
+            t, channels, ph, pw, sr, total, rois, roi_level, out_index, top_diff);
+    }
     count_launch();
     return check_launch();
 }

@@ -137,3 +137,88 @@ def all_gather_frames(dets, masks, group=None):
     dist.all_gather_into_tensor(d_out, dets.contiguous(), group=group)
     dist.all_gather_into_tensor(m_out, masks.contiguous(), group=group)
     return d_out, m_out
+
+
+class HostPipeline:
+    """Host-buffer front end of RegionPipeline.step: pinned host tensors in, pinned host tensors out.
+
+    Three CUDA streams (H2D, compute, D2H) and ``depth`` rotating slots, so that the upload of batch
+    i+1, the kernels of batch i and the download of batch i-1 overlap (PCIe is full duplex and the
+    copy engines run beside the SMs).  Every batch still pays its own H2D of all inputs and its own D2H
+    of the results; nothing is cached across batches.
+
+        hp = HostPipeline(RegionPipeline(cfg), frame_hw, im_scale, device)
+        for batch in clip: hp.submit(batch)        # dict of pinned host tensors, see ``INPUT_KEYS``
+        hp.synchronize(); out = hp.results(slot)
+    """
+    INPUT_KEYS = ("rpn", "im_info", "feats", "det_boxes", "det_cls", "det_masks")
+
+    def __init__(self, pipe, frame_hw, im_scale, device, depth=2):
+        self.pipe, self.frame_hw, self.im_scale, self.device, self.depth = pipe, frame_hw, im_scale, device, depth
+        self.s_h2d, self.s_cmp, self.s_d2h = (torch.cuda.Stream(device) for _ in range(3))
+        self.dev = [None] * depth          # device input slots (allocated on first use)
+        self.host_out = [None] * depth     # pinned output slots
+        self.dev_out = [None] * depth      # device results of the batch in flight in each slot
+        self.ev_h2d = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_cmp = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_d2h = [torch.cuda.Event() for _ in range(depth)]
+        self.count = 0
+
+    @staticmethod
+    def _like(x, device):
+        if isinstance(x, dict):
+            return {k: HostPipeline._like(v, device) for k, v in x.items()}
+        if isinstance(x, (tuple, list)):
+            return tuple(HostPipeline._like(v, device) for v in x)
+        return torch.empty(x.shape, dtype=x.dtype, device=device)
+
+    @staticmethod
+    def _copy(dst, src):
+        if isinstance(src, dict):
+            for k in src:
+                HostPipeline._copy(dst[k], src[k])
+        elif isinstance(src, (tuple, list)):
+            for d, s in zip(dst, src):
+                HostPipeline._copy(d, s)
+        else:
+            dst.copy_(src, non_blocking=True)
+
+    def submit(self, host):
+        """Enqueue one batch (H2D -> step -> D2H) without blocking the host; returns the slot index."""
+        slot = self.count % self.depth
+        self.count += 1
+        if self.dev[slot] is None:
+            self.dev[slot] = self._like({k: host[k] for k in self.INPUT_KEYS}, self.device)
+        d = self.dev[slot]
+        with torch.cuda.stream(self.s_h2d):
+            self.s_h2d.wait_event(self.ev_cmp[slot])        # the step that last read this slot is done
+            self._copy(d, {k: host[k] for k in self.INPUT_KEYS})
+            self.ev_h2d[slot].record(self.s_h2d)
+        with torch.cuda.stream(self.s_cmp):
+            self.s_cmp.wait_event(self.ev_h2d[slot])
+            out = self.pipe.step(d["rpn"], d["im_info"], d["feats"], d["det_boxes"], d["det_cls"], d["det_masks"],
+                                 self.frame_hw, self.im_scale)
+            self.ev_cmp[slot].record(self.s_cmp)
+        self.dev_out[slot] = out
+        with torch.cuda.stream(self.s_d2h):
+            self.s_d2h.wait_event(self.ev_cmp[slot])
+            if self.host_out[slot] is None:
+                self.host_out[slot] = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
+                                       for k in ("rois", "roi_count", "masks")}
+            for k, h in self.host_out[slot].items():
+                h.copy_(out[k], non_blocking=True)
+                out[k].record_stream(self.s_d2h)
+            self.ev_d2h[slot].record(self.s_d2h)
+        return slot
+
+    def synchronize(self):
+        for s in (self.s_h2d, self.s_cmp, self.s_d2h):
+            s.synchronize()
+
+    def results(self, slot):
+        """Host results of the batch last submitted to `slot` (blocks until its D2H finished); the RoIAlign
+        blobs stay on the device for the heads that consume them."""
+        self.ev_d2h[slot].synchronize()
+        out = dict(self.host_out[slot])
+        out["box_feats"], out["mask_feats"] = self.dev_out[slot]["box_feats"], self.dev_out[slot]["mask_feats"]
+        return out

@@ -325,12 +325,22 @@ def gpu_arm(args, rank, world, local_rank):
     stage_names = ["proposals", "collect_distribute", "roialign_box", "mask_rois", "roialign_mask", "paste", "end"]
     events = []
 
+    pending = []          # all-gathers in flight (N > 1): they overlap the next step's kernels
+
     def run_step(mark=None):
         out = pipe.step(d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks, frame_hw, im_scale, mark=mark)
         if world > 1:
+            while len(pending) > 1:                       # at most two gathers outstanding
+                for w in pending.pop(0)[2]:
+                    w.wait()
             dets = torch.cat([d_boxes, d_cls.unsqueeze(-1).float(), torch.ones_like(d_cls).unsqueeze(-1).float()], dim=2)
-            all_gather_frames(dets, pack_mask_bits(out["masks"]))
+            pending.append(all_gather_frames(dets, pack_mask_bits(out["masks"]), async_op=True))
         return out
+
+    def drain():
+        while pending:
+            for w in pending.pop(0)[2]:
+                w.wait()
 
     def barrier():
         if world > 1:
@@ -339,6 +349,7 @@ def gpu_arm(args, rank, world, local_rank):
 
     for _ in range(max(args.warmup, 3)):
         out = run_step()
+    drain()
     barrier()
 
     # ---- value: K steps, device-resident inputs ------------------------------------------
@@ -356,6 +367,7 @@ def gpu_arm(args, rank, world, local_rank):
     for _ in range(args.steps):
         events.append([])
         out = run_step(mark)
+    drain()               # every gather of the timed steps has completed before the closing event
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)

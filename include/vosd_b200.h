@@ -217,6 +217,12 @@ VOSD_API int vosd_paste_masks(const float* masks, const int* cls, const float* r
                      int num_dets, int num_classes, int mask_size, int im_h, int im_w,
                      float thresh, uint8_t* out, float* out_prob, cudaStream_t stream);
 
+/* Dense {0,1} uint8 masks (num_masks, pixels_per_mask) -> bit-packed (num_masks, ceil(pixels/8)) uint8,
+ * pixel 8j+k in bit k of byte j.  Lossless payload of the frame-sharded all-gather (the reference ships
+ * whole pickled results between its per-GPU processes instead, lib/core/test_engine.py:193-200). */
+VOSD_API int vosd_pack_mask_bits(const uint8_t* masks, int num_masks, long long pixels_per_mask,
+                                 uint8_t* packed, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -150,3 +150,12 @@ def test_launch_counter_counts_library_kernels(synth):
     f = torch.randn(1, 4, 10, 12, device="cuda")
     ops.roi_align_forward(f, torch.tensor([[0, 1, 1, 20, 20.]], device="cuda"), 7, 7, 0.25, 2)
     assert _lib.launch_count() == before + 1
+
+
+def test_pack_mask_bits_matches_torch_reference():
+    from vosdetectron_b200.pipeline import pack_mask_bits, unpack_mask_bits
+    for shape in ((3, 5, 480, 854), (2, 37, 53), (1, 1, 8, 8)):
+        m = (torch.rand(shape, device="cuda") > 0.5).to(torch.uint8)
+        p = pack_mask_bits(m)
+        assert torch.equal(p.cpu(), pack_mask_bits(m.cpu()))
+        assert torch.equal(unpack_mask_bits(p, shape[-2], shape[-1]), m)

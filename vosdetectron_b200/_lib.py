@@ -61,6 +61,7 @@ SIGNATURES = {
                                                ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
     "vosd_distribute": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
                                        vp, vp, vp, vp, vp]),
+    "vosd_pack_mask_bits": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_longlong, vp, vp]),
     "vosd_paste_masks": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_float, vp, vp, vp]),
 }

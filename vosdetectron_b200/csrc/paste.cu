@@ -255,9 +255,63 @@ paste_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
     }
 }
 
+// Dense {0,1} uint8 masks -> 1 bit per pixel, LSB first (pixel 8j+k -> bit k of byte j); the payload of the
+// final all-gather.  Each thread turns 64 mask bytes into 8 packed bytes: 4 x 128-bit loads, one 64-bit store.
+__global__ void __launch_bounds__(256)
+pack_bits_kernel(const uint8_t* __restrict__ in, long long n_in_per_mask, long long n_out_per_mask,
+                 uint8_t* __restrict__ out, int vec_ok) {
+    const long long m = blockIdx.y;
+    const uint8_t* src = in + m * n_in_per_mask;
+    uint8_t* dst = out + m * n_out_per_mask;
+    const long long groups = (n_out_per_mask + 7) / 8;              // 8 output bytes per thread
+    for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += (long long)gridDim.x * blockDim.x) {
+        const long long i0 = gi * 64;
+        unsigned long long packed = 0;
+        if (vec_ok && i0 + 64 <= n_in_per_mask) {
+            const uint4* p4 = reinterpret_cast<const uint4*>(src + i0);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint4 v = __ldg(p4 + q);
+                const unsigned long long lo = ((unsigned long long)v.y << 32) | v.x, hi = ((unsigned long long)v.w << 32) | v.z;
+                packed |= ((lo & 0x0101010101010101ull) * 0x0102040810204080ull >> 56) << (16 * q);
+                packed |= ((hi & 0x0101010101010101ull) * 0x0102040810204080ull >> 56) << (16 * q + 8);
+            }
+            *reinterpret_cast<unsigned long long*>(dst + gi * 8) = packed;
+        } else {
+            for (int b = 0; b < 8 && gi * 8 + b < n_out_per_mask; b++) {
+                unsigned v = 0;
+                for (int k = 0; k < 8; k++) {
+                    const long long i = i0 + b * 8 + k;
+                    if (i < n_in_per_mask && src[i]) v |= 1u << k;
+                }
+                dst[gi * 8 + b] = (uint8_t)v;
+            }
+        }
+    }
+}
+
 }  // namespace vosd
 
 using namespace vosd;
+
+extern "C" int vosd_pack_mask_bits(const uint8_t* masks, int num_masks, long long pixels_per_mask,
+                                   uint8_t* packed, cudaStream_t stream) {
+    if (num_masks < 0 || pixels_per_mask < 1) return VOSD_ERR_BAD_SHAPE;
+    if (num_masks == 0) return VOSD_OK;
+    if (!masks || !packed) return VOSD_ERR_BAD_ARG;
+    if (num_masks > 65535) return VOSD_ERR_UNSUPPORTED;
+    const long long n_out = (pixels_per_mask + 7) / 8;
+    const int vec_ok = aligned16(masks) && (reinterpret_cast<uintptr_t>(packed) & 7) == 0 &&
+                       pixels_per_mask % 16 == 0 && n_out % 8 == 0;
+    long long bx = ((n_out + 7) / 8 + 255) / 256;
+    if (bx > 4096) bx = 4096;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)num_masks);
+    pack_bits_kernel<<<grid, 256, 0, stream>>>(masks, pixels_per_mask, n_out, packed, vec_ok);
+    count_launch();
+    return check_launch();
+}
+
 
 extern "C" int vosd_paste_masks(const float* masks, const int* cls, const float* ref_boxes,
                                 int num_dets, int num_classes, int mask_size, int im_h, int im_w,

@@ -263,3 +263,17 @@ def paste_masks_cuda(masks, cls, ref_boxes, im_h, im_w, thresh=0.5, want_prob=Fa
     _lib.call("vosd_paste_masks", _ptr(m), _ptr(c), _ptr(b), R, K, M, int(im_h), int(im_w), float(thresh),
               _ptr(out), _ptr(prob), _stream())
     return (out, prob) if want_prob else out
+
+
+def pack_mask_bits_cuda(masks_u8):
+    """(..., H, W) uint8 {0,1} on the device -> (..., ceil(H*W/8)) uint8, 8 pixels per byte (LSB first)."""
+    m = _need_cuda(masks_u8, "masks", torch.uint8)
+    lead = m.shape[:-2]
+    pixels = int(m.shape[-2]) * int(m.shape[-1])
+    n = 1
+    for v in lead:
+        n *= int(v)
+    out = torch.empty(tuple(lead) + ((pixels + 7) // 8,), dtype=torch.uint8, device=m.device)
+    _bind(m)
+    _lib.call("vosd_pack_mask_bits", _ptr(m), n, pixels, _ptr(out), _stream())
+    return out

@@ -111,7 +111,9 @@ def shard_frames(num_frames, world_size, rank):
 def pack_mask_bits(masks_u8):
     """(…,H,W) uint8 {0,1} -> (…, ceil(H*W/8)) uint8, 8 pixels per byte (lossless; the payload
     of the all-gather)."""
-    flat = masks_u8.reshape(*masks_u8.shape[:-2], -1)
+    if masks_u8.is_cuda:
+        return ops.pack_mask_bits_cuda(masks_u8)          # one streaming kernel
+    flat = masks_u8.reshape(*masks_u8.shape[:-2], -1)     # CPU (gloo tests): same layout with torch ops
     n = flat.shape[-1]
     pad = (-n) % 8
     if pad:
@@ -126,16 +128,21 @@ def unpack_mask_bits(packed, h, w):
     return bits.reshape(*packed.shape[:-1], -1)[..., :h * w].reshape(*packed.shape[:-1], h, w)
 
 
-def all_gather_frames(dets, masks, group=None):
+def all_gather_frames(dets, masks, group=None, async_op=False):
     """All-gather per-frame detection records (F_r, D, 6) fp32 and masks (F_r, D, …) uint8 over the
     ranks of `group` (NCCL on GPUs, gloo on CPU in the tests).  Every rank must hold the same
-    number of frames (pad the clip); returns tensors with F = F_r * world frames in rank order."""
+    number of frames (pad the clip); returns tensors with F = F_r * world frames in rank order.
+    With ``async_op`` the collectives run on NCCL's stream behind the kernels already enqueued and a
+    third value, the list of work handles, is returned: call ``.wait()`` on them before reading the
+    outputs -- the next batch's kernels overlap the gather."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     d_out = torch.empty((world * dets.shape[0],) + tuple(dets.shape[1:]), dtype=dets.dtype, device=dets.device)
     m_out = torch.empty((world * masks.shape[0],) + tuple(masks.shape[1:]), dtype=masks.dtype, device=masks.device)
-    dist.all_gather_into_tensor(d_out, dets.contiguous(), group=group)
-    dist.all_gather_into_tensor(m_out, masks.contiguous(), group=group)
+    w1 = dist.all_gather_into_tensor(d_out, dets.contiguous(), group=group, async_op=async_op)
+    w2 = dist.all_gather_into_tensor(m_out, masks.contiguous(), group=group, async_op=async_op)
+    if async_op:
+        return d_out, m_out, [w1, w2]
     return d_out, m_out
 
 

@@ -377,61 +377,67 @@ __device__ __forceinline__ void sts_swizzled(unsigned a_lo, bool swap, float4 v)
     sts_v2(a_lo ^ 8u, swap ? v.w : v.z, swap ? v.z : v.w);
 }
 
-// Fast path of the bands x slabs loop: 2x2 sampling grid, 16-byte aligned rows, no tall rows.
-//
-// Software pipeline over the slabs of the CTA: the 16 vectors a thread stages for slab k+1
-// (4 channels x <= 4 vectors, 64 registers) are requested from L2/HBM BEFORE the gather of slab k and
-// written to the tile after it, so the global-load latency hides behind the gather instead of
-// stalling all warps at a barrier.  8 warps x 128 registers, 2 CTAs per SM.
-//
-// P = warp & 3 is the swizzle phase of the channels warp, warp+8, warp+16, warp+24 a warp stages; as a
-// template parameter the in-vector permutation is pure register renaming.  Warps of one CTA run
-// different instances and meet at the same hardware barrier.
 constexpr int kChPerWarp = kSlab / kFwdWarps;      // 4
 
-__device__ __forceinline__ void prefetch_slab(float4 (&v)[kChPerWarp][4], const float* __restrict__ p0,
-                                              size_t cstride, int nch, int warp, const int (&goff)[4]) {
+// Predicated (goff >= 0) ordered 128-bit read-only load: no branch around the volatile asm.
+__device__ __forceinline__ void ldg_v4_pred(float4& v, const float* p, int goff) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %5, 0;\n\t@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+                 : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w) : "l"(p + (goff >= 0 ? goff : 0)), "r"(goff));
+}
+// Predicated 128-bit shared store of channel 4*warp + H of the slab: its row is H * 2 KB further, its swizzle
+// phase is H, so texel j goes to position j ^ H -- a compile-time permutation of the operands.
+template <int H>
+__device__ __forceinline__ void sts_v4_pred(unsigned a, const float4& v, int goff) {
+    const float e0 = H == 0 ? v.x : H == 1 ? v.y : H == 2 ? v.z : v.w;
+    const float e1 = H == 0 ? v.y : H == 1 ? v.x : H == 2 ? v.w : v.z;
+    const float e2 = H == 0 ? v.z : H == 1 ? v.w : H == 2 ? v.x : v.y;
+    const float e3 = H == 0 ? v.w : H == 1 ? v.z : H == 2 ? v.y : v.x;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %5, 0;\n\t@p st.shared.v4.f32 [%0+%6], {%1, %2, %3, %4};\n\t}"
+                 :: "r"(a), "f"(e0), "f"(e1), "f"(e2), "f"(e3), "r"(goff), "n"(H * kTileWords * 4) : "memory");
+}
+
+// A warp stages channels 4*warp .. 4*warp+3 of the slab: same XOR group (c & ~3 = 4*warp), phases 0..3.
+__device__ __forceinline__ void prefetch_slab(float4 (&v)[kChPerWarp][4], const float* __restrict__ p0, size_t plane,
+                                              int mcnt, const int (&goff)[4]) {
 #pragma unroll
-    for (int h = 0; h < kChPerWarp; h++) {
-        const float* pc = p0 + (size_t)h * cstride;
-        const bool has = warp + h * kFwdWarps < nch;
+    for (int m = 0; m < 4; m++) {
+        if (m < mcnt) {                      // warp-uniform
 #pragma unroll
-        for (int m = 0; m < 4; m++)
-            if (goff[m] >= 0 && has) v[h][m] = ldg_v4_ordered(pc + goff[m]);
+            for (int h = 0; h < kChPerWarp; h++) ldg_v4_pred(v[h][m], p0 + (size_t)h * plane, goff[m]);
+        }
     }
 }
 
-__device__ __forceinline__ void commit_slab(const float4 (&v)[kChPerWarp][4], int nch, int warp, bool swap,
-                                            const int (&goff)[4], const unsigned (&ts0)[4]) {
+__device__ __forceinline__ void commit_slab(const float4 (&v)[kChPerWarp][4], int mcnt, const int (&goff)[4],
+                                            const unsigned (&ts0)[4]) {
 #pragma unroll
-    for (int h = 0; h < kChPerWarp; h++) {
-        const bool has = warp + h * kFwdWarps < nch;
-#pragma unroll
-        for (int m = 0; m < 4; m++)    // channel warp + 8h: row + 16 KB * h, XOR phase differs in word bits 3-4
-            if (goff[m] >= 0 && has)
-                sts_swizzled((ts0[m] ^ (unsigned)(h * kFwdWarps * 4)) + (unsigned)(h * kFwdWarps * kTileWords * 4), swap, v[h][m]);
+    for (int m = 0; m < 4; m++) {
+        if (m < mcnt) {
+            sts_v4_pred<0>(ts0[m], v[0][m], goff[m]);
+            sts_v4_pred<1>(ts0[m], v[1][m], goff[m]);
+            sts_v4_pred<2>(ts0[m], v[2][m], goff[m]);
+            sts_v4_pred<3>(ts0[m], v[3][m], goff[m]);
+        }
     }
 }
 
-// Fast path of the bands x slabs loop: 2x2 sampling grid, 16-byte aligned rows, no tall rows.
+// Fast path of the bands x slabs loop: 2x2 sampling grid, 16-byte aligned rows, no tall rows, C % 32 == 0.
 //
 // Software pipeline over the slabs of the CTA: the 16 vectors a thread stages for slab k+1
-// (4 channels x <= 4 vectors, 64 registers) are requested from L2/HBM BEFORE the gather of slab k and
-// written to the tile after it, so the global-load latency hides behind the gather instead of
-// stalling all warps at a barrier.  8 warps x 128 registers, 2 CTAs per SM.
+// (channels 4*warp..4*warp+3 x <= 4 vectors, 64 registers) are requested from L2/HBM BEFORE the gather of
+// slab k and written to the tile after it, so the global-load latency hides behind the gather instead of
+// stalling all warps at a barrier.  8 warps x 128 registers, 2 CTAs per SM.  The four channels of a warp share
+// the XOR group (c & ~3) and have swizzle phases 0..3, so the in-vector permutation is static register renaming.
 __device__ __noinline__ void run_bands_fast(const FwdCtx cx, FwdShared& sh) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int channels = cx.channels, pooled_w = cx.pooled_w, bins = cx.bins, obuf_stride = cx.obuf_stride;
-    const int W = cx.W, nx = cx.nx, slab0 = cx.slab0, nslab = cx.nslab;
+    const int pooled_w = cx.pooled_w, bins = cx.bins, obuf_stride = cx.obuf_stride;
+    const int W = cx.W, nx = cx.nx, nslab = cx.nslab;
     const int x_lo = sh.x_lo, tw = sh.tw;
     const size_t plane = (size_t)cx.H * W;
-    const size_t cstride = (size_t)kFwdWarps * plane;                          // between a warp's channels
     const unsigned tile_s = (unsigned)__cvta_generic_to_shared(cx.tile);      // 2 KB aligned
     const unsigned rec_s = (unsigned)__cvta_generic_to_shared(cx.rec);
     const unsigned obuf_s = (unsigned)__cvta_generic_to_shared(cx.obuf);
     const unsigned klane = (tile_s + (unsigned)lane * (kTileWords * 4)) ^ ((unsigned)lane * 4u);
-    const bool swap = (warp & 1) != 0;                      // swizzle phase of this warp's channels: warp & 3
-    const unsigned half = (unsigned)(warp & 2) * 4u;
     const int nbands = sh.nbands;
     const int tw4 = tw >> 2;
     const unsigned nxb = (unsigned)nx * 32u;                // bytes between the two sample rows of a bin
@@ -452,12 +458,13 @@ __device__ __noinline__ void run_bands_fast(const FwdCtx cx, FwdShared& sh) {
                 const int ry = (int)(((float)i + 0.5f) * inv);
                 const int rx = (i - ry * tw4) << 2;
                 goff[m] = i < nvec ? (y_lo + ry) * W + (x_lo + rx) : -1;
-                ts0[m] = (tile_s + 4u * (unsigned)(warp * kTileWords + ((ry * tw + rx) ^ (warp & ~3)))) ^ half;
+                ts0[m] = tile_s + 4u * (unsigned)(4 * warp * kTileWords + ((ry * tw + rx) ^ (4 * warp)));
             }
         }
-        const float* pw0 = cx.feat0 + (size_t)warp * plane;       // channel `warp` of the current slab
+        const int mcnt = (rows_total * tw4 + 31) >> 5;             // 32-vector groups in use (warp-uniform)
+        const float* pw0 = cx.feat0 + (size_t)(4 * warp) * plane;  // channel 4*warp of the current slab
         float4 v[kChPerWarp][4];
-        prefetch_slab(v, pw0, cstride, min(kSlab, channels - slab0 * kSlab), warp, goff);   // slab 0 in flight
+        prefetch_slab(v, pw0, plane, mcnt, goff);                  // slab 0 in flight
         // ---- once per band: sample records, bin -> first record (sign bit: some sample is outside) ----
         const int rec_n = (p1 - p0) * 2 * nx;
         for (int s2 = tid; s2 < rec_n; s2 += kFwdThreads) {
@@ -482,15 +489,14 @@ __device__ __noinline__ void run_bands_fast(const FwdCtx cx, FwdShared& sh) {
             const int first = pr * 2 * nx + pw * 2;
             cx.binrec[q] = all_in ? first : (first | (int)0x80000000);
         }
-        commit_slab(v, min(kSlab, channels - slab0 * kSlab), warp, swap, goff, ts0);
+        commit_slab(v, mcnt, goff, ts0);
         __syncthreads();                                            // tile(slab 0), records, binrec visible
 
         float* out = cx.out0 + p0 * pooled_w;
         for (int k = 0; k < nslab; k++) {
-            const int nch = min(kSlab, channels - (slab0 + k) * kSlab);
-            const int nch_next = k + 1 < nslab ? min(kSlab, channels - (slab0 + k + 1) * kSlab) : 0;
+            const int mnext = k + 1 < nslab ? mcnt : 0;
             pw0 += (size_t)kSlab * plane;
-            prefetch_slab(v, pw0, cstride, nch_next, warp, goff);              // slab k+1 -> registers
+            prefetch_slab(v, pw0, plane, mnext, goff);                         // slab k+1 -> registers
             // ---- gather slab k: lanes = channels, warps = bins ----
             for (int q = warp; q < band_bins; q += kFwdWarps) {
                 const int br = cx.binrec[q];
@@ -532,14 +538,17 @@ __device__ __noinline__ void run_bands_fast(const FwdCtx cx, FwdShared& sh) {
                 sts_f32(obuf_s + 4u * (unsigned)(lane * obuf_stride + q), __fmul_rn(acc, 0.25f));   // count == 4: exact
             }
             __syncthreads();                                        // every warp is done reading the tile
-            commit_slab(v, nch_next, warp, swap, goff, ts0);        // slab k+1 -> tile
-            // ---- contiguous streaming write of slab k: warp -> its 4 channels ----
+            commit_slab(v, mnext, goff, ts0);                        // slab k+1 -> tile
+            // ---- contiguous streaming write of slab k: warp -> its 4 channels (4*warp ..) ----
+            if (band_bins == bins && obuf_stride == bins) {          // one band, odd bin count: 4*bins contiguous floats
+                float* oc = out + (size_t)(4 * warp) * bins;
+                const float* ob = cx.obuf + 4 * warp * obuf_stride;
+                for (int i = lane; i < kChPerWarp * bins; i += 32) __stcs(oc + i, ob[i]);
+            } else {
 #pragma unroll
-            for (int h = 0; h < kChPerWarp; h++) {
-                const int c = warp + h * kFwdWarps;
-                if (c < nch) {
-                    float* oc = out + (size_t)c * bins;
-                    const float* ob = cx.obuf + c * obuf_stride;
+                for (int h = 0; h < kChPerWarp; h++) {
+                    float* oc = out + (size_t)(4 * warp + h) * bins;
+                    const float* ob = cx.obuf + (4 * warp + h) * obuf_stride;
                     for (int bq = lane; bq < band_bins; bq += 32) __stcs(oc + bq, ob[bq]);
                 }
             }
@@ -695,7 +704,7 @@ roialign_fwd_staged(const __grid_constant__ LevelTable lv, int channels, int poo
     cx.feat0 = lv.data[sh.level] + ((size_t)g.batch * channels + (size_t)cx.slab0 * kSlab) * H * W;
     cx.out0 = top + ((size_t)row * channels + (size_t)cx.slab0 * kSlab) * bins + ph_begin * pooled_w;
     // fast path: 2x2 sampling grid, 16-byte aligned rows, no output row taller than the tile
-    bool fast = gh == 2 && gw == 2 && sh.vec != 0;
+    bool fast = gh == 2 && gw == 2 && sh.vec != 0 && (channels % kSlab) == 0;
     for (int bnd = 0; bnd < sh.nbands; bnd++) fast = fast && sh.band_tall[bnd] == 0;
     if (fast) {
         run_bands_fast(cx, sh);

@@ -886,7 +886,298 @@ roialign_bwd_staged(const __grid_constant__ LevelTable lv, int channels, int poo
     }
 }
 
-// test hook (vosd_debug_force_generic): 0 = default (staged forward, atomic backward), 1 = generic kernels
+// ---------------------------------------------------------------------------------------
+// Record-based backward (default).  The generic kernel spends its time on arithmetic, not on the
+// reductions (ncu: 66 % issue-active, 9 % lg_throttle; 4 IEEE divisions for the coordinates and 4 for the
+// addends of every sample of every channel).  Here one CTA = one RoI x one group of output rows x a
+// chunk of channels: the per-axis tap tables and one record per sample -- the 4 plane offsets y*W+x and
+// the 4 corner weights, pre-divided by `count` when it is a power of two (x/2^k == x*2^-k exactly, and
+// scaling by 2^-k commutes with the rounding of top*w) -- are built once in shared memory; then a thread
+// per (channel, bin) element reads its top_diff (coalesced) and issues 16 reductions whose addends are
+// bit-identical to the reference's (top*w)/count (roi_align_kernel.cu:252-265).
+// ---------------------------------------------------------------------------------------
+struct __align__(16) BwdRec { int o1, o2, o3, o4; float w1, w2, w3, w4; };     // o1 < 0: sample outside the map
+
+__global__ void __launch_bounds__(256)
+roialign_bwd_records(const __grid_constant__ LevelTable lv, int channels, int pooled_h, int pooled_w,
+                     int sampling_ratio, int rows_per_group, int ch_per_cta,
+                     const float* __restrict__ rois, const int* __restrict__ roi_level,
+                     const int* __restrict__ out_index, const float* __restrict__ top_diff) {
+    extern __shared__ __align__(16) unsigned char dynb[];
+    BwdRec* rec = reinterpret_cast<BwdRec*>(dynb);                 // [<= kMaxRecords]
+    __shared__ FwdShared sh;
+
+    const int n = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int ph_begin = blockIdx.z * rows_per_group;
+    const int ph_end = min(pooled_h, ph_begin + rows_per_group);
+    const int bins = pooled_h * pooled_w;
+    roi_setup(sh, lv, rois, roi_level, n, pooled_h, pooled_w, sampling_ratio, ph_begin, ph_end, kMaxRecords);
+    const RoiGeom g = sh.g;
+    const int H = sh.H, W = sh.W;
+    const int gh = g.grid_h, gw = g.grid_w;
+    const int nx = pooled_w * gw, ny = (ph_end - ph_begin) * gh;
+    const int row = out_index ? out_index[n] : n;
+    const int c_begin = blockIdx.y * ch_per_cta, c_end = min(channels, c_begin + ch_per_cta);
+    const int group_bins = (ph_end - ph_begin) * pooled_w;
+    const size_t plane = (size_t)H * W;
+    float* gbase = lv.data[sh.level] + ((size_t)g.batch * channels + c_begin) * plane;
+    const float* tsrc = top_diff + ((size_t)row * channels + c_begin) * bins + ph_begin * pooled_w;
+    const bool fits = ny <= kMaxTaps && nx <= kMaxTaps && ny * nx <= kMaxRecords;     // as in roi_setup
+
+    if (!fits) {
+        // adaptive grids beyond the table budget: per-element geometry (same arithmetic)
+        for (int e = tid; e < (c_end - c_begin) * group_bins; e += 256) {
+            const int c = e / group_bins, b = e - c * group_bins;
+            const int ph = ph_begin + b / pooled_w, pw = b % pooled_w;
+            float* d = gbase + (size_t)c * plane;
+            const float t = tsrc[(size_t)c * bins + b];
+            for (int iy = 0; iy < gh; iy++) {
+                const AxisTap ty = axis_tap(sample_coord(g.start_h, g.bin_h, ph, iy, gh), H);
+                for (int ix = 0; ix < gw; ix++) {
+                    const AxisTap tx = axis_tap(sample_coord(g.start_w, g.bin_w, pw, ix, gw), W);
+                    if (!(ty.valid && tx.valid)) continue;
+                    atomicAdd(d + ty.low * W + tx.low, __fdiv_rn(__fmul_rn(t, __fmul_rn(ty.h, tx.h)), g.count));
+                    atomicAdd(d + ty.low * W + tx.high, __fdiv_rn(__fmul_rn(t, __fmul_rn(ty.h, tx.l)), g.count));
+                    atomicAdd(d + ty.high * W + tx.low, __fdiv_rn(__fmul_rn(t, __fmul_rn(ty.l, tx.h)), g.count));
+                    atomicAdd(d + ty.high * W + tx.high, __fdiv_rn(__fmul_rn(t, __fmul_rn(ty.l, tx.l)), g.count));
+                }
+            }
+        }
+        return;
+    }
+
+    const int icount = gh * gw;
+    const bool pow2 = (icount & (icount - 1)) == 0;
+    const float scale = pow2 ? 1.0f / g.count : 1.0f;
+    for (int s2 = tid; s2 < ny * nx; s2 += 256) {
+        const int sy = s2 / nx, sx = s2 - sy * nx;
+        const Tap ty = sh.ytab[sy], tx = sh.xtab[sx];
+        BwdRec r;
+        if (ty.low >= 0 && tx.low >= 0) {
+            r.o1 = ty.low * W + tx.low;  r.o2 = ty.low * W + tx.high;
+            r.o3 = ty.high * W + tx.low; r.o4 = ty.high * W + tx.high;
+            r.w1 = __fmul_rn(__fmul_rn(ty.h, tx.h), scale); r.w2 = __fmul_rn(__fmul_rn(ty.h, tx.l), scale);
+            r.w3 = __fmul_rn(__fmul_rn(ty.l, tx.h), scale); r.w4 = __fmul_rn(__fmul_rn(ty.l, tx.l), scale);
+        } else {
+            r.o1 = -1; r.o2 = r.o3 = r.o4 = 0; r.w1 = r.w2 = r.w3 = r.w4 = 0.f;
+        }
+        rec[s2] = r;
+    }
+    __syncthreads();
+
+    const int total = (c_end - c_begin) * group_bins;
+    const float inv_gb = 1.0f / (float)group_bins;
+    for (int e = tid; e < total; e += 256) {
+        const int c = (int)(((float)e + 0.5f) * inv_gb);
+        const int b = e - c * group_bins;
+        const int pr = b / pooled_w, pw = b - pr * pooled_w;
+        const float t = __ldg(tsrc + (size_t)c * bins + b);
+        float* d = gbase + (size_t)c * plane;
+        const BwdRec* rr = rec + (pr * gh) * nx + pw * gw;
+        for (int iy = 0; iy < gh; iy++) {
+            for (int ix = 0; ix < gw; ix++) {
+                const BwdRec r = rr[iy * nx + ix];
+                if (r.o1 < 0) continue;
+                if (pow2) {
+                    atomicAdd(d + r.o1, __fmul_rn(t, r.w1));
+                    atomicAdd(d + r.o2, __fmul_rn(t, r.w2));
+                    atomicAdd(d + r.o3, __fmul_rn(t, r.w3));
+                    atomicAdd(d + r.o4, __fmul_rn(t, r.w4));
+                } else {
+                    atomicAdd(d + r.o1, __fdiv_rn(__fmul_rn(t, r.w1), g.count));
+                    atomicAdd(d + r.o2, __fdiv_rn(__fmul_rn(t, r.w2), g.count));
+                    atomicAdd(d + r.o3, __fdiv_rn(__fmul_rn(t, r.w3), g.count));
+                    atomicAdd(d + r.o4, __fdiv_rn(__fmul_rn(t, r.w4), g.count));
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Tile-owner backward ("write once"): the gradient maps are cut into 16x32-texel tiles; a CTA owns one
+// tile x 32-channel slab, accumulates in shared memory the contributions of EVERY RoI whose footprint
+// overlaps the tile, and then writes the tile to HBM with plain coalesced stores.  No global atomics, no
+// memset (every texel is written exactly once: zero or sum), deterministic summation order, and the
+// reduction traffic drops from 16 L2 atomics per output element to shared-memory read-modify-writes.
+//   K_a bwd_prep_kernel : per RoI, the per-axis tap tables (same arithmetic as forward) + texel extents
+//   K_b bwd_bin_kernel  : per tile, the ordered list of RoIs overlapping it (block-wide stable compaction)
+//   K_c bwd_tile_kernel : per (tile, slab chunk): lanes = channels, each warp owns 2 tile rows -> plain RMW
+// Every addend is computed exactly like the reference's (top * (wy*wx)) / count.
+// ---------------------------------------------------------------------------------------
+constexpr int kTileH = 16, kTileW = 32;       // kTileH * kTileW == kTileWords
+
+struct BwdTiling {
+    int tiles_y[VOSD_MAX_LEVELS], tiles_x[VOSD_MAX_LEVELS], base[VOSD_MAX_LEVELS + 1];   // base: first tile id of a level
+    int num_levels, batch;
+};
+struct __align__(16) BwdRoiInfo { int level, batch, y0, y1, x0, x1, gh, gw; };   // extents inclusive; y1 < y0: empty
+
+// K_a.  grid = R, block = 128.
+__global__ void __launch_bounds__(128)
+bwd_prep_kernel(const __grid_constant__ LevelTable lv, int pooled_h, int pooled_w, int sampling_ratio,
+                const float* __restrict__ rois, const int* __restrict__ roi_level, int ny, int nx,
+                BwdRoiInfo* __restrict__ info, Tap* __restrict__ ytabs, Tap* __restrict__ xtabs) {
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const int l = roi_level ? roi_level[n] : 0;
+    const int H = lv.h[l], W = lv.w[l];
+    const RoiGeom g = roi_geometry(rois + 5 * (size_t)n, lv.scale[l], pooled_h, pooled_w, sampling_ratio);
+    __shared__ Tap sy[kMaxTaps], sx[kMaxTaps];
+    if (tid < ny) {
+        const AxisTap t = axis_tap(sample_coord(g.start_h, g.bin_h, tid / g.grid_h, tid % g.grid_h, g.grid_h), H);
+        sy[tid] = Tap{t.valid ? t.low : -1, t.high, t.l, t.h};
+        ytabs[(size_t)n * ny + tid] = sy[tid];
+    } else if (tid >= 64 && tid < 64 + nx) {
+        const int k = tid - 64;
+        const AxisTap t = axis_tap(sample_coord(g.start_w, g.bin_w, k / g.grid_w, k % g.grid_w, g.grid_w), W);
+        sx[k] = Tap{t.valid ? t.low : -1, t.high, t.l, t.h};
+        xtabs[(size_t)n * nx + k] = sx[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        BwdRoiInfo r;
+        r.level = l; r.batch = g.batch; r.gh = g.grid_h; r.gw = g.grid_w;
+        r.y0 = 1 << 30; r.y1 = -1; r.x0 = 1 << 30; r.x1 = -1;
+        for (int k = 0; k < ny; k++) if (sy[k].low >= 0) { r.y0 = min(r.y0, sy[k].low); r.y1 = max(r.y1, sy[k].high); }
+        for (int k = 0; k < nx; k++) if (sx[k].low >= 0) { r.x0 = min(r.x0, sx[k].low); r.x1 = max(r.x1, sx[k].high); }
+        if (r.x1 < r.x0) { r.y0 = 1 << 30; r.y1 = -1; }          // no valid column: contributes nothing
+        info[n] = r;
+    }
+}
+
+// K_b.  grid = tiles, block = 256.  list[tile*cap ..] = RoIs overlapping the tile, ascending RoI index.
+__global__ void __launch_bounds__(256)
+bwd_bin_kernel(const __grid_constant__ BwdTiling tl, const BwdRoiInfo* __restrict__ info, int num_rois, int cap,
+               int* __restrict__ list, int* __restrict__ list_count) {
+    const int tile = blockIdx.x;
+    int l = 0;
+    while (l + 1 < tl.num_levels && tile >= tl.base[l + 1]) l++;
+    const int rel = tile - tl.base[l];
+    const int per_img = tl.tiles_y[l] * tl.tiles_x[l];
+    const int img = rel / per_img, ty = (rel % per_img) / tl.tiles_x[l], tx = rel % tl.tiles_x[l];
+    const int y0 = ty * kTileH, y1 = y0 + kTileH - 1, x0 = tx * kTileW, x1 = x0 + kTileW - 1;
+    __shared__ int warp_cnt[8];
+    __shared__ int base_s;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int n0 = 0; n0 < num_rois; n0 += 256) {
+        const int n = n0 + threadIdx.x;
+        bool hit = false;
+        if (n < num_rois) {
+            const BwdRoiInfo r = info[n];
+            hit = r.level == l && r.batch == img && r.y1 >= y0 && r.y0 <= y1 && r.x1 >= x0 && r.x0 <= x1;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < warp; w++) off += warp_cnt[w];
+        if (hit) list[(size_t)tile * cap + off + __popc(bal & ((1u << lane) - 1u))] = n;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += warp_cnt[w]; base_s += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) list_count[tile] = base_s;
+}
+
+// K_c.  grid = (tiles, slab chunks), block = 256, dyn smem = acc tile + gbuf + tables.
+__global__ void __launch_bounds__(256, 2)
+bwd_tile_kernel(const __grid_constant__ LevelTable lv, const __grid_constant__ BwdTiling tl, int channels,
+                int pooled_h, int pooled_w, int ny, int nx, int slabs_per_cta, int gstride,
+                const BwdRoiInfo* __restrict__ info, const Tap* __restrict__ ytabs, const Tap* __restrict__ xtabs,
+                const int* __restrict__ list, const int* __restrict__ list_count, int cap,
+                const int* __restrict__ out_index, const float* __restrict__ top_diff) {
+    extern __shared__ __align__(16) unsigned char dyn_t[];
+    float* acc = reinterpret_cast<float*>(dyn_t);                                   // [32][512], word (t ^ c)
+    float* gbuf = acc + kSlab * kTileWords;                                         // [32][gstride]
+    Tap* ytab = reinterpret_cast<Tap*>(gbuf + kSlab * gstride);                     // [ny]
+    Tap* xtab = ytab + kMaxTaps;                                                    // [nx]
+
+    const int tile = blockIdx.x;
+    int l = 0;
+    while (l + 1 < tl.num_levels && tile >= tl.base[l + 1]) l++;
+    const int rel = tile - tl.base[l];
+    const int per_img = tl.tiles_y[l] * tl.tiles_x[l];
+    const int img = rel / per_img, ty = (rel % per_img) / tl.tiles_x[l], tx = rel % tl.tiles_x[l];
+    const int H = lv.h[l], W = lv.w[l];
+    const int y0 = ty * kTileH, x0 = tx * kTileW;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bins = pooled_h * pooled_w;
+    const int nroi = list_count[tile];
+    const int* my = list + (size_t)tile * cap;
+    float* accl = acc + lane * kTileWords;
+    const float* gl = gbuf + lane * gstride;
+    const size_t plane = (size_t)H * W;
+
+    for (int k = 0; k < slabs_per_cta; k++) {
+        const int c0 = (blockIdx.y * slabs_per_cta + k) * kSlab;
+        if (c0 >= channels) break;
+        const int nch = min(kSlab, channels - c0);
+        for (int i = tid; i < kSlab * kTileWords; i += 256) acc[i] = 0.f;
+        for (int j = 0; j < nroi; j++) {
+            const int n = my[j];
+            const BwdRoiInfo ri = info[n];
+            __syncthreads();                                    // previous RoI done with gbuf / tables (and acc zeroed)
+            // top_diff of this RoI for the slab -> gbuf[c][bin]; its tap tables -> shared memory
+            const int row = out_index ? out_index[n] : n;
+            const float* tsrc = top_diff + ((size_t)row * channels + c0) * bins;
+            for (int e = tid; e < nch * bins; e += 256) {
+                const int c = e / bins;
+                gbuf[c * gstride + (e - c * bins)] = __ldg(tsrc + e);
+            }
+            if (tid < ny) ytab[tid] = ytabs[(size_t)n * ny + tid];
+            else if (tid >= 64 && tid < 64 + nx) xtab[tid - 64] = xtabs[(size_t)n * nx + tid - 64];
+            __syncthreads();
+            const int gh = ri.gh, gw = ri.gw;
+            const int icount = gh * gw;
+            const bool pow2 = (icount & (icount - 1)) == 0;
+            const float count = (float)icount, inv_count = 1.0f / count;
+            // each warp owns tile rows warp and warp + 8: plain read-modify-write, no atomics
+            for (int rr = warp; rr < kTileH; rr += 8) {
+                const int y = y0 + rr;
+                for (int sy = 0; sy < ny; sy++) {
+                    const Tap t = ytab[sy];
+                    if (t.low < 0 || (t.low != y && t.high != y)) continue;          // uniform
+                    const int binrow = (sy / gh) * pooled_w;
+                    for (int half = 0; half < 2; half++) {
+                        if ((half == 0 ? t.low : t.high) != y) continue;
+                        const float wy = half == 0 ? t.h : t.l;
+                        for (int sx = 0; sx < nx; sx++) {
+                            const Tap u = xtab[sx];
+                            if (u.low < 0) continue;
+                            const int xl = u.low - x0, xh = u.high - x0;
+                            if (xh < 0 || xl >= kTileW) continue;
+                            const float tv = gl[binrow + sx / gw];
+                            if (xl >= 0) {
+                                const float a = __fmul_rn(tv, __fmul_rn(wy, u.h));
+                                const int i = (rr * kTileW + xl) ^ lane;
+                                accl[i] = __fadd_rn(accl[i], pow2 ? __fmul_rn(a, inv_count) : __fdiv_rn(a, count));
+                            }
+                            if (xh < kTileW) {
+                                const float a = __fmul_rn(tv, __fmul_rn(wy, u.l));
+                                const int i = (rr * kTileW + xh) ^ lane;
+                                accl[i] = __fadd_rn(accl[i], pow2 ? __fmul_rn(a, inv_count) : __fdiv_rn(a, count));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // write the finished tile: lanes along x, one coalesced 128-byte row per (channel, tile row)
+        float* dst = lv.data[l] + ((size_t)img * channels + c0) * plane;
+        for (int e = warp; e < nch * kTileH; e += 8) {
+            const int c = e / kTileH, rr = e - c * kTileH;
+            const int y = y0 + rr, x = x0 + lane;
+            if (y < H && x < W) dst[(size_t)c * plane + (size_t)y * W + x] = acc[c * kTileWords + ((rr * kTileW + lane) ^ c)];
+        }
+        __syncthreads();
+    }
+}
+
+// test hook (vosd_debug_force_generic): 0 = default (staged forward, record-based backward), 1 = generic kernels
 // everywhere, 2 = staged kernels everywhere (the staged backward is parity-tested but not yet faster than
 // the atomic scatter -- profiles/r01_roialign_bwd_staged_*_ncu.txt -- so it is not the default)
 static int g_force_generic = 0;
@@ -966,6 +1257,23 @@ static int ml_bwd(const LevelTable& t, int num_levels, int batch, int channels, 
     const int gs = sr > 0 ? sr : 1;
     while (rpg > 1 && rpg * gs > kMaxTaps) rpg--;
     groups = ceil_div(ph, rpg);
+    if (g_force_generic == 0) {
+        // default: record-based scatter; rows grouped so that one group's records fit (<= kMaxRecords)
+        int rg = ph;
+        while (rg > 1 && ((long long)rg * gs * pw * gs > kMaxRecords || rg * gs > kMaxTaps)) rg--;
+        const int ngroups = ceil_div(ph, rg);
+        long long cpc = (long long)channels * num_rois * ngroups / (3LL * 6 * kNumSMs);     // channels per CTA: ~3 waves of 6 CTAs/SM
+        if (cpc < 8) cpc = 8;
+        if (cpc > channels) cpc = channels;
+        const size_t dyn = (size_t)kMaxRecords * sizeof(BwdRec);
+        if (ngroups <= 65535) {
+            dim3 grid(num_rois, ceil_div(channels, (int)cpc), ngroups);
+            roialign_bwd_records<<<grid, 256, dyn, stream>>>(t, channels, ph, pw, sr, rg, (int)cpc, rois, roi_level,
+                                                             out_index, top_diff);
+            count_launch();
+            return check_launch();
+        }
+    }
     const bool staged_ok = g_force_generic == 2 && pw * gs <= kMaxTaps && rpg * gs <= kMaxTaps && groups <= 65535;
     if (staged_ok) {
         const int gbuf_stride = (rpg * pw) | 1;

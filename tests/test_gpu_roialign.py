@@ -1,10 +1,14 @@
 """GPU parity: RoIAlign forward / backward through the C ABI against
   (i)   the reference kernel itself (oracle/_ref/libref_roialign.so = the unmodified
-        roi_align_kernel.cu built for sm_100a) run on the same GPU -- forward must be bit-identical;
+        roi_align_kernel.cu built for sm_100a) run on the same GPU;
   (ii)  the CPU oracle (oracle/oracle.c);
   (iii) the torchvision golden (loose anchor).
-Tolerances: forward rtol 1e-5 of max|out| is the pass bar (target 0 ulp); backward
-rtol 1e-5 + atol 1e-6*max|grad| (atomics reorder the fp32 sum, also in the reference)."""
+Tolerances (north_star: RoIAlign within 1e-5 relative, fp32):
+  * "staged" and "generic" kernel families: forward BIT-IDENTICAL to the reference kernel (0 ulp);
+  * "default" family: the separable forward (csrc/roialign_sep.cuh) evaluates the same sum in a different
+    order -> |out - ref| <= 1e-5*|ref| + 1e-6*max|ref|; wherever the separable kernel does not apply
+    (sampling_ratio != 2, pooled width not 7/14/28, C % 32 != 0) the default is the staged kernel: 0 ulp;
+  * backward: rtol 1e-5 + atol 1e-6*max|grad| (atomics reorder the fp32 sum, also in the reference)."""
 import ctypes
 import os
 
@@ -65,6 +69,22 @@ def ulp_diff(a, b):
     return (ia - ib).abs()
 
 
+def sep_applies(path, C, pw, sr):
+    """True where the default family routes the forward through the separable kernel."""
+    return path == "default" and sr == 2 and pw in (7, 14, 28) and C % 32 == 0
+
+
+def assert_forward(out, ref, exact, what=""):
+    if exact:
+        d = ulp_diff(out, ref)
+        assert int(d.max()) == 0, "%s ulp histogram: %s" % (what, torch.bincount(d.flatten().clamp(max=8)).tolist())
+    else:
+        tol = 1e-5 * ref.abs() + 1e-6 * float(ref.abs().max())
+        bad = (out - ref).abs() > tol
+        assert not bool(bad.any()), "%s max err %g (max|ref| %g), %d elements out of tolerance" % (
+            what, float((out - ref).abs().max()), float(ref.abs().max()), int(bad.sum()))
+
+
 def _case(synth, lvl, R=150, C=16, N=2, seed=0, blob=None):
     blob = blob or synth.COCO_BLOB
     feats = synth.fpn_features(100 + seed, blob, N, (lvl,), C)[lvl]
@@ -73,16 +93,15 @@ def _case(synth, lvl, R=150, C=16, N=2, seed=0, blob=None):
 
 
 @pytest.mark.parametrize("lvl", [2, 3, 4, 5])
-@pytest.mark.parametrize("res,sr", [(7, 2), (14, 2), (7, 0), (3, 1)])
-def test_forward_bit_exact_vs_reference_kernel(refk, synth, orc, path, lvl, res, sr):
+@pytest.mark.parametrize("res,sr,C", [(7, 2, 16), (14, 2, 16), (7, 0, 16), (3, 1, 16), (7, 2, 64), (14, 2, 32), (28, 2, 32)])
+def test_forward_vs_reference_kernel(refk, synth, orc, path, lvl, res, sr, C):
     from vosdetectron_b200 import ops
-    f, rois = _case(synth, lvl, seed=lvl)
+    f, rois = _case(synth, lvl, C=C, seed=lvl)
     scale = 1.0 / 2 ** lvl
     out = ops.roi_align_forward(f, rois, res, res, scale, sr)
     ref = refk.fwd(f, rois, res, res, scale, sr)
     torch.cuda.synchronize()
-    d = ulp_diff(out, ref)
-    assert int(d.max()) == 0, "ulp histogram: %s" % torch.bincount(d.flatten().clamp(max=8)).tolist()
+    assert_forward(out, ref, not sep_applies(path, C, res, sr), "lvl %d res %d" % (lvl, res))
     o = orc.roi_align_forward(f.cpu().numpy(), rois.cpu().numpy(), res, res, scale, sr)
     err = np.abs(out.cpu().numpy() - o).max()
     assert err <= 1e-5 * np.abs(o).max(), err
@@ -91,27 +110,32 @@ def test_forward_bit_exact_vs_reference_kernel(refk, synth, orc, path, lvl, res,
 def test_forward_edge_rois_vs_reference_kernel(refk, synth, orc, path):
     from vosdetectron_b200 import ops
     for lvl in (2, 5):
-        f = torch.from_numpy(synth.fpn_features(7, synth.COCO_BLOB, 1, (lvl,), 8)[lvl]).cuda()
-        rois = torch.from_numpy(synth.edge_rois()).cuda()
-        for res, sr in ((7, 2), (14, 2), (7, 0)):
-            out = ops.roi_align_forward(f, rois, res, res, 1.0 / 2 ** lvl, sr)
-            ref = refk.fwd(f, rois, res, res, 1.0 / 2 ** lvl, sr)
-            assert torch.equal(out, ref), (lvl, res, sr)
-            o = orc.roi_align_forward(f.cpu().numpy(), rois.cpu().numpy(), res, res, 1.0 / 2 ** lvl, sr)
-            assert np.array_equal(out.cpu().numpy(), o), (lvl, res, sr)
+        for C in (8, 32):
+            f = torch.from_numpy(synth.fpn_features(7, synth.COCO_BLOB, 1, (lvl,), C)[lvl]).cuda()
+            rois = torch.from_numpy(synth.edge_rois()).cuda()
+            for res, sr in ((7, 2), (14, 2), (7, 0)):
+                out = ops.roi_align_forward(f, rois, res, res, 1.0 / 2 ** lvl, sr)
+                ref = refk.fwd(f, rois, res, res, 1.0 / 2 ** lvl, sr)
+                exact = not sep_applies(path, C, res, sr)
+                assert_forward(out, ref, exact, "edge lvl %d C %d res %d sr %d" % (lvl, C, res, sr))
+                o = orc.roi_align_forward(f.cpu().numpy(), rois.cpu().numpy(), res, res, 1.0 / 2 ** lvl, sr)
+                if exact:
+                    assert np.array_equal(out.cpu().numpy(), o), (lvl, res, sr)
 
 
-def test_forward_oversize_rois_and_odd_channels(refk, synth):
-    """RoIs far larger than the staged tile (banding + in-kernel fallback), C not a multiple of 32,
-    a non-square pooled size and a large fixed sampling grid."""
+@pytest.mark.parametrize("C", [40, 64])
+def test_forward_oversize_rois_and_odd_channels(refk, synth, path, C):
+    """RoIs far larger than the staged tile / the separable kernel's ring (banding + in-kernel direct
+    gather), C not a multiple of 32, non-square pooled sizes and a large fixed sampling grid."""
     from vosdetectron_b200 import ops
-    f = torch.from_numpy(synth.fpn_features(77, synth.COCO_BLOB, 2, (2,), 40)[2]).cuda()     # 200x336, C=40
+    f = torch.from_numpy(synth.fpn_features(77, synth.COCO_BLOB, 2, (2,), C)[2]).cuda()     # 200x336
     rois = torch.tensor([[0, 0, 0, 1343, 799], [1, 10, 20, 1300, 90], [0, 5, 5, 90, 790], [1, 300, 300, 340, 330],
-                         [0, 100, 100, 900, 700]], dtype=torch.float32, device="cuda")
-    for (ph, pw, sr) in ((7, 7, 2), (14, 14, 2), (7, 7, 0), (5, 9, 3), (2, 2, 20)):
+                         [0, 100, 100, 900, 700], [1, 40, 40, 160, 700], [0, 0, 0, 127, 127]],
+                        dtype=torch.float32, device="cuda")
+    for (ph, pw, sr) in ((7, 7, 2), (14, 14, 2), (10, 7, 2), (3, 14, 2), (7, 7, 0), (5, 9, 3), (2, 2, 20)):
         out = ops.roi_align_forward(f, rois, ph, pw, 0.25, sr)
         ref = refk.fwd(f, rois, ph, pw, 0.25, sr)
-        assert torch.equal(out, ref), (ph, pw, sr, float((out - ref).abs().max()))
+        assert_forward(out, ref, not sep_applies(path, C, pw, sr), "C %d %dx%d sr %d" % (C, ph, pw, sr))
 
 
 def test_forward_vs_torchvision_golden(golden):
@@ -190,7 +214,7 @@ def test_multilevel_matches_reference_loop(refk, synth, orc, path):
             if len(r):
                 parts.append(refk.fwd(blobs_in[5 - lvl], torch.from_numpy(r).cuda(), res, res, scales[5 - lvl], 2))
         ref = torch.cat(parts)[torch.from_numpy(blobs['rois_idx_restore_int32'].astype(np.int64)).cuda()]
-        assert torch.equal(out, ref)
+        assert torch.equal(out, ref)                    # C = 8: every family is bit-exact here
     # tensors in rpn_ret work too, and gradients flow to every level
     t_blobs = {k: torch.from_numpy(v).cuda() for k, v in blobs.items()}
     leaf = [b.clone().requires_grad_(True) for b in blobs_in]
@@ -207,6 +231,30 @@ def test_multilevel_matches_reference_loop(refk, synth, orc, path):
         tol = 1e-5 * ref.abs() + 1e-6 * float(ref.abs().max())
         assert bool(((got - ref).abs() <= tol).all()), lvl
     assert len(order) == len(rois)
+
+
+def test_full_size_vs_reference_kernel(refk, synth, path):
+    """BASELINE config 2 at full size (1000 RoIs x 256 ch over P2-P5, 7x7 and 14x14) against the reference
+    kernel launched per level (model_builder.py:271-303), every kernel family."""
+    from vosdetectron_b200 import ops
+    feats = synth.fpn_features(2000, synth.COCO_BLOB, 1, synth.ROI_LEVELS, 256)
+    rois = torch.from_numpy(synth.random_rois(2001, 1000, synth.COCO_BLOB, 1)).cuda()
+    fl = [torch.from_numpy(feats[l]).cuda() for l in synth.ROI_LEVELS]
+    sc = [1.0 / 2 ** l for l in synth.ROI_LEVELS]
+    level, _, order, restore = ops.distribute_cuda(rois)
+    lv = (level - 2).to(torch.int32)
+    for res in (7, 14):
+        out = ops.roi_align_ml_forward(fl, sc, rois, lv, res, res, 2)
+        ref = torch.empty_like(out)
+        for i in range(len(fl)):
+            idx = torch.nonzero(lv == i).flatten()
+            if len(idx):
+                ref[idx] = refk.fwd(fl[i], rois[idx].contiguous(), res, res, sc[i], 2)
+        assert_forward(out, ref, not sep_applies(path, 256, res, 2), "full size res %d" % res)
+        if sep_applies(path, 256, res, 2):
+            d = ulp_diff(out, ref).flatten()
+            print("separable forward res %d: ulp histogram (0..7, >=8) %s, max abs err %.3g" % (
+                res, torch.bincount(d.clamp(max=8), minlength=9).tolist(), float((out - ref).abs().max())))
 
 
 def test_full_size_properties(synth):

@@ -1177,7 +1177,11 @@ bwd_tile_kernel(const __grid_constant__ LevelTable lv, const __grid_constant__ B
     }
 }
 
-// test hook (vosd_debug_force_generic): 0 = default (staged forward, record-based backward), 1 = generic kernels
+}  // namespace vosd
+#include "roialign_sep.cuh"
+namespace vosd {
+
+// test hook (vosd_debug_force_generic): 0 = default (separable forward where it applies, record-based backward), 1 = generic kernels
 // everywhere, 2 = staged kernels everywhere (the staged backward is parity-tested but not yet faster than
 // the atomic scatter -- profiles/r01_roialign_bwd_staged_*_ncu.txt -- so it is not the default)
 static int g_force_generic = 0;
@@ -1207,6 +1211,36 @@ static int ml_fwd(const LevelTable& t, int channels, int ph, int pw, int sr, int
     if (channels <= 0 || ph <= 0 || pw <= 0 || num_rois < 0) return VOSD_ERR_BAD_SHAPE;
     if (num_rois == 0) return VOSD_OK;
     if (!rois || !top) return VOSD_ERR_BAD_ARG;
+    if (g_force_generic == 0 && sr == 2 && (pw == 7 || pw == 14 || pw == 28) && channels % kSlab == 0) {
+        // separable row-streaming kernel (roialign_sep.cuh): T warps per (RoI, slab) team, NPH output rows per CTA
+        const int T = pw / 7, nph = 7, teams = kSepWarps / T;
+        const int slabs_all = channels / kSlab, rgroups = ceil_div(ph, nph);
+        if (rgroups <= 65535) {
+            // slabs per CTA: a multiple of the teams, few enough that the grid has >= ~12 CTAs per SM
+            long long spc = (long long)slabs_all * num_rois * rgroups / (12LL * kNumSMs);
+            spc = spc / teams * teams;
+            if (spc < teams) spc = teams;
+            if (spc > slabs_all) spc = slabs_all;
+            dim3 grid(num_rois, ceil_div(slabs_all, (int)spc), rgroups);
+            cudaError_t e;
+            if (T == 1) {
+                e = cudaFuncSetAttribute(roialign_fwd_sep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sep_dyn_bytes<1>());
+                if (e == cudaSuccess)
+                    roialign_fwd_sep<1><<<grid, kSepThreads, sep_dyn_bytes<1>(), stream>>>(t, channels, ph, (int)spc, rois, roi_level, out_index, top);
+            } else if (T == 2) {
+                e = cudaFuncSetAttribute(roialign_fwd_sep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sep_dyn_bytes<2>());
+                if (e == cudaSuccess)
+                    roialign_fwd_sep<2><<<grid, kSepThreads, sep_dyn_bytes<2>(), stream>>>(t, channels, ph, (int)spc, rois, roi_level, out_index, top);
+            } else {
+                e = cudaFuncSetAttribute(roialign_fwd_sep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sep_dyn_bytes<4>());
+                if (e == cudaSuccess)
+                    roialign_fwd_sep<4><<<grid, kSepThreads, sep_dyn_bytes<4>(), stream>>>(t, channels, ph, (int)spc, rois, roi_level, out_index, top);
+            }
+            if (e != cudaSuccess) return VOSD_ERR_LAUNCH;
+            count_launch();
+            return check_launch();
+        }
+    }
     // staged path: row groups of <= ~112 bins, sample records <= kMaxRecords, >= ~8 waves of CTAs
     const int slabs = ceil_div(channels, kSlab);
     int groups = ceil_div(ph * pw, 112);

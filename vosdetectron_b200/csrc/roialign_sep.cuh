@@ -1,0 +1,448 @@
+// Separable row-streaming RoIAlign forward for the fixed 2x2 sampling grid (sampling_ratio == 2), the
+// configuration every model builder of the reference uses (lib/core/config.py: *_ROI_XFORM_SAMPLING_RATIO = 2;
+// kernel: lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.cu:65-121).  Included by roialign.cu.
+//
+// The bilinear weight of sample (iy, ix) factors into wy * wx and the validity test of the reference
+// (y < -1 || y > H || x < -1 || x > W) is per axis, so for one channel
+//     out[ph][pw] = sum_y Wy[y][ph] * R[y][pw],     R[y][pw] = sum over the <= 4 x taps of bin pw of wx * F[y][x]
+// with Wy[y][ph] = (1/4) * (sum of the y weights with which texel row y enters output row ph).  Each texel
+// row of the RoI's footprint is therefore read from shared memory ONCE per output column (4 loads) instead
+// of once per sample (16 loads per output element): 4*th*PW shared loads per channel instead of 16*PH*PW
+// (th = texel rows of the footprint, typically 9..16 for the FPN level assignment).  The staged kernel is
+// bound by the shared-memory / L1 data pipe (profiles/r01_roialign_fwd_v2h_ncu.txt: 71 % of the LSU
+// wavefront peak), so this is the lever; the sum is evaluated in a different order than the reference's,
+// which is why this path is gated at rtol 1e-5 (north_star), while the staged kernel stays bit-exact.
+//
+// Warp-specialised CTA of 8 warps (one RoI x 7 output rows x a range of 32-channel slabs):
+//   * CONSUMER warps 0..3 form 4 / T teams; a team owns one slab at a time, lanes = channels, warp `sub` of
+//     the team owns output columns 7*sub .. 7*sub+6 and keeps acc[7][7] in registers (PW = 7*T).  Per texel
+//     row: 4 tap loads per output column (the high tap is the next column: +132 bytes), 4 FMAs -> R, then
+//     7 FMAs into acc.  No global loads, no staging: it only waits on the row's FULL barrier and arrives
+//     on its EMPTY barrier.
+//   * PRODUCER warps 4..7 stream the texel rows of the footprint -- of ALL the slabs of a team, as one flat
+//     sequence, so the pipeline never drains between slabs -- into the team's ring of row slots:
+//     global -> registers (128-bit loads where rows are 16-byte aligned, lanes along x: coalesced; four
+//     register sets keep up to four rows in flight per producer: the measured load latency under this
+//     access pattern is ~1400 cycles, so ~64 KB must be in flight per SM) -> slot[x][c], pitch 33 words per
+//     column (bank = (x + c) mod 32: the transposing stores and the lanes-are-channels tap loads are both
+//     conflict-free).
+//   * mbarrier FULL / EMPTY pair per ring slot (the Hopper/Blackwell producer-consumer idiom); no CTA-wide
+//     barrier after the setup.  Results leave through obuf[c][bin] (odd stride) as contiguous streaming stores.
+// RoIs whose footprint exceeds the ring (wider than 32 texels, taller than kSepMaxRows) take the direct
+// gather below, inside the same kernel.
+#pragma once
+
+namespace vosd {
+
+constexpr int kSepWarps = 4;                           // consumer warps
+constexpr int kSepProducers = 4;                       // producer warps (one per stream)
+constexpr int kSepThreads = 32 * (kSepWarps + kSepProducers);
+constexpr int kSepColBytes = 33 * 4;                   // pitch of a tile column: 33 words
+constexpr int kSepRingBytes = 16384;                   // per consumer warp: 7 slots of <= 16 columns .. 3 of 33
+constexpr int kSepMaxSlots = 8;
+constexpr int kSepMaxRows = 48;                        // texel rows of a footprint (Wy table)
+constexpr int kSepWyStride = 8;                        // floats per Wy row (7 output rows per CTA, padded to 2 x 128 bit)
+
+__device__ __forceinline__ float lds_off(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_off132(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+132];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 lds_v4(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void cp_async4(unsigned dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <int T>
+__device__ __forceinline__ void team_sync(int team) {
+    if (T == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" :: "r"(team + 1), "n"(32 * T) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(unsigned a, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned a) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned a, unsigned parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" :: "r"(a), "r"(parity) : "memory");
+}
+
+struct SepShared {
+    Tap ytab[16];                 // sample rows of this CTA's 7 output rows
+    Tap xtab[64];                 // all sample columns (2 * PW <= 56)
+    float wy[kSepMaxRows * kSepWyStride];
+    int xoff[28][2];              // per output column: byte offset (column * 132) of the low tap of its two samples
+    float xw[28][4];              // h0, l0, h1, l1 (0 for an invalid sample)
+    unsigned long long full[kSepWarps][kSepMaxSlots], empty[kSepWarps][kSepMaxSlots];   // [team][slot]
+};
+
+// T consumer warps per team.  grid = (RoIs, slab splits, groups of 7 output rows), block = 256,
+// dynamic shared memory = 4 rings + 4 / T epilogue buffers.
+template <int T>
+__global__ void __launch_bounds__(kSepThreads, 2)
+roialign_fwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled_h, int slabs_per_cta,
+                 const float* __restrict__ rois, const int* __restrict__ roi_level,
+                 const int* __restrict__ out_index, float* __restrict__ top) {
+    constexpr int PW = 7 * T;
+    constexpr int NPH = 7;
+    constexpr int kTeams = kSepWarps / T;
+    constexpr int kRun = NPH * PW;                      // floats per channel leaving per slab
+    constexpr int kObufStride = kRun | 1;
+    __shared__ SepShared sh;
+    extern __shared__ __align__(16) unsigned char sep_dyn[];     // [4 rings][kTeams obufs]
+
+    const int n = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ph_begin = blockIdx.z * NPH;
+    const int nph = min(NPH, pooled_h - ph_begin);
+    const int bins = pooled_h * PW;
+
+    // ---- per-CTA setup.  One CTA-wide barrier: every thread derives the RoI geometry itself (broadcast
+    //      loads), 2*(NPH+PW) threads fill the tap tables, then every warp reduces the footprint redundantly.
+    const int level = roi_level ? __ldg(roi_level + n) : 0;
+    const int H = lv.h[level], W = lv.w[level];
+    const RoiGeom g = roi_geometry(rois + 5 * (size_t)n, lv.scale[level], pooled_h, PW, 2);
+    const int row = out_index ? __ldg(out_index + n) : n;
+    if (tid < 2 * nph) {
+        const int sy = 2 * ph_begin + tid;
+        const AxisTap t = axis_tap(sample_coord(g.start_h, g.bin_h, sy >> 1, sy & 1, 2), H);
+        sh.ytab[tid] = Tap{t.valid ? t.low : -1, t.high, t.l, t.h};
+    } else if (tid >= 64 && tid < 64 + 2 * PW) {
+        const int k = tid - 64;
+        const AxisTap t = axis_tap(sample_coord(g.start_w, g.bin_w, k >> 1, k & 1, 2), W);
+        Tap e = Tap{t.valid ? t.low : -1, t.high, t.l, t.h};
+        // A sample clamped to the last column (low == high == W-1, weights 1 / 0) is re-expressed as
+        // low = W-2, high = W-1 with weights 0 / 1: same value, and the high tap is always "next column".
+        if (t.valid && t.low == t.high && W >= 2) e = Tap{W - 2, W - 1, 1.f, 0.f};
+        sh.xtab[k] = e;
+    } else if (tid >= 128 && tid < 128 + kTeams * kSepMaxSlots) {
+        // one elected lane per warp arrives (after __syncwarp): 32 arrivals on one address would serialise
+        const int k = tid - 128;
+        mbar_init((unsigned)__cvta_generic_to_shared(&sh.full[0][0]) + 8u * (unsigned)k, 1);
+        mbar_init((unsigned)__cvta_generic_to_shared(&sh.empty[0][0]) + 8u * (unsigned)k, T);
+    }
+    for (int i = tid; i < kSepMaxRows * kSepWyStride; i += kSepThreads) sh.wy[i] = 0.f;
+    __syncthreads();
+    int x_lo, tw, y_lo, th;
+    {
+        int lo = 1 << 30, hi = -1, lo2 = 1 << 30, hi2 = -1;
+        for (int k = lane; k < 2 * PW; k += 32) {
+            const Tap t = sh.xtab[k];
+            if (t.low >= 0) { lo = min(lo, t.low); hi = max(hi, t.high); }
+        }
+        if (lane < 2 * nph) {
+            const Tap t = sh.ytab[lane];
+            if (t.low >= 0) { lo2 = t.low; hi2 = t.high; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            lo2 = min(lo2, __shfl_xor_sync(0xffffffffu, lo2, o));
+            hi2 = max(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
+        }
+        x_lo = lo; tw = hi - lo + 1; y_lo = lo2; th = hi2 - lo2 + 1;
+    }
+    const int slab0 = blockIdx.y * slabs_per_cta;
+    const int nslab = min(slabs_per_cta, channels / kSlab - slab0);
+    float* __restrict__ out_roi = top + ((size_t)row * channels + (size_t)slab0 * kSlab) * bins + ph_begin * PW;
+    const int group_bins = nph * PW;
+
+    if (tw <= 0 || th <= 0) {
+        // no valid sample at all: the reference writes zeros
+        for (int e = tid; e < nslab * kSlab * group_bins; e += kSepThreads) {
+            const int c = e / group_bins, b = e - c * group_bins;
+            __stcs(out_roi + (size_t)c * bins + b, 0.f);
+        }
+        return;
+    }
+    if (tw > 32 || th > kSepMaxRows || W < 2) {
+        // footprint beyond the ring: direct gather, the reference's arithmetic element by element
+        const float* fbase = lv.data[level] + ((size_t)g.batch * channels + (size_t)slab0 * kSlab) * H * W;
+        for (int e = tid; e < nslab * kSlab * group_bins; e += kSepThreads) {
+            const int c = e / group_bins, b = e - c * group_bins;
+            const int ph = ph_begin + b / PW, pw = b % PW;
+            const float* d = fbase + (size_t)c * H * W;
+            float acc = 0.f;
+            for (int iy = 0; iy < 2; iy++) {
+                const AxisTap ty = axis_tap(sample_coord(g.start_h, g.bin_h, ph, iy, 2), H);
+                for (int ix = 0; ix < 2; ix++) {
+                    const AxisTap tx = axis_tap(sample_coord(g.start_w, g.bin_w, pw, ix, 2), W);
+                    float val = 0.f;
+                    if (ty.valid && tx.valid)
+                        val = bilinear_value(ty.h, ty.l, tx.h, tx.l, __ldg(d + ty.low * W + tx.low),
+                                             __ldg(d + ty.low * W + tx.high), __ldg(d + ty.high * W + tx.low),
+                                             __ldg(d + ty.high * W + tx.high));
+                    acc = __fadd_rn(acc, val);
+                }
+            }
+            __stcs(out_roi + (size_t)c * bins + b, __fmul_rn(acc, 0.25f));
+        }
+        return;
+    }
+
+    // ---- ring geometry (same for every team of the CTA).  Every tap reads a column the producers write:
+    //      valid samples lie inside the footprint by construction, invalid ones (weight 0) read columns 0, 1.
+    const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(lv.data[level]) & 15) == 0 &&
+                     tw + (x_lo & 3) <= 32;             // 128-bit staging: tile origin aligned down to 4 texels
+    const int x0 = vec ? (x_lo & ~3) : x_lo;
+    const int twt = x_lo + tw - x0;                     // tile columns in use (>= 2)
+    const int cols = vec ? ((twt + 3) & ~3) : twt;
+    const int slot_bytes = cols * kSepColBytes;
+    const int NS = min(kSepMaxSlots, T * kSepRingBytes / slot_bytes);
+    const unsigned dyn_s = (unsigned)__cvta_generic_to_shared(sep_dyn);
+    const size_t plane = (size_t)H * W;
+    const int slab_end = slab0 + nslab;
+
+    if (warp >= kSepWarps) {
+        // =========================== PRODUCER ===========================
+        // 4 streams per CTA, one per producer warp; stream q = (team, phase) feeds rows r = phase,
+        // phase + nphase, ... of the team's flat row sequence (slab k = r / th, texel row y = r % th).
+        constexpr int nphase = T;                       // T = 1: 4 teams x 1, T = 2: 2 x 2, T = 4: 1 x 4
+        const int q = warp - kSepWarps;
+        const int pteam = q / nphase;
+        const float* f_img = lv.data[level] + ((size_t)g.batch * channels + (size_t)(slab0 + pteam) * kSlab) * plane +
+                             (size_t)y_lo * W + x0;
+        // per-lane staging map
+        unsigned sdst;                                  // byte offset inside a slot
+        bool active;
+        size_t cstep;                                   // element stride between the lane's consecutive loads
+        const bool wide = twt > 16;
+        int xwl = 0;
+        if (vec) {
+            // lanes: j = vector (4 texels), cq = channel group; load i covers channel cb + 4 * i with
+            // cb = (cq & 3) + 16 * (cq >> 2): the 4 scalar stores of a vector hit banks 4j + e + cb + 4i, all distinct
+            const int j = lane & 3, cq = lane >> 2, cb = (cq & 3) + 16 * (cq >> 2);
+            sdst = (unsigned)(4 * j * kSepColBytes + cb * 4);
+            f_img += (size_t)cb * plane + 4 * j;
+            active = 4 * j < twt;                       // the second half-row (j + 4) is tested separately
+            cstep = 4 * plane;
+        } else {
+            // lanes: lx = column, lc = channel group; load i covers channel i + XW * lc (bank lx + i + XW * lc)
+            xwl = twt <= 8 ? 3 : (twt <= 16 ? 4 : 5);
+            const int XW = 1 << xwl;
+            const int lx = lane & (XW - 1), lc = lane >> xwl;
+            sdst = (unsigned)(lx * kSepColBytes + XW * lc * 4);
+            f_img += (size_t)(XW * lc) * plane + lx;
+            active = lx < twt;
+            cstep = plane;
+        }
+        const bool active2 = vec && 4 * ((lane & 3) + 4) < twt;
+        const int nsl = pteam < nslab ? (nslab - pteam + kTeams - 1) / kTeams : 0;
+        const int rows = nsl * th;                      // rows of the team's flat sequence
+        const size_t kstep = (size_t)kTeams * kSlab * plane;
+        // cursor of the next row to request
+        int nr = q % nphase, nk = 0, ny = nr;
+        while (ny >= th) { ny -= th; nk++; }
+        float v[4][16];                                 // 4 register sets of 16 floats
+        // loads of chunk `ch` (0: columns 0..15 / channels 0..15, 1: the rest) of row (k, y) into set b
+        auto load_set = [&](int b, int k, int y, int ch) {
+            const float* src = f_img + (size_t)k * kstep + (size_t)y * W;
+            if (vec) {
+                if (ch ? active2 : active) {
+                    src += 16 * ch;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const float4 t4 = __ldg(reinterpret_cast<const float4*>(src + (size_t)i * cstep));
+                        v[b][4 * i] = t4.x; v[b][4 * i + 1] = t4.y; v[b][4 * i + 2] = t4.z; v[b][4 * i + 3] = t4.w;
+                    }
+                }
+            } else if (active) {
+                src += (size_t)(16 * ch) * plane;
+                const int nld = xwl == 3 ? 8 : 16;
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    if (i < nld) v[b][i] = __ldg(src + (size_t)i * cstep);
+            }
+        };
+        auto store_set = [&](int b, unsigned slot_s, int ch) {
+            if (vec) {
+                if (ch ? active2 : active) {
+                    const unsigned a = slot_s + sdst + (unsigned)(ch * 16 * kSepColBytes);
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) sts_f32(a + (unsigned)(e * kSepColBytes + 16 * i), v[b][4 * i + e]);
+                }
+            } else if (active) {
+                const unsigned a = slot_s + sdst + (unsigned)(64 * ch);
+                const int nld = xwl == 3 ? 8 : 16;
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    if (i < nld) sts_f32(a + 4u * (unsigned)i, v[b][i]);
+            }
+        };
+        const unsigned full_s = (unsigned)__cvta_generic_to_shared(&sh.full[pteam][0]);
+        const unsigned empty_s = (unsigned)__cvta_generic_to_shared(&sh.empty[pteam][0]);
+        const unsigned ring_s = dyn_s + (unsigned)(pteam * T) * kSepRingBytes;
+        auto advance = [&]() {
+            nr += nphase; ny += nphase;
+            while (ny >= th) { ny -= th; nk++; }
+        };
+        if (!wide) {
+            // one set per row: 4 rows of the stream in flight
+            int rb[4];                                  // row held by set b
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                rb[b] = nr;
+                if (nr < rows) load_set(b, nk, ny, 0);
+                advance();
+            }
+            while (rb[0] < rows) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    if (rb[b] < rows) {
+                        const int slot = rb[b] % NS, use = rb[b] / NS;
+                        if (use > 0) mbar_wait(empty_s + 8u * (unsigned)slot, (unsigned)((use - 1) & 1));
+                        store_set(b, ring_s + (unsigned)(slot * slot_bytes), 0);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full_s + 8u * (unsigned)slot);
+                        rb[b] = nr;
+                        if (nr < rows) load_set(b, nk, ny, 0);
+                        advance();
+                    }
+                }
+            }
+        } else {
+            // two sets per row: 2 rows of the stream in flight
+            int rb[2];
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                rb[b] = nr;
+                if (nr < rows) { load_set(2 * b, nk, ny, 0); load_set(2 * b + 1, nk, ny, 1); }
+                advance();
+            }
+            while (rb[0] < rows) {
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    if (rb[b] < rows) {
+                        const int slot = rb[b] % NS, use = rb[b] / NS;
+                        if (use > 0) mbar_wait(empty_s + 8u * (unsigned)slot, (unsigned)((use - 1) & 1));
+                        const unsigned slot_s = ring_s + (unsigned)(slot * slot_bytes);
+                        store_set(2 * b, slot_s, 0);
+                        store_set(2 * b + 1, slot_s, 1);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full_s + 8u * (unsigned)slot);
+                        rb[b] = nr;
+                        if (nr < rows) { load_set(2 * b, nk, ny, 0); load_set(2 * b + 1, nk, ny, 1); }
+                        advance();
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // =========================== CONSUMER ===========================
+    // per-column x taps and Wy, built by the consumers while the producers already request rows
+    if (tid < PW) {
+        const Tap t0 = sh.xtab[2 * tid], t1 = sh.xtab[2 * tid + 1];
+        sh.xoff[tid][0] = t0.low >= 0 ? (t0.low - x0) * kSepColBytes : 0;
+        sh.xoff[tid][1] = t1.low >= 0 ? (t1.low - x0) * kSepColBytes : 0;
+        sh.xw[tid][0] = t0.low >= 0 ? t0.h : 0.f; sh.xw[tid][1] = t0.low >= 0 ? t0.l : 0.f;
+        sh.xw[tid][2] = t1.low >= 0 ? t1.h : 0.f; sh.xw[tid][3] = t1.low >= 0 ? t1.l : 0.f;
+    } else if (tid >= 32 && tid < 32 + nph) {
+        // thread = output row: its two sample rows enter <= 4 texel rows (0.25 = 1 / count, exact)
+        const int pr = tid - 32;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const Tap t = sh.ytab[2 * pr + k];
+            if (t.low >= 0) {
+                sh.wy[(t.low - y_lo) * kSepWyStride + pr] += 0.25f * t.h;
+                if (t.high != t.low) sh.wy[(t.high - y_lo) * kSepWyStride + pr] += 0.25f * t.l;
+            }
+        }
+    }
+    asm volatile("bar.sync 15, %0;" :: "n"(32 * kSepWarps) : "memory");
+    const int team = warp / T, sub = warp % T;
+    const unsigned ring_s = dyn_s + (unsigned)(team * T) * kSepRingBytes;
+    float* obuf = reinterpret_cast<float*>(sep_dyn + kSepWarps * kSepRingBytes) + team * (kSlab * kObufStride);
+    const unsigned full_s = (unsigned)__cvta_generic_to_shared(&sh.full[team][0]);
+    const unsigned empty_s = (unsigned)__cvta_generic_to_shared(&sh.empty[team][0]);
+    unsigned a0[7], a1[7];
+    float xw[7][4];
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        a0[i] = ring_s + (unsigned)lane * 4u + (unsigned)sh.xoff[7 * sub + i][0];
+        a1[i] = ring_s + (unsigned)lane * 4u + (unsigned)sh.xoff[7 * sub + i][1];
+#pragma unroll
+        for (int k = 0; k < 4; k++) xw[i][k] = sh.xw[7 * sub + i][k];
+    }
+    const unsigned wy_s = (unsigned)__cvta_generic_to_shared(sh.wy);
+    int slot = 0;
+    unsigned parity = 0, c_off = 0;
+    for (int s = slab0 + team; s < slab_end; s += kTeams) {
+        float acc[NPH][7];
+#pragma unroll
+        for (int p = 0; p < NPH; p++)
+#pragma unroll
+            for (int i = 0; i < 7; i++) acc[p][i] = 0.f;
+        unsigned wy_a = wy_s;
+        for (int y = 0; y < th; y++) {
+            mbar_wait(full_s + 8u * (unsigned)slot, parity);
+            const float4 q0 = lds_v4(wy_a), q1 = lds_v4(wy_a + 16);
+            const float wy[7] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z};
+            float f[7][4];
+#pragma unroll
+            for (int i = 0; i < 7; i++) {
+                f[i][0] = lds_off(a0[i] + c_off);
+                f[i][1] = lds_off132(a0[i] + c_off);
+                f[i][2] = lds_off(a1[i] + c_off);
+                f[i][3] = lds_off132(a1[i] + c_off);
+            }
+#pragma unroll
+            for (int i = 0; i < 7; i++) {
+                const float r = fmaf(xw[i][3], f[i][3], fmaf(xw[i][2], f[i][2], fmaf(xw[i][1], f[i][1], xw[i][0] * f[i][0])));
+#pragma unroll
+                for (int p = 0; p < NPH; p++) acc[p][i] = fmaf(wy[p], r, acc[p][i]);
+            }
+            __syncwarp();                                       // every lane's taps are in registers
+            if (lane == 0) mbar_arrive(empty_s + 8u * (unsigned)slot);
+            wy_a += kSepWyStride * 4;
+            c_off += slot_bytes;
+            if (++slot == NS) { slot = 0; c_off = 0; parity ^= 1u; }
+        }
+        // ---- epilogue: acc -> obuf[c][bin] (odd stride) -> contiguous streaming stores ----
+        float* __restrict__ out_s = out_roi + (size_t)(s - slab0) * kSlab * bins;
+        team_sync<T>(team);                             // previous slab's obuf fully drained
+#pragma unroll
+        for (int p = 0; p < NPH; p++)
+#pragma unroll
+            for (int i = 0; i < 7; i++)
+                obuf[lane * kObufStride + p * PW + 7 * sub + i] = acc[p][i];
+        team_sync<T>(team);
+        const int run = nph * PW;
+        if (T == 1 && run == bins) {
+            // whole slab contiguous (7x7 head): 32 * 49 floats
+            for (int i = lane; i < kSlab * kRun / 4; i += 32)
+                __stcs(reinterpret_cast<float4*>(out_s) + i, reinterpret_cast<const float4*>(obuf)[i]);
+        } else {
+            for (int i = lane + 32 * sub; i < kSlab * kRun; i += 32 * T) {
+                const int c = i / kRun, b = i - c * kRun;
+                if (b < run) __stcs(out_s + (size_t)c * bins + b, obuf[c * kObufStride + b]);
+            }
+        }
+    }
+}
+
+template <int T>
+constexpr size_t sep_dyn_bytes() {
+    return (size_t)kSepWarps * kSepRingBytes + (size_t)(kSepWarps / T) * kSlab * ((49 * T) | 1) * sizeof(float);
+}
+
+}  // namespace vosd

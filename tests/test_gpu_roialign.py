@@ -161,12 +161,16 @@ def test_empty_and_cpu_inputs(synth):
         ops.roi_align_forward(f, torch.zeros((3, 4), device="cuda"), 7, 7, 0.25, 2)
 
 
-@pytest.mark.parametrize("lvl,res,sr", [(2, 7, 2), (3, 14, 2), (4, 7, 0), (5, 14, 2)])
-def test_backward_vs_reference_kernel_and_oracle(refk, synth, orc, path, lvl, res, sr):
+@pytest.mark.parametrize("lvl,res,sr,C", [(2, 7, 2, 8), (3, 14, 2, 8), (4, 7, 0, 8), (5, 14, 2, 8),
+                                          (2, 7, 2, 64), (3, 7, 2, 32), (4, 14, 2, 32), (5, 7, 2, 32), (5, 14, 2, 64),
+                                          (3, 28, 2, 32), (4, 7, 0, 32)])
+def test_backward_vs_reference_kernel_and_oracle(refk, synth, orc, path, lvl, res, sr, C):
+    """C % 32 == 0 with sampling_ratio 2 and pooled width 7 / 14 / 28 routes the default family through the
+    separable scatter (csrc/roialign_sep.cuh); everything else through the record-based atomics."""
     from vosdetectron_b200 import ops
-    f, rois = _case(synth, lvl, R=120, C=8, seed=10 + lvl)
+    f, rois = _case(synth, lvl, R=120, C=C, seed=10 + lvl)
     scale = 1.0 / 2 ** lvl
-    g = torch.from_numpy(np.random.RandomState(lvl).standard_normal((rois.shape[0], 8, res, res)).astype(np.float32)).cuda()
+    g = torch.from_numpy(np.random.RandomState(lvl).standard_normal((rois.shape[0], C, res, res)).astype(np.float32)).cuda()
     mine = ops.roi_align_backward(g, rois, f.shape, res, res, scale, sr)
     ref = refk.bwd(g, rois, tuple(f.shape), res, res, scale, sr)
     tol = 1e-5 * ref.abs() + 1e-6 * float(ref.abs().max())
@@ -255,6 +259,41 @@ def test_full_size_vs_reference_kernel(refk, synth, path):
             d = ulp_diff(out, ref).flatten()
             print("separable forward res %d: ulp histogram (0..7, >=8) %s, max abs err %.3g" % (
                 res, torch.bincount(d.clamp(max=8), minlength=9).tolist(), float((out - ref).abs().max())))
+
+
+def test_backward_edge_and_oversize_rois(refk, synth, path):
+    """Degenerate / out-of-map RoIs and footprints beyond the separable kernel's ring, C % 32 == 0."""
+    from vosdetectron_b200 import ops
+    f = torch.from_numpy(synth.fpn_features(78, synth.COCO_BLOB, 2, (2,), 32)[2]).cuda()
+    big = np.array([[0, 0, 0, 1343, 799], [1, 10, 20, 1300, 90], [0, 5, 5, 90, 790], [1, 300, 300, 340, 330],
+                    [0, 100, 100, 900, 700], [1, 40, 40, 160, 700], [0, 0, 0, 127, 127]], np.float32)
+    rois = torch.from_numpy(np.concatenate([synth.edge_rois(), big])).cuda()
+    for res in (7, 14):
+        g = torch.randn((rois.shape[0], 32, res, res), device="cuda")
+        mine = ops.roi_align_backward(g, rois, f.shape, res, res, 0.25, 2)
+        ref = refk.bwd(g, rois, tuple(f.shape), res, res, 0.25, 2)
+        tol = 1e-5 * ref.abs() + 1e-6 * float(ref.abs().max())
+        assert bool(((mine - ref).abs() <= tol).all()), (res, float((mine - ref).abs().max()))
+
+
+def test_full_size_backward_vs_reference_kernel(refk, synth, path):
+    """BASELINE config 4 box head at full size: 1024 RoIs x 256 ch x 7x7 over 2 frames, and the 14x14 mask head
+    on 256 RoIs, against the reference kernel per level."""
+    from vosdetectron_b200 import ops
+    feats = synth.fpn_features(2000, synth.COCO_BLOB, 2, synth.ROI_LEVELS, 256)
+    shapes = [feats[l].shape for l in synth.ROI_LEVELS]
+    sc = [1.0 / 2 ** l for l in synth.ROI_LEVELS]
+    for R, res in ((1024, 7), (256, 14)):
+        rois = torch.from_numpy(synth.random_rois(2001 + res, R, synth.COCO_BLOB, 2)).cuda()
+        level, _, order, restore = ops.distribute_cuda(rois)
+        lv = (level - 2).to(torch.int32)
+        g = torch.randn((R, 256, res, res), device="cuda")
+        grads = ops.roi_align_ml_backward(g, shapes, sc, rois, lv, res, res, 2)
+        for i in range(len(shapes)):
+            idx = torch.nonzero(lv == i).flatten()
+            ref = refk.bwd(g[idx].contiguous(), rois[idx].contiguous(), tuple(shapes[i]), res, res, sc[i], 2)
+            tol = 1e-5 * ref.abs() + 1e-6 * float(ref.abs().max())
+            assert bool(((grads[i] - ref).abs() <= tol).all()), (res, i, float((grads[i] - ref).abs().max()))
 
 
 def test_full_size_properties(synth):

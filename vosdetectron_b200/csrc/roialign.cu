@@ -1291,8 +1291,37 @@ static int ml_bwd(const LevelTable& t, int num_levels, int batch, int channels, 
     const int gs = sr > 0 ? sr : 1;
     while (rpg > 1 && rpg * gs > kMaxTaps) rpg--;
     groups = ceil_div(ph, rpg);
+    if (g_force_generic == 0 && sr == 2 && (pw == 7 || pw == 14 || pw == 28) && channels % kSlab == 0) {
+        // separable row-streaming scatter (roialign_sep.cuh): one reduction per (channel, texel) of the footprint
+        const int T = pw / 7, teams = kSepWarps / T;
+        const int slabs_all = channels / kSlab, rgroups = ceil_div(ph, 7);
+        if (rgroups <= 65535) {
+            long long spc = (long long)slabs_all * num_rois * rgroups / (12LL * kNumSMs);
+            spc = spc / teams * teams;
+            if (spc < teams) spc = teams;
+            if (spc > slabs_all) spc = slabs_all;
+            dim3 grid(num_rois, ceil_div(slabs_all, (int)spc), rgroups);
+            cudaError_t e;
+            if (T == 1) {
+                e = cudaFuncSetAttribute(roialign_bwd_sep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sep_bwd_dyn_bytes<1>());
+                if (e == cudaSuccess)
+                    roialign_bwd_sep<1><<<grid, kSepThreads, sep_bwd_dyn_bytes<1>(), stream>>>(t, channels, ph, (int)spc, rois, roi_level, out_index, top_diff);
+            } else if (T == 2) {
+                e = cudaFuncSetAttribute(roialign_bwd_sep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sep_bwd_dyn_bytes<2>());
+                if (e == cudaSuccess)
+                    roialign_bwd_sep<2><<<grid, kSepThreads, sep_bwd_dyn_bytes<2>(), stream>>>(t, channels, ph, (int)spc, rois, roi_level, out_index, top_diff);
+            } else {
+                e = cudaFuncSetAttribute(roialign_bwd_sep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sep_bwd_dyn_bytes<4>());
+                if (e == cudaSuccess)
+                    roialign_bwd_sep<4><<<grid, kSepThreads, sep_bwd_dyn_bytes<4>(), stream>>>(t, channels, ph, (int)spc, rois, roi_level, out_index, top_diff);
+            }
+            if (e != cudaSuccess) return VOSD_ERR_LAUNCH;
+            count_launch();
+            return check_launch();
+        }
+    }
     if (g_force_generic == 0) {
-        // default: record-based scatter; rows grouped so that one group's records fit (<= kMaxRecords)
+        // record-based scatter; rows grouped so that one group's records fit (<= kMaxRecords)
         int rg = ph;
         while (rg > 1 && ((long long)rg * gs * pw * gs > kMaxRecords || rg * gs > kMaxTaps)) rg--;
         const int ngroups = ceil_div(ph, rg);

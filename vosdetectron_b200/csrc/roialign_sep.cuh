@@ -445,4 +445,337 @@ constexpr size_t sep_dyn_bytes() {
     return (size_t)kSepWarps * kSepRingBytes + (size_t)(kSepWarps / T) * kSlab * ((49 * T) | 1) * sizeof(float);
 }
 
+
+// =======================================================================================================
+// Separable row-streaming BACKWARD (reference: roi_align_kernel.cu:195-270), the mirror image of the forward
+// kernel above.  For one channel the gradient of a texel row y of the RoI's footprint is
+//     G[y][x] = sum_pw A[x][pw] * U[y][pw],      U[y][pw] = sum_ph Wy[y][ph] * top_diff[ph][pw]
+// with A[x][pw] = the summed x weights with which column x enters output column pw and Wy as in the forward
+// (the 1/4 of the 2x2 grid folded in).  A whole texel row is finished in registers / shared memory before it
+// touches global memory, so the scatter issues ONE reduction per (channel, texel) of the footprint -- as a
+// 128-bit red.global.add.v4.f32 where rows are 16-byte aligned -- instead of 16 scalar atomics per output
+// element: ~10x fewer L2 atomic operations for the FPN level assignment.
+//   * COMPUTE warps 0..3 (teams of T): lanes = channels, g[7][7] = the slab's top_diff of the warp's 7 output
+//     columns in registers; per texel row 49 FMAs -> U[7], then per tile column 7 FMAs with the column's A
+//     weights (two broadcast 128-bit loads) -> slot[x][c].  Warps sub > 0 of a team add their partial sums
+//     into the slot behind a team barrier.
+//   * FLUSH warps 4..7 (one per stream, as the forward's producers) drain finished slots into the gradient
+//     map with reductions, lanes along x (coalesced), fire-and-forget.
+//   * the same FULL / EMPTY mbarrier ring as the forward, roles swapped.
+// Sums are formed in a different order than the reference's atomics (which are unordered anyway); gated at
+// rtol 1e-5 + atol 1e-6 * max|grad| like every other backward path.
+// =======================================================================================================
+constexpr int kSepBwdRingBytes = 12288;                // per compute warp
+
+template <int T>
+struct SepBwdShared {
+    Tap ytab[16];
+    Tap xtab[64];
+    float wy[kSepMaxRows * kSepWyStride];
+    float ax[32 * 8 * T];         // [column][8 * T]: A[x][pw]
+    unsigned long long full[kSepWarps][kSepMaxSlots], empty[kSepWarps][kSepMaxSlots];
+};
+
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+
+template <int T>
+constexpr size_t sep_bwd_dyn_bytes() {
+    return (size_t)kSepWarps * kSepBwdRingBytes + (size_t)2 * (kSepWarps / T) * kSlab * ((49 * T) | 1) * sizeof(float);
+}
+
+template <int T>
+__global__ void __launch_bounds__(kSepThreads, 2)
+roialign_bwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled_h, int slabs_per_cta,
+                 const float* __restrict__ rois, const int* __restrict__ roi_level,
+                 const int* __restrict__ out_index, const float* __restrict__ top_diff) {
+    constexpr int PW = 7 * T;
+    constexpr int NPH = 7;
+    constexpr int kTeams = kSepWarps / T;
+    constexpr int kRun = NPH * PW;
+    constexpr int kIbufStride = kRun | 1;
+    __shared__ SepBwdShared<T> sh;
+    extern __shared__ __align__(16) unsigned char sep_dyn[];     // [4 rings][2 x kTeams ibufs]
+
+    const int n = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ph_begin = blockIdx.z * NPH;
+    const int nph = min(NPH, pooled_h - ph_begin);
+    const int bins = pooled_h * PW;
+
+    const int level = roi_level ? __ldg(roi_level + n) : 0;
+    const int H = lv.h[level], W = lv.w[level];
+    const RoiGeom g = roi_geometry(rois + 5 * (size_t)n, lv.scale[level], pooled_h, PW, 2);
+    const int row = out_index ? __ldg(out_index + n) : n;
+    if (tid < 2 * nph) {
+        const int sy = 2 * ph_begin + tid;
+        const AxisTap t = axis_tap(sample_coord(g.start_h, g.bin_h, sy >> 1, sy & 1, 2), H);
+        sh.ytab[tid] = Tap{t.valid ? t.low : -1, t.high, t.l, t.h};
+    } else if (tid >= 64 && tid < 64 + 2 * PW) {
+        const int k = tid - 64;
+        const AxisTap t = axis_tap(sample_coord(g.start_w, g.bin_w, k >> 1, k & 1, 2), W);
+        sh.xtab[k] = Tap{t.valid ? t.low : -1, t.high, t.l, t.h};
+    } else if (tid >= 128 && tid < 128 + kTeams * kSepMaxSlots) {
+        const int k = tid - 128;
+        mbar_init((unsigned)__cvta_generic_to_shared(&sh.full[0][0]) + 8u * (unsigned)k, 1);
+        mbar_init((unsigned)__cvta_generic_to_shared(&sh.empty[0][0]) + 8u * (unsigned)k, 1);
+    }
+    for (int i = tid; i < kSepMaxRows * kSepWyStride; i += kSepThreads) sh.wy[i] = 0.f;
+    for (int i = tid; i < 32 * 8 * T; i += kSepThreads) sh.ax[i] = 0.f;
+    // 7x7 head: the first slab's top_diff (32 * 49 contiguous floats per team) is requested before anything
+    // else, so its latency hides behind the setup
+    if (T == 1 && pooled_h == NPH && warp < kSepWarps) {
+        const int s_first = blockIdx.y * slabs_per_cta + warp;
+        if (s_first < channels / kSlab && s_first < (blockIdx.y + 1) * slabs_per_cta) {
+            const float* src = top_diff + ((size_t)row * channels + (size_t)s_first * kSlab) * bins;
+            const unsigned ib_s = (unsigned)__cvta_generic_to_shared(sep_dyn + kSepWarps * kSepBwdRingBytes) +
+                                  (unsigned)(2 * warp) * (kSlab * kIbufStride * 4);
+            for (int i = lane; i < kSlab * kRun / 4; i += 32) cp_async16(ib_s + 16u * (unsigned)i, src + 4 * i);
+        }
+        cp_async_commit();
+    }
+    __syncthreads();
+    int x_lo, tw, y_lo, th;
+    {
+        int lo = 1 << 30, hi = -1, lo2 = 1 << 30, hi2 = -1;
+        for (int k = lane; k < 2 * PW; k += 32) {
+            const Tap t = sh.xtab[k];
+            if (t.low >= 0) { lo = min(lo, t.low); hi = max(hi, t.high); }
+        }
+        if (lane < 2 * nph) {
+            const Tap t = sh.ytab[lane];
+            if (t.low >= 0) { lo2 = t.low; hi2 = t.high; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            lo2 = min(lo2, __shfl_xor_sync(0xffffffffu, lo2, o));
+            hi2 = max(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
+        }
+        x_lo = lo; tw = hi - lo + 1; y_lo = lo2; th = hi2 - lo2 + 1;
+    }
+    const int slab0 = blockIdx.y * slabs_per_cta;
+    const int nslab = min(slabs_per_cta, channels / kSlab - slab0);
+    const float* __restrict__ top_roi = top_diff + ((size_t)row * channels + (size_t)slab0 * kSlab) * bins + ph_begin * PW;
+    const int group_bins = nph * PW;
+    const size_t plane = (size_t)H * W;
+
+    if (tw <= 0 || th <= 0) return;                     // no valid sample: no gradient
+    if (tw > 32 || th > kSepMaxRows) {
+        // footprint beyond the ring: the reference's scatter, element by element
+        float* gbase = lv.data[level] + ((size_t)g.batch * channels + (size_t)slab0 * kSlab) * plane;
+        for (int e = tid; e < nslab * kSlab * group_bins; e += kSepThreads) {
+            const int c = e / group_bins, b = e - c * group_bins;
+            const int ph = ph_begin + b / PW, pw = b % PW;
+            float* d = gbase + (size_t)c * plane;
+            const float t = __ldg(top_roi + (size_t)c * bins + b);
+            for (int iy = 0; iy < 2; iy++) {
+                const AxisTap ty = axis_tap(sample_coord(g.start_h, g.bin_h, ph, iy, 2), H);
+                for (int ix = 0; ix < 2; ix++) {
+                    const AxisTap tx = axis_tap(sample_coord(g.start_w, g.bin_w, pw, ix, 2), W);
+                    if (!(ty.valid && tx.valid)) continue;
+                    atomicAdd(d + ty.low * W + tx.low, __fmul_rn(__fmul_rn(t, __fmul_rn(ty.h, tx.h)), 0.25f));
+                    atomicAdd(d + ty.low * W + tx.high, __fmul_rn(__fmul_rn(t, __fmul_rn(ty.h, tx.l)), 0.25f));
+                    atomicAdd(d + ty.high * W + tx.low, __fmul_rn(__fmul_rn(t, __fmul_rn(ty.l, tx.h)), 0.25f));
+                    atomicAdd(d + ty.high * W + tx.high, __fmul_rn(__fmul_rn(t, __fmul_rn(ty.l, tx.l)), 0.25f));
+                }
+            }
+        }
+        return;
+    }
+
+    const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(lv.data[level]) & 15) == 0 &&
+                     tw + (x_lo & 3) <= 32;
+    const int x0 = vec ? (x_lo & ~3) : x_lo;
+    const int twt = x_lo + tw - x0;
+    const int cols = vec ? ((twt + 3) & ~3) : twt;
+    const int slot_bytes = cols * kSepColBytes;
+    const int NS = min(kSepMaxSlots, T * kSepBwdRingBytes / slot_bytes);
+    const unsigned dyn_s = (unsigned)__cvta_generic_to_shared(sep_dyn);
+    const int slab_end = slab0 + nslab;
+
+    if (warp >= kSepWarps) {
+        // =========================== FLUSH ===========================
+        // stream q = (team, phase): rows r = phase, phase + nphase, ... of the team's flat row sequence
+        constexpr int nphase = T;
+        const int q = warp - kSepWarps;
+        const int pteam = q / nphase;
+        float* g_img = lv.data[level] + ((size_t)g.batch * channels + (size_t)(slab0 + pteam) * kSlab) * plane +
+                       (size_t)y_lo * W + x0;
+        unsigned ssrc;
+        bool active, active2 = false;
+        size_t cstep;
+        int nst, xwl = 0;                               // reductions per lane per chunk
+        if (vec) {
+            const int j = lane & 3, cq = lane >> 2, cb = (cq & 3) + 16 * (cq >> 2);
+            ssrc = (unsigned)(4 * j * kSepColBytes + cb * 4);
+            g_img += (size_t)cb * plane + 4 * j;
+            active = 4 * j < twt;
+            active2 = 4 * (j + 4) < twt;
+            cstep = 4 * plane;
+            nst = 4;
+        } else {
+            xwl = twt <= 8 ? 3 : (twt <= 16 ? 4 : 5);
+            const int XW = 1 << xwl;
+            const int lx = lane & (XW - 1), lc = lane >> xwl;
+            ssrc = (unsigned)(lx * kSepColBytes + XW * lc * 4);
+            g_img += (size_t)(XW * lc) * plane + lx;
+            active = lx < twt;
+            cstep = plane;
+            nst = xwl == 3 ? 8 : 16;
+        }
+        const int nsl = pteam < nslab ? (nslab - pteam + kTeams - 1) / kTeams : 0;
+        const int rows = nsl * th;
+        const size_t kstep = (size_t)kTeams * kSlab * plane;
+        const unsigned full_s = (unsigned)__cvta_generic_to_shared(&sh.full[pteam][0]);
+        const unsigned empty_s = (unsigned)__cvta_generic_to_shared(&sh.empty[pteam][0]);
+        const unsigned ring_s = dyn_s + (unsigned)(pteam * T) * kSepBwdRingBytes;
+        int r = q % nphase, k = 0, y = r;
+        while (y >= th) { y -= th; k++; }
+        const int nchunk = (vec ? twt > 16 : xwl == 5) ? 2 : 1;
+        for (; r < rows; r += nphase) {
+            const int slot = r % NS, use = r / NS;
+            mbar_wait(full_s + 8u * (unsigned)slot, (unsigned)(use & 1));
+            float* dst = g_img + (size_t)k * kstep + (size_t)y * W;
+            const unsigned a = ring_s + (unsigned)(slot * slot_bytes) + ssrc;
+            for (int ch = 0; ch < nchunk; ch++) {
+                if (vec) {
+                    if (ch ? active2 : active) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const unsigned ai = a + (unsigned)(ch * 16 * kSepColBytes + 16 * i);
+                            float4 v;
+                            v.x = lds_off(ai); v.y = lds_off132(ai);
+                            v.z = lds_off(ai + 2 * kSepColBytes); v.w = lds_off132(ai + 2 * kSepColBytes);
+                            red_add_v4(dst + 16 * ch + (size_t)i * cstep, v);
+                        }
+                    }
+                } else if (active) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        if (i < nst) red_add_f32(dst + (size_t)(16 * ch + i) * cstep, lds_off(a + (unsigned)(64 * ch + 4 * i)));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_s + 8u * (unsigned)slot);
+            y += nphase;
+            while (y >= th) { y -= th; k++; }
+        }
+        return;
+    }
+
+    // =========================== COMPUTE ===========================
+    if (tid < PW) {
+        // thread = output column: its two samples enter <= 4 tile columns
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const Tap t = sh.xtab[2 * tid + k];
+            if (t.low >= 0) {
+                sh.ax[(t.low - x0) * (8 * T) + (tid / 7) * 8 + tid % 7] += t.h;
+                if (t.high != t.low) sh.ax[(t.high - x0) * (8 * T) + (tid / 7) * 8 + tid % 7] += t.l;
+            }
+        }
+    } else if (tid >= 32 && tid < 32 + nph) {
+        const int pr = tid - 32;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const Tap t = sh.ytab[2 * pr + k];
+            if (t.low >= 0) {
+                sh.wy[(t.low - y_lo) * kSepWyStride + pr] += 0.25f * t.h;
+                if (t.high != t.low) sh.wy[(t.high - y_lo) * kSepWyStride + pr] += 0.25f * t.l;
+            }
+        }
+    }
+    asm volatile("bar.sync 15, %0;" :: "n"(32 * kSepWarps) : "memory");
+    const int team = warp / T, sub = warp % T;
+    const unsigned ring_s = dyn_s + (unsigned)(team * T) * kSepBwdRingBytes;
+    float* ibuf0 = reinterpret_cast<float*>(sep_dyn + kSepWarps * kSepBwdRingBytes) + (2 * team) * (kSlab * kIbufStride);
+    const unsigned full_s = (unsigned)__cvta_generic_to_shared(&sh.full[team][0]);
+    const unsigned empty_s = (unsigned)__cvta_generic_to_shared(&sh.empty[team][0]);
+    const unsigned wy_s = (unsigned)__cvta_generic_to_shared(sh.wy);
+    const unsigned ax_s = (unsigned)__cvta_generic_to_shared(sh.ax) + 32u * (unsigned)sub;
+    const int run = nph * PW;
+    const bool contiguous = T == 1 && pooled_h == NPH;  // 7x7 head: a slab's top_diff is 32 * 49 contiguous floats
+    // top_diff of slab s -> ibuf[buf][c][bin]
+    auto fetch = [&](int s, int buf, bool async) {
+        const float* src = top_roi + (size_t)(s - slab0) * kSlab * bins;
+        float* ib = ibuf0 + buf * (kSlab * kIbufStride);
+        if (async) {
+            const unsigned ib_s = (unsigned)__cvta_generic_to_shared(ib);
+            for (int i = lane; i < kSlab * kRun / 4; i += 32) cp_async16(ib_s + 16u * (unsigned)i, src + 4 * i);
+        } else {
+            for (int i = lane + 32 * sub; i < kSlab * kRun; i += 32 * T) {
+                const int c = i / kRun, b = i - c * kRun;
+                ib[c * kIbufStride + b] = b < run ? __ldg(src + (size_t)c * bins + b) : 0.f;
+            }
+        }
+    };
+    int slot = 0, buf = 0;
+    unsigned parity = 0, c_off = 0;
+    for (int s = slab0 + team; s < slab_end; s += kTeams) {
+        if (contiguous) {
+            if (s + kTeams < slab_end) fetch(s + kTeams, buf ^ 1, true);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            team_sync<T>(team);                         // everybody done reading the previous slab's ibuf
+            fetch(s, buf, false);
+        }
+        team_sync<T>(team);
+        float gt[NPH][7];
+        {
+            const float* ib = ibuf0 + buf * (kSlab * kIbufStride) + lane * kIbufStride + 7 * sub;
+#pragma unroll
+            for (int p = 0; p < NPH; p++)
+#pragma unroll
+                for (int i = 0; i < 7; i++) gt[p][i] = ib[p * PW + i];
+        }
+        if (contiguous) buf ^= 1;
+        unsigned wy_a = wy_s;
+        for (int y = 0; y < th; y++) {
+            const float4 q0 = lds_v4(wy_a), q1 = lds_v4(wy_a + 16);
+            const float wy[7] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z};
+            float u[7];
+#pragma unroll
+            for (int i = 0; i < 7; i++) {
+                float a = wy[0] * gt[0][i];
+#pragma unroll
+                for (int p = 1; p < NPH; p++) a = fmaf(wy[p], gt[p][i], a);
+                u[i] = a;
+            }
+            if (sub == 0) mbar_wait(empty_s + 8u * (unsigned)slot, parity ^ 1u);     // passes at once on the first use
+            unsigned dst = ring_s + c_off + (unsigned)lane * 4u;
+            unsigned aw = ax_s;
+#pragma unroll 1
+            for (int t = 0; t < T; t++) {
+                // team order: sub 0 stores its partial sum, every later sub adds its own behind a barrier
+                if (t == sub) {
+#pragma unroll 4
+                    for (int x = 0; x < cols; x++) {
+                        const float4 w0 = lds_v4(aw), w1 = lds_v4(aw + 16);
+                        float v = fmaf(w0.w, u[3], fmaf(w0.z, u[2], fmaf(w0.y, u[1], w0.x * u[0])));
+                        const float v2 = fmaf(w1.z, u[6], fmaf(w1.y, u[5], w1.x * u[4]));
+                        v += v2;
+                        if (T > 1 && sub > 0) v += lds_off(dst);
+                        sts_f32(dst, v);
+                        dst += kSepColBytes;
+                        aw += 32 * T;
+                    }
+                }
+                if (T > 1) team_sync<T>(team);
+            }
+            __syncwarp();
+            if (sub == T - 1 && lane == 0) mbar_arrive(full_s + 8u * (unsigned)slot);
+            wy_a += kSepWyStride * 4;
+            c_off += slot_bytes;
+            if (++slot == NS) { slot = 0; c_off = 0; parity ^= 1u; }
+        }
+    }
+}
+
 }  // namespace vosd

@@ -237,6 +237,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's kernel, from the committed
+# `ncu --set full` capture of this same bench command (10 frames / step); not measured live.
+NCU_TRAFFIC = {
+    "roialign_box": {"bytes": 315785216 + 459859712, "source": "profiles/r01_roialign_fwd_v3g_sep_ncu.txt"},
+    "roialign_mask": {"bytes": 663342848 + 195825408, "source": "profiles/r01_roialign_fwd_v3f_sep_box_mask_ncu.txt"},
+}
+
+
 def touched_texel_bytes(rois, levels, res, sr, shapes, channels):
     """Exact algorithmic input bytes of a multi-level RoIAlign: 4*C*|unique (frame,level,y,x) texels
     read|, from the RoIs (host replay of the sampling geometry, fp32 like the kernel)."""
@@ -445,7 +453,8 @@ def gpu_arm(args, rank, world, local_rank):
     dom = max(alg, key=lambda k: stage_ms[k])
     ach = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": stage_ms[dom],
+                "traffic": NCU_TRAFFIC.get(dom, {}).get("bytes"), "traffic_source": NCU_TRAFFIC.get(dom, {}).get("source"),
+                "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": stage_ms[dom],
                 "peak_source": peak_src,
                 "stages": {k: {"ms": stage_ms[k], "algorithmic_bytes": alg.get(k),
                                "gbs": (alg[k] / (stage_ms[k] * 1e-3) / 1e9) if k in alg and stage_ms[k] > 0 else None}

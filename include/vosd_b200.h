@@ -220,6 +220,37 @@ VOSD_API int vosd_paste_masks(const float* masks, const int* cls, const float* r
                      int num_dets, int num_classes, int mask_size, int im_h, int im_w,
                      float thresh, uint8_t* out, float* out_prob, cudaStream_t stream);
 
+/* ------------------------------------------------------------------------------------ */
+/* Box-head post-processing.                                */
+/* vosd_bbox_transform replaces the decode of im_detect_bbox (lib/core/test.py:166-181):  */
+/* box_utils.bbox_transform(boxes, deltas, weights) (lib/utils/boxes.py:156-205) followed */
+/* by clip_tiled_boxes (:138-153) when clip_h, clip_w > 0.                                 */
+/*   boxes (n,4), deltas (n,4k), weights HOST float[4], out (n,4k); all fp32, 16-byte      */
+/*   aligned.                                                                              */
+/* ------------------------------------------------------------------------------------ */
+VOSD_API int vosd_bbox_transform(const float* boxes, const float* deltas, int n, int k,
+                        const float* weights /*host*/, float clip_h, float clip_w,
+                        float* out, cudaStream_t stream);
+
+/* vosd_box_results replaces box_results_with_nms_and_limit (lib/core/test.py:733-797;    */
+/* twin lib_vos/tools/vos_test.py:748-865) for a batch of images: per class j >= 1 keep    */
+/* scores >= score_thresh (:747), greedy NMS at nms_thresh (:761-762, cython_nms           */
+/* arithmetic), results in ascending proposal index; then the over-all-classes limit       */
+/* (:775-784): if more than max_per_image survive, keep score >= the max_per_image-th      */
+/* largest score (ties kept, so the count can exceed max_per_image).  Soft-NMS and box     */
+/* voting (off by default) are not implemented.                                            */
+/*   scores (N,R,K) fp32; boxes (N,R,4K) fp32 (pred_boxes, class-major per row);           */
+/*   rows (N) int32 or NULL: valid proposals per image (NULL = R);                         */
+/*   out_dets (N,cap,6) fp32 [x1,y1,x2,y2,score,class], class-major / proposal index       */
+/*   order = np.vstack(cls_boxes[1:]) (:790); out_count (N) = true count (rows beyond cap  */
+/*   are dropped); out_cls_count (N,K) int32 or NULL.  max_per_image <= 0: no limit.       */
+/* ------------------------------------------------------------------------------------ */
+VOSD_API size_t vosd_box_results_workspace_bytes(int num_images, int rois_per_image, int num_classes);
+VOSD_API int vosd_box_results(const float* scores, const float* boxes, const int* rows, int num_images,
+                     int rois_per_image, int num_classes, float score_thresh, float nms_thresh,
+                     int max_per_image, int cap, float* out_dets, int* out_count, int* out_cls_count,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 /* Dense {0,1} uint8 masks (num_masks, pixels_per_mask) -> bit-packed (num_masks, ceil(pixels/8)) uint8,
  * pixel 8j+k in bit k of byte j.  Lossless payload of the frame-sharded all-gather (the reference ships
  * whole pickled results between its per-GPU processes instead, lib/core/test_engine.py:193-200). */

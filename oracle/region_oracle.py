@@ -241,6 +241,40 @@ def distribute(rois, k_min=2, k_max=5, prefix='rois'):
 
 
 # --------------------------------------------------------------------------- #
+# (f1) box-head post-processing -- lib/core/test.py:166-181 (decode) and :733-797
+# --------------------------------------------------------------------------- #
+def box_decode(boxes, deltas, weights=(10.0, 10.0, 5.0, 5.0), im_shape=None):
+    """pred_boxes = bbox_transform(boxes, box_deltas, BBOX_REG_WEIGHTS); clip_tiled_boxes(pred_boxes, im.shape)
+    (test.py:178-179)."""
+    pred = bbox_transform(boxes, deltas, weights)
+    return clip_tiled_boxes(pred, im_shape) if im_shape is not None else pred
+
+
+def box_results_with_nms_and_limit(scores, boxes, num_classes, score_thresh=0.05, nms_thresh=0.3,
+                                   detections_per_im=100, num_det_per_class=0):
+    """test.py:733-797 without the (default-off) Soft-NMS / box-voting branches."""
+    cls_boxes = [[] for _ in range(num_classes)]
+    for j in range(1, num_classes):
+        inds = np.where(scores[:, j] >= score_thresh)[0]                       # :747
+        dets_j = np.hstack((boxes[inds, j * 4:(j + 1) * 4], scores[inds, j][:, np.newaxis])).astype(np.float32, copy=False)
+        keep = nms(dets_j, nms_thresh)                                         # :761
+        cls_boxes[j] = dets_j[keep, :]
+    if detections_per_im > 0:                                                  # :775-784
+        image_scores = np.hstack([cls_boxes[j][:, -1] for j in range(1, num_classes)])
+        if len(image_scores) > detections_per_im:
+            image_thresh = np.sort(image_scores)[-detections_per_im]
+            for j in range(1, num_classes):
+                keep = np.where(cls_boxes[j][:, -1] >= image_thresh)[0]
+                cls_boxes[j] = cls_boxes[j][keep, :]
+    if num_det_per_class > 0:                                                  # :785-788
+        for j in range(1, num_classes):
+            keep = np.argsort(-cls_boxes[j][:, -1])[:num_det_per_class]
+            cls_boxes[j] = cls_boxes[j][keep, :]
+    im_results = np.vstack([cls_boxes[j] for j in range(1, num_classes)])
+    return im_results[:, -1], im_results[:, :-1], cls_boxes
+
+
+# --------------------------------------------------------------------------- #
 # (a14/a15) RoIAlign -- roi_xfrom/roi_align/src/roi_align_kernel.cu:16-121,150-270
 # --------------------------------------------------------------------------- #
 def roi_align_forward(features, rois, ph, pw, spatial_scale, sampling_ratio, nthreads=0):

@@ -113,6 +113,28 @@ def main():
     np.savez_compressed(os.path.join(HERE, "paste.npz"), boxes=bx, cls=cls, masks=masks,
                         frame_hw=np.array([fh, fw]), packed=np.packbits(cap, axis=-1))
 
+    # ---- box head: decode (core/test.py:178-179) + box_results_with_nms_and_limit (:733-797) ----
+    # lib/core/test.py:785 reads cfg.TEST.NUM_DET_PER_CLASS, a key lib/core/config.py never defines (it has
+    # NUM_DET_PER_CLASS_PRE/_POST, :948-949): the unmodified function raises AttributeError there.  The fixture
+    # adds the key (= 0, i.e. the branch is skipped) to the cfg OBJECT; nothing under /root/reference changes.
+    Kd, Rd = 9, 400
+    cfg.MODEL.NUM_CLASSES = Kd
+    cfg.TEST.NUM_DET_PER_CLASS = 0
+    props, sc, dl = synth.box_head_outputs(4711, Rd, Kd, BLOB)
+    pred = r.box_utils.bbox_transform(props, dl, cfg.MODEL.BBOX_REG_WEIGHTS)
+    pred = r.box_utils.clip_tiled_boxes(pred, np.array([BLOB[0], BLOB[1]], dtype=np.float32))
+    g = {"props": props, "scores": sc, "deltas": dl, "pred_boxes": pred, "num_classes": Kd,
+         "score_thresh": cfg.TEST.SCORE_THRESH, "weights": np.asarray(cfg.MODEL.BBOX_REG_WEIGHTS, np.float32)}
+    for tag, nms_t, per_im in (("a", 0.5, 100), ("b", 0.3, 30), ("c", 0.5, 0)):
+        cfg.TEST.NMS, cfg.TEST.DETECTIONS_PER_IM = nms_t, per_im
+        s_out, b_out, cls_boxes = r.core_test.box_results_with_nms_and_limit(sc, pred)
+        g["nms_" + tag], g["per_im_" + tag] = nms_t, per_im
+        g["out_scores_" + tag], g["out_boxes_" + tag] = s_out, b_out
+        g["cls_count_" + tag] = np.array([len(cls_boxes[j]) for j in range(Kd)], dtype=np.int32)
+    assert len(g["out_scores_a"]) >= 100 and len(g["out_scores_c"]) > len(g["out_scores_a"])
+    np.savez_compressed(os.path.join(HERE, "box_results.npz"), **g)
+    cfg.MODEL.NUM_CLASSES = K
+
     # ---- RoIAlign: the reference is a CUDA kernel (not runnable here).  Loose
     # CPU anchor: torchvision aligned=False implements the same Caffe2 formula.
     import torchvision

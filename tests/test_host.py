@@ -96,15 +96,19 @@ def test_anchors_match_golden(golden):
 def test_config_adapter():
     from vosdetectron_b200.config import RegionConfig, set_cfg, get_cfg
     ns = types.SimpleNamespace
-    rpn = lambda pre, post: ns(RPN_PRE_NMS_TOP_N=pre, RPN_POST_NMS_TOP_N=post, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=0)
+    rpn = lambda pre, post: ns(RPN_PRE_NMS_TOP_N=pre, RPN_POST_NMS_TOP_N=post, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=0,
+                               SCORE_THRESH=0.05, NMS=0.5, DETECTIONS_PER_IM=100, SOFT_NMS=ns(ENABLED=False),
+                               BBOX_VOTE=ns(ENABLED=False))
     cfg = ns(TRAIN=rpn(2000, 2000), TEST=rpn(1000, 1000),
              FPN=ns(RPN_MIN_LEVEL=2, RPN_MAX_LEVEL=6, ROI_MIN_LEVEL=2, ROI_MAX_LEVEL=5, ROI_CANONICAL_SCALE=224,
                     ROI_CANONICAL_LEVEL=4, RPN_COLLECT_SCALE=1, RPN_ANCHOR_START_SIZE=32, RPN_ASPECT_RATIOS=(0.5, 1, 2)),
-             BBOX_XFORM_CLIP=np.log(1000. / 16.), MODEL=ns(NUM_CLASSES=81),
+             BBOX_XFORM_CLIP=np.log(1000. / 16.), MODEL=ns(NUM_CLASSES=81, BBOX_REG_WEIGHTS=(10., 10., 5., 5.)),
              MRCNN=ns(RESOLUTION=28, THRESH_BINARIZE=0.5, CLS_SPECIFIC_MASK=True))
     rc = RegionConfig.from_cfg(cfg)
     assert rc.mode(True).pre_nms_topN == 2000 and rc.mode(False).post_nms_topN == 1000
     assert rc.collect_post_topN(False) == 1000 and rc.num_classes == 81
+    assert rc.test_nms == 0.5 and rc.test_detections_per_im == 100 and rc.test_num_det_per_class == 0
+    assert rc.bbox_reg_weights == (10., 10., 5., 5.) and not rc.test_soft_nms
     old = get_cfg()
     try:
         assert set_cfg(cfg).train.post_nms_topN == 2000 and get_cfg().test.pre_nms_topN == 1000

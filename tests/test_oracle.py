@@ -130,3 +130,17 @@ def test_roialign_oracle_threads_agree(orc, synth):
     a = orc.roi_align_forward(feats, rois, 7, 7, 0.125, 2, nthreads=1)
     b = orc.roi_align_forward(feats, rois, 7, 7, 0.125, 2, nthreads=4)
     assert np.array_equal(a, b)
+
+
+def test_box_results_golden(orc, golden):
+    """Box-head decode + box_results_with_nms_and_limit (lib/core/test.py:178-179, 733-797) against the
+    reference's own outputs."""
+    g = golden("box_results")
+    K = int(g["num_classes"])
+    pred = orc.box_decode(g["props"], g["deltas"], tuple(g["weights"]), np.array([192, 256], dtype=np.float32))
+    assert np.array_equal(pred, g["pred_boxes"])
+    for tag in "abc":
+        s, b, cls_boxes = orc.box_results_with_nms_and_limit(g["scores"], g["pred_boxes"], K, float(g["score_thresh"]),
+                                                            float(g["nms_" + tag]), int(g["per_im_" + tag]))
+        assert np.array_equal(s, g["out_scores_" + tag]) and np.array_equal(b, g["out_boxes_" + tag]), tag
+        assert [len(c) for c in cls_boxes[1:]] == g["cls_count_" + tag][1:].tolist()

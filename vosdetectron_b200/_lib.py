@@ -61,6 +61,11 @@ SIGNATURES = {
                                                ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
     "vosd_distribute": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
                                        vp, vp, vp, vp, vp]),
+    "vosd_bbox_transform": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_float,
+                                           ctypes.c_float, vp, vp]),
+    "vosd_box_results_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 3),
+    "vosd_box_results": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                        ctypes.c_float, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_size_t, vp]),
     "vosd_pack_mask_bits": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_longlong, vp, vp]),
     "vosd_paste_masks": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_float, vp, vp, vp]),

@@ -41,6 +41,14 @@ class RegionConfig:
     mrcnn_resolution: int = 28
     mrcnn_thresh_binarize: float = 0.5
     mrcnn_cls_specific_mask: bool = True
+    # TEST.* / MODEL.* read by box_results_with_nms_and_limit and im_detect_bbox (config.py:190,219,224,359,371,417)
+    test_score_thresh: float = 0.05
+    test_nms: float = 0.3
+    test_detections_per_im: int = 100
+    test_num_det_per_class: int = 0
+    test_soft_nms: bool = False
+    test_bbox_vote: bool = False
+    bbox_reg_weights: tuple = (10.0, 10.0, 5.0, 5.0)
 
     def mode(self, training):
         return self.train if training else self.test
@@ -68,6 +76,13 @@ class RegionConfig:
             mrcnn_resolution=int(cfg.MRCNN.RESOLUTION),
             mrcnn_thresh_binarize=float(cfg.MRCNN.THRESH_BINARIZE),
             mrcnn_cls_specific_mask=bool(cfg.MRCNN.CLS_SPECIFIC_MASK),
+            test_score_thresh=float(cfg.TEST.SCORE_THRESH), test_nms=float(cfg.TEST.NMS),
+            test_detections_per_im=int(cfg.TEST.DETECTIONS_PER_IM),
+            # lib/core/test.py:785 reads TEST.NUM_DET_PER_CLASS, which lib/core/config.py never defines
+            # (it has NUM_DET_PER_CLASS_PRE / _POST, config.py:948-949): absent means 0 here
+            test_num_det_per_class=int(getattr(cfg.TEST, "NUM_DET_PER_CLASS", 0) or 0),
+            test_soft_nms=bool(cfg.TEST.SOFT_NMS.ENABLED), test_bbox_vote=bool(cfg.TEST.BBOX_VOTE.ENABLED),
+            bbox_reg_weights=tuple(float(x) for x in cfg.MODEL.BBOX_REG_WEIGHTS),
         )
 
 

@@ -1,5 +1,5 @@
-"""Drop-in for segm_results (lib/core/test.py:801-855; identical copy in
-lib_vos/tools/vos_test.py:867-921).
+"""Drop-ins for segm_results (lib/core/test.py:801-855; identical copy in
+lib_vos/tools/vos_test.py:867-921) and box_results_with_nms_and_limit (lib/core/test.py:733-797).
 
 ``segm_results(cls_boxes, masks, ref_boxes, im_h, im_w)`` keeps the reference signature and
 returns ``cls_segms``: per class a list of COCO RLE dicts.  The expand / resize / threshold /
@@ -17,6 +17,40 @@ try:                                     # pragma: no cover - optional dependenc
     import pycocotools.mask as mask_util
 except Exception:                        # noqa: BLE001
     mask_util = None
+
+
+def box_results_with_nms_and_limit(scores, boxes, cfg=None):
+    """Drop-in for lib/core/test.py:733-797: ``scores`` (R,K), ``boxes`` (R,4K) ndarrays (or CUDA tensors) ->
+    ``(scores, boxes, cls_boxes)`` ndarrays, cls_boxes[j] = (n_j,5) [x1,y1,x2,y2,score].  One upload, four
+    launches (threshold + sort per class, IoU bitmask, greedy reduce, over-all-classes limit), one download."""
+    cfg = cfg or get_cfg()
+    if cfg.test_soft_nms or cfg.test_bbox_vote:
+        raise NotImplementedError("TEST.SOFT_NMS / TEST.BBOX_VOTE (off by default) are not implemented on the device")
+    K = cfg.num_classes
+    s = scores if isinstance(scores, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(scores, dtype=np.float32))
+    b = boxes if isinstance(boxes, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(boxes, dtype=np.float32))
+    R = int(s.shape[0])
+    assert s.shape[1] == K and b.shape[1] == 4 * K
+    cls_boxes = [[] for _ in range(K)]
+    if R == 0:
+        for j in range(1, K):
+            cls_boxes[j] = np.zeros((0, 5), dtype=np.float32)
+        return np.zeros((0,), np.float32), np.zeros((0, 4), np.float32), cls_boxes
+    dets, count, cls_count = ops.box_results_cuda(s.cuda()[None], b.cuda()[None], cfg.test_score_thresh, cfg.test_nms,
+                                                  cfg.test_detections_per_im, cap=R * (K - 1))
+    n = int(count[0].item())
+    d = dets[0, :n].cpu().numpy()
+    cc = cls_count[0].cpu().numpy()
+    start = 0
+    for j in range(1, K):
+        cls_boxes[j] = d[start:start + cc[j], :5].copy()
+        start += int(cc[j])
+    if cfg.test_num_det_per_class > 0:                       # test.py:785-788
+        for j in range(1, K):
+            keep = np.argsort(-cls_boxes[j][:, -1])[:cfg.test_num_det_per_class]
+            cls_boxes[j] = cls_boxes[j][keep, :]
+    im_results = np.vstack([cls_boxes[j] for j in range(1, K)])
+    return im_results[:, -1], im_results[:, :-1], cls_boxes
 
 
 def rle_encode(mask):

@@ -208,7 +208,8 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ count,
 // a time: resolve the chunk against itself sequentially, then OR the rows of its survivors
 // into the running `removed` bitmap.
 //   mode 0: write [img, box] / score of the first `post` kept boxes (proposal path);
-//   mode 1: set keep_flag[orig_index[pos]] for every kept box (standalone nms).
+//   mode 1: set keep_flag[orig_index[pos]] for every kept box (standalone nms);
+//   mode 2: as 1 with orig_index / keep_flag laid out per segment (class-segmented nms, detections.cuh).
 constexpr int kMaxWords = VOSD_MAX_TOPK / 64;
 __global__ void __launch_bounds__(32)
 nms_reduce_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
@@ -227,6 +228,7 @@ nms_reduce_kernel(const float4* __restrict__ boxes, const float* __restrict__ sc
     const unsigned long long* mrow = mask + (size_t)seg * seg_stride * words_per_row;
     const int limit = post > 0 ? post : n;
     const float img = (float)(seg % num_images);
+    if (mode == 2) { orig_index += (size_t)seg * seg_stride; keep_flag += (size_t)seg * seg_stride; }   // per-segment flags
     for (int w = lane; w < nblk; w += 32) removed[w] = 0;
     __syncwarp();
     int kept_total = 0;
@@ -303,6 +305,7 @@ nms_reduce_warp_kernel(const float4* __restrict__ boxes, const float* __restrict
     const unsigned long long* mrow = mask + (size_t)seg * seg_stride * words_per_row;
     const int limit = post > 0 ? post : n;
     const float img = (float)(seg % num_images);
+    if (mode == 2) { orig_index += (size_t)seg * seg_stride; keep_flag += (size_t)seg * seg_stride; }   // per-segment flags
     unsigned long long rem = 0;          // removed bits of word `lane`
     int kept_total = 0;
     for (int c = 0; c < nblk && kept_total < limit; c++) {
@@ -643,3 +646,5 @@ extern "C" int vosd_nms(const float* dets, int n, float thresh, int64_t* keep, i
     count_launch(4);
     return check_launch();
 }
+
+#include "detections.cuh"

@@ -247,6 +247,47 @@ def distribute_cuda(rois, k_min=2, k_max=5, canonical_scale=224.0, canonical_lev
     return level[:R], lc, order[:R], restore[:R]
 
 
+# ----------------------------------------------------------------------------- box head post-processing
+def bbox_transform_cuda(boxes, deltas, weights=(1.0, 1.0, 1.0, 1.0), clip_hw=None):
+    """boxes (n,4), deltas (n,4k) -> pred_boxes (n,4k): box_utils.bbox_transform (boxes.py:156-205) and, with
+    clip_hw = (h, w), clip_tiled_boxes (:138-153) -- the decode of im_detect_bbox (core/test.py:178-179)."""
+    b = _need_cuda(boxes, "boxes")
+    d = _need_cuda(deltas, "deltas")
+    if b.dim() != 2 or b.size(1) != 4 or d.dim() != 2 or d.size(0) != b.size(0) or d.size(1) % 4:
+        raise ValueError("boxes must be (n,4) and deltas (n,4k)")
+    out = torch.empty_like(d)
+    w = (ctypes.c_float * 4)(*[float(x) for x in weights])
+    ch, cw = (float(clip_hw[0]), float(clip_hw[1])) if clip_hw is not None else (-1.0, -1.0)
+    _bind(b)
+    _lib.call("vosd_bbox_transform", _ptr(b), _ptr(d), b.size(0), d.size(1) // 4, w, ch, cw, _ptr(out), _stream())
+    return out
+
+
+def box_results_cuda(scores, boxes, score_thresh=0.05, nms_thresh=0.3, max_per_image=100, rows=None, cap=None):
+    """scores (N,R,K), boxes (N,R,4K) -> (dets (N,cap,6) [x1,y1,x2,y2,score,class], count (N,), cls_count (N,K)):
+    box_results_with_nms_and_limit (core/test.py:733-797) for N images in four launches, nothing leaves the device.
+    ``count`` can exceed ``cap`` (rows beyond it are dropped): pass cap=R*(K-1) for the lossless worst case."""
+    s = _need_cuda(scores, "scores")
+    b = _need_cuda(boxes, "boxes")
+    if s.dim() != 3 or b.dim() != 3 or b.shape[:2] != s.shape[:2] or b.size(2) != 4 * s.size(2):
+        raise ValueError("scores must be (N,R,K) and boxes (N,R,4K)")
+    N, R, K = (int(v) for v in s.shape)
+    if cap is None:
+        cap = min(R * (K - 1), 4 * max_per_image) if max_per_image > 0 else R * (K - 1)
+    cap = max(int(cap), 1)
+    dev = s.device
+    dets = torch.zeros((N, cap, 6), dtype=torch.float32, device=dev)
+    count = torch.empty((N,), dtype=torch.int32, device=dev)
+    cls_count = torch.empty((N, K), dtype=torch.int32, device=dev)
+    r = None if rows is None else _need_cuda(rows, "rows", torch.int32)
+    _bind(s)
+    nbytes = int(_lib.load().vosd_box_results_workspace_bytes(N, R, K))
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    _lib.call("vosd_box_results", _ptr(s), _ptr(b), _ptr(r), N, R, K, float(score_thresh), float(nms_thresh),
+              int(max_per_image), cap, _ptr(dets), _ptr(count), _ptr(cls_count), _ptr(ws), nbytes, _stream())
+    return dets, count, cls_count
+
+
 # ----------------------------------------------------------------------------- paste
 def paste_masks_cuda(masks, cls, ref_boxes, im_h, im_w, thresh=0.5, want_prob=False):
     """masks (R,K,M,M), cls (R) int32 or None, ref_boxes (R,4) -> uint8 (R,im_h,im_w)

@@ -136,3 +136,25 @@ def detections(seed, R=100, frame_hw=DAVIS_FRAME, M=28, K=81):
     noise = 0.3 * rs.standard_normal((R, K, M, M)).astype(np.float32)
     masks = (1.0 / (1.0 + np.exp(-(2.5 * up + noise)))).astype(np.float32)
     return boxes, cls, masks
+
+
+def box_head_outputs(seed, R=1000, K=81, im_hw=COCO_BLOB, fg_frac=0.25):
+    """Synthetic Fast R-CNN head outputs for one image: proposals (R,4) in image pixels (clustered, so per-class
+    NMS really suppresses), softmax scores (R,K) with ``fg_frac`` of the rows confident in one of ~12 classes
+    (distinct values: tie-free), box deltas (R,4K) ~ N(0, 0.5) / N(0, 0.25) as the RPN deltas."""
+    rs = np.random.RandomState(seed)
+    props = clustered_dets(seed + 1, R, im_hw, n_centres=max(8, R // 25))[:, :4].copy()
+    logits = rs.standard_normal((R, K)).astype(np.float64) * 0.5
+    logits[:, 0] += 3.0
+    fg = rs.uniform(size=R) < fg_frac
+    cls = rs.choice(np.arange(1, K), size=min(12, K - 1), replace=False)
+    which = cls[rs.randint(0, len(cls), R)]
+    logits[np.arange(R)[fg], which[fg]] += rs.uniform(3.0, 8.0, int(fg.sum()))
+    e = np.exp(logits - logits.max(1, keepdims=True))
+    scores = (e / e.sum(1, keepdims=True)).astype(np.float32)
+    # make every score distinct (tie-free ordering and image_thresh)
+    scores = (scores * (1.0 + 1e-4 * rs.permutation(R * K).reshape(R, K) / (R * K))).astype(np.float32)
+    d = np.empty((R, 4 * K), dtype=np.float32)
+    d[:, 0::4] = rs.normal(0, 0.5, (R, K)); d[:, 1::4] = rs.normal(0, 0.5, (R, K))
+    d[:, 2::4] = rs.normal(0, 0.25, (R, K)); d[:, 3::4] = rs.normal(0, 0.25, (R, K))
+    return props.astype(np.float32), scores, d

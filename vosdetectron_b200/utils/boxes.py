@@ -1,5 +1,7 @@
 """CUDA-backed subset of lib/utils/boxes.py with the reference's ndarray signatures.
 
+``bbox_transform(boxes, deltas, weights)`` replaces boxes.py:156-205 (one thread per (row, class)).
+
 ``nms(dets, thresh)`` replaces boxes.py:329-333 -> cython_nms.pyx:37-87: ndarray (n,5) float32
 in, int64 ndarray of kept indices (ascending) out, ``[]`` for empty input.  One H2D copy in,
 one D2H copy out; the work is done by the bitmask kernels of csrc/proposals.cu.
@@ -20,6 +22,15 @@ def nms(dets, thresh):
     keep, num = ops.nms_cuda(d, thresh)
     n = int(num.item())
     return keep[:n].cpu().numpy()
+
+
+def bbox_transform(boxes, deltas, weights=(1.0, 1.0, 1.0, 1.0)):
+    """boxes.py:156-205 with the reference's ndarray signature: (n,4) x (n,4k) -> (n,4k) float32."""
+    if boxes.shape[0] == 0:
+        return np.zeros((0, deltas.shape[1]), dtype=deltas.dtype)
+    b = torch.from_numpy(np.ascontiguousarray(boxes, dtype=np.float32)).cuda()
+    d = torch.from_numpy(np.ascontiguousarray(deltas, dtype=np.float32)).cuda()
+    return ops.bbox_transform_cuda(b, d, weights).cpu().numpy()
 
 
 def expand_boxes(boxes, scale):

@@ -127,6 +127,9 @@ __device__ __forceinline__ void store_chunk(uint8_t* __restrict__ out, float* __
 // visible part of the box, so the per-pixel work is 2 table loads, 4 mask loads and 6 flops -- no double
 // precision and no bounds checks in the pixel loop.
 struct __align__(16) AxisCoef { int i0, i1; float c0, c1; };      // value = S[i0]*c0 + S[i1]*c1
+// Column-table slot of entry j: one pad entry per 16, so that the lanes of a warp (16 entries apart: one
+// 16-pixel chunk each) read 128-bit entries from different bank groups.
+__device__ __forceinline__ int xpad(int j) { return j + (j >> 4); }
 
 // cv2 column table entry for destination x-offset dx (zeroes the far tap at the border)
 __device__ __forceinline__ AxisCoef cv2_x_coef(int dx, double scale, int S) {
@@ -153,8 +156,8 @@ paste_det_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
     extern __shared__ __align__(16) unsigned char smem[];
     const int S = M + 2;
     float* smask = reinterpret_cast<float*>(smem);                                   // [S*S]
-    AxisCoef* xt = reinterpret_cast<AxisCoef*>(smem + (((size_t)S * S * 4 + 15) & ~(size_t)15));   // [<= im_w]
-    AxisCoef* yt = xt + im_w;                                                         // [rows of this CTA]
+    AxisCoef* xt = reinterpret_cast<AxisCoef*>(smem + (((size_t)S * S * 4 + 15) & ~(size_t)15));   // [<= im_w, padded: xpad]
+    AxisCoef* yt = xt + im_w + im_w / 16 + 1;                                         // [rows of this CTA]
 
     const int r = blockIdx.y;
     const unsigned frame = (unsigned)im_h * (unsigned)im_w;
@@ -179,7 +182,7 @@ paste_det_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
         for (int x = xa + threadIdx.x; x < xb; x += 256) {
             AxisCoef e = cv2_x_coef(x - g.x0, g.sx, S);
             if (g.area2x) e = AxisCoef{2 * (x - g.x0), 2 * (x - g.x0) + 1, 0.5f, 0.5f};       // exact 2x shrink: INTER_AREA
-            xt[x - xa] = e;
+            xt[xpad(x - xa)] = e;
         }
         for (int y = ra + threadIdx.x; y < rb; y += 256) {
             AxisCoef e = cv2_y_coef(y - g.y0, g.sy, S);
@@ -198,30 +201,54 @@ paste_det_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
         }
         if (hit) {
             int y = (int)(f0 / (unsigned)im_w), x = (int)(f0 - (unsigned)y * (unsigned)im_w);
-            int done = 0;
-            while (done < 16) {                                       // runs never leave this detection's frame
-                const int run = min(16 - done, im_w - x);
-                const int x0r = max(xa, x), x1r = min(xb, x + run);
-                if (y >= ra && y < rb && x0r < x1r) {
+            if (x + 16 <= im_w) {
+                // the chunk lies in one image row (all but one chunk per row): fully unrolled, static bit positions;
+                // pixels outside [xa, xb) evaluate a clamped table entry and are masked out
+                if (y >= ra && y < rb && x < xb && x + 16 > xa) {
                     const AxisCoef ey = yt[y - ra];
                     const float* s0 = smask + ey.i0;
                     const float* s1 = smask + ey.i1;
-                    for (int xx = x0r; xx < x1r; xx++) {
-                        const AxisCoef ex = xt[xx - xa];
+                    const int last = xb - xa - 1;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int j = x + i - xa;
+                        const AxisCoef ex = xt[xpad(min(max(j, 0), last))];
                         const float r0 = __fadd_rn(__fmul_rn(s0[ex.i0], ex.c0), __fmul_rn(s0[ex.i1], ex.c1));
                         const float r1 = __fadd_rn(__fmul_rn(s1[ex.i0], ex.c0), __fmul_rn(s1[ex.i1], ex.c1));
                         const float v = __fadd_rn(__fmul_rn(r0, ey.c0), __fmul_rn(r1, ey.c1));
-                        const int i = done + (xx - x);
-                        if (v > thresh) {
-                            const unsigned long long bit = 1ull << (8 * (i & 7));
-                            if (i < 8) lo |= bit; else hi |= bit;
+                        const bool in = j >= 0 && j <= last;
+                        if (in && v > thresh) {
+                            if (i < 8) lo |= 1ull << (8 * i); else hi |= 1ull << (8 * (i - 8));
                         }
-                        if (kProb) pv[i] = v;
+                        if (kProb) pv[i] = in ? v : 0.f;
                     }
                 }
-                done += run;
-                x += run;
-                if (x >= im_w) { x = 0; ++y; }
+            } else {
+                int done = 0;
+                while (done < 16) {                                   // runs never leave this detection's frame
+                    const int run = min(16 - done, im_w - x);
+                    const int x0r = max(xa, x), x1r = min(xb, x + run);
+                    if (y >= ra && y < rb && x0r < x1r) {
+                        const AxisCoef ey = yt[y - ra];
+                        const float* s0 = smask + ey.i0;
+                        const float* s1 = smask + ey.i1;
+                        for (int xx = x0r; xx < x1r; xx++) {
+                            const AxisCoef ex = xt[xpad(xx - xa)];
+                            const float r0 = __fadd_rn(__fmul_rn(s0[ex.i0], ex.c0), __fmul_rn(s0[ex.i1], ex.c1));
+                            const float r1 = __fadd_rn(__fmul_rn(s1[ex.i0], ex.c0), __fmul_rn(s1[ex.i1], ex.c1));
+                            const float v = __fadd_rn(__fmul_rn(r0, ey.c0), __fmul_rn(r1, ey.c1));
+                            const int i = done + (xx - x);
+                            if (v > thresh) {
+                                const unsigned long long bit = 1ull << (8 * (i & 7));
+                                if (i < 8) lo |= bit; else hi |= bit;
+                            }
+                            if (kProb) pv[i] = v;
+                        }
+                    }
+                    done += run;
+                    x += run;
+                    if (x >= im_w) { x = 0; ++y; }
+                }
             }
         }
         const uint32_t packed[4] = {(uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)};
@@ -331,7 +358,7 @@ extern "C" int vosd_paste_masks(const float* masks, const int* cls, const float*
         const unsigned bx = (unsigned)((frame / 16 + chunks_per_cta - 1) / chunks_per_cta);
         const int rows_per_cta = (chunks_per_cta * 16 + im_w - 1) / im_w + 2;
         const int S = mask_size + 2;
-        const size_t smem = (((size_t)S * S * 4 + 15) & ~(size_t)15) + (size_t)(im_w + rows_per_cta) * 16;
+        const size_t smem = (((size_t)S * S * 4 + 15) & ~(size_t)15) + (size_t)(im_w + im_w / 16 + 1 + rows_per_cta) * 16;
         if (smem > 200 * 1024) return VOSD_ERR_UNSUPPORTED;
         dim3 grid(bx, (unsigned)num_dets);
         if (out_prob) {

@@ -130,34 +130,52 @@ roialign_fwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
         // low = W-2, high = W-1 with weights 0 / 1: same value, and the high tap is always "next column".
         if (t.valid && t.low == t.high && W >= 2) e = Tap{W - 2, W - 1, 1.f, 0.f};
         sh.xtab[k] = e;
-    } else if (tid >= 128 && tid < 128 + kTeams * kSepMaxSlots) {
+    } else if (tid >= 128 && tid < 128 + kSepWarps * kSepMaxSlots) {
         // one elected lane per warp arrives (after __syncwarp): 32 arrivals on one address would serialise
         const int k = tid - 128;
         mbar_init((unsigned)__cvta_generic_to_shared(&sh.full[0][0]) + 8u * (unsigned)k, 1);
-        mbar_init((unsigned)__cvta_generic_to_shared(&sh.empty[0][0]) + 8u * (unsigned)k, T);
+        mbar_init((unsigned)__cvta_generic_to_shared(&sh.empty[0][0]) + 8u * (unsigned)k, 1);
     }
     for (int i = tid; i < kSepMaxRows * kSepWyStride; i += kSepThreads) sh.wy[i] = 0.f;
     __syncthreads();
-    int x_lo, tw, y_lo, th;
+    // Footprint.  The T column groups ("halves": output columns 7h .. 7h+6) are independent pipelines with their
+    // own column extent; the row extent is shared.  Every warp derives all of them (warp-uniform).
+    const int myhalf = (warp % kSepWarps) % T;          // consumer warp w and producer warp 4 + w serve half w % T
+    int xlo_h[T], tw_h[T];
+    int x_lo = 1 << 30, x_hi = -1, y_lo, th;
     {
-        int lo = 1 << 30, hi = -1, lo2 = 1 << 30, hi2 = -1;
-        for (int k = lane; k < 2 * PW; k += 32) {
-            const Tap t = sh.xtab[k];
-            if (t.low >= 0) { lo = min(lo, t.low); hi = max(hi, t.high); }
-        }
+        int lo2 = 1 << 30, hi2 = -1;
         if (lane < 2 * nph) {
             const Tap t = sh.ytab[lane];
             if (t.low >= 0) { lo2 = t.low; hi2 = t.high; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
             lo2 = min(lo2, __shfl_xor_sync(0xffffffffu, lo2, o));
             hi2 = max(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
         }
-        x_lo = lo; tw = hi - lo + 1; y_lo = lo2; th = hi2 - lo2 + 1;
+        y_lo = lo2; th = hi2 - lo2 + 1;
+#pragma unroll
+        for (int h = 0; h < T; h++) {
+            int lo = 1 << 30, hi = -1;
+            if (lane < 14) {
+                const Tap t = sh.xtab[14 * h + lane];
+                if (t.low >= 0) { lo = t.low; hi = t.high; }
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            lo = __shfl_sync(0xffffffffu, lo, 0); hi = __shfl_sync(0xffffffffu, hi, 0);
+            xlo_h[h] = lo; tw_h[h] = hi - lo + 1;
+            x_lo = min(x_lo, lo); x_hi = max(x_hi, hi);
+        }
     }
+    const int tw = x_hi - x_lo + 1;                     // whole RoI (<= 0: nothing valid)
+    int tw_max = 0;
+#pragma unroll
+    for (int h = 0; h < T; h++) tw_max = max(tw_max, tw_h[h]);
     const int slab0 = blockIdx.y * slabs_per_cta;
     const int nslab = min(slabs_per_cta, channels / kSlab - slab0);
     float* __restrict__ out_roi = top + ((size_t)row * channels + (size_t)slab0 * kSlab) * bins + ph_begin * PW;
@@ -171,7 +189,7 @@ roialign_fwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
         }
         return;
     }
-    if (tw > 32 || th > kSepMaxRows || W < 2) {
+    if (tw_max > 32 || th > kSepMaxRows || W < 2) {
         // footprint beyond the ring: direct gather, the reference's arithmetic element by element
         const float* fbase = lv.data[level] + ((size_t)g.batch * channels + (size_t)slab0 * kSlab) * H * W;
         for (int e = tid; e < nslab * kSlab * group_bins; e += kSepThreads) {
@@ -196,15 +214,21 @@ roialign_fwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
         return;
     }
 
-    // ---- ring geometry (same for every team of the CTA).  Every tap reads a column the producers write:
-    //      valid samples lie inside the footprint by construction, invalid ones (weight 0) read columns 0, 1.
+    // ---- ring geometry of this warp's half.  Every tap reads a column the producer writes: valid samples lie
+    //      inside the half's footprint by construction, invalid ones (weight 0) read columns 0, 1.
+    int hx = 0, htw = 0;
+#pragma unroll
+    for (int h = 0; h < T; h++) if (h == myhalf) { hx = xlo_h[h]; htw = tw_h[h]; }
+    const bool half_empty = htw <= 0;                   // no valid sample column in this half: its outputs are 0
+    const int th_my = half_empty ? 0 : th;
+    if (half_empty) { hx = x_lo; htw = 2; }
     const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(lv.data[level]) & 15) == 0 &&
-                     tw + (x_lo & 3) <= 32;             // 128-bit staging: tile origin aligned down to 4 texels
-    const int x0 = vec ? (x_lo & ~3) : x_lo;
-    const int twt = x_lo + tw - x0;                     // tile columns in use (>= 2)
+                     htw + (hx & 3) <= 32;              // 128-bit staging: tile origin aligned down to 4 texels
+    const int x0 = vec ? (hx & ~3) : hx;
+    const int twt = hx + htw - x0;                      // tile columns in use (>= 2)
     const int cols = vec ? ((twt + 3) & ~3) : twt;
     const int slot_bytes = cols * kSepColBytes;
-    const int NS = min(kSepMaxSlots, T * kSepRingBytes / slot_bytes);
+    const int NS = min(kSepMaxSlots, kSepRingBytes / slot_bytes);
     const unsigned dyn_s = (unsigned)__cvta_generic_to_shared(sep_dyn);
     const size_t plane = (size_t)H * W;
     const int slab_end = slab0 + nslab;
@@ -213,9 +237,9 @@ roialign_fwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
         // =========================== PRODUCER ===========================
         // 4 streams per CTA, one per producer warp; stream q = (team, phase) feeds rows r = phase,
         // phase + nphase, ... of the team's flat row sequence (slab k = r / th, texel row y = r % th).
-        constexpr int nphase = T;                       // T = 1: 4 teams x 1, T = 2: 2 x 2, T = 4: 1 x 4
+        constexpr int nphase = 1;                       // producer q feeds consumer warp q: slab lane q / T, half q % T
         const int q = warp - kSepWarps;
-        const int pteam = q / nphase;
+        const int pteam = q / T;
         const float* f_img = lv.data[level] + ((size_t)g.batch * channels + (size_t)(slab0 + pteam) * kSlab) * plane +
                              (size_t)y_lo * W + x0;
         // per-lane staging map
@@ -244,11 +268,10 @@ roialign_fwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
         }
         const bool active2 = vec && 4 * ((lane & 3) + 4) < twt;
         const int nsl = pteam < nslab ? (nslab - pteam + kTeams - 1) / kTeams : 0;
-        const int rows = nsl * th;                      // rows of the team's flat sequence
+        const int rows = nsl * th_my;                   // rows of the stream's flat sequence
         const size_t kstep = (size_t)kTeams * kSlab * plane;
         // cursor of the next row to request
-        int nr = q % nphase, nk = 0, ny = nr;
-        while (ny >= th) { ny -= th; nk++; }
+        int nr = 0, nk = 0, ny = 0;
         float v[4][16];                                 // 4 register sets of 16 floats
         // loads of chunk `ch` (0: columns 0..15 / channels 0..15, 1: the rest) of row (k, y) into set b
         auto load_set = [&](int b, int k, int y, int ch) {
@@ -287,12 +310,12 @@ roialign_fwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
                     if (i < nld) sts_f32(a + 4u * (unsigned)i, v[b][i]);
             }
         };
-        const unsigned full_s = (unsigned)__cvta_generic_to_shared(&sh.full[pteam][0]);
-        const unsigned empty_s = (unsigned)__cvta_generic_to_shared(&sh.empty[pteam][0]);
-        const unsigned ring_s = dyn_s + (unsigned)(pteam * T) * kSepRingBytes;
+        const unsigned full_s = (unsigned)__cvta_generic_to_shared(&sh.full[q][0]);
+        const unsigned empty_s = (unsigned)__cvta_generic_to_shared(&sh.empty[q][0]);
+        const unsigned ring_s = dyn_s + (unsigned)q * kSepRingBytes;
         auto advance = [&]() {
-            nr += nphase; ny += nphase;
-            while (ny >= th) { ny -= th; nk++; }
+            nr += nphase;
+            if (++ny == th) { ny = 0; nk++; }
         };
         if (!wide) {
             // one set per row: 4 rows of the stream in flight
@@ -352,8 +375,14 @@ roialign_fwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
     // per-column x taps and Wy, built by the consumers while the producers already request rows
     if (tid < PW) {
         const Tap t0 = sh.xtab[2 * tid], t1 = sh.xtab[2 * tid + 1];
-        sh.xoff[tid][0] = t0.low >= 0 ? (t0.low - x0) * kSepColBytes : 0;
-        sh.xoff[tid][1] = t1.low >= 0 ? (t1.low - x0) * kSepColBytes : 0;
+        // origin of the tile of this column's half (same rule as `x0` above)
+        int ox = 0, otw = 0;
+#pragma unroll
+        for (int h = 0; h < T; h++) if (h == tid / 7) { ox = xlo_h[h]; otw = tw_h[h]; }
+        const bool ovec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(lv.data[level]) & 15) == 0 && otw + (ox & 3) <= 32;
+        if (ovec) ox &= ~3;
+        sh.xoff[tid][0] = t0.low >= 0 ? (t0.low - ox) * kSepColBytes : 0;
+        sh.xoff[tid][1] = t1.low >= 0 ? (t1.low - ox) * kSepColBytes : 0;
         sh.xw[tid][0] = t0.low >= 0 ? t0.h : 0.f; sh.xw[tid][1] = t0.low >= 0 ? t0.l : 0.f;
         sh.xw[tid][2] = t1.low >= 0 ? t1.h : 0.f; sh.xw[tid][3] = t1.low >= 0 ? t1.l : 0.f;
     } else if (tid >= 32 && tid < 32 + nph) {
@@ -370,10 +399,10 @@ roialign_fwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
     }
     asm volatile("bar.sync 15, %0;" :: "n"(32 * kSepWarps) : "memory");
     const int team = warp / T, sub = warp % T;
-    const unsigned ring_s = dyn_s + (unsigned)(team * T) * kSepRingBytes;
+    const unsigned ring_s = dyn_s + (unsigned)warp * kSepRingBytes;
     float* obuf = reinterpret_cast<float*>(sep_dyn + kSepWarps * kSepRingBytes) + team * (kSlab * kObufStride);
-    const unsigned full_s = (unsigned)__cvta_generic_to_shared(&sh.full[team][0]);
-    const unsigned empty_s = (unsigned)__cvta_generic_to_shared(&sh.empty[team][0]);
+    const unsigned full_s = (unsigned)__cvta_generic_to_shared(&sh.full[warp][0]);
+    const unsigned empty_s = (unsigned)__cvta_generic_to_shared(&sh.empty[warp][0]);
     unsigned a0[7], a1[7];
     float xw[7][4];
 #pragma unroll
@@ -393,7 +422,7 @@ roialign_fwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
 #pragma unroll
             for (int i = 0; i < 7; i++) acc[p][i] = 0.f;
         unsigned wy_a = wy_s;
-        for (int y = 0; y < th; y++) {
+        for (int y = 0; y < th_my; y++) {
             mbar_wait(full_s + 8u * (unsigned)slot, parity);
             const float4 q0 = lds_v4(wy_a), q1 = lds_v4(wy_a + 16);
             const float wy[7] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z};

@@ -486,8 +486,8 @@ constexpr size_t sep_dyn_bytes() {
 // element: ~10x fewer L2 atomic operations for the FPN level assignment.
 //   * COMPUTE warps 0..3 (teams of T): lanes = channels, g[7][7] = the slab's top_diff of the warp's 7 output
 //     columns in registers; per texel row 49 FMAs -> U[7], then per tile column 7 FMAs with the column's A
-//     weights (two broadcast 128-bit loads) -> slot[x][c].  Warps sub > 0 of a team add their partial sums
-//     into the slot behind a team barrier.
+//     weights (two broadcast 128-bit loads) -> slot[x][c].  Each group of 7 output columns is its own
+//     compute -> flush pipeline with its own tile; the partial gradients meet in the map through the reductions.
 //   * FLUSH warps 4..7 (one per stream, as the forward's producers) drain finished slots into the gradient
 //     map with reductions, lanes along x (coalesced), fire-and-forget.
 //   * the same FULL / EMPTY mbarrier ring as the forward, roles swapped.
@@ -548,7 +548,7 @@ roialign_bwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
         const int k = tid - 64;
         const AxisTap t = axis_tap(sample_coord(g.start_w, g.bin_w, k >> 1, k & 1, 2), W);
         sh.xtab[k] = Tap{t.valid ? t.low : -1, t.high, t.l, t.h};
-    } else if (tid >= 128 && tid < 128 + kTeams * kSepMaxSlots) {
+    } else if (tid >= 128 && tid < 128 + kSepWarps * kSepMaxSlots) {
         const int k = tid - 128;
         mbar_init((unsigned)__cvta_generic_to_shared(&sh.full[0][0]) + 8u * (unsigned)k, 1);
         mbar_init((unsigned)__cvta_generic_to_shared(&sh.empty[0][0]) + 8u * (unsigned)k, 1);
@@ -568,26 +568,44 @@ roialign_bwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
         cp_async_commit();
     }
     __syncthreads();
-    int x_lo, tw, y_lo, th;
+    // Footprint: shared row extent, one column extent per group of 7 output columns ("half"), each half being an
+    // independent compute -> flush pipeline (its partial gradients meet in the map through the reductions).
+    const int myhalf = (warp % kSepWarps) % T;
+    int xlo_h[T], tw_h[T];
+    int x_lo = 1 << 30, x_hi = -1, y_lo, th;
     {
-        int lo = 1 << 30, hi = -1, lo2 = 1 << 30, hi2 = -1;
-        for (int k = lane; k < 2 * PW; k += 32) {
-            const Tap t = sh.xtab[k];
-            if (t.low >= 0) { lo = min(lo, t.low); hi = max(hi, t.high); }
-        }
+        int lo2 = 1 << 30, hi2 = -1;
         if (lane < 2 * nph) {
             const Tap t = sh.ytab[lane];
             if (t.low >= 0) { lo2 = t.low; hi2 = t.high; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
             lo2 = min(lo2, __shfl_xor_sync(0xffffffffu, lo2, o));
             hi2 = max(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
         }
-        x_lo = lo; tw = hi - lo + 1; y_lo = lo2; th = hi2 - lo2 + 1;
+        y_lo = lo2; th = hi2 - lo2 + 1;
+#pragma unroll
+        for (int h = 0; h < T; h++) {
+            int lo = 1 << 30, hi = -1;
+            if (lane < 14) {
+                const Tap t = sh.xtab[14 * h + lane];
+                if (t.low >= 0) { lo = t.low; hi = t.high; }
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            lo = __shfl_sync(0xffffffffu, lo, 0); hi = __shfl_sync(0xffffffffu, hi, 0);
+            xlo_h[h] = lo; tw_h[h] = hi - lo + 1;
+            x_lo = min(x_lo, lo); x_hi = max(x_hi, hi);
+        }
     }
+    const int tw = x_hi - x_lo + 1;
+    int tw_max = 0;
+#pragma unroll
+    for (int h = 0; h < T; h++) tw_max = max(tw_max, tw_h[h]);
     const int slab0 = blockIdx.y * slabs_per_cta;
     const int nslab = min(slabs_per_cta, channels / kSlab - slab0);
     const float* __restrict__ top_roi = top_diff + ((size_t)row * channels + (size_t)slab0 * kSlab) * bins + ph_begin * PW;
@@ -595,7 +613,7 @@ roialign_bwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
     const size_t plane = (size_t)H * W;
 
     if (tw <= 0 || th <= 0) return;                     // no valid sample: no gradient
-    if (tw > 32 || th > kSepMaxRows) {
+    if (tw_max > 32 || th > kSepMaxRows) {
         // footprint beyond the ring: the reference's scatter, element by element
         float* gbase = lv.data[level] + ((size_t)g.batch * channels + (size_t)slab0 * kSlab) * plane;
         for (int e = tid; e < nslab * kSlab * group_bins; e += kSepThreads) {
@@ -618,22 +636,28 @@ roialign_bwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
         return;
     }
 
+    int hx = 0, htw = 0;
+#pragma unroll
+    for (int h = 0; h < T; h++) if (h == myhalf) { hx = xlo_h[h]; htw = tw_h[h]; }
+    const bool half_empty = htw <= 0;                   // no valid sample column in this half: nothing to add
+    const int th_my = half_empty ? 0 : th;
+    if (half_empty) { hx = x_lo; htw = 1; }
     const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(lv.data[level]) & 15) == 0 &&
-                     tw + (x_lo & 3) <= 32;
-    const int x0 = vec ? (x_lo & ~3) : x_lo;
-    const int twt = x_lo + tw - x0;
+                     htw + (hx & 3) <= 32;
+    const int x0 = vec ? (hx & ~3) : hx;
+    const int twt = hx + htw - x0;
     const int cols = vec ? ((twt + 3) & ~3) : twt;
     const int slot_bytes = cols * kSepColBytes;
-    const int NS = min(kSepMaxSlots, T * kSepBwdRingBytes / slot_bytes);
+    const int NS = min(kSepMaxSlots, kSepBwdRingBytes / slot_bytes);
     const unsigned dyn_s = (unsigned)__cvta_generic_to_shared(sep_dyn);
     const int slab_end = slab0 + nslab;
 
     if (warp >= kSepWarps) {
         // =========================== FLUSH ===========================
         // stream q = (team, phase): rows r = phase, phase + nphase, ... of the team's flat row sequence
-        constexpr int nphase = T;
+        constexpr int nphase = 1;                       // flusher q drains compute warp q: slab lane q / T, half q % T
         const int q = warp - kSepWarps;
-        const int pteam = q / nphase;
+        const int pteam = q / T;
         float* g_img = lv.data[level] + ((size_t)g.batch * channels + (size_t)(slab0 + pteam) * kSlab) * plane +
                        (size_t)y_lo * W + x0;
         unsigned ssrc;
@@ -659,13 +683,12 @@ roialign_bwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
             nst = xwl == 3 ? 8 : 16;
         }
         const int nsl = pteam < nslab ? (nslab - pteam + kTeams - 1) / kTeams : 0;
-        const int rows = nsl * th;
+        const int rows = nsl * th_my;
         const size_t kstep = (size_t)kTeams * kSlab * plane;
-        const unsigned full_s = (unsigned)__cvta_generic_to_shared(&sh.full[pteam][0]);
-        const unsigned empty_s = (unsigned)__cvta_generic_to_shared(&sh.empty[pteam][0]);
-        const unsigned ring_s = dyn_s + (unsigned)(pteam * T) * kSepBwdRingBytes;
-        int r = q % nphase, k = 0, y = r;
-        while (y >= th) { y -= th; k++; }
+        const unsigned full_s = (unsigned)__cvta_generic_to_shared(&sh.full[q][0]);
+        const unsigned empty_s = (unsigned)__cvta_generic_to_shared(&sh.empty[q][0]);
+        const unsigned ring_s = dyn_s + (unsigned)q * kSepBwdRingBytes;
+        int r = 0, k = 0, y = 0;
         const int nchunk = (vec ? twt > 16 : xwl == 5) ? 2 : 1;
         for (; r < rows; r += nphase) {
             const int slot = r % NS, use = r / NS;
@@ -692,21 +715,25 @@ roialign_bwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty_s + 8u * (unsigned)slot);
-            y += nphase;
-            while (y >= th) { y -= th; k++; }
+            if (++y == th) { y = 0; k++; }
         }
         return;
     }
 
     // =========================== COMPUTE ===========================
     if (tid < PW) {
-        // thread = output column: its two samples enter <= 4 tile columns
+        // thread = output column: its two samples enter <= 4 tile columns of its half's tile
+        int ox = 0, otw = 0;
+#pragma unroll
+        for (int h = 0; h < T; h++) if (h == tid / 7) { ox = xlo_h[h]; otw = tw_h[h]; }
+        const bool ovec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(lv.data[level]) & 15) == 0 && otw + (ox & 3) <= 32;
+        if (ovec) ox &= ~3;
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             const Tap t = sh.xtab[2 * tid + k];
             if (t.low >= 0) {
-                sh.ax[(t.low - x0) * (8 * T) + (tid / 7) * 8 + tid % 7] += t.h;
-                if (t.high != t.low) sh.ax[(t.high - x0) * (8 * T) + (tid / 7) * 8 + tid % 7] += t.l;
+                sh.ax[(t.low - ox) * (8 * T) + (tid / 7) * 8 + tid % 7] += t.h;
+                if (t.high != t.low) sh.ax[(t.high - ox) * (8 * T) + (tid / 7) * 8 + tid % 7] += t.l;
             }
         }
     } else if (tid >= 32 && tid < 32 + nph) {
@@ -722,10 +749,10 @@ roialign_bwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
     }
     asm volatile("bar.sync 15, %0;" :: "n"(32 * kSepWarps) : "memory");
     const int team = warp / T, sub = warp % T;
-    const unsigned ring_s = dyn_s + (unsigned)(team * T) * kSepBwdRingBytes;
+    const unsigned ring_s = dyn_s + (unsigned)warp * kSepBwdRingBytes;
     float* ibuf0 = reinterpret_cast<float*>(sep_dyn + kSepWarps * kSepBwdRingBytes) + (2 * team) * (kSlab * kIbufStride);
-    const unsigned full_s = (unsigned)__cvta_generic_to_shared(&sh.full[team][0]);
-    const unsigned empty_s = (unsigned)__cvta_generic_to_shared(&sh.empty[team][0]);
+    const unsigned full_s = (unsigned)__cvta_generic_to_shared(&sh.full[warp][0]);
+    const unsigned empty_s = (unsigned)__cvta_generic_to_shared(&sh.empty[warp][0]);
     const unsigned wy_s = (unsigned)__cvta_generic_to_shared(sh.wy);
     const unsigned ax_s = (unsigned)__cvta_generic_to_shared(sh.ax) + 32u * (unsigned)sub;
     const int run = nph * PW;
@@ -766,7 +793,7 @@ roialign_bwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
         }
         if (contiguous) buf ^= 1;
         unsigned wy_a = wy_s;
-        for (int y = 0; y < th; y++) {
+        for (int y = 0; y < th_my; y++) {
             const float4 q0 = lds_v4(wy_a), q1 = lds_v4(wy_a + 16);
             const float wy[7] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z};
             float u[7];
@@ -777,29 +804,20 @@ roialign_bwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
                 for (int p = 1; p < NPH; p++) a = fmaf(wy[p], gt[p][i], a);
                 u[i] = a;
             }
-            if (sub == 0) mbar_wait(empty_s + 8u * (unsigned)slot, parity ^ 1u);     // passes at once on the first use
+            mbar_wait(empty_s + 8u * (unsigned)slot, parity ^ 1u);     // passes at once on the first use
             unsigned dst = ring_s + c_off + (unsigned)lane * 4u;
             unsigned aw = ax_s;
-#pragma unroll 1
-            for (int t = 0; t < T; t++) {
-                // team order: sub 0 stores its partial sum, every later sub adds its own behind a barrier
-                if (t == sub) {
 #pragma unroll 4
-                    for (int x = 0; x < cols; x++) {
-                        const float4 w0 = lds_v4(aw), w1 = lds_v4(aw + 16);
-                        float v = fmaf(w0.w, u[3], fmaf(w0.z, u[2], fmaf(w0.y, u[1], w0.x * u[0])));
-                        const float v2 = fmaf(w1.z, u[6], fmaf(w1.y, u[5], w1.x * u[4]));
-                        v += v2;
-                        if (T > 1 && sub > 0) v += lds_off(dst);
-                        sts_f32(dst, v);
-                        dst += kSepColBytes;
-                        aw += 32 * T;
-                    }
-                }
-                if (T > 1) team_sync<T>(team);
+            for (int x = 0; x < cols; x++) {
+                const float4 w0 = lds_v4(aw), w1 = lds_v4(aw + 16);
+                float v = fmaf(w0.w, u[3], fmaf(w0.z, u[2], fmaf(w0.y, u[1], w0.x * u[0])));
+                const float v2 = fmaf(w1.z, u[6], fmaf(w1.y, u[5], w1.x * u[4]));
+                sts_f32(dst, v + v2);
+                dst += kSepColBytes;
+                aw += 32 * T;
             }
             __syncwarp();
-            if (sub == T - 1 && lane == 0) mbar_arrive(full_s + 8u * (unsigned)slot);
+            if (lane == 0) mbar_arrive(full_s + 8u * (unsigned)slot);
             wy_a += kSepWyStride * 4;
             c_off += slot_bytes;
             if (++slot == NS) { slot = 0; c_off = 0; parity ^= 1u; }

@@ -330,7 +330,8 @@ def gpu_arm(args, rank, world, local_rank):
     d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks = upload()
     torch.cuda.synchronize()
 
-    stage_names = ["proposals", "collect_distribute", "roialign_box", "mask_rois", "roialign_mask", "paste", "end"]
+    stage_names = ["proposals", "collect_distribute", "join_wait", "roialign_box", "mask_rois", "roialign_mask", "paste"]
+    pipe.overlap = not args.no_overlap
     events = []
 
     pending = []          # all-gathers in flight (N > 1): they overlap the next step's kernels
@@ -363,8 +364,8 @@ def gpu_arm(args, rank, world, local_rank):
     # ---- value: K steps, device-resident inputs ------------------------------------------
     def mark(name):
         e = torch.cuda.Event(enable_timing=True)
-        e.record()
-        events[-1].append((name, e))
+        e.record()              # on the current stream: the mask chain marks its own (second) stream
+        events[-1].append((name, e, torch.cuda.current_stream().cuda_stream))
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -386,10 +387,14 @@ def gpu_arm(args, rank, world, local_rank):
         ms = float(t.item())
     value = world * B * args.steps / (ms / 1000.0)
 
-    stage_ms = {n: 0.0 for n in stage_names[:-1]}
+    # stage duration = distance to the next mark on the SAME stream ("end" / "mask_end" close a chain)
+    stage_ms = {n: 0.0 for n in stage_names}
     for ev in events:
-        for (n0, a), (_, b) in zip(ev[:-1], ev[1:]):
-            stage_ms[n0] += a.elapsed_time(b)
+        for sid in {x[2] for x in ev}:
+            chain = [x for x in ev if x[2] == sid]
+            for (n0, a, _), (_, b, _) in zip(chain[:-1], chain[1:]):
+                if n0 in stage_ms:
+                    stage_ms[n0] += a.elapsed_time(b)
     stage_ms = {n: v / args.steps for n, v in stage_ms.items()}
 
     # ---- e2e: host buffers through HostPipeline (H2D + step + D2H per batch, 3 streams, 2 slots) ----
@@ -466,6 +471,8 @@ def gpu_arm(args, rank, world, local_rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(B), "frames_per_gpu": B, "global_frames_per_step": B * world,
                    "l2": "inputs larger than L2 (%.2f GB touched per step)" % (h2d_bytes / 1e9),
+                   "streams": ("2: proposal chain on a high-priority stream beside mask RoIAlign + paste, joined before the box RoIAlign"
+                               if pipe.overlap else "1"),
                    "parallelism": "frame-sharded x%d%s" % (world, ", all-gather of dets + bit-packed masks per step" if world > 1 else "")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
@@ -489,6 +496,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-gpu", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run the mask chain behind the box chain on one stream")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

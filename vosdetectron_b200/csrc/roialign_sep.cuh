@@ -77,6 +77,15 @@ __device__ __forceinline__ void mbar_init(unsigned a, int count) {
 __device__ __forceinline__ void mbar_arrive(unsigned a) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(a) : "memory");
 }
+// Bulk shared -> global store through the TMA engine (cp.async.bulk, non-tensor form): one instruction moves a
+// whole contiguous run without touching the LSU pipe.  L2 evict-first like the st.global.cs path it replaces.
+__device__ __forceinline__ void bulk_store_evict_first(void* gdst, unsigned ssrc, unsigned bytes) {
+    asm volatile("{\n\t.reg .b64 pol;\n\tcreatepolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
+                 "cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, pol;\n\t"
+                 "cp.async.bulk.commit_group;\n\t}" :: "l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(unsigned a, unsigned parity) {
     asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
                  "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" :: "r"(a), "r"(parity) : "memory");
@@ -448,18 +457,30 @@ roialign_fwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
         }
         // ---- epilogue: acc -> obuf[c][bin] (odd stride) -> contiguous streaming stores ----
         float* __restrict__ out_s = out_roi + (size_t)(s - slab0) * kSlab * bins;
-        team_sync<T>(team);                             // previous slab's obuf fully drained
+        const int run = nph * PW;
+        // whole slab contiguous (7x7 head): 32 * 49 floats, 16-byte aligned whenever `top` is
+        const bool bulk = T == 1 && run == bins && (reinterpret_cast<uintptr_t>(top) & 15) == 0;
+        if (bulk) {
+            if (lane == 0) bulk_store_wait_read();      // the previous slab's bulk store has read obuf
+            __syncwarp();
+        } else {
+            team_sync<T>(team);                         // previous slab's obuf fully drained
+        }
 #pragma unroll
         for (int p = 0; p < NPH; p++)
 #pragma unroll
             for (int i = 0; i < 7; i++)
                 obuf[lane * kObufStride + p * PW + 7 * sub + i] = acc[p][i];
+        if (bulk) {
+            // obuf[c][bin] with stride 49 IS the output layout: one TMA-engine bulk store per slab
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0)
+                bulk_store_evict_first(out_s, (unsigned)__cvta_generic_to_shared(obuf), kSlab * kRun * 4);
+            continue;
+        }
         team_sync<T>(team);
-        const int run = nph * PW;
-        if (T == 1 && run == bins) {
-            // whole slab contiguous (7x7 head): 32 * 49 floats
-            for (int i = lane; i < kSlab * kRun / 4; i += 32)
-                __stcs(reinterpret_cast<float4*>(out_s) + i, reinterpret_cast<const float4*>(obuf)[i]);
+        if (false) {
         } else {
             for (int i = lane + 32 * sub; i < kSlab * kRun; i += 32 * T) {
                 const int c = i / kRun, b = i - c * kRun;
@@ -467,6 +488,8 @@ roialign_fwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
             }
         }
     }
+    // a CTA must not retire (and hand its shared memory on) while a bulk store still reads obuf
+    if (T == 1 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 template <int T>

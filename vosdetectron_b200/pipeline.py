@@ -34,6 +34,8 @@ class RegionPipeline:
         self.anchors = {l: fpn_level_anchors(l, c.rpn_anchor_start_size, c.rpn_aspect_ratios, c.rpn_min_level)
                         for l in self.rpn_levels}
         self._ws = None
+        self.overlap = True
+        self._side = None
 
     # ---- stage 1: proposals -> top RoIs + FPN levels (rows of frame f are in group f) ----------
     def proposals(self, rpn, im_info, images_per_group=1, mark=None):
@@ -60,24 +62,11 @@ class RegionPipeline:
                                         self.sampling_ratio)
 
     # ---- whole step on device-resident inputs -------------------------------------------------
-    def step(self, rpn, im_info, feats, det_boxes, det_cls, det_masks, frame_hw, im_scale, mark=None):
-        """One batch of B frames.
-        det_boxes (B,D,4) original-frame coords, det_cls (B,D) int32, det_masks (B,D,K,M,M):
-        the box-head / mask-head outputs the pipeline sits between (synthetic in the benchmark).
-        ``mark(name)`` (optional) is called on the launching stream right before each stage
-        (bench.py records CUDA events there).  Returns dict of device tensors."""
+    def _mask_branch(self, feats, det_boxes, det_cls, det_masks, frame_hw, im_scale, mark):
+        """detections -> blob coords -> level -> mask RoIAlign (im_detect_mask, test.py:366-402), and the
+        paste of the mask-head output (segm_results, test.py:801-855)."""
         c = self.cfg
-        mark = mark or (lambda name: None)
         B, D = det_boxes.shape[:2]
-        mark("proposals")
-        prop = self.proposals(rpn, im_info, mark=mark)
-        post = prop["rois"].shape[1]
-        rois = prop["rois"].view(B * post, 5)
-        mark("roialign_box")
-        # rows beyond count[g] are zero boxes on frame 0 level k_min: harmless filler, masked by count
-        box_feats = self.roi_features(feats, rois, prop["level"].view(-1).clamp_(c.roi_min_level, c.roi_max_level),
-                                      self.box_resolution)
-        # mask branch: detections -> blob coords -> level -> RoIAlign (im_detect_mask, test.py:366-402)
         mark("mask_rois")
         frame_idx = torch.arange(B, device=det_boxes.device, dtype=torch.float32).view(B, 1, 1).expand(B, D, 1)
         mask_rois = torch.cat([frame_idx, det_boxes * im_scale], dim=2).view(B * D, 5).contiguous()
@@ -90,7 +79,63 @@ class RegionPipeline:
         pasted = ops.paste_masks_cuda(det_masks.view(B * D, K, M, M),
                                       det_cls.view(-1) if c.mrcnn_cls_specific_mask else None,
                                       det_boxes.view(B * D, 4), frame_hw[0], frame_hw[1], c.mrcnn_thresh_binarize)
+        mark("mask_end")
+        return mask_rois, mlevel, mask_feats, pasted
+
+    def step(self, rpn, im_info, feats, det_boxes, det_cls, det_masks, frame_hw, im_scale, mark=None, overlap=None):
+        """One batch of B frames.
+        det_boxes (B,D,4) original-frame coords, det_cls (B,D) int32, det_masks (B,D,K,M,M):
+        the box-head / mask-head outputs the pipeline sits between (synthetic in the benchmark).
+        ``mark(name)`` (optional) is called on the launching stream right before each stage
+        (bench.py records CUDA events there).  Returns dict of device tensors.
+
+        The step has two chains that only meet through the heads outside this library: proposals ->
+        collect -> box RoIAlign, and mask RoIs -> mask RoIAlign / paste.  The proposal chain is a
+        latency-bound sequence on a few SMs (one cluster per (level, frame) segment, one warp per
+        segment in the NMS reduce), so with ``overlap`` (default: ``self.overlap``) it runs on a second,
+        high-priority stream beside the mask chain and both join before the box RoIAlign, which then has
+        the GPU to itself."""
+        c = self.cfg
+        mark = mark or (lambda name: None)
+        overlap = self.overlap if overlap is None else overlap
+        B, D = det_boxes.shape[:2]
+        main = torch.cuda.current_stream()
+
+        def proposal_chain():
+            mark("proposals")
+            prop = self.proposals(rpn, im_info, mark=mark)
+            # rows beyond count[g] are zero boxes on frame 0 level k_min: harmless filler, masked by count
+            level = prop["level"].view(-1).clamp_(c.roi_min_level, c.roi_max_level)
+            mark("proposals_end")
+            return prop, level
+
+        if overlap:
+            # The proposal chain goes to a HIGH-PRIORITY second stream: its few CTAs (clusters of 8 per segment,
+            # one warp per segment in the NMS reduce) are placed ahead of the pending CTAs of the mask RoIAlign /
+            # paste kernels that fill the rest of the GPU from the caller's stream.
+            if self._side is None:
+                self._side = torch.cuda.Stream(det_boxes.device, priority=-1)
+            side = self._side
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                prop, level = proposal_chain()
+            # No record_stream on the side stream's tensors: it would park every freed block behind an event and
+            # make the caching allocator cudaMalloc fresh outputs each step.  Reuse is safe without it: the blocks
+            # are only re-allocated by the side stream, whose next use starts with wait_stream(main) above.
+            mask_rois, mlevel, mask_feats, pasted = self._mask_branch(feats, det_boxes, det_cls, det_masks,
+                                                                      frame_hw, im_scale, mark)
+            mark("join_wait")
+            main.wait_stream(side)
+        else:
+            prop, level = proposal_chain()
+        post = prop["rois"].shape[1]
+        rois = prop["rois"].view(B * post, 5)
+        mark("roialign_box")
+        box_feats = self.roi_features(feats, rois, level, self.box_resolution)
         mark("end")
+        if not overlap:
+            mask_rois, mlevel, mask_feats, pasted = self._mask_branch(feats, det_boxes, det_cls, det_masks,
+                                                                      frame_hw, im_scale, mark)
         return {"rois": prop["rois"], "roi_count": prop["count"], "roi_level": prop["level"],
                 "box_feats": box_feats, "mask_feats": mask_feats, "mask_rois": mask_rois, "mask_level": mlevel,
                 "masks": pasted.view(B, D, frame_hw[0], frame_hw[1])}

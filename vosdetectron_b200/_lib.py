@@ -8,7 +8,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvosd_b200.so")
+# VOSD_B200_LIB: A/B tuning builds (tools/ab_build.sh); the product is always the in-tree library
+LIB_PATH = os.environ.get("VOSD_B200_LIB") or os.path.join(HERE, "libvosd_b200.so")
 
 MAX_LEVELS = 8
 MAX_ANCHORS = 16

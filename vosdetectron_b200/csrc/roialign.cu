@@ -1217,7 +1217,10 @@ static int ml_fwd(const LevelTable& t, int channels, int ph, int pw, int sr, int
         const int slabs_all = channels / kSlab, rgroups = ceil_div(ph, nph);
         if (rgroups <= 65535) {
             // slabs per CTA: a multiple of the teams, few enough that the grid has >= ~12 CTAs per SM
-            long long spc = (long long)slabs_all * num_rois * rgroups / (12LL * kNumSMs);
+#ifndef VOSD_SEP_CTAS_PER_SM
+#define VOSD_SEP_CTAS_PER_SM 12
+#endif
+            long long spc = (long long)slabs_all * num_rois * rgroups / ((long long)VOSD_SEP_CTAS_PER_SM * kNumSMs);
             spc = spc / teams * teams;
             if (spc < teams) spc = teams;
             if (spc > slabs_all) spc = slabs_all;
@@ -1296,7 +1299,10 @@ static int ml_bwd(const LevelTable& t, int num_levels, int batch, int channels, 
         const int T = pw / 7, teams = kSepWarps / T;
         const int slabs_all = channels / kSlab, rgroups = ceil_div(ph, 7);
         if (rgroups <= 65535) {
-            long long spc = (long long)slabs_all * num_rois * rgroups / (12LL * kNumSMs);
+#ifndef VOSD_SEP_CTAS_PER_SM
+#define VOSD_SEP_CTAS_PER_SM 12
+#endif
+            long long spc = (long long)slabs_all * num_rois * rgroups / ((long long)VOSD_SEP_CTAS_PER_SM * kNumSMs);
             spc = spc / teams * teams;
             if (spc < teams) spc = teams;
             if (spc > slabs_all) spc = slabs_all;

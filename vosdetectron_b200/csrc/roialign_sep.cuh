@@ -40,6 +40,10 @@ constexpr int kSepThreads = 32 * (kSepWarps + kSepProducers);
 constexpr int kSepColBytes = 33 * 4;                   // pitch of a tile column: 33 words
 constexpr int kSepRingBytes = 16384;                   // per consumer warp: 7 slots of <= 16 columns .. 3 of 33
 constexpr int kSepMaxSlots = 8;
+#ifndef VOSD_SEP_SETS
+#define VOSD_SEP_SETS 4
+#endif
+constexpr int kSepSets = VOSD_SEP_SETS;                            // producer register sets of 16 floats (rows / half rows in flight)
 constexpr int kSepMaxRows = 48;                        // texel rows of a footprint (Wy table)
 constexpr int kSepWyStride = 8;                        // floats per Wy row (7 output rows per CTA, padded to 2 x 128 bit)
 
@@ -281,7 +285,7 @@ roialign_fwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
         const size_t kstep = (size_t)kTeams * kSlab * plane;
         // cursor of the next row to request
         int nr = 0, nk = 0, ny = 0;
-        float v[4][16];                                 // 4 register sets of 16 floats
+        float v[kSepSets][16];                          // register sets of 16 floats
         // loads of chunk `ch` (0: columns 0..15 / channels 0..15, 1: the rest) of row (k, y) into set b
         auto load_set = [&](int b, int k, int y, int ch) {
             const float* src = f_img + (size_t)k * kstep + (size_t)y * W;
@@ -327,17 +331,17 @@ roialign_fwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
             if (++ny == th) { ny = 0; nk++; }
         };
         if (!wide) {
-            // one set per row: 4 rows of the stream in flight
-            int rb[4];                                  // row held by set b
+            // one set per row: kSepSets rows of the stream in flight
+            int rb[kSepSets];                           // row held by set b
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
+            for (int b = 0; b < kSepSets; b++) {
                 rb[b] = nr;
                 if (nr < rows) load_set(b, nk, ny, 0);
                 advance();
             }
             while (rb[0] < rows) {
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
+                for (int b = 0; b < kSepSets; b++) {
                     if (rb[b] < rows) {
                         const int slot = rb[b] % NS, use = rb[b] / NS;
                         if (use > 0) mbar_wait(empty_s + 8u * (unsigned)slot, (unsigned)((use - 1) & 1));
@@ -351,17 +355,17 @@ roialign_fwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
                 }
             }
         } else {
-            // two sets per row: 2 rows of the stream in flight
-            int rb[2];
+            // two sets per row: kSepSets / 2 rows of the stream in flight
+            int rb[kSepSets / 2];                       // (an odd last set stays unused here)
 #pragma unroll
-            for (int b = 0; b < 2; b++) {
+            for (int b = 0; b < kSepSets / 2; b++) {
                 rb[b] = nr;
                 if (nr < rows) { load_set(2 * b, nk, ny, 0); load_set(2 * b + 1, nk, ny, 1); }
                 advance();
             }
             while (rb[0] < rows) {
 #pragma unroll
-                for (int b = 0; b < 2; b++) {
+                for (int b = 0; b < kSepSets / 2; b++) {
                     if (rb[b] < rows) {
                         const int slot = rb[b] % NS, use = rb[b] / NS;
                         if (use > 0) mbar_wait(empty_s + 8u * (unsigned)slot, (unsigned)((use - 1) & 1));

@@ -332,6 +332,7 @@ def gpu_arm(args, rank, world, local_rank):
 
     stage_names = ["proposals", "collect_distribute", "join_wait", "roialign_box", "mask_rois", "roialign_mask", "paste"]
     pipe.overlap = not args.no_overlap
+    pipe.packed_masks = world > 1          # all-gather payload, written by the paste kernel itself
     events = []
 
     pending = []          # all-gathers in flight (N > 1): they overlap the next step's kernels
@@ -343,7 +344,7 @@ def gpu_arm(args, rank, world, local_rank):
                 for w in pending.pop(0)[2]:
                     w.wait()
             dets = torch.cat([d_boxes, d_cls.unsqueeze(-1).float(), torch.ones_like(d_cls).unsqueeze(-1).float()], dim=2)
-            pending.append(all_gather_frames(dets, pack_mask_bits(out["masks"]), async_op=True))
+            pending.append(all_gather_frames(dets, out["masks_packed"], async_op=True))
         return out
 
     def drain():

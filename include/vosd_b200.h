@@ -220,6 +220,41 @@ VOSD_API int vosd_paste_masks(const float* masks, const int* cls, const float* r
                      int num_dets, int num_classes, int mask_size, int im_h, int im_w,
                      float thresh, uint8_t* out, float* out_prob, cudaStream_t stream);
 
+/* Same paste, with the result (also) as 1 bit per pixel: out_packed (R, ceil(im_h*im_w/8)) uint8, pixel 8j+k of a
+ * detection's frame -> bit k of byte j (LSB first; the layout of vosd_pack_mask_bits and the payload of the
+ * frame-sharded all-gather).  `out` (dense uint8, reference layout) may be NULL when im_h*im_w % 16 == 0: the
+ * kernel then writes 1/8 of the bytes.  Written by the paste kernel itself, no second pass over the dense masks. */
+VOSD_API int vosd_paste_masks_packed(const float* masks, const int* cls, const float* ref_boxes,
+                                     int num_dets, int num_classes, int mask_size, int im_h, int im_w,
+                                     float thresh, uint8_t* out, uint8_t* out_packed, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* Fused paste -> COCO RLE ("next" row).  Replaces the whole per-detection */
+/* body of segm_results INCLUDING `mask_util.encode(np.array(im_mask[:, :, np.newaxis],      */
+/* order='F'))[0]` (lib/core/test.py:814-848; copy lib_vos/tools/vos_test.py:880-914): the   */
+/* dense (im_h, im_w) canvas is never written.  pycocotools (third party, not vendored,      */
+/* unpinned: README.md:63-74) algorithm = common/maskApi.c rleEncode + rleToString.          */
+/*   inputs as vosd_paste_masks.  Per detection r:                                          */
+/*     run_arena[run_offset[r] .. + run_count[r]]  uint32 run lengths of the column-major    */
+/*       (Fortran-order) pixel sequence, first run = zeros (may be 0);                       */
+/*     str_arena[str_offset[r] .. + str_len[r]]    the 'counts' string of the RLE dict       */
+/*       (ASCII, not NUL-terminated);                                                        */
+/*     status[r] 0 ok, 1 run arena too small, 2 string arena too small (nothing written for  */
+/*       that detection; cursors still advance, so cursors[0] / cursors[1] = the capacities  */
+/*       a retry needs).                                                                     */
+/*   cursors: 2 x uint64 scratch, cleared by the call; arenas are caller-allocated; segments */
+/*   are reserved with one atomicAdd per detection, so their ORDER in the arena varies from  */
+/*   run to run while their contents do not.  Dynamic shared memory:                         */
+/*   vosd_paste_rle_smem_bytes(mask_size, im_h, im_w) must be <= 220 KB (1333x800 frames:    */
+/*   171 KB), else VOSD_ERR_UNSUPPORTED.                                                     */
+/* ------------------------------------------------------------------------------------ */
+VOSD_API size_t vosd_paste_rle_smem_bytes(int mask_size, int im_h, int im_w);
+VOSD_API int vosd_paste_rle(const float* masks, const int* cls, const float* ref_boxes,
+                            int num_dets, int num_classes, int mask_size, int im_h, int im_w, float thresh,
+                            uint32_t* run_arena, long long run_capacity, uint8_t* str_arena, long long str_capacity,
+                            unsigned long long* cursors, long long* run_offset, int* run_count,
+                            long long* str_offset, int* str_len, int* status, cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------------ */
 /* Box-head post-processing.                                */
 /* vosd_bbox_transform replaces the decode of im_detect_bbox (lib/core/test.py:166-181):  */

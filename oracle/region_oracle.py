@@ -370,5 +370,96 @@ def paste_masks(masks, cls, ref_boxes, im_h, im_w, thresh=0.5, cls_specific=True
     return (out, prob) if want_prob else out
 
 
+# --------------------------------------------------------------------------- #
+# COCO RLE (pycocotools): the last line of segm_results' loop body,
+#   rle = mask_util.encode(np.array(im_mask[:, :, np.newaxis], order='F'))[0]   (lib/core/test.py:843-846)
+# pycocotools is a third-party dependency the reference does not vendor or pin (README.md:63-74) and it is
+# absent from this image, so this is a restatement of its published algorithm, cocoapi common/maskApi.c:
+# rleEncode (runs of the column-major pixel sequence, the first run counts zeros), rleToString / rleFrString
+# (per run, for i > 2 the difference to the run two back; 5-bit groups, bit 5 = continuation, sign-extended
+# from bit 4 of the last group; + 48 to land in printable ASCII).  PARITY UNPINNED for the string form: no
+# golden vector is available offline; the tests pin it by round trip (rle_from_string . rle_to_string == id,
+# rle_decode . rle_counts == id) and against the dense paste, which IS pinned to the reference.
+# --------------------------------------------------------------------------- #
+def rle_counts(mask):
+    """maskApi.c rleEncode for one (h, w) uint8 mask: list of run lengths, Fortran order, zeros first."""
+    flat = np.asarray(mask, dtype=np.uint8).ravel(order='F')
+    counts, p, c = [], 0, 0
+    for v in flat.tolist():
+        if v != p:
+            counts.append(c)
+            c = 0
+            p = v
+        c += 1
+    counts.append(c)
+    return counts
+
+
+def rle_counts_fast(mask):
+    """Vectorised rle_counts (same result; the loop above is the restatement, this is for full-size frames)."""
+    flat = np.asarray(mask, dtype=np.uint8).ravel(order='F')
+    change = np.flatnonzero(flat[1:] != flat[:-1]) + 1
+    bounds = np.concatenate(([0], change, [flat.size]))
+    counts = np.diff(bounds).tolist()
+    if flat.size and flat[0] != 0:
+        counts = [0] + counts
+    return counts
+
+
+def rle_to_string(counts):
+    """maskApi.c rleToString."""
+    out = []
+    for i, x in enumerate(counts):
+        x = int(x)
+        if i > 2:
+            x -= int(counts[i - 2])
+        more = True
+        while more:
+            c = x & 0x1f
+            x >>= 5
+            more = (x != -1) if (c & 0x10) else (x != 0)
+            if more:
+                c |= 0x20
+            out.append(chr(c + 48))
+    return ''.join(out)
+
+
+def rle_from_string(s):
+    """maskApi.c rleFrString."""
+    counts, p = [], 0
+    while p < len(s):
+        x, k, more = 0, 0, True
+        while more:
+            c = ord(s[p]) - 48
+            x |= (c & 0x1f) << (5 * k)
+            more = bool(c & 0x20)
+            p += 1
+            k += 1
+            if not more and (c & 0x10):
+                x |= -1 << (5 * k)
+        if len(counts) > 2:
+            x += counts[-2]
+        counts.append(x)
+    return counts
+
+
+def rle_decode(counts, h, w):
+    """maskApi.c rleDecode: (h, w) uint8 mask from Fortran-order run lengths."""
+    flat = np.zeros(h * w, dtype=np.uint8)
+    p, v = 0, 0
+    for c in counts:
+        if v:
+            flat[p:p + c] = 1
+        p += c
+        v ^= 1
+    assert p == h * w
+    return flat.reshape((h, w), order='F')
+
+
+def rle_encode(mask):
+    h, w = mask.shape
+    return {'size': [int(h), int(w)], 'counts': rle_to_string(rle_counts_fast(mask))}
+
+
 def num_threads():
     return lib().orc_num_threads()

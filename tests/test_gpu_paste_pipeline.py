@@ -12,6 +12,16 @@ def _cu(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
+class _Ops:
+    """module-level `ops` for the tests below (imported lazily: collection must not need the .so)"""
+    def __getattr__(self, name):
+        from vosdetectron_b200 import ops as real
+        return getattr(real, name)
+
+
+ops = _Ops()
+
+
 def test_paste_golden(golden, orc):
     from vosdetectron_b200 import ops
     g = golden("paste")
@@ -159,3 +169,90 @@ def test_pack_mask_bits_matches_torch_reference():
         p = pack_mask_bits(m)
         assert torch.equal(p.cpu(), pack_mask_bits(m.cpu()))
         assert torch.equal(unpack_mask_bits(p, shape[-2], shape[-1]), m)
+
+
+def test_paste_packed_equals_packing_the_dense_paste(synth):
+    """vosd_paste_masks_packed: the 1-bit copy written by the paste kernel itself == pack_mask_bits(dense paste),
+    with and without the dense output, on the DAVIS frame (fast kernel) and an odd frame (flat kernel + packer)."""
+    from vosdetectron_b200.pipeline import pack_mask_bits
+    for (fh, fw), R in (((480, 854), 40), ((37, 53), 9)):
+        boxes, cls, masks = synth.detections(77, R, (fh, fw), 28, 5)
+        dense = ops.paste_masks_cuda(_cu(masks), _cu(cls), _cu(boxes), fh, fw, 0.5)
+        want = pack_mask_bits(dense)
+        d2, p2 = ops.paste_masks_packed_cuda(_cu(masks), _cu(cls), _cu(boxes), fh, fw, 0.5)
+        assert torch.equal(d2, dense) and torch.equal(p2, want)
+        if (fh * fw) % 16 == 0:
+            d3, p3 = ops.paste_masks_packed_cuda(_cu(masks), _cu(cls), _cu(boxes), fh, fw, 0.5, want_dense=False)
+            assert d3 is None and torch.equal(p3, want)
+        else:
+            with pytest.raises(Exception):
+                ops.paste_masks_packed_cuda(_cu(masks), _cu(cls), _cu(boxes), fh, fw, 0.5, want_dense=False)
+
+
+def _rle_check(orc, masks, cls, boxes, fh, fw):
+    dense = ops.paste_masks_cuda(_cu(masks), None if cls is None else _cu(cls), _cu(boxes), fh, fw, 0.5).cpu().numpy()
+    small = fh * fw < 4096          # tiny frames with noisy masks: worst-case arenas; else the defaults
+    out = ops.paste_rle_cuda(_cu(masks), None if cls is None else _cu(cls), _cu(boxes), fh, fw, 0.5,
+                             run_capacity=len(boxes) * (fh * fw + 2) if small else None,
+                             str_capacity=len(boxes) * 6 * (fh * fw + 2) if small else None)
+    assert int(out["status"].abs().max().item()) == 0
+    runs = out["runs"].cpu().numpy().view(np.uint32)
+    ro, rc = out["run_offset"].cpu().numpy(), out["run_count"].cpu().numpy()
+    chars = out["chars"].cpu().numpy().tobytes()
+    so, sl = out["str_offset"].cpu().numpy(), out["str_len"].cpu().numpy()
+    used = out["cursors"].cpu().numpy()
+    assert used[0] == rc.sum() and used[1] == sl.sum()
+    for i in range(len(boxes)):
+        want = orc.rle_counts_fast(dense[i])
+        got = runs[ro[i]:ro[i] + rc[i]].tolist()
+        assert got == want, (i, boxes[i], got[:8], want[:8])
+        s = chars[so[i]:so[i] + sl[i]].decode('ascii')
+        assert s == orc.rle_to_string(want)
+        assert np.array_equal(orc.rle_decode(orc.rle_from_string(s), fh, fw), dense[i])
+    return dense
+
+
+def test_paste_rle_matches_oracle_on_the_dense_paste(orc, synth, golden):
+    """vosd_paste_rle: run lengths and 'counts' strings == the oracle's rleEncode / rleToString of the dense paste
+    (which is pinned to the reference), bit for bit; decoding the string gives the dense mask back."""
+    g = golden("paste")
+    fh, fw = (int(v) for v in g["frame_hw"])
+    _rle_check(orc, g["masks"], g["cls"], g["boxes"], fh, fw)
+    boxes, cls, masks = synth.detections(31, 60, (480, 854), 28, 7)
+    _rle_check(orc, masks, cls, boxes, 480, 854)
+
+
+def test_paste_rle_edge_boxes(orc, synth):
+    """Boxes that miss the frame, cover it completely (all-ones mask: counts [0, HW]), touch the bottom but not the top
+    edge (the run continues into row 0 of the next column), touch only the top, a 1-pixel box; odd frame size."""
+    fh, fw, M = 37, 53, 28
+    boxes = np.array([[-50, -50, -20, -20],          # outside
+                      [-30, -30, 90, 90],            # covers everything
+                      [10, 20, 30, 36.5],            # bottom edge, not top
+                      [10, -5, 30, 12],              # top edge, not bottom
+                      [5, 0, 6, 36.9],               # full height, narrow
+                      [20, 20, 20.4, 20.4],          # ~1 pixel
+                      [0, 0, 52.9, 36.9],            # exactly the frame
+                      [40, 10, 70, 60]], np.float32)  # hangs over right and bottom
+    R = len(boxes)
+    masks = np.ones((R, 1, M, M), np.float32)
+    dense = _rle_check(orc, masks, None, boxes, fh, fw)
+    assert dense[0].sum() == 0 and dense[1].all()
+    rs = np.random.RandomState(3)
+    masks = rs.rand(R, 1, M, M).astype(np.float32)      # noisy masks: many runs per column
+    _rle_check(orc, masks, None, boxes, fh, fw)
+    _, _, m2 = synth.detections(5, R, (fh, fw), M, 3)
+    _rle_check(orc, m2, np.zeros(R, np.int32) + 2, boxes, fh, fw)
+
+
+def test_paste_rle_overflow_status_and_retry(orc, synth):
+    boxes, cls, masks = synth.detections(11, 12, (96, 128), 28, 3)
+    out = ops.paste_rle_cuda(_cu(masks), _cu(cls), _cu(boxes), 96, 128, 0.5, run_capacity=20, str_capacity=40)
+    st = out["status"].cpu().numpy()
+    assert (st != 0).any() and set(st.tolist()) <= {0, 1, 2}
+    need = out["cursors"].cpu().numpy()
+    assert need[0] == out["run_count"].sum().item()          # what a retry must provide
+    rles = ops.rle_results(_cu(masks), _cu(cls), _cu(boxes), 96, 128, 0.5)
+    dense = ops.paste_masks_cuda(_cu(masks), _cu(cls), _cu(boxes), 96, 128, 0.5).cpu().numpy()
+    assert rles == [orc.rle_encode(d) for d in dense]
+    assert ops.rle_results(_cu(masks[:0]), _cu(cls[:0]), _cu(boxes[:0]), 96, 128, 0.5) == []

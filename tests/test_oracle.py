@@ -144,3 +144,25 @@ def test_box_results_golden(orc, golden):
                                                             float(g["nms_" + tag]), int(g["per_im_" + tag]))
         assert np.array_equal(s, g["out_scores_" + tag]) and np.array_equal(b, g["out_boxes_" + tag]), tag
         assert [len(c) for c in cls_boxes[1:]] == g["cls_count_" + tag][1:].tolist()
+
+
+def test_rle_restatement_round_trips_and_hand_vectors(orc):
+    """maskApi.c restatement: rleFrString . rleToString == id, rleDecode . rleEncode == id, the loop and the
+    vectorised run extraction agree; vectors worked by hand from rleToString (6 -> '6'; 20 = 0b10100 has bit 4
+    set in its last group, so a continuation group follows: 'd0')."""
+    rs = np.random.RandomState(5)
+    for _ in range(100):
+        h, w = rs.randint(1, 24), rs.randint(1, 24)
+        m = (rs.rand(h, w) > rs.rand()).astype(np.uint8)
+        c = orc.rle_counts(m)
+        assert c == orc.rle_counts_fast(m) and sum(c) == h * w
+        assert orc.rle_from_string(orc.rle_to_string(c)) == c
+        assert np.array_equal(orc.rle_decode(c, h, w), m)
+    assert orc.rle_counts(np.zeros((3, 4), np.uint8)) == [12]
+    assert orc.rle_counts(np.ones((3, 4), np.uint8)) == [0, 12]
+    assert orc.rle_counts(np.array([[0, 1], [1, 1]], np.uint8)) == [1, 3]          # column-major: 0,1 | 1,1
+    assert orc.rle_to_string([6]) == '6' and orc.rle_to_string([20]) == 'd0'
+    assert orc.rle_from_string('d0') == [20]
+    # negative differences (run i smaller than run i-2) survive the sign extension
+    c = [5, 1000, 3, 2, 70000, 1]
+    assert orc.rle_from_string(orc.rle_to_string(c)) == c

@@ -68,6 +68,12 @@ SIGNATURES = {
     "vosd_box_results": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                         ctypes.c_float, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_size_t, vp]),
     "vosd_pack_mask_bits": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_longlong, vp, vp]),
+    "vosd_paste_rle_smem_bytes": (ctypes.c_size_t, [ctypes.c_int] * 3),
+    "vosd_paste_rle": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_float, vp, ctypes.c_longlong, vp, ctypes.c_longlong, vp, vp, vp, vp, vp,
+                                      vp, vp]),
+    "vosd_paste_masks_packed": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_float, vp, vp, vp]),
     "vosd_paste_masks": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_float, vp, vp, vp]),
 }

@@ -3,8 +3,8 @@ lib_vos/tools/vos_test.py:867-921) and box_results_with_nms_and_limit (lib/core/
 
 ``segm_results(cls_boxes, masks, ref_boxes, im_h, im_w)`` keeps the reference signature and
 returns ``cls_segms``: per class a list of COCO RLE dicts.  The expand / resize / threshold /
-paste work is ONE kernel over all detections (csrc/paste.cu); the RLE step stays on the host
-(pycocotools when present, else the equivalent NumPy encoder below).
+paste / RLE work is ONE kernel over all detections (csrc/paste.cu: paste_rle_kernel); ``rle_encode``
+below is the host restatement kept for callers that already hold a dense mask.
 ``paste_masks`` returns the dense (R, im_h, im_w) uint8 masks without the RLE step.
 """
 import numpy as np
@@ -12,11 +12,6 @@ import torch
 
 from .. import ops
 from ..config import get_cfg
-
-try:                                     # pragma: no cover - optional dependency of the reference
-    import pycocotools.mask as mask_util
-except Exception:                        # noqa: BLE001
-    mask_util = None
 
 
 def box_results_with_nms_and_limit(scores, boxes, cfg=None):
@@ -86,13 +81,12 @@ def _class_order(cls_boxes, num_classes):
     return np.asarray(cls, dtype=np.int32)
 
 
-def paste_masks(cls_boxes, masks, ref_boxes, im_h, im_w, cfg=None):
-    cfg = cfg or get_cfg()
+def _device_inputs(cls_boxes, masks, ref_boxes, cfg):
     cls = _class_order(cls_boxes, cfg.num_classes)
     R = cls.shape[0]
     assert R == masks.shape[0]                                    # test.py:854
     if R == 0:
-        return np.zeros((0, im_h, im_w), dtype=np.uint8), cls
+        return cls, None, None, None
     if isinstance(masks, torch.Tensor) and masks.is_cuda:
         m = masks
         c = torch.from_numpy(cls if cfg.mrcnn_cls_specific_mask else np.zeros_like(cls)).to(m.device)
@@ -102,19 +96,29 @@ def paste_masks(cls_boxes, masks, ref_boxes, im_h, im_w, cfg=None):
         m = torch.from_numpy(np.ascontiguousarray(sel[:, None])).cuda()
         c = None
     b = torch.from_numpy(np.ascontiguousarray(ref_boxes, dtype=np.float32)).to(m.device)
+    return cls, m, c, b
+
+
+def paste_masks(cls_boxes, masks, ref_boxes, im_h, im_w, cfg=None):
+    """Dense (R, im_h, im_w) uint8 masks of segm_results (the `im_mask` canvases, test.py:825-841) + mask channels."""
+    cfg = cfg or get_cfg()
+    cls, m, c, b = _device_inputs(cls_boxes, masks, ref_boxes, cfg)
+    if m is None:
+        return np.zeros((0, im_h, im_w), dtype=np.uint8), cls
     out = ops.paste_masks_cuda(m, c, b, int(im_h), int(im_w), cfg.mrcnn_thresh_binarize)
     return out.cpu().numpy(), cls
 
 
 def segm_results(cls_boxes, masks, ref_boxes, im_h, im_w, cfg=None):
+    """lib/core/test.py:801-855 end to end on the device: expand / resize / threshold / paste / RLE encode are ONE
+    kernel (vosd_paste_rle); only the 'counts' strings (a few hundred bytes per detection) come back, the dense
+    (im_h, im_w) canvases of the reference are never materialised."""
     cfg = cfg or get_cfg()
-    im_masks, cls = paste_masks(cls_boxes, masks, ref_boxes, im_h, im_w, cfg)
+    cls, m, c, b = _device_inputs(cls_boxes, masks, ref_boxes, cfg)
     cls_segms = [[] for _ in range(cfg.num_classes)]
+    if m is None:
+        return cls_segms
+    rles = ops.rle_results(m, c, b, int(im_h), int(im_w), cfg.mrcnn_thresh_binarize)
     for i, j in enumerate(cls):
-        if mask_util is not None:
-            rle = mask_util.encode(np.array(im_masks[i][:, :, np.newaxis], order='F'))[0]
-            rle['counts'] = rle['counts'].decode('ascii')
-        else:
-            rle = rle_encode(im_masks[i])
-        cls_segms[int(j)].append(rle)
+        cls_segms[int(j)].append(rles[i])
     return cls_segms

@@ -152,7 +152,7 @@ template <bool kProb>
 __global__ void __launch_bounds__(256)
 paste_det_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
                  const float* __restrict__ ref_boxes, int K, int M, int im_h, int im_w, int chunks_per_cta,
-                 float thresh, uint8_t* __restrict__ out, float* __restrict__ out_prob) {
+                 float thresh, uint8_t* __restrict__ out, float* __restrict__ out_prob, uint8_t* __restrict__ out_packed) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int S = M + 2;
     float* smask = reinterpret_cast<float*>(smem);                                   // [S*S]
@@ -168,8 +168,11 @@ paste_det_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
     const int row_first = (int)(f_begin / (unsigned)im_w), row_last = (int)((f_end - 1u) / (unsigned)im_w);
     const int ra = max(ya, row_first), rb = min(yb, row_last + 1);     // box rows this CTA touches
     const bool hit = ra < rb && xa < xb;                              // uniform across the CTA
-    uint8_t* __restrict__ o = out + (size_t)r * frame;
+    uint8_t* __restrict__ o = out ? out + (size_t)r * frame : nullptr;
     float* __restrict__ op = kProb ? out_prob + (size_t)r * frame : nullptr;
+    // optional 1-bit-per-pixel copy (pixel 8j+k -> bit k of byte j, the layout of vosd_pack_mask_bits): the 16
+    // pixels of a chunk are two bytes, so a warp writes 64 contiguous bytes -- no second pass over the dense masks
+    uint8_t* __restrict__ opk = out_packed ? out_packed + (size_t)r * (frame / 8u) : nullptr;
 
     if (hit) {
         det_scales(g, M);
@@ -252,7 +255,20 @@ paste_det_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
             }
         }
         const uint32_t packed[4] = {(uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)};
-        store_chunk<kProb>(o, op, (long long)f0, 16, packed, pv);
+        if (o || kProb) {
+            if (o) store_chunk<kProb>(o, op, (long long)f0, 16, packed, pv);
+            else if (kProb) {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    st_stream_f4(op + f0 + 4 * q, make_float4(pv[4 * q], pv[4 * q + 1], pv[4 * q + 2], pv[4 * q + 3]));
+            }
+        }
+        if (opk) {
+            // bytes {0,1} -> bits: gather bit 0 of each byte (multiply trick, as pack_bits_kernel)
+            const unsigned b0 = (unsigned)((lo * 0x0102040810204080ull) >> 56);
+            const unsigned b1 = (unsigned)((hi * 0x0102040810204080ull) >> 56);
+            *reinterpret_cast<uint16_t*>(opk + (f0 >> 3)) = (uint16_t)(b0 | (b1 << 8));
+        }
     }
 }
 
@@ -317,6 +333,241 @@ pack_bits_kernel(const uint8_t* __restrict__ in, long long n_in_per_mask, long l
     }
 }
 
+
+// =======================================================================================================
+// Fused paste -> COCO RLE: the last step of segm_results (lib/core/test.py:843-848,
+// `rle = mask_util.encode(np.array(im_mask[:, :, np.newaxis], order='F'))[0]`) without ever materialising the
+// dense (im_h, im_w) canvas.  pycocotools is a third-party dependency that is not vendored by the reference
+// (unpinned, README.md:63-74); the algorithm restated here is its published common/maskApi.c: rleEncode (runs
+// of the column-major pixel sequence, starting with a run of zeros) and rleToString (per run the difference to
+// the run two back for i > 2, as 5-bit groups with a continuation bit, sign-extended, + 48).
+//
+// One CTA per detection.  Only the box can hold ones, so the CTA evaluates just the box's pixels (same tables
+// and arithmetic as paste_det_kernel: identical bits), one warp per image column, lanes along y, and keeps the
+// result as 32-row bit words in shared memory (column-major, like the RLE order).  A transition is a pixel that
+// differs from its predecessor in column-major order; t = w ^ ((w << 1) | carry) marks the transitions of a word.
+// Transitions are counted per thread segment, a block scan gives every thread its first run index and the last
+// transition before its segment, the detection reserves T + 1 runs in the caller's arena with one atomicAdd, and
+// the runs are written in order.  The string pass repeats the pattern over the runs.
+// =======================================================================================================
+__device__ __forceinline__ int block_scan_excl(int v, int* warp_buf, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();                               // warp_buf free (previous use consumed)
+    if (lane == 31) warp_buf[warp] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const int x = warp_buf[w];
+        if (w < warp) base += x;
+        tot += x;
+    }
+    total = tot;
+    return base + inc - v;
+}
+// exclusive running maximum (identity 0) over the threads of the block
+__device__ __forceinline__ int block_scan_excl_max(int v, int* warp_buf, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc = max(inc, t);
+    }
+    int exc = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) exc = 0;
+    __syncthreads();
+    if (lane == 31) warp_buf[warp] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const int x = warp_buf[w];
+        if (w < warp) base = max(base, x);
+        tot = max(tot, x);
+    }
+    total = tot;
+    return max(base, exc);
+}
+
+// chars rleToString emits for run value x (maskApi.c: `long x`, arithmetic shifts)
+__device__ __forceinline__ int rle_chars(long long x, uint8_t* dst) {
+    int n = 0;
+    bool more = true;
+    while (more) {
+        int c = (int)(x & 0x1f);
+        x >>= 5;
+        more = (c & 0x10) ? x != -1 : x != 0;
+        if (more) c |= 0x20;
+        if (dst) dst[n] = (uint8_t)(c + 48);
+        n++;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(256)
+paste_rle_kernel(const float* __restrict__ masks, const int* __restrict__ cls, const float* __restrict__ ref_boxes,
+                 int K, int M, int im_h, int im_w, float thresh,
+                 uint32_t* __restrict__ run_arena, long long run_cap, uint8_t* __restrict__ str_arena, long long str_cap,
+                 unsigned long long* __restrict__ cursors, long long* __restrict__ run_offset, int* __restrict__ run_count,
+                 long long* __restrict__ str_offset, int* __restrict__ str_len, int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int warp_buf[8];
+    __shared__ long long s_base[2];
+    const int S = M + 2;
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = im_h * im_w;
+    DetGeom g = det_geometry(ref_boxes + 4 * (size_t)r, M);
+    const int ya = max(g.y0, 0), yb = min(g.y1 + 1, im_h), xa = max(g.x0, 0), xb = min(g.x1 + 1, im_w);
+    const bool hit = ya < yb && xa < xb;
+    // bit matrix: columns [xa, xb2), rows [ya2, yb2): one zero column / row beyond the box so that the 1 -> 0
+    // transition behind it is seen; a box that touches the bottom edge is extended to the top edge, because the
+    // pixel after (x, H-1) is (x+1, 0)
+    const int ya2 = hit ? (yb >= im_h ? 0 : ya) : 0, yb2 = hit ? min(yb + 1, im_h) : 0;
+    const int xb2 = hit ? min(xb + 1, im_w) : xa;
+    const int cols = hit ? xb2 - xa : 0, rows = yb2 - ya2, words = (rows + 31) >> 5;
+    const bool wraps = ya2 == 0 && yb2 == im_h;        // a column's predecessor is the last pixel of the column before
+
+    float* smask = reinterpret_cast<float*>(smem);
+    AxisCoef* xt = reinterpret_cast<AxisCoef*>(smem + (((size_t)S * S * 4 + 15) & ~(size_t)15));     // [im_w]
+    AxisCoef* yt = xt + im_w;                                                                        // [im_h]
+    uint32_t* bits = reinterpret_cast<uint32_t*>(yt + im_h);                                         // [cols * words]
+
+    if (hit) {
+        det_scales(g, M);
+        const int c = cls ? cls[r] : 0;
+        const float* m = masks + ((size_t)r * K + c) * M * M;
+        for (int i = tid; i < S * S; i += 256) {
+            const int y = i / S, x = i - y * S;
+            smask[i] = (y >= 1 && y <= M && x >= 1 && x <= M) ? __ldg(m + (y - 1) * M + (x - 1)) : 0.f;
+        }
+        for (int x = xa + tid; x < xb; x += 256) {
+            AxisCoef e = cv2_x_coef(x - g.x0, g.sx, S);
+            if (g.area2x) e = AxisCoef{2 * (x - g.x0), 2 * (x - g.x0) + 1, 0.5f, 0.5f};
+            xt[x - xa] = e;
+        }
+        for (int y = ya + tid; y < yb; y += 256) {
+            AxisCoef e = cv2_y_coef(y - g.y0, g.sy, S);
+            if (g.area2x) e = AxisCoef{2 * (y - g.y0) * S, (2 * (y - g.y0) + 1) * S, 0.5f, 0.5f};
+            yt[y - ya] = e;
+        }
+        __syncthreads();
+        // ---- bits: warp per column, lanes along y ----
+        for (int j = warp; j < cols; j += 8) {
+            const int x = xa + j;
+            const bool colin = x < xb;
+            AxisCoef ex = AxisCoef{0, 0, 0.f, 0.f};
+            if (colin) ex = xt[j];
+            for (int wd = 0; wd < words; wd++) {
+                const int y = ya2 + 32 * wd + lane;
+                bool bit = false;
+                if (colin && y >= ya && y < yb) {
+                    const AxisCoef ey = yt[y - ya];
+                    const float* s0 = smask + ey.i0;
+                    const float* s1 = smask + ey.i1;
+                    const float r0 = __fadd_rn(__fmul_rn(s0[ex.i0], ex.c0), __fmul_rn(s0[ex.i1], ex.c1));
+                    const float r1 = __fadd_rn(__fmul_rn(s1[ex.i0], ex.c0), __fmul_rn(s1[ex.i1], ex.c1));
+                    bit = __fadd_rn(__fmul_rn(r0, ey.c0), __fmul_rn(r1, ey.c1)) > thresh;
+                }
+                const unsigned w = __ballot_sync(0xffffffffu, bit);
+                if (lane == 0) bits[j * words + wd] = w;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- transitions of this thread's segment of (column, word) entries ----
+    const int n = cols * words;
+    const int per = (n + 255) / 256;
+    const int e0 = min(n, tid * per), e1 = min(n, e0 + per);
+    const unsigned last_valid = (rows & 31) ? ((1u << (rows & 31)) - 1u) : 0xffffffffu;
+    auto trans = [&](int e, int& pos0) -> unsigned {
+        const int j = e / words, wd = e - j * words;
+        const unsigned w = bits[e];
+        unsigned prev;
+        if (wd > 0) prev = bits[e - 1] >> 31;
+        else if (wraps && j > 0) prev = (bits[e - 1] >> ((rows - 1) & 31)) & 1u;
+        else prev = 0u;
+        unsigned t = w ^ ((w << 1) | prev);
+        if (wd == words - 1) t &= last_valid;
+        pos0 = (xa + j) * im_h + ya2 + 32 * wd;
+        return t;
+    };
+    int cnt = 0, last = 0;
+    for (int e = e0; e < e1; e++) {
+        int pos0;
+        const unsigned t = trans(e, pos0);
+        if (t) { cnt += __popc(t); last = pos0 + 31 - __clz(t); }
+    }
+    int T, last_all;
+    const int k0 = block_scan_excl(cnt, warp_buf, T);
+    int prev_pos = block_scan_excl_max(last, warp_buf, last_all);
+    const int nruns = T + 1;
+    if (tid == 0) {
+        const long long base = (long long)atomicAdd(cursors, (unsigned long long)nruns);
+        s_base[0] = base;
+        run_offset[r] = base;
+        run_count[r] = nruns;
+    }
+    __syncthreads();
+    const long long rbase = s_base[0];
+    const bool run_ok = rbase + nruns <= run_cap;
+    uint32_t* __restrict__ runs = run_arena + rbase;
+    if (run_ok) {
+        int k = k0;
+        for (int e = e0; e < e1; e++) {
+            int pos0;
+            unsigned t = trans(e, pos0);
+            while (t) {
+                const int b = __ffs(t) - 1;
+                t &= t - 1;
+                const int pos = pos0 + b;
+                runs[k++] = (uint32_t)(pos - prev_pos);
+                prev_pos = pos;
+            }
+        }
+        if (tid == 0) runs[T] = (uint32_t)(frame - last_all);
+    }
+    __syncthreads();                                    // the runs of this detection are visible to the whole CTA
+
+    // ---- rleToString over the runs ----
+    const int per2 = (nruns + 255) / 256;
+    const int i0 = min(nruns, tid * per2), i1 = min(nruns, i0 + per2);
+    int nch = 0;
+    if (run_ok)
+        for (int i = i0; i < i1; i++) {
+            long long x = (long long)runs[i];
+            if (i > 2) x -= (long long)runs[i - 2];
+            nch += rle_chars(x, nullptr);
+        }
+    int L;
+    const int c0 = block_scan_excl(nch, warp_buf, L);
+    if (tid == 0) {
+        const long long base = run_ok ? (long long)atomicAdd(cursors + 1, (unsigned long long)L) : 0;
+        s_base[1] = base;
+        str_offset[r] = base;
+        str_len[r] = run_ok ? L : 0;
+    }
+    __syncthreads();
+    const long long sbase = s_base[1];
+    const bool str_ok = run_ok && sbase + L <= str_cap;
+    if (str_ok) {
+        uint8_t* __restrict__ dst = str_arena + sbase + c0;
+        for (int i = i0; i < i1; i++) {
+            long long x = (long long)runs[i];
+            if (i > 2) x -= (long long)runs[i - 2];
+            dst += rle_chars(x, dst);
+        }
+    }
+    if (tid == 0) status[r] = run_ok ? (str_ok ? 0 : 2) : 1;
+}
+
 }  // namespace vosd
 
 using namespace vosd;
@@ -340,13 +591,15 @@ extern "C" int vosd_pack_mask_bits(const uint8_t* masks, int num_masks, long lon
 }
 
 
-extern "C" int vosd_paste_masks(const float* masks, const int* cls, const float* ref_boxes,
-                                int num_dets, int num_classes, int mask_size, int im_h, int im_w,
-                                float thresh, uint8_t* out, float* out_prob, cudaStream_t stream) {
+static int paste_impl(const float* masks, const int* cls, const float* ref_boxes,
+                      int num_dets, int num_classes, int mask_size, int im_h, int im_w,
+                      float thresh, uint8_t* out, float* out_prob, uint8_t* out_packed, bool want_packed,
+                      cudaStream_t stream) {
     if (num_dets < 0 || num_classes < 1 || mask_size < 1 || im_h < 1 || im_w < 1) return VOSD_ERR_BAD_SHAPE;
     if (num_dets == 0) return VOSD_OK;
-    if (!masks || !ref_boxes || !out) return VOSD_ERR_BAD_ARG;
-    if (!aligned16(out) || (out_prob && !aligned16(out_prob))) return VOSD_ERR_BAD_ARG;
+    if (!masks || !ref_boxes || (want_packed ? !out_packed : !out)) return VOSD_ERR_BAD_ARG;
+    if ((out && !aligned16(out)) || (out_prob && !aligned16(out_prob))) return VOSD_ERR_BAD_ARG;
+    if (out_packed && (reinterpret_cast<uintptr_t>(out_packed) & 1)) return VOSD_ERR_BAD_ARG;
     const long long total = (long long)num_dets * im_h * im_w;
     const long long chunks = (total + 15) / 16;
     long long blocks = (chunks + 255) / 256;
@@ -365,20 +618,71 @@ extern "C" int vosd_paste_masks(const float* masks, const int* cls, const float*
             if (cudaFuncSetAttribute(paste_det_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                 return VOSD_ERR_LAUNCH;
             paste_det_kernel<true><<<grid, 256, smem, stream>>>(masks, cls, ref_boxes, num_classes, mask_size, im_h, im_w,
-                                                                chunks_per_cta, thresh, out, out_prob);
+                                                                chunks_per_cta, thresh, out, out_prob, out_packed);
         } else {
             if (cudaFuncSetAttribute(paste_det_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                 return VOSD_ERR_LAUNCH;
             paste_det_kernel<false><<<grid, 256, smem, stream>>>(masks, cls, ref_boxes, num_classes, mask_size, im_h, im_w,
-                                                                 chunks_per_cta, thresh, out, out_prob);
+                                                                 chunks_per_cta, thresh, out, out_prob, out_packed);
         }
-    } else if (out_prob) {
+        count_launch();
+        return check_launch();
+    }
+    // odd frame sizes: flat dense kernel, then (if asked) the stand-alone packer over the dense result
+    if (!out) return VOSD_ERR_UNSUPPORTED;
+    if (out_prob) {
         paste_kernel<true><<<(int)blocks, 256, 0, stream>>>(masks, cls, ref_boxes, total, num_classes, mask_size,
                                                             im_h, im_w, thresh, out, out_prob);
     } else {
         paste_kernel<false><<<(int)blocks, 256, 0, stream>>>(masks, cls, ref_boxes, total, num_classes, mask_size,
                                                              im_h, im_w, thresh, out, out_prob);
     }
+    count_launch();
+    const int st = check_launch();
+    if (st != VOSD_OK || !out_packed) return st;
+    return vosd_pack_mask_bits(out, num_dets, frame, out_packed, stream);
+}
+
+extern "C" int vosd_paste_masks(const float* masks, const int* cls, const float* ref_boxes,
+                                int num_dets, int num_classes, int mask_size, int im_h, int im_w,
+                                float thresh, uint8_t* out, float* out_prob, cudaStream_t stream) {
+    return paste_impl(masks, cls, ref_boxes, num_dets, num_classes, mask_size, im_h, im_w, thresh, out, out_prob,
+                      nullptr, false, stream);
+}
+
+extern "C" int vosd_paste_masks_packed(const float* masks, const int* cls, const float* ref_boxes,
+                                       int num_dets, int num_classes, int mask_size, int im_h, int im_w,
+                                       float thresh, uint8_t* out, uint8_t* out_packed, cudaStream_t stream) {
+    return paste_impl(masks, cls, ref_boxes, num_dets, num_classes, mask_size, im_h, im_w, thresh, out, nullptr,
+                      out_packed, true, stream);
+}
+
+extern "C" size_t vosd_paste_rle_smem_bytes(int mask_size, int im_h, int im_w) {
+    const int S = mask_size + 2;
+    return (((size_t)S * S * 4 + 15) & ~(size_t)15) + (size_t)(im_w + im_h) * 16 +
+           (size_t)im_w * ((im_h + 31) / 32) * 4;
+}
+
+extern "C" int vosd_paste_rle(const float* masks, const int* cls, const float* ref_boxes,
+                              int num_dets, int num_classes, int mask_size, int im_h, int im_w, float thresh,
+                              uint32_t* run_arena, long long run_capacity, uint8_t* str_arena, long long str_capacity,
+                              unsigned long long* cursors, long long* run_offset, int* run_count,
+                              long long* str_offset, int* str_len, int* status, cudaStream_t stream) {
+    if (num_dets < 0 || num_classes < 1 || mask_size < 1 || im_h < 1 || im_w < 1) return VOSD_ERR_BAD_SHAPE;
+    if (run_capacity < 0 || str_capacity < 0) return VOSD_ERR_BAD_SHAPE;
+    if ((long long)im_h * im_w >= (1LL << 31)) return VOSD_ERR_UNSUPPORTED;
+    if (!cursors) return VOSD_ERR_BAD_ARG;
+    if (cudaMemsetAsync(cursors, 0, 2 * sizeof(unsigned long long), stream) != cudaSuccess) return VOSD_ERR_LAUNCH;
+    if (num_dets == 0) return VOSD_OK;
+    if (!masks || !ref_boxes || !run_arena || !str_arena || !run_offset || !run_count || !str_offset || !str_len || !status)
+        return VOSD_ERR_BAD_ARG;
+    const size_t smem = vosd_paste_rle_smem_bytes(mask_size, im_h, im_w);
+    if (smem > 220 * 1024) return VOSD_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(paste_rle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return VOSD_ERR_LAUNCH;
+    paste_rle_kernel<<<num_dets, 256, smem, stream>>>(masks, cls, ref_boxes, num_classes, mask_size, im_h, im_w, thresh,
+                                                     run_arena, run_capacity, str_arena, str_capacity, cursors,
+                                                     run_offset, run_count, str_offset, str_len, status);
     count_launch();
     return check_launch();
 }

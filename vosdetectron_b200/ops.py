@@ -306,6 +306,79 @@ def paste_masks_cuda(masks, cls, ref_boxes, im_h, im_w, thresh=0.5, want_prob=Fa
     return (out, prob) if want_prob else out
 
 
+def paste_masks_packed_cuda(masks, cls, ref_boxes, im_h, im_w, thresh=0.5, want_dense=True):
+    """Paste with the bit-packed copy written by the same kernel: returns (dense uint8 (R,im_h,im_w) or None,
+    packed uint8 (R, ceil(im_h*im_w/8)), 8 pixels per byte LSB first)."""
+    m = _need_cuda(masks, "masks")
+    b = _need_cuda(ref_boxes, "ref_boxes")
+    c = None if cls is None else _need_cuda(cls, "cls", torch.int32)
+    R, K, M, M2 = m.shape
+    if M != M2 or b.shape != (R, 4):
+        raise ValueError("masks must be (R,K,M,M) and ref_boxes (R,4)")
+    out = torch.empty((R, im_h, im_w), dtype=torch.uint8, device=m.device) if want_dense else None
+    packed = torch.empty((R, (im_h * im_w + 7) // 8), dtype=torch.uint8, device=m.device)
+    _bind(m)
+    _lib.call("vosd_paste_masks_packed", _ptr(m), _ptr(c), _ptr(b), R, K, M, int(im_h), int(im_w), float(thresh),
+              _ptr(out), _ptr(packed), _stream())
+    return out, packed
+
+
+def paste_rle_cuda(masks, cls, ref_boxes, im_h, im_w, thresh=0.5, run_capacity=None, str_capacity=None):
+    """Fused paste -> COCO RLE on the device (vosd_paste_rle).  Returns a dict of device tensors:
+    runs (arena, uint32 stored as int32), run_offset (R) int64, run_count (R) int32, chars (arena, uint8),
+    str_offset (R) int64, str_len (R) int32, status (R) int32, cursors (2) int64 [runs used, chars used].
+    Default capacities hold ~8 runs per box column per detection on average; a detection that does not fit
+    gets status != 0 (see ``rle_results`` for the retry)."""
+    m = _need_cuda(masks, "masks")
+    b = _need_cuda(ref_boxes, "ref_boxes")
+    c = None if cls is None else _need_cuda(cls, "cls", torch.int32)
+    R, K, M, M2 = m.shape
+    if M != M2 or b.shape != (R, 4):
+        raise ValueError("masks must be (R,K,M,M) and ref_boxes (R,4)")
+    dev = m.device
+    if run_capacity is None:
+        run_capacity = max(1024, R * (8 * min(int(im_w), 512) + 2))
+    if str_capacity is None:
+        str_capacity = 3 * run_capacity
+    out = {
+        "runs": torch.empty(int(run_capacity), dtype=torch.int32, device=dev),
+        "chars": torch.empty(int(str_capacity), dtype=torch.uint8, device=dev),
+        "cursors": torch.empty(2, dtype=torch.int64, device=dev),
+        "run_offset": torch.empty(R, dtype=torch.int64, device=dev),
+        "run_count": torch.empty(R, dtype=torch.int32, device=dev),
+        "str_offset": torch.empty(R, dtype=torch.int64, device=dev),
+        "str_len": torch.empty(R, dtype=torch.int32, device=dev),
+        "status": torch.empty(R, dtype=torch.int32, device=dev),
+    }
+    _bind(m)
+    _lib.call("vosd_paste_rle", _ptr(m), _ptr(c), _ptr(b), R, K, M, int(im_h), int(im_w), float(thresh),
+              _ptr(out["runs"]), int(run_capacity), _ptr(out["chars"]), int(str_capacity), _ptr(out["cursors"]),
+              _ptr(out["run_offset"]), _ptr(out["run_count"]), _ptr(out["str_offset"]), _ptr(out["str_len"]),
+              _ptr(out["status"]), _stream())
+    return out
+
+
+def rle_results(masks, cls, ref_boxes, im_h, im_w, thresh=0.5):
+    """Host view of paste_rle_cuda: list of R COCO RLE dicts {'size': [h, w], 'counts': str} (what
+    mask_util.encode returns per mask, counts decoded to str as segm_results does, test.py:847).  One retry with the
+    exact capacities if the default arenas were too small."""
+    R = int(masks.shape[0])
+    if R == 0:
+        return []
+    out = paste_rle_cuda(masks, cls, ref_boxes, im_h, im_w, thresh)
+    used = out["cursors"].cpu().numpy()
+    if int(out["status"].max().item()) != 0:
+        out = paste_rle_cuda(masks, cls, ref_boxes, im_h, im_w, thresh, run_capacity=int(used[0]),
+                             str_capacity=max(int(used[1]), 6 * int(used[0])))
+        used = out["cursors"].cpu().numpy()
+        if int(out["status"].max().item()) != 0:
+            raise RuntimeError("vosd_paste_rle: arena overflow after retry")
+    chars = out["chars"][:int(used[1])].cpu().numpy().tobytes()
+    so, sl = out["str_offset"].cpu().numpy(), out["str_len"].cpu().numpy()
+    return [{'size': [int(im_h), int(im_w)], 'counts': chars[int(so[i]):int(so[i]) + int(sl[i])].decode('ascii')}
+            for i in range(R)]
+
+
 def pack_mask_bits_cuda(masks_u8):
     """(..., H, W) uint8 {0,1} on the device -> (..., ceil(H*W/8)) uint8, 8 pixels per byte (LSB first)."""
     m = _need_cuda(masks_u8, "masks", torch.uint8)

@@ -35,6 +35,7 @@ class RegionPipeline:
                         for l in self.rpn_levels}
         self._ws = None
         self.overlap = True
+        self.packed_masks = False      # step() also returns the bit-packed masks (frame-sharded clips)
         self._side = None
 
     # ---- stage 1: proposals -> top RoIs + FPN levels (rows of frame f are in group f) ----------
@@ -76,11 +77,17 @@ class RegionPipeline:
         mask_feats = self.roi_features(feats, mask_rois, mlevel, self.mask_resolution)
         mark("paste")
         K, M = det_masks.shape[2], det_masks.shape[3]
-        pasted = ops.paste_masks_cuda(det_masks.view(B * D, K, M, M),
-                                      det_cls.view(-1) if c.mrcnn_cls_specific_mask else None,
-                                      det_boxes.view(B * D, 4), frame_hw[0], frame_hw[1], c.mrcnn_thresh_binarize)
+        cls = det_cls.view(-1) if c.mrcnn_cls_specific_mask else None
+        if self.packed_masks:
+            # the paste kernel also writes the 1-bit-per-pixel copy (the all-gather payload of a sharded clip)
+            pasted, packed = ops.paste_masks_packed_cuda(det_masks.view(B * D, K, M, M), cls, det_boxes.view(B * D, 4),
+                                                         frame_hw[0], frame_hw[1], c.mrcnn_thresh_binarize)
+        else:
+            pasted = ops.paste_masks_cuda(det_masks.view(B * D, K, M, M), cls, det_boxes.view(B * D, 4),
+                                          frame_hw[0], frame_hw[1], c.mrcnn_thresh_binarize)
+            packed = None
         mark("mask_end")
-        return mask_rois, mlevel, mask_feats, pasted
+        return mask_rois, mlevel, mask_feats, pasted, packed
 
     def step(self, rpn, im_info, feats, det_boxes, det_cls, det_masks, frame_hw, im_scale, mark=None, overlap=None):
         """One batch of B frames.
@@ -122,7 +129,7 @@ class RegionPipeline:
             # No record_stream on the side stream's tensors: it would park every freed block behind an event and
             # make the caching allocator cudaMalloc fresh outputs each step.  Reuse is safe without it: the blocks
             # are only re-allocated by the side stream, whose next use starts with wait_stream(main) above.
-            mask_rois, mlevel, mask_feats, pasted = self._mask_branch(feats, det_boxes, det_cls, det_masks,
+            mask_rois, mlevel, mask_feats, pasted, packed = self._mask_branch(feats, det_boxes, det_cls, det_masks,
                                                                       frame_hw, im_scale, mark)
             mark("join_wait")
             main.wait_stream(side)
@@ -134,11 +141,12 @@ class RegionPipeline:
         box_feats = self.roi_features(feats, rois, level, self.box_resolution)
         mark("end")
         if not overlap:
-            mask_rois, mlevel, mask_feats, pasted = self._mask_branch(feats, det_boxes, det_cls, det_masks,
+            mask_rois, mlevel, mask_feats, pasted, packed = self._mask_branch(feats, det_boxes, det_cls, det_masks,
                                                                       frame_hw, im_scale, mark)
         return {"rois": prop["rois"], "roi_count": prop["count"], "roi_level": prop["level"],
                 "box_feats": box_feats, "mask_feats": mask_feats, "mask_rois": mask_rois, "mask_level": mlevel,
-                "masks": pasted.view(B, D, frame_hw[0], frame_hw[1])}
+                "masks": pasted.view(B, D, frame_hw[0], frame_hw[1]),
+                "masks_packed": None if packed is None else packed.view(B, D, -1)}
 
 
 # Number of library kernels one RegionPipeline.step enqueues (counted, see bench.py):

@@ -304,6 +304,9 @@ def gpu_arm(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL's own log lines (the "NCCL version ..." banner under NCCL_DEBUG=VERSION/INFO) go to stderr: stdout
+        # carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B = args.frames_per_gpu
     host = make_host_inputs(B, 3000 + 100 * rank)

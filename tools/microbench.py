@@ -203,6 +203,20 @@ def main():
             alg = B * 100 * (480 * 854 + 28 * 28 * 4 + 16)
             report(out, "paste_%dframes_100dets_480x854" % B, timer,
                    lambda: ops.paste_masks_cuda(masks, cls, boxes, 480, 854, 0.5), alg, {"dets": B * 100})
+            report(out, "paste_dense_plus_packed_%dframes_100dets_480x854" % B, timer,
+                   lambda: ops.paste_masks_packed_cuda(masks, cls, boxes, 480, 854, 0.5), alg + alg // 8, {"dets": B * 100})
+            report(out, "paste_packed_only_%dframes_100dets_480x854" % B, timer,
+                   lambda: ops.paste_masks_packed_cuda(masks, cls, boxes, 480, 854, 0.5, want_dense=False),
+                   B * 100 * (480 * 854 // 8 + 28 * 28 * 4 + 16), {"dets": B * 100})
+            # fused paste -> COCO RLE: algorithmic bytes = masks in + runs and string out (measured once)
+            r = ops.paste_rle_cuda(masks, cls, boxes, 480, 854, 0.5)
+            used = r["cursors"].cpu().numpy()
+            rc, rs = int(used[0]), int(used[1])
+            cap_r, cap_s = r["runs"].numel(), r["chars"].numel()
+            report(out, "paste_rle_%dframes_100dets_480x854" % B, timer,
+                   lambda: ops.paste_rle_cuda(masks, cls, boxes, 480, 854, 0.5, run_capacity=cap_r, str_capacity=cap_s),
+                   B * 100 * (28 * 28 * 4 + 16 + 28) + 4 * rc + rs,
+                   {"dets": B * 100, "runs": rc, "string_bytes": rs, "dense_equivalent_bytes": B * 100 * 480 * 854})
 
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump({"peak_gbs_measured": PEAK, "gpu": torch.cuda.get_device_name(0), "results": out}, open(args.out, "w"), indent=1)

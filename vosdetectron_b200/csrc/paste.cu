@@ -130,6 +130,7 @@ struct __align__(16) AxisCoef { int i0, i1; float c0, c1; };      // value = S[i
 // Column-table slot of entry j: one pad entry per 16, so that the lanes of a warp (16 entries apart: one
 // 16-pixel chunk each) read 128-bit entries from different bank groups.
 __device__ __forceinline__ int xpad(int j) { return j + (j >> 4); }
+constexpr int kPasteHFloats = 6144;               // shared-memory budget of the per-CTA horizontal-pass table
 
 // cv2 column table entry for destination x-offset dx (zeroes the far tap at the border)
 __device__ __forceinline__ AxisCoef cv2_x_coef(int dx, double scale, int S) {
@@ -151,7 +152,7 @@ __device__ __forceinline__ AxisCoef cv2_y_coef(int dy, double scale, int S) {
 template <bool kProb>
 __global__ void __launch_bounds__(256)
 paste_det_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
-                 const float* __restrict__ ref_boxes, int K, int M, int im_h, int im_w, int chunks_per_cta,
+                 const float* __restrict__ ref_boxes, int K, int M, int im_h, int im_w, int chunks_per_cta, int rows_cap,
                  float thresh, uint8_t* __restrict__ out, float* __restrict__ out_prob, uint8_t* __restrict__ out_packed) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int S = M + 2;
@@ -168,6 +169,9 @@ paste_det_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
     const int row_first = (int)(f_begin / (unsigned)im_w), row_last = (int)((f_end - 1u) / (unsigned)im_w);
     const int ra = max(ya, row_first), rb = min(yb, row_last + 1);     // box rows this CTA touches
     const bool hit = ra < rb && xa < xb;                              // uniform across the CTA
+    float* ht = reinterpret_cast<float*>(yt + rows_cap);              // [source rows of this CTA][hpitch]
+    bool use_h = false;
+    int hpitch = 0;
     uint8_t* __restrict__ o = out ? out + (size_t)r * frame : nullptr;
     float* __restrict__ op = kProb ? out_prob + (size_t)r * frame : nullptr;
     // optional 1-bit-per-pixel copy (pixel 8j+k -> bit k of byte j, the layout of vosd_pack_mask_bits): the 16
@@ -193,6 +197,31 @@ paste_det_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
             yt[y - ra] = e;
         }
         __syncthreads();
+        // Separable form: cv2 resizes horizontally, then vertically, and the horizontal result of source row s at
+        // column x, h[s][x] = S[s][i0(x)] * c0(x) + S[s][i1(x)] * c1(x), does not depend on the output row.  The
+        // rows of this CTA touch only a few source rows, so h is built once per CTA (same two products and one
+        // sum as the per-pixel path: identical bits) and a pixel then costs 2 loads and 3 flops instead of 2 table
+        // entries, 4 mask loads and 6 flops.  Falls back to the per-pixel path when h does not fit (wide, flat boxes).
+        const int s_lo = yt[0].i0 / S, s_hi = yt[rb - ra - 1].i1 / S;       // the y table is monotone
+        const int nsr = s_hi - s_lo + 1;
+        hpitch = xpad(xb - xa - 1) + 1;
+        use_h = nsr * hpitch <= kPasteHFloats;
+        if (use_h) {
+            for (int e = threadIdx.x; e < nsr * (xb - xa); e += 256) {
+                const int k = e / (xb - xa), j = e - k * (xb - xa);
+                const AxisCoef ex = xt[xpad(j)];
+                const float* srow = smask + (s_lo + k) * S;
+                ht[k * hpitch + xpad(j)] = __fadd_rn(__fmul_rn(srow[ex.i0], ex.c0), __fmul_rn(srow[ex.i1], ex.c1));
+            }
+            __syncthreads();                            // every thread has read the source-row range of the y table
+            for (int y = ra + threadIdx.x; y < rb; y += 256) {
+                AxisCoef e = yt[y - ra];
+                e.i0 = (e.i0 / S - s_lo) * hpitch;      // from now on: offsets of the two h rows
+                e.i1 = (e.i1 / S - s_lo) * hpitch;
+                yt[y - ra] = e;
+            }
+            __syncthreads();
+        }
     }
 
     for (unsigned f0 = f_begin + threadIdx.x * 16u; f0 < f_end; f0 += 256u * 16u) {
@@ -209,15 +238,21 @@ paste_det_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
                 // pixels outside [xa, xb) evaluate a clamped table entry and are masked out
                 if (y >= ra && y < rb && x < xb && x + 16 > xa) {
                     const AxisCoef ey = yt[y - ra];
-                    const float* s0 = smask + ey.i0;
-                    const float* s1 = smask + ey.i1;
+                    const float* s0 = (use_h ? ht : smask) + ey.i0;
+                    const float* s1 = (use_h ? ht : smask) + ey.i1;
                     const int last = xb - xa - 1;
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
                         const int j = x + i - xa;
-                        const AxisCoef ex = xt[xpad(min(max(j, 0), last))];
-                        const float r0 = __fadd_rn(__fmul_rn(s0[ex.i0], ex.c0), __fmul_rn(s0[ex.i1], ex.c1));
-                        const float r1 = __fadd_rn(__fmul_rn(s1[ex.i0], ex.c0), __fmul_rn(s1[ex.i1], ex.c1));
+                        const int jp = xpad(min(max(j, 0), last));
+                        float r0, r1;
+                        if (use_h) {
+                            r0 = s0[jp]; r1 = s1[jp];
+                        } else {
+                            const AxisCoef ex = xt[jp];
+                            r0 = __fadd_rn(__fmul_rn(s0[ex.i0], ex.c0), __fmul_rn(s0[ex.i1], ex.c1));
+                            r1 = __fadd_rn(__fmul_rn(s1[ex.i0], ex.c0), __fmul_rn(s1[ex.i1], ex.c1));
+                        }
                         const float v = __fadd_rn(__fmul_rn(r0, ey.c0), __fmul_rn(r1, ey.c1));
                         const bool in = j >= 0 && j <= last;
                         if (in && v > thresh) {
@@ -233,12 +268,17 @@ paste_det_kernel(const float* __restrict__ masks, const int* __restrict__ cls,
                     const int x0r = max(xa, x), x1r = min(xb, x + run);
                     if (y >= ra && y < rb && x0r < x1r) {
                         const AxisCoef ey = yt[y - ra];
-                        const float* s0 = smask + ey.i0;
-                        const float* s1 = smask + ey.i1;
+                        const float* s0 = (use_h ? ht : smask) + ey.i0;
+                        const float* s1 = (use_h ? ht : smask) + ey.i1;
                         for (int xx = x0r; xx < x1r; xx++) {
-                            const AxisCoef ex = xt[xpad(xx - xa)];
-                            const float r0 = __fadd_rn(__fmul_rn(s0[ex.i0], ex.c0), __fmul_rn(s0[ex.i1], ex.c1));
-                            const float r1 = __fadd_rn(__fmul_rn(s1[ex.i0], ex.c0), __fmul_rn(s1[ex.i1], ex.c1));
+                            float r0, r1;
+                            if (use_h) {
+                                r0 = s0[xpad(xx - xa)]; r1 = s1[xpad(xx - xa)];
+                            } else {
+                                const AxisCoef ex = xt[xpad(xx - xa)];
+                                r0 = __fadd_rn(__fmul_rn(s0[ex.i0], ex.c0), __fmul_rn(s0[ex.i1], ex.c1));
+                                r1 = __fadd_rn(__fmul_rn(s1[ex.i0], ex.c0), __fmul_rn(s1[ex.i1], ex.c1));
+                            }
                             const float v = __fadd_rn(__fmul_rn(r0, ey.c0), __fmul_rn(r1, ey.c1));
                             const int i = done + (xx - x);
                             if (v > thresh) {
@@ -607,23 +647,27 @@ static int paste_impl(const float* masks, const int* cls, const float* ref_boxes
     const long long frame = (long long)im_h * im_w;
     if (frame % 16 == 0 && frame < (1LL << 31) && num_dets <= 65535) {
         // 2048 chunks (32 KB of output) per CTA: few, fat CTAs; tables cover at most the rows a CTA spans
-        const int chunks_per_cta = 2048;
+#ifndef VOSD_PASTE_CHUNKS
+#define VOSD_PASTE_CHUNKS 2048
+#endif
+        const int chunks_per_cta = VOSD_PASTE_CHUNKS;
         const unsigned bx = (unsigned)((frame / 16 + chunks_per_cta - 1) / chunks_per_cta);
         const int rows_per_cta = (chunks_per_cta * 16 + im_w - 1) / im_w + 2;
         const int S = mask_size + 2;
-        const size_t smem = (((size_t)S * S * 4 + 15) & ~(size_t)15) + (size_t)(im_w + im_w / 16 + 1 + rows_per_cta) * 16;
+        const size_t smem = (((size_t)S * S * 4 + 15) & ~(size_t)15) + (size_t)(im_w + im_w / 16 + 1 + rows_per_cta) * 16 +
+                            (size_t)kPasteHFloats * 4;
         if (smem > 200 * 1024) return VOSD_ERR_UNSUPPORTED;
         dim3 grid(bx, (unsigned)num_dets);
         if (out_prob) {
             if (cudaFuncSetAttribute(paste_det_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                 return VOSD_ERR_LAUNCH;
             paste_det_kernel<true><<<grid, 256, smem, stream>>>(masks, cls, ref_boxes, num_classes, mask_size, im_h, im_w,
-                                                                chunks_per_cta, thresh, out, out_prob, out_packed);
+                                                                chunks_per_cta, rows_per_cta, thresh, out, out_prob, out_packed);
         } else {
             if (cudaFuncSetAttribute(paste_det_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                 return VOSD_ERR_LAUNCH;
             paste_det_kernel<false><<<grid, 256, smem, stream>>>(masks, cls, ref_boxes, num_classes, mask_size, im_h, im_w,
-                                                                 chunks_per_cta, thresh, out, out_prob, out_packed);
+                                                                 chunks_per_cta, rows_per_cta, thresh, out, out_prob, out_packed);
         }
         count_launch();
         return check_launch();

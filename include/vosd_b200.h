@@ -292,6 +292,45 @@ VOSD_API int vosd_box_results(const float* scores, const float* boxes, const int
 VOSD_API int vosd_pack_mask_bits(const uint8_t* masks, int num_masks, long long pixels_per_mask,
                                  uint8_t* packed, cudaStream_t stream);
 
+/* ------------------------------------------------------------------------------------ */
+/* FlowAlign: warp a feature map by an optical-flow field ("next" row). */
+/* Replaces FlowAlignForward / FlowAlignBackward                                          */
+/* (lib_vos/vos_model/flow_align/src/flow_align_cuda_kernel.h:11,15; kernels              */
+/* flow_align_cuda_kernel.cu:15-55 and :57-117) with the SAME argument order.             */
+/*   bottom (N,C,H,W) fp32; flow (N,2,H,W) fp32, plane 0 = x displacement, plane 1 = y,   */
+/*   in pixels of THIS map; top (N,C,H,W): top[n,c,h,w] = bilinear(bottom[n,c], h+fy,     */
+/*   w+fx), or 0 when the sample lies outside [0,H-1) x [0,W-1) (:37-41).                 */
+/* Forward: bit-identical to the reference kernel built for sm_100a (same mixed           */
+/* float/double expression, :48-51).  Backward: the reference's addends (:89-112); where   */
+/* neighbouring pixels hit the same texel they are summed in registers first, and the     */
+/* flow gradient is summed over a channel chunk before it is added, so only the order of  */
+/* the fp32 sum differs (the reference's atomics are unordered as well).                  */
+/* bottomdiff / flowdiff are ACCUMULATED into; FlowAlignFunction.backward zero-fills them */
+/* (functions/flow_align.py:41-43): pass zero_init != 0 to have the library clear them on */
+/* `stream`.  N*C*H*W must be < 2^31 (the reference indexes with int).                     */
+/* ------------------------------------------------------------------------------------ */
+VOSD_API int vosd_flow_align_fwd(int batches, int height, int width, int channels, const float* bottom,
+                                 const float* flow, float* top, cudaStream_t stream);
+VOSD_API int vosd_flow_align_bwd(int batches, int height, int width, int channels, const float* topdiff,
+                                 const float* bottom, const float* flow, float* bottomdiff, float* flowdiff,
+                                 int zero_init, cudaStream_t stream);
+
+/* All FPN levels in ONE launch: replaces the `for i in range(5): self.FlowAligns[i](hidden_states[i], flow)` */
+/* loop of lib_vos/vos_modeling/vos_model_builder.py:329-335 (per level: its own map and its own, already     */
+/* down-sampled, flow).  level_h / level_w and the pointer tables are HOST arrays of num_levels entries       */
+/* (<= VOSD_MAX_LEVELS); every level has `batches` images and `channels` channels.                            */
+VOSD_API int vosd_flow_align_ml_fwd(int num_levels, int batches, int channels, const int* level_h,
+                                    const int* level_w, const float* const* bottom, const float* const* flow,
+                                    float* const* top, cudaStream_t stream);
+VOSD_API int vosd_flow_align_ml_bwd(int num_levels, int batches, int channels, const int* level_h,
+                                    const int* level_w, const float* const* topdiff, const float* const* bottom,
+                                    const float* const* flow, float* const* bottomdiff, float* const* flowdiff,
+                                    int zero_init, cudaStream_t stream);
+/* Test / tuning hook: 1 = plain fp32 bilinear weights in the forward (not bit-identical to the reference,   */
+/* |err| <= 1e-6 relative), 0 = the reference's mixed float/double expression (default).  Returns the        */
+/* previous setting.  Process-wide; not for production use. */
+VOSD_API int vosd_debug_flow_align_fast(int on);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,8 @@ sources for the hot path, from where they lie under /root/reference, into
   oracle/_ref/cython_bbox*.so     <- lib/utils/cython_bbox.pyx  (needed to import utils.boxes)
   oracle/_ref/libref_roialign.so  <- lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.cu
                                      compiled UNMODIFIED for sm_100a (GPU oracle + speed baseline)
+  oracle/_ref/libref_flowalign.so <- lib_vos/vos_model/flow_align/src/flow_align_cuda_kernel.cu
+                                     compiled UNMODIFIED for sm_100a (GPU oracle + speed baseline)
 
 No reference source is copied into the repo: the .pyx is read, a 2-token
 NumPy-2 compatibility substitution (``np.int_t``->``np.int64_t``,
@@ -64,6 +66,13 @@ def build(force=False):
                 "nvcc", "-shared", "-Xcompiler", "-fPIC", "-O3",
                 "-gencode", "arch=compute_100a,code=sm_100a", "-I" + src,
                 "-x", "cu", os.path.join(src, "roi_align_kernel.cu"), "-o", so])
+        so = os.path.join(OUT, "libref_flowalign.so")
+        if force or not os.path.exists(so):
+            src = os.path.join(REF_ROOT, "lib_vos/vos_model/flow_align/src")
+            subprocess.check_call([
+                "nvcc", "-shared", "-Xcompiler", "-fPIC", "-O3",
+                "-gencode", "arch=compute_100a,code=sm_100a", "-I" + src,
+                "-x", "cu", os.path.join(src, "flow_align_cuda_kernel.cu"), "-o", so])
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     return True

@@ -254,3 +254,98 @@ int orc_num_threads(void) {
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------- */
+/* FlowAlign -- lib_vos/vos_model/flow_align/src/flow_align_cuda_kernel.cu    */
+/*   forward :15-55, backward :57-117.  The reference mixes float and double  */
+/*   operands (`1.` is a double literal, `h_ratio` a float), and nvcc         */
+/*   contracts some of the double products into fma: the operation order and  */
+/*   the fma() placements below are read from the reference's sm_100a SASS    */
+/*   (DMUL/DFMA/DADD/F2F sequence), so on an IEEE machine this produces the   */
+/*   reference kernel's bits.  The reference is CUDA-only (functions/         */
+/*   flow_align.py:27-30 raises on CPU tensors): its pin is the reference     */
+/*   kernel run on the GPU (tests/test_gpu_flowalign.py).                     */
+/* ------------------------------------------------------------------------- */
+typedef struct { int off; float h, w; } orc_flow_geom;
+
+/* :24-45.  off < 0: sample outside [0,H-1) x [0,W-1) -> output 0, no gradient. */
+static orc_flow_geom orc_flow_geometry(const float* flow_n, int H, int W, int h, int w) {
+    orc_flow_geom g; g.off = -1; g.h = g.w = 0.f;
+    float flo_x = flow_n[h * W + w];
+    float flo_y = flow_n[H * W + h * W + w];
+    float w_flo = (float)w + flo_x;
+    float h_flo = (float)h + flo_y;
+    if (h_flo < 0 || h_flo >= (float)(H - 1) || w_flo < 0 || w_flo >= (float)(W - 1)) return g;
+    if (h_flo != h_flo || w_flo != w_flo) {          /* NaN passes the tests above; CUDA's float->int gives 0 */
+        if (H < 2 || W < 2) return g;
+        g.off = 0; g.h = h_flo; g.w = w_flo;          /* NaN - 0.f */
+        return g;
+    }
+    int h_start = (int)floorf(h_flo), w_start = (int)floorf(w_flo);
+    g.h = h_flo - (float)h_start;
+    g.w = w_flo - (float)w_start;
+    g.off = w_start + W * h_start;
+    return g;
+}
+
+void orc_flow_align_fwd(const float* bottom, const float* flow, int N, int C, int H, int W,
+                        float* top, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    #pragma omp parallel for schedule(static) collapse(2)
+    for (int n = 0; n < N; n++) for (int c = 0; c < C; c++) {
+        const float* b = bottom + ((size_t)n * C + c) * H * W;
+        float* t = top + ((size_t)n * C + c) * H * W;
+        for (int h = 0; h < H; h++) for (int w = 0; w < W; w++) {
+            orc_flow_geom g = orc_flow_geometry(flow + (size_t)n * 2 * H * W, H, W, h, w);
+            if (g.off < 0) { t[h * W + w] = 0.f; continue; }
+            const float* p = b + g.off;
+            double A = 1.0 - (double)g.h, B = 1.0 - (double)g.w;
+            double acc = ((double)p[1] * A) * (double)g.w;                  /* :49 */
+            acc = fma((double)p[0] * A, B, acc);                            /* :48 */
+            acc = fma(B, (double)(p[W] * g.h), acc);                        /* :50, float product first */
+            acc = acc + (double)((p[W + 1] * g.h) * g.w);                   /* :51, all float */
+            t[h * W + w] = (float)acc;
+        }
+    }
+}
+
+/* bottomdiff (N,C,H,W) and flowdiff (N,2,H,W) must be zero-filled by the caller
+ * (functions/flow_align.py:41-43).  Fixed (c, h, w) summation order: deterministic, unlike the
+ * reference's atomics. */
+void orc_flow_align_bwd(const float* topdiff, const float* bottom, const float* flow,
+                        int N, int C, int H, int W, float* bottomdiff, float* flowdiff, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    #pragma omp parallel for schedule(static)
+    for (int n = 0; n < N; n++) {
+        float* fdx = flowdiff + (size_t)n * 2 * H * W;
+        float* fdy = fdx + H * W;
+        for (int c = 0; c < C; c++) {
+            const float* b = bottom + ((size_t)n * C + c) * H * W;
+            const float* t = topdiff + ((size_t)n * C + c) * H * W;
+            float* d = bottomdiff + ((size_t)n * C + c) * H * W;
+            for (int h = 0; h < H; h++) for (int w = 0; w < W; w++) {
+                orc_flow_geom g = orc_flow_geometry(flow + (size_t)n * 2 * H * W, H, W, h, w);
+                if (g.off < 0) continue;
+                float tv = t[h * W + w];
+                double A = 1.0 - (double)g.h, B = 1.0 - (double)g.w;
+                d[g.off]         += (float)(((double)tv * A) * B);           /* :89 */
+                d[g.off + 1]     += (float)((A * (double)tv) * (double)g.w); /* :90 */
+                d[g.off + W]     += (float)(B * (double)(g.h * tv));         /* :91 */
+                d[g.off + W + 1] += g.w * (g.h * tv);                        /* :92 */
+                float f1 = b[g.off], f2 = b[g.off + 1], f3 = b[g.off + W], f4 = b[g.off + W + 1];
+                double dx = fma(A, (double)(-f1), A * (double)f2);           /* :104 */
+                dx = dx - (double)(g.h * f3);
+                dx = dx + (double)(g.h * f4);
+                double dy = fma(B, (double)(-f1), -(double)(g.w * f2));      /* :106 */
+                dy = fma(B, (double)f3, dy);
+                dy = dy + (double)(g.w * f4);
+                fdx[h * W + w] += tv * (float)dx;                            /* :111 */
+                fdy[h * W + w] += tv * (float)dy;                            /* :112 */
+            }
+        }
+    }
+}

@@ -55,6 +55,8 @@ def lib():
         L.orc_roialign_fwd.argtypes = sig
         L.orc_roialign_bwd.argtypes = sig
         L.orc_resize_linear.argtypes = [fp, ctypes.c_int, ctypes.c_int, fp, ctypes.c_int, ctypes.c_int]
+        L.orc_flow_align_fwd.argtypes = [fp, fp] + [ctypes.c_int] * 4 + [fp, ctypes.c_int]
+        L.orc_flow_align_bwd.argtypes = [fp, fp, fp] + [ctypes.c_int] * 4 + [fp, fp, ctypes.c_int]
         L.orc_num_threads.restype = ctypes.c_int
         _LIB = L
     return _LIB
@@ -297,6 +299,33 @@ def roi_align_backward(top_grad, rois, feat_shape, ph, pw, spatial_scale, sampli
         lib().orc_roialign_bwd(_fp(t), N, C, H, W, _fp(r), r.shape[0], ph, pw,
                                np.float32(spatial_scale), sampling_ratio, _fp(g), nthreads)
     return g
+
+
+# --------------------------------------------------------------------------- #
+# (f4) FlowAlign -- lib_vos/vos_model/flow_align/src/flow_align_cuda_kernel.cu:15-117
+# --------------------------------------------------------------------------- #
+def flow_align_forward(features, flows, nthreads=0):
+    f = np.ascontiguousarray(features, dtype=np.float32)
+    fl = np.ascontiguousarray(flows, dtype=np.float32)
+    N, C, H, W = f.shape
+    assert fl.shape == (N, 2, H, W)
+    out = np.zeros_like(f)
+    if f.size:
+        lib().orc_flow_align_fwd(_fp(f), _fp(fl), N, C, H, W, _fp(out), nthreads)
+    return out
+
+
+def flow_align_backward(top_grad, features, flows, nthreads=0):
+    """-> (grad_feature (N,C,H,W), grad_flow (N,2,H,W)), functions/flow_align.py:33-50."""
+    t = np.ascontiguousarray(top_grad, dtype=np.float32)
+    f = np.ascontiguousarray(features, dtype=np.float32)
+    fl = np.ascontiguousarray(flows, dtype=np.float32)
+    N, C, H, W = f.shape
+    gf = np.zeros_like(f)
+    gfl = np.zeros((N, 2, H, W), dtype=np.float32)
+    if f.size:
+        lib().orc_flow_align_bwd(_fp(t), _fp(f), _fp(fl), N, C, H, W, _fp(gf), _fp(gfl), nthreads)
+    return gf, gfl
 
 
 def roi_feature_transform(blobs_in, rpn_ret, blob_rois, resolution, spatial_scales, sampling_ratio,

@@ -166,3 +166,40 @@ def test_rle_restatement_round_trips_and_hand_vectors(orc):
     # negative differences (run i smaller than run i-2) survive the sign extension
     c = [5, 1000, 3, 2, 70000, 1]
     assert orc.rle_from_string(orc.rle_to_string(c)) == c
+
+
+def test_flow_align_oracle_vs_grid_sample_anchor(orc, synth):
+    """FlowAlign restatement (flow_align_cuda_kernel.cu:15-117) against a loose CPU anchor: inside the valid
+    range it is torch's bilinear grid_sample (align_corners=True), forward and both gradients; outside
+    [0,H-1) x [0,W-1) the reference writes 0 and propagates nothing.  The pin proper is the reference kernel on
+    the GPU (tests/test_gpu_flowalign.py)."""
+    import torch
+    N, C, H, W = 2, 5, 14, 19
+    rs = np.random.RandomState(3)
+    f = rs.standard_normal((N, C, H, W)).astype(np.float32)
+    fl = synth.flow_field(4, N, H, W, "smooth", 2.5)
+    out = orc.flow_align_forward(f, fl)
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    gx, gy = xs + fl[:, 0].astype(np.float64), ys + fl[:, 1].astype(np.float64)
+    inb = (gx >= 0) & (gx < W - 1) & (gy >= 0) & (gy < H - 1)
+    assert 0.3 < inb.mean() < 1.0
+    tf = torch.from_numpy(f).double().requires_grad_(True)
+    tfl = torch.from_numpy(fl).double().requires_grad_(True)
+    grid = torch.stack([(torch.from_numpy(xs) + tfl[:, 0]) / (W - 1) * 2 - 1,
+                        (torch.from_numpy(ys) + tfl[:, 1]) / (H - 1) * 2 - 1], -1)
+    ref = torch.nn.functional.grid_sample(tf, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+    m = torch.from_numpy(inb)[:, None].expand(N, C, H, W)
+    assert np.all(out[~m.numpy()] == 0)
+    assert np.abs(out - ref.detach().numpy())[m.numpy()].max() < 1e-5
+    g = rs.standard_normal((N, C, H, W)).astype(np.float32)
+    (ref * torch.from_numpy(g).double() * m).sum().backward()
+    gf, gfl = orc.flow_align_backward(g, f, fl)
+    assert np.abs(gf - tf.grad.numpy()).max() < 1e-4
+    assert np.abs(gfl - tfl.grad.numpy()).max() < 1e-4 * max(1.0, float(np.abs(gfl).max()))
+    # thread count does not change a bit
+    assert np.array_equal(out, orc.flow_align_forward(f, fl, nthreads=1))
+    # identity and integer shift are exact
+    z = orc.flow_align_forward(f, synth.flow_field(0, N, H, W, "zero"))
+    assert np.array_equal(z[:, :, :H - 1, :W - 1], f[:, :, :H - 1, :W - 1]) and not z[:, :, H - 1].any()
+    sh = orc.flow_align_forward(f, synth.flow_field(0, N, H, W, "shift"))
+    assert np.array_equal(sh[:, :, 1:H, :W - 3], f[:, :, 0:H - 1, 2:W - 1])

@@ -100,7 +100,7 @@ def main():
     scales = [1.0 / 2 ** l for l in lvls]
 
     # ---------------- cfg 2: multi-level RoIAlign fwd, 1000 RoIs x 256 ch, COCO blob ----------------
-    for N, R, tag in ((1, 1000, "cfg2"), (2, 1024, "cfg4box"), (2, 256, "cfg4mask")):
+    for N, R, tag in (((1, 1000, "cfg2"), (2, 1024, "cfg4box"), (2, 256, "cfg4mask")) if want("fwd") or want("bwd") else ()):
         feats = synth.fpn_features(2000, synth.COCO_BLOB, N, lvls, 256)
         fl = [cu(feats[l]) for l in lvls]
         shapes = {l: feats[l].shape[2:] for l in lvls}
@@ -217,6 +217,52 @@ def main():
                    lambda: ops.paste_rle_cuda(masks, cls, boxes, 480, 854, 0.5, run_capacity=cap_r, str_capacity=cap_s),
                    B * 100 * (28 * 28 * 4 + 16 + 28) + 4 * rc + rs,
                    {"dets": B * 100, "runs": rc, "string_bytes": rs, "dense_equivalent_bytes": B * 100 * 480 * 854})
+
+    # ---------------- FlowAlign: hidden states of the 5 FPN levels of DAVIS frames ----------------
+    if want("flow"):
+        from vosdetectron_b200 import _lib
+        so = os.path.join(ROOT, "oracle", "_ref", "libref_flowalign.so")
+        rlib = ctypes.CDLL(so) if os.path.exists(so) else None
+        if rlib is not None:
+            vp = ctypes.c_void_p
+            rlib.FlowAlignForward.argtypes = [ctypes.c_int] * 4 + [vp, vp, vp, vp]
+            rlib.FlowAlignBackward.argtypes = [ctypes.c_int] * 4 + [vp, vp, vp, vp, vp, vp]
+        for B in (1, 4):
+            shapes = [synth.level_shape(synth.DAVIS_BLOB, l) for l in synth.FPN_LEVELS]
+            feats = [torch.randn((B, 256, h, w), device="cuda") for h, w in shapes]
+            flows = [cu(synth.flow_field(4000 + i, B, h, w, "smooth", 2.0)) for i, (h, w) in enumerate(shapes)]
+            grads = [torch.randn_like(f) for f in feats]
+            elems = sum(f.numel() for f in feats)
+            flow_bytes = sum(f.numel() for f in flows) * 4
+            # forward: read every feature texel once + the flow, write every output element
+            alg_f = 2 * elems * 4 + flow_bytes
+            report(out, "flowalign_fwd_5lvl_%dframes" % B, timer, lambda: ops.flow_align_ml_forward(feats, flows), alg_f,
+                   {"elements": elems})
+            old = _lib.load().vosd_debug_flow_align_fast(1)
+            report(out, "flowalign_fwd_fp32variant_5lvl_%dframes" % B, timer,
+                   lambda: ops.flow_align_ml_forward(feats, flows), alg_f, {"elements": elems})
+            _lib.load().vosd_debug_flow_align_fast(old)
+            # backward: read topdiff + features + flow, write both gradients once (zero or sum)
+            alg_b = 3 * elems * 4 + 2 * flow_bytes
+            report(out, "flowalign_bwd_5lvl_%dframes" % B, timer,
+                   lambda: ops.flow_align_ml_backward(grads, feats, flows), alg_b, {"elements": elems})
+            if rlib is not None:
+                tops = [torch.empty_like(f) for f in feats]
+                gfs = [torch.empty_like(f) for f in feats]
+                gfls = [torch.empty_like(f) for f in flows]
+
+                def ref_f():
+                    for f, fl_, t in zip(feats, flows, tops):
+                        rlib.FlowAlignForward(B, f.shape[2], f.shape[3], 256, f.data_ptr(), fl_.data_ptr(), t.data_ptr(), stream())
+
+                def ref_b():
+                    for g, f, fl_, gf, gfl in zip(grads, feats, flows, gfs, gfls):
+                        gf.zero_(), gfl.zero_()
+                        rlib.FlowAlignBackward(B, f.shape[2], f.shape[3], 256, g.data_ptr(), f.data_ptr(), fl_.data_ptr(),
+                                               gf.data_ptr(), gfl.data_ptr(), stream())
+                report(out, "REFERENCE_flowalign_fwd_5lvl_%dframes" % B, timer, ref_f, alg_f, {"elements": elems})
+                report(out, "REFERENCE_flowalign_bwd_5lvl_%dframes" % B, timer, ref_b, alg_b, {"elements": elems})
+
 
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump({"peak_gbs_measured": PEAK, "gpu": torch.cuda.get_device_name(0), "results": out}, open(args.out, "w"), indent=1)

@@ -13,6 +13,8 @@ reference's Python call signatures:
     modeling.model_builder.roi_feature_transform
     utils.boxes.nms
     core.test.segm_results
+    vos_model.flow_align.functions.flow_align.FlowAlignFunction
+    vos_model.flow_align.modules.flow_align.FlowAlign
 
 ``install_reference_aliases()`` registers them under the reference's own module names so the
 unmodified lib/ and lib_vos/ model builders pick them up.
@@ -40,6 +42,13 @@ def install_reference_aliases(legacy_model_roi_align=True):
 
     put('modeling.roi_xfrom.roi_align.functions.roi_align', fn_mod)
     put('modeling.roi_xfrom.roi_align.modules.roi_align', mod_mod)
+    # lib_vos/vos_modeling/vos_model_builder.py:22 imports the module class; FAN.py:19 the package
+    from .vos_model import flow_align as fa_pkg
+    from .vos_model.flow_align.functions import flow_align as fa_fn
+    from .vos_model.flow_align.modules import flow_align as fa_mod
+    put('vos_model.flow_align', fa_pkg)
+    put('vos_model.flow_align.functions.flow_align', fa_fn)
+    put('vos_model.flow_align.modules.flow_align', fa_mod)
     if legacy_model_roi_align:
         # lib/model/roi_align is the dead 3-argument variant with different maths
         # (src/roi_align_kernel.cu:40-46); alias only the 4-argument form.
@@ -57,4 +66,4 @@ def install_reference_aliases(legacy_model_roi_align=True):
         if ref_name in sys.modules:
             for n in names:
                 setattr(sys.modules[ref_name], n, getattr(m, n))
-    return sorted(k for k in sys.modules if k.startswith(('modeling.roi_xfrom', 'model.roi_align')))
+    return sorted(k for k in sys.modules if k.startswith(('modeling.roi_xfrom', 'model.roi_align', 'vos_model.flow_align')))

@@ -74,6 +74,13 @@ SIGNATURES = {
                                       vp, vp]),
     "vosd_paste_masks_packed": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int, ctypes.c_float, vp, vp, vp]),
+    "vosd_flow_align_fwd": (ctypes.c_int, [ctypes.c_int] * 4 + [vp, vp, vp, vp]),
+    "vosd_flow_align_bwd": (ctypes.c_int, [ctypes.c_int] * 4 + [vp, vp, vp, vp, vp, ctypes.c_int, vp]),
+    "vosd_flow_align_ml_fwd": (ctypes.c_int, [ctypes.c_int] * 3 + [c_int_p, c_int_p, ctypes.POINTER(vp),
+                                              ctypes.POINTER(vp), ctypes.POINTER(vp), vp]),
+    "vosd_flow_align_ml_bwd": (ctypes.c_int, [ctypes.c_int] * 3 + [c_int_p, c_int_p] + [ctypes.POINTER(vp)] * 5
+                               + [ctypes.c_int, vp]),
+    "vosd_debug_flow_align_fast": (ctypes.c_int, [ctypes.c_int]),
     "vosd_paste_masks": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_float, vp, vp, vp]),
 }

@@ -106,6 +106,84 @@ def roi_align_ml_backward(grad_output, level_shapes, level_scales, rois, roi_lev
     return grads
 
 
+# ----------------------------------------------------------------------------- FlowAlign
+def _flow_pair(features, flows):
+    f = _need_cuda(features, "features")
+    fl = _need_cuda(flows, "flows")
+    if f.dim() != 4 or fl.dim() != 4:
+        raise ValueError("features must be (N,C,H,W) and flows (N,2,H,W)")
+    N, C, H, W = f.shape
+    if tuple(fl.shape) != (N, 2, H, W):
+        # the reference only asserts this (functions/flow_align.py:23-25) and would read out of bounds
+        raise ValueError("flows %s does not match features %s" % (tuple(fl.shape), tuple(f.shape)))
+    return f, fl
+
+
+def flow_align_forward(features, flows):
+    """(N,C,H,W) x (N,2,H,W) -> (N,C,H,W); flow_align_cuda_kernel.cu:15-55 semantics, bit-identical."""
+    f, fl = _flow_pair(features, flows)
+    N, C, H, W = f.shape
+    out = torch.empty_like(f)
+    _bind(f)
+    _lib.call("vosd_flow_align_fwd", N, H, W, C, _ptr(f), _ptr(fl), _ptr(out), _stream())
+    return out
+
+
+def flow_align_backward(grad_output, features, flows):
+    """-> (grad_feature, grad_flow); flow_align_cuda_kernel.cu:57-117.  Both gradients are cleared on the
+    stream by the library (zero_init=1)."""
+    f, fl = _flow_pair(features, flows)
+    g = _need_cuda(grad_output, "grad_output")
+    if g.shape != f.shape:
+        raise ValueError("grad_output %s does not match features %s" % (tuple(g.shape), tuple(f.shape)))
+    N, C, H, W = f.shape
+    gf = torch.empty_like(f)
+    gfl = torch.empty_like(fl)
+    _bind(f)
+    _lib.call("vosd_flow_align_bwd", N, H, W, C, _ptr(g), _ptr(f), _ptr(fl), _ptr(gf), _ptr(gfl), 1, _stream())
+    return gf, gfl
+
+
+def _ptr_table(tensors):
+    return (vp * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def flow_align_ml_forward(level_features, level_flows):
+    """Every FPN level in one launch (the loop of vos_model_builder.py:329-335); level k warps
+    ``level_features[k]`` by ``level_flows[k]`` (already at that level's resolution)."""
+    pairs = [_flow_pair(f, fl) for f, fl in zip(level_features, level_flows)]
+    if not pairs:
+        return []
+    N, C = pairs[0][0].shape[:2]
+    if any(f.shape[:2] != (N, C) for f, _ in pairs):
+        raise ValueError("all levels must share batch size and channel count")
+    outs = [torch.empty_like(f) for f, _ in pairs]
+    L = len(pairs)
+    hs = (ctypes.c_int * L)(*[int(f.shape[2]) for f, _ in pairs])
+    ws = (ctypes.c_int * L)(*[int(f.shape[3]) for f, _ in pairs])
+    _bind(pairs[0][0])
+    _lib.call("vosd_flow_align_ml_fwd", L, N, C, hs, ws, _ptr_table([f for f, _ in pairs]),
+              _ptr_table([fl for _, fl in pairs]), _ptr_table(outs), _stream())
+    return outs
+
+
+def flow_align_ml_backward(level_grads, level_features, level_flows):
+    pairs = [_flow_pair(f, fl) for f, fl in zip(level_features, level_flows)]
+    if not pairs:
+        return [], []
+    grads = [_need_cuda(g, "grad_output") for g in level_grads]
+    N, C = pairs[0][0].shape[:2]
+    gfs = [torch.empty_like(f) for f, _ in pairs]
+    gfls = [torch.empty_like(fl) for _, fl in pairs]
+    L = len(pairs)
+    hs = (ctypes.c_int * L)(*[int(f.shape[2]) for f, _ in pairs])
+    ws = (ctypes.c_int * L)(*[int(f.shape[3]) for f, _ in pairs])
+    _bind(pairs[0][0])
+    _lib.call("vosd_flow_align_ml_bwd", L, N, C, hs, ws, _ptr_table(grads), _ptr_table([f for f, _ in pairs]),
+              _ptr_table([fl for _, fl in pairs]), _ptr_table(gfs), _ptr_table(gfls), 1, _stream())
+    return gfs, gfls
+
+
 # ----------------------------------------------------------------------------- proposals
 def make_rpn_levels(level_inputs):
     """level_inputs: list of (scores (N,A,H,W), deltas (N,4A,H,W), anchors ndarray (A,4) float64,

@@ -158,3 +158,32 @@ def box_head_outputs(seed, R=1000, K=81, im_hw=COCO_BLOB, fg_frac=0.25):
     d[:, 0::4] = rs.normal(0, 0.5, (R, K)); d[:, 1::4] = rs.normal(0, 0.5, (R, K))
     d[:, 2::4] = rs.normal(0, 0.25, (R, K)); d[:, 3::4] = rs.normal(0, 0.25, (R, K))
     return props.astype(np.float32), scores, d
+
+
+def flow_field(seed, N, H, W, kind="smooth", magnitude=2.0):
+    """Synthetic optical flow (N,2,H,W) fp32 at feature-map resolution, plane 0 = x, plane 1 = y.
+
+    ``smooth``: a low-frequency displacement field (a few Fourier modes, |flow| <~ magnitude) plus 2 % pixel
+    noise -- what a down-sampled DAVIS flow looks like; ``noise``: i.i.d. N(0, magnitude^2), every pixel its own
+    geometry; ``zero`` / ``shift``: constant fields (identity / integer translation by (+2, -1))."""
+    rs = np.random.RandomState(seed)
+    if kind == "zero":
+        return np.zeros((N, 2, H, W), dtype=np.float32)
+    if kind == "shift":
+        f = np.zeros((N, 2, H, W), dtype=np.float32)
+        f[:, 0] = 2.0
+        f[:, 1] = -1.0
+        return f
+    if kind == "noise":
+        return (rs.standard_normal((N, 2, H, W)) * magnitude).astype(np.float32)
+    ys, xs = np.meshgrid(np.arange(H) / max(H, 1), np.arange(W) / max(W, 1), indexing="ij")
+    f = np.zeros((N, 2, H, W), dtype=np.float64)
+    for n in range(N):
+        for p in range(2):
+            for _ in range(4):
+                ky, kx = rs.randint(0, 3, size=2)
+                ph = rs.uniform(0, 2 * np.pi, size=2)
+                f[n, p] += rs.uniform(-1, 1) * np.sin(2 * np.pi * ky * ys + ph[0]) * np.cos(2 * np.pi * kx * xs + ph[1])
+            f[n, p] *= magnitude / 2.0
+    f += rs.standard_normal(f.shape) * 0.02 * magnitude
+    return f.astype(np.float32)

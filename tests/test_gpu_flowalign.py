@@ -49,6 +49,16 @@ def refk():
     return R
 
 
+@pytest.fixture(params=["alu", "cvt"])
+def exact_mode(request):
+    """Both bit-exact arithmetic variants of the kernels: 2 = float->double widening on the ALU pipe (default),
+    0 = the reference's expression as written (F2F conversions)."""
+    from vosdetectron_b200 import _lib
+    old = _lib.load().vosd_debug_flow_align_fast({"alu": 2, "cvt": 0}[request.param])
+    yield request.param
+    _lib.load().vosd_debug_flow_align_fast(old)
+
+
 def same_bits(a, b):
     """Bitwise equality, except that any NaN matches any NaN (payloads are not part of the contract)."""
     a, b = a.contiguous(), b.contiguous()
@@ -85,7 +95,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "%dx%dx%dx%d-%s" % c[:5])
-def test_forward_bit_identical(case, refk, orc, synth):
+def test_forward_bit_identical(case, refk, orc, synth, exact_mode):
     from vosdetectron_b200 import ops
     N, C, H, W, kind, mag = case
     f, fl, _ = make(synth, 11, N, C, H, W, kind, mag)
@@ -97,7 +107,7 @@ def test_forward_bit_identical(case, refk, orc, synth):
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "%dx%dx%dx%d-%s" % c[:5])
-def test_backward_vs_reference_kernel_and_oracle(case, refk, orc, synth):
+def test_backward_vs_reference_kernel_and_oracle(case, refk, orc, synth, exact_mode):
     from vosdetectron_b200 import ops
     N, C, H, W, kind, mag = case
     f, fl, g = make(synth, 13, N, C, H, W, kind, mag)
@@ -126,7 +136,7 @@ def test_forward_fast_variant_within_1e5(refk, synth):
     assert ok, "max err %g (scale %g)" % (err, scale)
 
 
-def test_nan_and_inf_flow_follow_the_reference(refk, synth):
+def test_nan_and_inf_flow_follow_the_reference(refk, synth, exact_mode):
     from vosdetectron_b200 import ops
     f, fl, g = make(synth, 19, 1, 6, 12, 16, "smooth", 1.0)
     fl[0, 0, 3, 4] = float("nan")
@@ -140,6 +150,30 @@ def test_nan_and_inf_flow_follow_the_reference(refk, synth):
     rf, rfl = refk.bwd(g, f, fl)
     assert bool((torch.isnan(gf) == torch.isnan(rf)).all()) and bool((torch.isnan(gfl) == torch.isnan(rfl)).all())
     fin = ~torch.isnan(rf)
+    assert close(gf[fin], rf[fin])[0]
+
+
+def test_non_finite_and_denormal_features_are_bit_identical(refk, synth, exact_mode):
+    """The ALU widening is exact for zero / denormal taps; Inf / NaN taps take the reference expression."""
+    from vosdetectron_b200 import ops
+    f, fl, g = make(synth, 23, 1, 8, 16, 40, "smooth", 1.0)
+    rs = np.random.RandomState(5)
+    idx = rs.randint(0, f.numel(), size=200)
+    flat = f.view(-1)
+    flat[idx[:50]] = float("inf")
+    flat[idx[50:80]] = float("-inf")
+    flat[idx[80:120]] = float("nan")
+    flat[idx[120:160]] = 1e-42          # denormal
+    flat[idx[160:180]] = -0.0
+    flat[idx[180:]] = 3e38              # finite, but the 4-tap sum can overflow
+    g.view(-1)[rs.randint(0, g.numel(), size=20)] = float("inf")
+    g.view(-1)[rs.randint(0, g.numel(), size=20)] = 2e-44
+    assert same_bits(ops.flow_align_forward(f, fl), refk.fwd(f, fl))
+    gf, gfl = ops.flow_align_backward(g, f, fl)
+    rf, rfl = refk.bwd(g, f, fl)
+    assert bool((torch.isnan(gf) == torch.isnan(rf)).all()) and bool((torch.isnan(gfl) == torch.isnan(rfl)).all())
+    assert bool((torch.isinf(gf) == torch.isinf(rf)).all())
+    fin = torch.isfinite(rf)
     assert close(gf[fin], rf[fin])[0]
 
 

@@ -236,16 +236,16 @@ def main():
             flow_bytes = sum(f.numel() for f in flows) * 4
             # forward: read every feature texel once + the flow, write every output element
             alg_f = 2 * elems * 4 + flow_bytes
-            report(out, "flowalign_fwd_5lvl_%dframes" % B, timer, lambda: ops.flow_align_ml_forward(feats, flows), alg_f,
-                   {"elements": elems})
-            old = _lib.load().vosd_debug_flow_align_fast(1)
-            report(out, "flowalign_fwd_fp32variant_5lvl_%dframes" % B, timer,
-                   lambda: ops.flow_align_ml_forward(feats, flows), alg_f, {"elements": elems})
-            _lib.load().vosd_debug_flow_align_fast(old)
             # backward: read topdiff + features + flow, write both gradients once (zero or sum)
             alg_b = 3 * elems * 4 + 2 * flow_bytes
-            report(out, "flowalign_bwd_5lvl_%dframes" % B, timer,
-                   lambda: ops.flow_align_ml_backward(grads, feats, flows), alg_b, {"elements": elems})
+            for mode, tag in ((2, ""), (0, "_cvtvariant"), (1, "_fp32variant")):
+                old = _lib.load().vosd_debug_flow_align_fast(mode)
+                report(out, "flowalign_fwd%s_5lvl_%dframes" % (tag, B), timer,
+                       lambda: ops.flow_align_ml_forward(feats, flows), alg_f, {"elements": elems})
+                if mode != 1:
+                    report(out, "flowalign_bwd%s_5lvl_%dframes" % (tag, B), timer,
+                           lambda: ops.flow_align_ml_backward(grads, feats, flows), alg_b, {"elements": elems})
+                _lib.load().vosd_debug_flow_align_fast(old)
             if rlib is not None:
                 tops = [torch.empty_like(f) for f in feats]
                 gfs = [torch.empty_like(f) for f in feats]

@@ -88,65 +88,131 @@ __device__ __forceinline__ int flow_geometry(const float* __restrict__ flow_n, i
 }
 
 // ------------------------------------------------------------------------------------- forward
-template <bool EXACT>
+// Arithmetic variants of the forward (same loads, same stores):
+//   kFlowExactCvt   the reference's expression as written (:48-51): 4 F2F.F64.F32 + 1 F2F.F32.F64 per element, all on
+//                   the 16-lane XU pipe, which then bounds the kernel (63 % XU utilisation in the first capture);
+//   kFlowExactAlu   the same double-precision operation sequence with the float->double widening done as a bit
+//                   shuffle on the ALU pipe: widen_scaled(x) = x * 2^-896 exactly (finite x, zero and denormals
+//                   included); the 2^896 is folded into the per-pixel factors, so every rounding happens on the same
+//                   real value as in the reference -> the same bits.  Elements with a non-finite tap take the
+//                   F2F expression;
+//   kFlowFp32       plain fp32 bilinear weights (test / tuning hook, not bit-identical).
+enum { kFlowExactCvt = 0, kFlowFp32 = 1, kFlowExactAlu = 2 };
+
+// x * 2^-896 as a double, exact for every finite float (a float's exponent field e8 becomes the double's
+// exponent field; denormals map to double denormals with the same scale factor).
+__device__ __forceinline__ double widen_scaled(float x) {
+    const int u = __float_as_int(x);
+    return __hiloint2double((u >> 3) & 0x8FFFFFFF, (int)((unsigned)u << 29));
+}
+
+// flow_align_cuda_kernel.cu:48-51 exactly as written there (operand types included).
+__device__ __forceinline__ float flow_bilinear_ref(float b1, float b2, float b3, float b4, float h_ratio, float w_ratio) {
+    return b1 * (1. - h_ratio) * (1. - w_ratio)
+         + b2 * (1. - h_ratio) * (w_ratio)
+         + b3 * (h_ratio) * (1. - w_ratio)
+         + b4 * (h_ratio) * (w_ratio);
+}
+__device__ __noinline__ float flow_bilinear_ref_cold(float b1, float b2, float b3, float b4, float h_ratio, float w_ratio) {
+    return flow_bilinear_ref(b1, b2, b3, b4, h_ratio, w_ratio);
+}
+
+// Per-pixel double factors kept in registers across the channel loop.
+template <int MODE> struct FlowFactors;
+template <> struct FlowFactors<kFlowExactCvt> { __device__ void set(float, float) {} };
+template <> struct FlowFactors<kFlowFp32> { __device__ void set(float, float) {} };
+template <> struct FlowFactors<kFlowExactAlu> {
+    double oh_s, ow, ow_s, wd;      // (1-h)*2^896, (1-w), (1-w)*2^896, (double)w
+    __device__ void set(float h_ratio, float w_ratio) {
+        const double oh = 1. - h_ratio;
+        ow = 1. - w_ratio;
+        oh_s = oh * 0x1p896;
+        ow_s = ow * 0x1p896;
+        wd = w_ratio;
+    }
+};
+
+template <int MODE>
+__device__ __forceinline__ float flow_bilinear(float b1, float b2, float b3, float b4, float h_ratio, float w_ratio,
+                                               const FlowFactors<MODE>& f) {
+    if constexpr (MODE == kFlowFp32) {
+        const float fh = 1.f - h_ratio, fw = 1.f - w_ratio;
+        return fmaf(b4, h_ratio * w_ratio, fmaf(b3, h_ratio * fw, fmaf(b2, fh * w_ratio, b1 * (fh * fw))));
+    } else if constexpr (MODE == kFlowExactAlu) {
+        // operation order of the reference's SASS: T2 = (b2*A)*w; fma(b1*A, B, T2); fma(B, b3*h, .); + b4*h*w
+        double acc = __dmul_rn(__dmul_rn(widen_scaled(b2), f.oh_s), f.wd);
+        acc = __fma_rn(__dmul_rn(widen_scaled(b1), f.oh_s), f.ow, acc);
+        acc = __fma_rn(f.ow_s, widen_scaled(__fmul_rn(b3, h_ratio)), acc);
+        acc = __fma_rn(widen_scaled(__fmul_rn(__fmul_rn(b4, h_ratio), w_ratio)), 0x1p896, acc);
+        float v = __double2float_rn(acc);
+        const float s = (b1 + b2) + (b3 + b4);                      // non-finite iff some tap is (or the sum overflows)
+        if ((__float_as_uint(s) & 0x7f800000u) == 0x7f800000u)      // rare: the widening shuffle is for finite taps
+            v = flow_bilinear_ref_cold(b1, b2, b3, b4, h_ratio, w_ratio);
+        return v;
+    } else {
+        return flow_bilinear_ref(b1, b2, b3, b4, h_ratio, w_ratio);
+    }
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(kFlowThreads) flow_align_fwd_kernel(const __grid_constant__ FlowArgs a) {
     const FlowTile t = decode_tile(a);
     const FlowLevelArgs& L = a.lv[t.level];
-    const int H = L.H, W = L.W, plane = H * W;
+    const int H = L.H, W = L.W, plane = H * W;      // H, W >= 2 (smaller maps never reach the kernel)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w = t.tx * 32 + lane;
     const int h0 = (t.ty * kFlowWarps + warp) * kFlowRows;
     if (h0 >= H) return;   // warp-uniform
 
     int off[kFlowRows];         // -2: no pixel here, -1: pixel written as 0, >= 0: up-left tap
+    int ld[kFlowRows];          // tap offset actually loaded: taps are fetched unconditionally (offset 0 for dead pixels)
     float hr[kFlowRows], wr[kFlowRows];
+    FlowFactors<MODE> fac[kFlowRows];
     const float* flow_n = L.flow + (size_t)t.n * 2 * plane;
 #pragma unroll
     for (int r = 0; r < kFlowRows; ++r) {
         off[r] = -2;
         hr[r] = wr[r] = 0.f;
         if (h0 + r < H && w < W) off[r] = flow_geometry(flow_n, plane, H, W, h0 + r, w, hr[r], wr[r]);
-    }
-
-    double oh[kFlowRows], ow[kFlowRows], wd[kFlowRows];
-#pragma unroll
-    for (int r = 0; r < kFlowRows; ++r) {
-        oh[r] = 1. - hr[r];
-        ow[r] = 1. - wr[r];
-        wd[r] = wr[r];
+        ld[r] = max(off[r], 0);
+        fac[r].set(hr[r], wr[r]);
     }
 
     const int c0 = t.chunk * a.chunk;
     const int c1 = min(c0 + a.chunk, a.C);
     const float* base = L.bottom + ((size_t)t.n * a.C + c0) * plane;
     float* out = L.out0 + ((size_t)t.n * a.C + c0) * plane + (size_t)h0 * W + w;
-#pragma unroll 2
-    for (int c = c0; c < c1; ++c, base += plane, out += plane) {
-        float v[kFlowRows];
+
+    // Two register sets: the taps of channel c+1 are in flight while channel c is computed and stored.
+    float cur[kFlowRows][4], nxt[kFlowRows][4];
+    auto fetch = [&](float (&b)[kFlowRows][4], const float* p) {
 #pragma unroll
         for (int r = 0; r < kFlowRows; ++r) {
-            v[r] = 0.f;
-            if (off[r] >= 0) {
-                const float* p = base + off[r];
-                const float b1 = __ldg(p), b2 = __ldg(p + 1), b3 = __ldg(p + W), b4 = __ldg(p + W + 1);
-                const float h_ratio = hr[r], w_ratio = wr[r];
-                if (EXACT) {
-                    // flow_align_cuda_kernel.cu:48-51, operand types as in the reference; the two double
-                    // factors (1. - h_ratio), (1. - w_ratio) and the widened w_ratio are per pixel and kept in registers
-                    v[r] = b1 * oh[r] * ow[r]
-                         + b2 * oh[r] * wd[r]
-                         + b3 * (h_ratio) * ow[r]
-                         + b4 * (h_ratio) * (w_ratio);
-                } else {
-                    const float oh = 1.f - h_ratio, ow = 1.f - w_ratio;
-                    v[r] = fmaf(b4, h_ratio * w_ratio, fmaf(b3, h_ratio * ow, fmaf(b2, oh * w_ratio, b1 * (oh * ow))));
-                }
-            }
+            b[r][0] = __ldg(p + ld[r]);
+            b[r][1] = __ldg(p + ld[r] + 1);
+            b[r][2] = __ldg(p + ld[r] + W);
+            b[r][3] = __ldg(p + ld[r] + W + 1);
         }
+    };
+    auto emit = [&](const float (&b)[kFlowRows][4], float* o) {
 #pragma unroll
-        for (int r = 0; r < kFlowRows; ++r)
-            if (off[r] != -2) __stcs(out + r * W, v[r]);
+        for (int r = 0; r < kFlowRows; ++r) {
+            float v = flow_bilinear<MODE>(b[r][0], b[r][1], b[r][2], b[r][3], hr[r], wr[r], fac[r]);
+            if (off[r] < 0) v = 0.f;
+            if (off[r] != -2) __stcs(o + r * W, v);
+        }
+    };
+    fetch(cur, base);
+    int c = c0;
+    for (; c + 2 <= c1; c += 2) {
+        fetch(nxt, base + plane);
+        emit(cur, out);
+        if (c + 2 < c1) fetch(cur, base + 2 * (size_t)plane);
+        emit(nxt, out + plane);
+        base += 2 * (size_t)plane;
+        out += 2 * (size_t)plane;
     }
+    if (c < c1) emit(cur, out);
 }
 
 // ------------------------------------------------------------------------------------- backward
@@ -154,28 +220,96 @@ __device__ __forceinline__ void red_add(float* p, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
 }
 
+// The six values of one element, flow_align_cuda_kernel.cu:89-112 exactly as written there:
+// a1..a4 = what the reference hands to atomicAdd(bottomdiff + tap, .), dx / dy = its flow-gradient factors.
+struct FlowGrad {
+    float a1, a2, a3, a4, dx, dy;
+};
+__device__ __forceinline__ FlowGrad flow_grad_ref(float g, float f1, float f2, float f3, float f4,
+                                                  float h_ratio, float w_ratio) {
+    FlowGrad o;
+    o.a1 = g * (1. - h_ratio) * (1. - w_ratio);
+    o.a2 = g * (1. - h_ratio) * (w_ratio);
+    o.a3 = g * (h_ratio) * (1. - w_ratio);
+    o.a4 = g * (h_ratio) * (w_ratio);
+    o.dx = -f1 * (1. - h_ratio) + f2 * (1. - h_ratio) - f3 * (h_ratio) + f4 * (h_ratio);
+    o.dy = -f1 * (1. - w_ratio) - f2 * (w_ratio) + f3 * (1. - w_ratio) + f4 * (w_ratio);
+    return o;
+}
+__device__ __noinline__ void flow_grad_ref_cold(FlowGrad* o, float g, float f1, float f2, float f3, float f4,
+                                                float h_ratio, float w_ratio) {
+    *o = flow_grad_ref(g, f1, f2, f3, f4, h_ratio, w_ratio);
+}
+
+// Same double-precision operation sequence (read from the reference's SASS, see oracle/oracle.c) with most
+// float->double widenings done on the ALU pipe (widen_scaled) and the 2^896 folded into the pixel's factors;
+// three widenings stay on the XU pipe to balance the two.  Bit-identical for finite inputs; anything else
+// takes the expression as written.
+struct FlowBwdFactors {
+    double oh, oh_s, ow, ow_s, wd;
+    __device__ __forceinline__ void set(float h_ratio, float w_ratio) {
+        oh = 1. - h_ratio;
+        ow = 1. - w_ratio;
+        oh_s = oh * 0x1p896;
+        ow_s = ow * 0x1p896;
+        wd = w_ratio;
+    }
+};
+__device__ __forceinline__ FlowGrad flow_grad(float g, float f1, float f2, float f3, float f4, float h_ratio,
+                                              float w_ratio, const FlowBwdFactors& k) {
+    FlowGrad o;
+    const float gh = __fmul_rn(g, h_ratio);
+    const double ga = __dmul_rn(widen_scaled(g), k.oh_s);                         // d(g) * (1-h)
+    o.a1 = __double2float_rn(__dmul_rn(ga, k.ow));
+    o.a2 = __double2float_rn(__dmul_rn(ga, k.wd));
+    o.a3 = __double2float_rn(__dmul_rn(k.ow, (double)gh));
+    o.a4 = __fmul_rn(gh, w_ratio);
+    const double nf1 = widen_scaled(-f1);
+    double x = __dmul_rn(k.oh_s, widen_scaled(f2));                               // A*f2
+    x = __fma_rn(k.oh_s, nf1, x);                                                 // A*(-f1) + .
+    x = __fma_rn(widen_scaled(__fmul_rn(h_ratio, f3)), -0x1p896, x);              // . - d(h*f3)
+    x = __fma_rn(widen_scaled(__fmul_rn(h_ratio, f4)), 0x1p896, x);               // . + d(h*f4)
+    o.dx = __double2float_rn(x);
+    double y = __dmul_rn(widen_scaled(__fmul_rn(w_ratio, f2)), -0x1p896);         // -d(w*f2), exact
+    y = __fma_rn(k.ow_s, nf1, y);                                                 // B*(-f1) - d(w*f2)
+    y = __fma_rn(k.ow, (double)f3, y);                                            // B*f3 + .
+    y = y + (double)__fmul_rn(w_ratio, f4);                                       // . + d(w*f4)
+    o.dy = __double2float_rn(y);
+    const float s = ((f1 + f2) + (f3 + f4)) + g;
+    if ((__float_as_uint(s) & 0x7f800000u) == 0x7f800000u)                        // rare: some input is not finite
+        flow_grad_ref_cold(&o, g, f1, f2, f3, f4, h_ratio, w_ratio);
+    return o;
+}
+
+template <bool ALU>
 __global__ void __launch_bounds__(kFlowThreads) flow_align_bwd_kernel(const __grid_constant__ FlowArgs a) {
     const FlowTile t = decode_tile(a);
     const FlowLevelArgs& L = a.lv[t.level];
-    const int H = L.H, W = L.W, plane = H * W;
+    const int H = L.H, W = L.W, plane = H * W;      // H, W >= 2
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w = t.tx * 32 + lane;
     const int h0 = (t.ty * kFlowWarps + warp) * kFlowRows;
     if (h0 >= H) return;   // warp-uniform: every shuffle below is executed by all 32 lanes
 
-    int off[kFlowRows];
+    int off[kFlowRows];         // < 0: nothing flows back from this pixel
+    int ld[kFlowRows], ldg[kFlowRows];
     float hr[kFlowRows], wr[kFlowRows];
+    FlowBwdFactors fac[kFlowRows];
     const float* flow_n = L.flow + (size_t)t.n * 2 * plane;
 #pragma unroll
     for (int r = 0; r < kFlowRows; ++r) {
         off[r] = -1;
         hr[r] = wr[r] = 0.f;
-        if (h0 + r < H && w < W) off[r] = flow_geometry(flow_n, plane, H, W, h0 + r, w, hr[r], wr[r]);
+        const bool inside = h0 + r < H && w < W;
+        if (inside) off[r] = flow_geometry(flow_n, plane, H, W, h0 + r, w, hr[r], wr[r]);
+        ld[r] = max(off[r], 0);                                  // loads are unconditional: dead pixels read texel 0
+        ldg[r] = inside ? (h0 + r) * W + w : 0;
+        if (ALU) fac[r].set(hr[r], wr[r]);
     }
     // Merge flags, one bit per row (pixel-only, hoisted out of the channel loop):
     //   vm: this pixel's top taps are the previous row's bottom taps (same thread) -> the pending pair is folded in
     //   hl: this pixel's left taps are the left lane's right taps -> that lane's right column is folded in here
-    //   hr: the right lane folds this lane's right column -> this lane does not emit it
+    //   hrm: the right lane folds this lane's right column -> this lane does not emit it
     unsigned vm = 0, hl = 0, hrm = 0;
 #pragma unroll
     for (int r = 0; r < kFlowRows; ++r) {
@@ -191,37 +325,28 @@ __global__ void __launch_bounds__(kFlowThreads) flow_align_bwd_kernel(const __gr
     const int c1 = min(c0 + a.chunk, a.C);
     const size_t cbase = ((size_t)t.n * a.C + c0) * plane;
     const float* base = L.bottom + cbase;
-    const float* td = L.topdiff + cbase + (size_t)h0 * W + w;
+    const float* td = L.topdiff + cbase;
     float* bd = L.out0 + cbase;
     float gx[kFlowRows], gy[kFlowRows];
 #pragma unroll
     for (int r = 0; r < kFlowRows; ++r) gx[r] = gy[r] = 0.f;
 
-    for (int c = c0; c < c1; ++c, base += plane, td += plane, bd += plane) {
-        float a1[kFlowRows], a2[kFlowRows], a3[kFlowRows], a4[kFlowRows];
+    // Two register sets: the five loads per pixel of channel c+1 are in flight while channel c is scattered.
+    float cur[kFlowRows][5], nxt[kFlowRows][5];
+    auto fetch = [&](float (&b)[kFlowRows][5], const float* p, const float* q) {
 #pragma unroll
         for (int r = 0; r < kFlowRows; ++r) {
-            a1[r] = a2[r] = a3[r] = a4[r] = 0.f;
-            if (off[r] >= 0) {
-                const float* p = base + off[r];
-                const float f1 = __ldg(p), f2 = __ldg(p + 1), f3 = __ldg(p + W), f4 = __ldg(p + W + 1);
-                const float g = __ldcs(td + r * W);
-                const float h_ratio = hr[r], w_ratio = wr[r];
-                // flow_align_cuda_kernel.cu:89-92: the values handed to atomicAdd(float*, float)
-                a1[r] = g * (1. - h_ratio) * (1. - w_ratio);
-                a2[r] = g * (1. - h_ratio) * (w_ratio);
-                a3[r] = g * (h_ratio) * (1. - w_ratio);
-                a4[r] = g * (h_ratio) * (w_ratio);
-                // :95-110
-                const float dx = -f1 * (1. - h_ratio) + f2 * (1. - h_ratio) - f3 * (h_ratio) + f4 * (h_ratio);
-                const float dy = -f1 * (1. - w_ratio) - f2 * (w_ratio) + f3 * (1. - w_ratio) + f4 * (w_ratio);
-                gx[r] += __fmul_rn(g, dx);
-                gy[r] += __fmul_rn(g, dy);
-            }
+            b[r][0] = __ldg(p + ld[r]);
+            b[r][1] = __ldg(p + ld[r] + 1);
+            b[r][2] = __ldg(p + ld[r] + W);
+            b[r][3] = __ldg(p + ld[r] + W + 1);
+            b[r][4] = __ldcs(q + ldg[r]);
         }
-        // emit: top taps of row r (+ the pending bottom taps of row r-1 when they coincide), bottom taps of the
-        // last row; horizontally, a lane's right column goes to the right lane when that lane's left column is
-        // the same texel column.
+    };
+    // emit: top taps of row r (+ the pending bottom taps of row r-1 when they coincide), bottom taps of the last
+    // row; horizontally, a lane's right column goes to the right lane when that lane's left column is the same
+    // texel column.
+    auto scatter = [&](const float (&b)[kFlowRows][5], float* d) {
         float pl = 0.f, pr = 0.f;     // pending bottom pair of the previous row
 #pragma unroll
         for (int r = 0; r <= kFlowRows; ++r) {
@@ -229,17 +354,22 @@ __global__ void __launch_bounds__(kFlowThreads) flow_align_bwd_kernel(const __gr
             int o;
             unsigned bit;
             if (r < kFlowRows) {
+                FlowGrad v = ALU ? flow_grad(b[r][4], b[r][0], b[r][1], b[r][2], b[r][3], hr[r], wr[r], fac[r])
+                                 : flow_grad_ref(b[r][4], b[r][0], b[r][1], b[r][2], b[r][3], hr[r], wr[r]);
+                if (off[r] < 0) v.a1 = v.a2 = v.a3 = v.a4 = v.dx = v.dy = 0.f;
+                gx[r] += __fmul_rn(b[r][4], v.dx);               // :111-112, summed over the chunk first
+                gy[r] += __fmul_rn(b[r][4], v.dy);
                 if (r > 0 && !((vm >> r) & 1u) && off[r - 1] >= 0) {   // previous row's bottom pair stands alone
-                    red_add(bd + off[r - 1] + W, pl);
-                    red_add(bd + off[r - 1] + W + 1, pr);
+                    red_add(d + off[r - 1] + W, pl);
+                    red_add(d + off[r - 1] + W + 1, pr);
                     pl = pr = 0.f;
                 }
-                tl = a1[r] + (((vm >> r) & 1u) ? pl : 0.f);
-                tr = a2[r] + (((vm >> r) & 1u) ? pr : 0.f);
+                tl = v.a1 + (((vm >> r) & 1u) ? pl : 0.f);
+                tr = v.a2 + (((vm >> r) & 1u) ? pr : 0.f);
                 o = off[r];
                 bit = r;
-                pl = a3[r];
-                pr = a4[r];
+                pl = v.a3;
+                pr = v.a4;
             } else {                                                   // bottom pair of the thread's last row
                 tl = pl;
                 tr = pr;
@@ -249,23 +379,34 @@ __global__ void __launch_bounds__(kFlowThreads) flow_align_bwd_kernel(const __gr
             const float from_left = __shfl_up_sync(0xffffffffu, tr, 1);
             if ((hl >> bit) & 1u) tl += from_left;
             if (o >= 0) {
-                red_add(bd + o, tl);
-                if (!((hrm >> bit) & 1u)) red_add(bd + o + 1, tr);
+                red_add(d + o, tl);
+                if (!((hrm >> bit) & 1u)) red_add(d + o + 1, tr);
             }
         }
+    };
+    fetch(cur, base, td);
+    int c = c0;
+    for (; c + 2 <= c1; c += 2) {
+        fetch(nxt, base + plane, td + plane);
+        scatter(cur, bd);
+        if (c + 2 < c1) fetch(cur, base + 2 * (size_t)plane, td + 2 * (size_t)plane);
+        scatter(nxt, bd + plane);
+        base += 2 * (size_t)plane;
+        td += 2 * (size_t)plane;
+        bd += 2 * (size_t)plane;
     }
-    // flow gradient: one reduction per (pixel, channel chunk) instead of one per channel (:111-112)
-    float* fd = L.out1 + (size_t)t.n * 2 * plane + (size_t)h0 * W + w;
+    if (c < c1) scatter(cur, bd);
+    // flow gradient: one reduction per (pixel, channel chunk) instead of one per channel
+    float* fd = L.out1 + (size_t)t.n * 2 * plane;
 #pragma unroll
     for (int r = 0; r < kFlowRows; ++r)
         if (off[r] >= 0) {
-            red_add(fd + r * W, gx[r]);
-            red_add(fd + plane + r * W, gy[r]);
+            red_add(fd + ldg[r], gx[r]);
+            red_add(fd + plane + ldg[r], gy[r]);
         }
 }
 
-
-std::atomic<int> g_flow_fast{0};
+std::atomic<int> g_flow_fast{kFlowExactAlu};
 
 // Fills the block ranges; returns the grid size (0: nothing to do) or a negative status.
 long long plan(FlowArgs& a, int num_levels, int batches, int channels, const int* level_h, const int* level_w) {
@@ -280,8 +421,11 @@ long long plan(FlowArgs& a, int num_levels, int batches, int channels, const int
         if ((long long)batches * channels * level_h[l] * level_w[l] >= (1ll << 31)) return VOSD_ERR_UNSUPPORTED;
         a.lv[l].H = level_h[l];
         a.lv[l].W = level_w[l];
-        a.lv[l].tiles_x = ceil_div(level_w[l], 32);
-        a.lv[l].tiles_y = ceil_div(level_h[l], kFlowWarps * kFlowRows);
+        // a map with H < 2 or W < 2 has no sample inside [0,H-1) x [0,W-1): the output is all zero and nothing
+        // flows back; it gets no tiles (the kernels fetch the 2x2 taps of offset 0 unconditionally)
+        const bool live = level_h[l] >= 2 && level_w[l] >= 2;
+        a.lv[l].tiles_x = live ? ceil_div(level_w[l], 32) : 0;
+        a.lv[l].tiles_y = live ? ceil_div(level_h[l], kFlowWarps * kFlowRows) : 0;
         tiles += (long long)a.lv[l].tiles_x * a.lv[l].tiles_y;
     }
     if (tiles == 0 || batches == 0 || channels == 0) return 0;
@@ -305,17 +449,22 @@ int flow_fwd(int num_levels, int batches, int channels, const int* level_h, cons
     if (num_levels > 0 && (!level_h || !level_w || !bottom || !flow || !top)) return VOSD_ERR_BAD_ARG;
     FlowArgs a = {};
     const long long grid = plan(a, num_levels, batches, channels, level_h, level_w);
-    if (grid <= 0) return (int)grid;
+    if (grid < 0) return (int)grid;
     for (int l = 0; l < num_levels; ++l) {
-        if (a.lv[l].H * a.lv[l].W && (!bottom[l] || !flow[l] || !top[l])) return VOSD_ERR_BAD_ARG;
+        const size_t elems = (size_t)batches * channels * a.lv[l].H * a.lv[l].W;
+        if (elems && (!bottom[l] || !flow[l] || !top[l])) return VOSD_ERR_BAD_ARG;
         a.lv[l].bottom = bottom[l];
         a.lv[l].flow = flow[l];
         a.lv[l].out0 = top[l];
+        if (elems && a.lv[l].tiles_x == 0 &&
+            cudaMemsetAsync(top[l], 0, elems * sizeof(float), stream) != cudaSuccess) return VOSD_ERR_LAUNCH;
     }
-    if (g_flow_fast.load(std::memory_order_relaxed))
-        flow_align_fwd_kernel<false><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a);
-    else
-        flow_align_fwd_kernel<true><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a);
+    if (grid == 0) return VOSD_OK;
+    switch (g_flow_fast.load(std::memory_order_relaxed)) {
+        case kFlowFp32: flow_align_fwd_kernel<kFlowFp32><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a); break;
+        case kFlowExactCvt: flow_align_fwd_kernel<kFlowExactCvt><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a); break;
+        default: flow_align_fwd_kernel<kFlowExactAlu><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a); break;
+    }
     count_launch();
     return check_launch();
 }
@@ -346,7 +495,10 @@ int flow_bwd(int num_levels, int batches, int channels, const int* level_h, cons
         }
     }
     if (grid == 0) return VOSD_OK;
-    flow_align_bwd_kernel<<<(unsigned)grid, kFlowThreads, 0, stream>>>(a);
+    if (g_flow_fast.load(std::memory_order_relaxed) == kFlowExactAlu)
+        flow_align_bwd_kernel<true><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a);
+    else
+        flow_align_bwd_kernel<false><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a);
     count_launch();
     return check_launch();
 }
@@ -380,5 +532,5 @@ extern "C" int vosd_flow_align_ml_bwd(int num_levels, int batches, int channels,
 }
 
 extern "C" int vosd_debug_flow_align_fast(int on) {
-    return vosd::g_flow_fast.exchange(on ? 1 : 0, std::memory_order_relaxed);
+    return vosd::g_flow_fast.exchange(on, std::memory_order_relaxed);
 }

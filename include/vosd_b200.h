@@ -327,9 +327,9 @@ VOSD_API int vosd_flow_align_ml_bwd(int num_levels, int batches, int channels, c
                                     const float* const* flow, float* const* bottomdiff, float* const* flowdiff,
                                     int zero_init, cudaStream_t stream);
 /* Test / tuning hook selecting the arithmetic of the FlowAlign kernels, so every variant stays covered:      */
-/*   2 = default: the reference's double-precision operation sequence with the float->double widenings done  */
-/*       as bit shuffles on the ALU pipe (bit-identical; non-finite taps take the expression as written),    */
-/*   0 = the reference's expression as written (F2F conversions on the XU pipe; bit-identical),              */
+/*   0 = default: the reference's expression as written (F2F conversions on the XU pipe; bit-identical),     */
+/*   2 = the same double-precision operation sequence with the float->double widenings done as bit shuffles  */
+/*       on the ALU pipe (bit-identical; non-finite taps take the expression as written; measured slower),   */
 /*   1 = plain fp32 bilinear weights in the forward (NOT bit-identical, |err| <= 1e-6 relative).             */
 /* Returns the previous setting.  Process-wide; not for production use. */
 VOSD_API int vosd_debug_flow_align_fast(int on);

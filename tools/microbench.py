@@ -238,7 +238,7 @@ def main():
             alg_f = 2 * elems * 4 + flow_bytes
             # backward: read topdiff + features + flow, write both gradients once (zero or sum)
             alg_b = 3 * elems * 4 + 2 * flow_bytes
-            for mode, tag in ((2, ""), (0, "_cvtvariant"), (1, "_fp32variant")):
+            for mode, tag in ((0, ""), (2, "_aluvariant"), (1, "_fp32variant")):
                 old = _lib.load().vosd_debug_flow_align_fast(mode)
                 report(out, "flowalign_fwd%s_5lvl_%dframes" % (tag, B), timer,
                        lambda: ops.flow_align_ml_forward(feats, flows), alg_f, {"elements": elems})

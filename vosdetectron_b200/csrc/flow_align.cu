@@ -7,17 +7,24 @@
 //   launchers                :120-156 (512-thread 1-D grid, exit(-1) on a launch error)
 //
 // Design (B200): the geometry (flow fetch, bounds test, floor, ratios) depends on the pixel only, so a
-// thread owns a column of kFlowRows pixels, derives their geometry ONCE and then streams over a chunk of
-// channels with lanes along x: coalesced 128-byte stores, near-coalesced tap loads through L1 (the flow is a
-// small displacement, so the four taps of neighbouring lanes share lines), kFlowRows x 4 independent loads
-// in flight per thread.  All FPN levels go in one launch (block ranges per level).
+// thread owns a short column of pixels (2 rows forward, 1 backward), derives their geometry ONCE and then
+// streams over a chunk of up to 64 channels with lanes along x: coalesced 128-byte stores, near-coalesced tap
+// loads through L1 (the flow is a small displacement, so the four taps of neighbouring lanes share lines).
+// Taps are fetched unconditionally (dead pixels read texel 0) into two register sets, channel c+1 in flight
+// while channel c is computed, and the tap rows of channel c+4 are prefetched into L2: the kernels are
+// bound by bytes in flight (measured: 0.34 -> 0.21 ms with the prefetch, -> 0.175 ms with 2 rows per thread
+// and a 73-register cap; 62 % of the measured HBM copy bandwidth).  All FPN levels go in one launch
+// (block ranges per level).
 //
 // Arithmetic: the reference's expressions mix float and double operands (the literals `1.` are doubles);
-// the EXACT kernels spell the same expressions with the same operand types, so nvcc emits the same
-// multiply / fma sequence and the forward is BIT-identical to the reference kernel (gated by the tests).
-// The backward's addends are the reference's; they are pre-summed in registers where two pixels of a
-// thread (vertical neighbours) or of adjacent lanes (horizontal neighbours) hit the same texel, which the
-// reference's atomics would add one by one in arbitrary order.
+// the kernels spell the same expressions with the same operand types, so nvcc emits the same multiply / fma
+// sequence and the forward is BIT-identical to the reference kernel (gated by the tests).  The backward's
+// addends are the reference's; they are pre-summed in registers where adjacent lanes (horizontal neighbours)
+// or consecutive rows of a thread hit the same texel, which the reference's atomics would add one by one in
+// arbitrary order, and the flow gradient is summed over the channel chunk before one reduction per pixel.
+// An alternative that widens float->double on the ALU pipe instead of the 16-lane XU pipe (also
+// bit-identical) is kept behind vosd_debug_flow_align_fast(2): it measured slower (more issue slots and
+// registers than the conversions cost).
 #include <atomic>
 #include "common.cuh"
 
@@ -25,8 +32,27 @@ namespace vosd {
 namespace {
 
 constexpr int kFlowWarps = 4;   // row bands per CTA (one warp each)
-constexpr int kFlowRows = 4;    // rows per thread
 constexpr int kFlowThreads = kFlowWarps * 32;
+// Tuning (A/B builds on the B200, profiles/README.md): rows per thread, channels per thread, register cap.
+// The kernels are bound by bytes in flight, so occupancy beats per-thread reuse: 2 rows (forward) / 1 row
+// (backward: the vertical pre-summing of shared texels is worth less than the extra warps).
+#ifndef VOSD_FLOW_ROWS_FWD
+#define VOSD_FLOW_ROWS_FWD 2
+#endif
+#ifndef VOSD_FLOW_ROWS_BWD
+#define VOSD_FLOW_ROWS_BWD 1
+#endif
+#ifndef VOSD_FLOW_CHUNK
+#define VOSD_FLOW_CHUNK 64
+#endif
+#ifndef VOSD_FLOW_MINB_FWD
+#define VOSD_FLOW_MINB_FWD 7
+#endif
+#ifndef VOSD_FLOW_MINB_BWD
+#define VOSD_FLOW_MINB_BWD 8
+#endif
+constexpr int kFlowRowsFwd = VOSD_FLOW_ROWS_FWD;
+constexpr int kFlowRowsBwd = VOSD_FLOW_ROWS_BWD;
 
 struct FlowLevelArgs {
     const float* bottom;    // (N,C,H,W) features
@@ -35,7 +61,7 @@ struct FlowLevelArgs {
     float* out0;            // forward: top (N,C,H,W); backward: bottomdiff (N,C,H,W)
     float* out1;            // backward: flowdiff (N,2,H,W)
     int H, W;
-    int tiles_x, tiles_y;   // tiles of 32 columns x (kFlowWarps * kFlowRows) rows
+    int tiles_x, tiles_y;   // tiles of 32 columns x (kFlowWarps * rows per thread) rows
     int block_begin;        // first block of this level in the grid
     int pad;
 };
@@ -85,6 +111,18 @@ __device__ __forceinline__ int flow_geometry(const float* __restrict__ flow_n, i
     h_ratio = h_flo - (float)h_start;
     w_ratio = w_flo - (float)w_start;
     return w_start + W * h_start;
+}
+
+// L2 prefetch distance in channels (0 = off): the tap rows of channel c + kFlowPrefetch are requested into L2 while
+// channel c is computed, so the register-held loads of the next channel see L2 latency instead of DRAM latency
+// (the kernels are bound by bytes in flight: 12-24 resident warps x 2 channels of taps per thread).
+#ifndef VOSD_FLOW_PF
+#define VOSD_FLOW_PF 4
+#endif
+constexpr int kFlowPrefetch = VOSD_FLOW_PF;
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
 }
 
 // ------------------------------------------------------------------------------------- forward
@@ -155,7 +193,8 @@ __device__ __forceinline__ float flow_bilinear(float b1, float b2, float b3, flo
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kFlowThreads) flow_align_fwd_kernel(const __grid_constant__ FlowArgs a) {
+__global__ void __launch_bounds__(kFlowThreads, VOSD_FLOW_MINB_FWD) flow_align_fwd_kernel(const __grid_constant__ FlowArgs a) {
+    constexpr int kFlowRows = kFlowRowsFwd;
     const FlowTile t = decode_tile(a);
     const FlowLevelArgs& L = a.lv[t.level];
     const int H = L.H, W = L.W, plane = H * W;      // H, W >= 2 (smaller maps never reach the kernel)
@@ -202,12 +241,19 @@ __global__ void __launch_bounds__(kFlowThreads) flow_align_fwd_kernel(const __gr
             if (off[r] != -2) __stcs(o + r * W, v);
         }
     };
+    auto prefetch = [&](const float* p) {          // one line per tap row of the thread's pixel column
+#pragma unroll
+        for (int r = 0; r < kFlowRows; ++r) prefetch_l2(p + ld[r]);
+        prefetch_l2(p + ld[kFlowRows - 1] + W);
+    };
     fetch(cur, base);
     int c = c0;
     for (; c + 2 <= c1; c += 2) {
         fetch(nxt, base + plane);
+        if (kFlowPrefetch && c + kFlowPrefetch < c1) prefetch(base + kFlowPrefetch * (size_t)plane);
         emit(cur, out);
         if (c + 2 < c1) fetch(cur, base + 2 * (size_t)plane);
+        if (kFlowPrefetch && c + 1 + kFlowPrefetch < c1) prefetch(base + (1 + kFlowPrefetch) * (size_t)plane);
         emit(nxt, out + plane);
         base += 2 * (size_t)plane;
         out += 2 * (size_t)plane;
@@ -282,7 +328,8 @@ __device__ __forceinline__ FlowGrad flow_grad(float g, float f1, float f2, float
 }
 
 template <bool ALU>
-__global__ void __launch_bounds__(kFlowThreads) flow_align_bwd_kernel(const __grid_constant__ FlowArgs a) {
+__global__ void __launch_bounds__(kFlowThreads, VOSD_FLOW_MINB_BWD) flow_align_bwd_kernel(const __grid_constant__ FlowArgs a) {
+    constexpr int kFlowRows = kFlowRowsBwd;
     const FlowTile t = decode_tile(a);
     const FlowLevelArgs& L = a.lv[t.level];
     const int H = L.H, W = L.W, plane = H * W;      // H, W >= 2
@@ -384,12 +431,24 @@ __global__ void __launch_bounds__(kFlowThreads) flow_align_bwd_kernel(const __gr
             }
         }
     };
+    auto prefetch = [&](const float* p, const float* q) {
+#pragma unroll
+        for (int r = 0; r < kFlowRows; ++r) {
+            prefetch_l2(p + ld[r]);
+            prefetch_l2(q + ldg[r]);
+        }
+        prefetch_l2(p + ld[kFlowRows - 1] + W);
+    };
     fetch(cur, base, td);
     int c = c0;
     for (; c + 2 <= c1; c += 2) {
         fetch(nxt, base + plane, td + plane);
+        if (kFlowPrefetch && c + kFlowPrefetch < c1)
+            prefetch(base + kFlowPrefetch * (size_t)plane, td + kFlowPrefetch * (size_t)plane);
         scatter(cur, bd);
         if (c + 2 < c1) fetch(cur, base + 2 * (size_t)plane, td + 2 * (size_t)plane);
+        if (kFlowPrefetch && c + 1 + kFlowPrefetch < c1)
+            prefetch(base + (1 + kFlowPrefetch) * (size_t)plane, td + (1 + kFlowPrefetch) * (size_t)plane);
         scatter(nxt, bd + plane);
         base += 2 * (size_t)plane;
         td += 2 * (size_t)plane;
@@ -406,10 +465,10 @@ __global__ void __launch_bounds__(kFlowThreads) flow_align_bwd_kernel(const __gr
         }
 }
 
-std::atomic<int> g_flow_fast{kFlowExactAlu};
+std::atomic<int> g_flow_fast{kFlowExactCvt};
 
 // Fills the block ranges; returns the grid size (0: nothing to do) or a negative status.
-long long plan(FlowArgs& a, int num_levels, int batches, int channels, const int* level_h, const int* level_w) {
+long long plan(FlowArgs& a, int rows, int num_levels, int batches, int channels, const int* level_h, const int* level_w) {
     if (num_levels < 0 || num_levels > VOSD_MAX_LEVELS || batches < 0 || channels < 0) return VOSD_ERR_BAD_SHAPE;
     a.num_levels = num_levels;
     a.N = batches;
@@ -425,12 +484,12 @@ long long plan(FlowArgs& a, int num_levels, int batches, int channels, const int
         // flows back; it gets no tiles (the kernels fetch the 2x2 taps of offset 0 unconditionally)
         const bool live = level_h[l] >= 2 && level_w[l] >= 2;
         a.lv[l].tiles_x = live ? ceil_div(level_w[l], 32) : 0;
-        a.lv[l].tiles_y = live ? ceil_div(level_h[l], kFlowWarps * kFlowRows) : 0;
+        a.lv[l].tiles_y = live ? ceil_div(level_h[l], kFlowWarps * rows) : 0;
         tiles += (long long)a.lv[l].tiles_x * a.lv[l].tiles_y;
     }
     if (tiles == 0 || batches == 0 || channels == 0) return 0;
     // channel chunk per thread: long enough to amortise the per-pixel geometry, short enough to fill 148 SMs
-    int chunk = 32;
+    int chunk = VOSD_FLOW_CHUNK;
     while (chunk > 8 && tiles * batches * ceil_div(channels, chunk) < (long long)kNumSMs * 16) chunk /= 2;
     a.chunk = chunk;
     a.chunks = ceil_div(channels, chunk);
@@ -448,7 +507,7 @@ int flow_fwd(int num_levels, int batches, int channels, const int* level_h, cons
              const float* const* bottom, const float* const* flow, float* const* top, cudaStream_t stream) {
     if (num_levels > 0 && (!level_h || !level_w || !bottom || !flow || !top)) return VOSD_ERR_BAD_ARG;
     FlowArgs a = {};
-    const long long grid = plan(a, num_levels, batches, channels, level_h, level_w);
+    const long long grid = plan(a, kFlowRowsFwd, num_levels, batches, channels, level_h, level_w);
     if (grid < 0) return (int)grid;
     for (int l = 0; l < num_levels; ++l) {
         const size_t elems = (size_t)batches * channels * a.lv[l].H * a.lv[l].W;
@@ -461,9 +520,10 @@ int flow_fwd(int num_levels, int batches, int channels, const int* level_h, cons
     }
     if (grid == 0) return VOSD_OK;
     switch (g_flow_fast.load(std::memory_order_relaxed)) {
-        case kFlowFp32: flow_align_fwd_kernel<kFlowFp32><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a); break;
         case kFlowExactCvt: flow_align_fwd_kernel<kFlowExactCvt><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a); break;
-        default: flow_align_fwd_kernel<kFlowExactAlu><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a); break;
+        case kFlowFp32: flow_align_fwd_kernel<kFlowFp32><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a); break;
+        case kFlowExactAlu: flow_align_fwd_kernel<kFlowExactAlu><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a); break;
+        default: return VOSD_ERR_BAD_ARG;
     }
     count_launch();
     return check_launch();
@@ -475,7 +535,7 @@ int flow_bwd(int num_levels, int batches, int channels, const int* level_h, cons
     if (num_levels > 0 && (!level_h || !level_w || !topdiff || !bottom || !flow || !bottomdiff || !flowdiff))
         return VOSD_ERR_BAD_ARG;
     FlowArgs a = {};
-    const long long grid = plan(a, num_levels, batches, channels, level_h, level_w);
+    const long long grid = plan(a, kFlowRowsBwd, num_levels, batches, channels, level_h, level_w);
     if (grid < 0) return (int)grid;
     for (int l = 0; l < num_levels; ++l) {
         const size_t plane = (size_t)level_h[l] * level_w[l];

@@ -334,6 +334,31 @@ VOSD_API int vosd_flow_align_ml_bwd(int num_levels, int batches, int channels, c
 /* Returns the previous setting.  Process-wide; not for production use. */
 VOSD_API int vosd_debug_flow_align_fast(int on);
 
+/* ------------------------------------------------------------------------------------ */
+/* Mask-IoU suppression ("next" row, SURVEY 8f rank 2, second half).  Replaces the O(R^2)  */
+/* loop of nms_with_mask_iou (lib_vos/tools/vos_test.py:985-1029) over decoded full-frame   */
+/* masks with AND + POPC over bit-packed masks.                                            */
+/*   packed (num_masks, bytes_per_mask) uint8, 1 bit per pixel, any pixel order shared by   */
+/*   all masks (vosd_paste_masks_packed or vosd_rle_to_bits), bytes_per_mask % 4 == 0,      */
+/*   padding bits zero; order (num_masks) int32: mask index at each position of the         */
+/*   descending-score order (vos_test.py:995-998), NULL = identity.                         */
+/*   Position j is removed when an earlier surviving position i has                         */
+/*   inter/(area_i + 1e-6) > iou_th or inter/(area_j + 1e-6) > iou_th in float64            */
+/*   (iou_half_numpy, :953-959; test :1009).  removed (num_masks) int32 0/1 per POSITION,   */
+/*   num_keep (1) int32.  num_masks <= 2048.                                                */
+/* ------------------------------------------------------------------------------------ */
+VOSD_API size_t vosd_mask_iou_nms_workspace_bytes(int num_masks);
+VOSD_API int vosd_mask_iou_nms(const uint8_t* packed, int num_masks, long long bytes_per_mask, const int* order,
+                               double iou_th, int* removed, int* num_keep, void* workspace, size_t workspace_bytes,
+                               cudaStream_t stream);
+/* COCO run lengths -> bits (the mask_util.decode(segms) of vos_test.py:993, as 1 bit per pixel in the RLE's    */
+/* own column-major pixel order): mask m = runs[run_offset[m] .. + run_count[m]) uint32, alternating 0-runs and  */
+/* 1-runs, first run zeros; out_packed (num_masks, ceil(pixels/32)*4) uint8, every byte written.                 */
+/* max_run_count = max over run_count (host value) must be <= 12000.                                             */
+VOSD_API int vosd_rle_to_bits(const uint32_t* runs, const long long* run_offset, const int* run_count,
+                              int num_masks, long long pixels, uint8_t* out_packed, int max_run_count,
+                              cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -490,5 +490,83 @@ def rle_encode(mask):
     return {'size': [int(h), int(w)], 'counts': rle_to_string(rle_counts_fast(mask))}
 
 
+
+# --------------------------------------------------------------------------- #
+# (f1/f2 extras) lib_vos/tools/vos_test.py: box_results_with_nms_and_limit :748-865,
+# bb_intersection_over_union :961-982, nms_with_mask_iou :985-1029, iou_half_numpy :953-959
+# --------------------------------------------------------------------------- #
+def bb_intersection_over_union(boxA, boxB):
+    xA, yA = max(boxA[0], boxB[0]), max(boxA[1], boxB[1])
+    xB, yB = min(boxA[2], boxB[2]), min(boxA[3], boxB[3])
+    interArea = max(0, xB - xA + 1) * max(0, yB - yA + 1)
+    boxAArea = (boxA[2] - boxA[0] + 1) * (boxA[3] - boxA[1] + 1)
+    boxBArea = (boxB[2] - boxB[0] + 1) * (boxB[3] - boxB[1] + 1)
+    return interArea / float(boxAArea + boxBArea - interArea)
+
+
+def vos_box_results(scores, boxes, num_classes, score_thresh, nms_thresh, detections_per_im, nms_cross_class=0.,
+                    num_det_per_class_pre=0, nms_small_box_iou=0., nms_small_box_score_threshold=0.,
+                    prev_cls_boxes=None):
+    _, _, cls_boxes = box_results_with_nms_and_limit(scores, boxes, num_classes, score_thresh, nms_thresh,
+                                                     detections_per_im)
+    K = num_classes
+    if nms_cross_class > 0.:                                                    # :816-837
+        all_dets = np.vstack([cls_boxes[j] for j in range(1, K)])
+        class_ids = np.vstack([np.ones(shape=(len(cls_boxes[j]), 1)) * j for j in range(1, K)])
+        keep = nms(all_dets, nms_cross_class)
+        all_dets, class_ids = all_dets[keep, :], class_ids[keep, :]
+        for j in range(1, K):
+            cls_boxes[j] = all_dets[np.where(class_ids == j)[0], :]
+    if num_det_per_class_pre > 0:                                               # :839-843
+        for j in range(1, K):
+            cls_boxes[j] = cls_boxes[j][np.argsort(-cls_boxes[j][:, -1])[:num_det_per_class_pre], :]
+    if nms_small_box_iou > 0 and prev_cls_boxes is not None:                    # :845-860
+        for j in range(1, K):
+            if len(prev_cls_boxes[j]) == 1 and not prev_cls_boxes[j][0][-1] < nms_small_box_score_threshold:
+                prev = prev_cls_boxes[j][0][:-1]
+                rm = [i for i in range(len(cls_boxes[j]) - 1, -1, -1)
+                      if bb_intersection_over_union(prev, cls_boxes[j][i][:-1]) < nms_small_box_iou]
+                cls_boxes[j] = np.delete(cls_boxes[j], rm, 0)
+    im_results = np.vstack([cls_boxes[j] for j in range(1, K)])
+    return im_results[:, -1], im_results[:, :-1], cls_boxes
+
+
+def mask_iou_greedy(masks_sorted, iou_th):
+    """masks_sorted: sequence of equal-shape uint8 masks in descending score order -> removed flags per position
+    (vos_test.py:1000-1010 with iou_half_numpy :953-959, float64 arithmetic)."""
+    n = len(masks_sorted)
+    flat = [np.asarray(m, dtype=np.uint8).ravel() for m in masks_sorted]
+    area = [int(f.sum()) for f in flat]
+    removed = np.zeros(n, dtype=np.int32)
+    for i in range(n):
+        if removed[i]:
+            continue
+        for j in range(i + 1, n):
+            inter = int(np.sum(flat[i] & flat[j]))
+            if inter / (area[i] + 1e-6) > iou_th or inter / (area[j] + 1e-6) > iou_th:
+                removed[j] = 1
+    return removed
+
+
+def nms_with_mask_iou(cls_boxes, cls_segms, num_classes, iou_th=0.9, max_per_class=1):
+    box_list = [np.asarray(b).reshape(-1, 5) for b in cls_boxes if len(b) > 0]
+    if not box_list:
+        return cls_boxes, cls_segms
+    boxes = np.concatenate(box_list)
+    segms = [s for sl in cls_segms for s in sl]
+    classes = np.array([j for j in range(len(cls_boxes)) for _ in range(len(cls_boxes[j]))])
+    order = np.argsort(-boxes[:, -1])
+    masks = [rle_decode(rle_from_string(segms[k]['counts']), *segms[k]['size']) for k in order]
+    keep = np.flatnonzero(mask_iou_greedy(masks, iou_th) == 0)
+    out_b = [[] for _ in range(num_classes)]
+    out_s = [[] for _ in range(num_classes)]
+    for k in keep:
+        c = int(classes[order[k]])
+        if len(out_b[c]) < max_per_class:
+            out_b[c].append(boxes[order[k], :])
+            out_s[c].append(rle_encode(masks[k]))
+    return out_b, out_s
+
+
 def num_threads():
     return lib().orc_num_threads()

@@ -203,3 +203,55 @@ def test_flow_align_oracle_vs_grid_sample_anchor(orc, synth):
     assert np.array_equal(z[:, :, :H - 1, :W - 1], f[:, :, :H - 1, :W - 1]) and not z[:, :, H - 1].any()
     sh = orc.flow_align_forward(f, synth.flow_field(0, N, H, W, "shift"))
     assert np.array_equal(sh[:, :, 1:H, :W - 3], f[:, :, 0:H - 1, 2:W - 1])
+
+
+def _vos_prev(g, K):
+    prev, start = [[] for _ in range(K)], 0
+    for j in range(1, K):
+        n = int(g["prev_count"][j])
+        prev[j] = g["prev_boxes"][start:start + n]
+        start += n
+    return prev
+
+
+def test_vos_box_results_golden(orc, golden):
+    """lib_vos box_results_with_nms_and_limit (vos_test.py:748-865: cross-class NMS, per-class top-k, previous-box
+    filter) against the reference's own outputs."""
+    g, b = golden("vos_post"), golden("box_results")
+    K = int(b["num_classes"])
+    prev = _vos_prev(g, K)
+    for tag in "xyzw":
+        cross, pre, small, small_th = g["set_" + tag]
+        s, bx, cls_boxes = orc.vos_box_results(b["scores"], b["pred_boxes"], K, float(b["score_thresh"]), 0.5, 100,
+                                               float(cross), int(pre), float(small), float(small_th), prev)
+        assert np.array_equal(s, g["out_scores_" + tag]) and np.array_equal(bx, g["out_boxes_" + tag]), tag
+        assert [len(c) for c in cls_boxes[1:]] == g["cls_count_" + tag][1:].tolist()
+
+
+def _mask_case(g):
+    Km = int(g["m_cls"].max()) + 1
+    cls_boxes = [[] for _ in range(Km)]
+    cls_segms = [[] for _ in range(Km)]
+    h, w = (int(v) for v in g["m_frame"])
+    for i, c in enumerate(g["m_cls"]):
+        cls_segms[int(c)].append({'size': [h, w], 'counts': str(g["m_counts"][i])})
+    for j in range(1, Km):
+        cls_boxes[j] = g["m_boxes"][g["m_cls"] == j]
+    return Km, cls_boxes, cls_segms
+
+
+def test_nms_with_mask_iou_golden(orc, golden):
+    """vos_test.py:985-1029 against the reference's own outputs (its mask codec bound to the maskApi.c restatement);
+    the RLE strings the reference produced from ITS segm_results are reproduced by the oracle's paste + encode."""
+    g = golden("vos_post")
+    Km, cls_boxes, cls_segms = _mask_case(g)
+    h, w = (int(v) for v in g["m_frame"])
+    pasted = orc.paste_masks(g["m_masks"], g["m_cls"], g["m_boxes"][:, :4], h, w)
+    assert [orc.rle_encode(m)['counts'] for m in pasted] == [str(c) for c in g["m_counts"]]
+    for tag in "pqr":
+        th, per = g["mset_" + tag]
+        ob, os_ = orc.nms_with_mask_iou(cls_boxes, cls_segms, 6, float(th), int(per))
+        assert [len(c) for c in ob] == g["mout_count_" + tag].tolist(), tag
+        got = np.vstack([np.vstack(c) for c in ob if len(c)])
+        assert np.array_equal(got, g["mout_boxes_" + tag])
+        assert [s['counts'] for sl in os_ for s in sl] == [str(c) for c in g["mout_counts_" + tag]]

@@ -60,6 +60,8 @@ def install_reference_aliases(legacy_model_roi_align=True):
              ['collect', 'distribute', 'CollectAndDistributeFpnRpnProposalsOp']),
         'utils.boxes': ('.utils.boxes', ['nms']),
         'core.test': ('.core.test', ['segm_results']),
+        # lib_vos/tools/vos_test.py is imported as the top-level module `vos_test` (infer_davis_sequential.py:27)
+        'vos_test': ('.core.vos_test', ['segm_results', 'box_results_with_nms_and_limit', 'nms_with_mask_iou']),
     }
     for ref_name, (mine, names) in patches.items():
         m = importlib.import_module(mine, __name__)

@@ -81,6 +81,10 @@ SIGNATURES = {
     "vosd_flow_align_ml_bwd": (ctypes.c_int, [ctypes.c_int] * 3 + [c_int_p, c_int_p] + [ctypes.POINTER(vp)] * 5
                                + [ctypes.c_int, vp]),
     "vosd_debug_flow_align_fast": (ctypes.c_int, [ctypes.c_int]),
+    "vosd_mask_iou_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "vosd_mask_iou_nms": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_longlong, vp, ctypes.c_double, vp, vp, vp,
+                                         ctypes.c_size_t, vp]),
+    "vosd_rle_to_bits": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_longlong, vp, ctypes.c_int, vp]),
     "vosd_paste_masks": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_float, vp, vp, vp]),
 }

@@ -49,6 +49,13 @@ class RegionConfig:
     test_soft_nms: bool = False
     test_bbox_vote: bool = False
     bbox_reg_weights: tuple = (10.0, 10.0, 5.0, 5.0)
+    # lib_vos extras of box_results_with_nms_and_limit / nms_with_mask_iou (config.py:948-953)
+    test_num_det_per_class_pre: int = 0
+    test_num_det_per_class_post: int = 0
+    test_nms_cross_class: float = 0.0
+    test_nms_with_mask_iou: float = 0.0
+    test_nms_small_box_iou: float = 0.0
+    test_nms_small_box_score_threshold: float = 0.0
 
     def mode(self, training):
         return self.train if training else self.test
@@ -83,6 +90,12 @@ class RegionConfig:
             test_num_det_per_class=int(getattr(cfg.TEST, "NUM_DET_PER_CLASS", 0) or 0),
             test_soft_nms=bool(cfg.TEST.SOFT_NMS.ENABLED), test_bbox_vote=bool(cfg.TEST.BBOX_VOTE.ENABLED),
             bbox_reg_weights=tuple(float(x) for x in cfg.MODEL.BBOX_REG_WEIGHTS),
+            test_num_det_per_class_pre=int(getattr(cfg.TEST, "NUM_DET_PER_CLASS_PRE", 0) or 0),
+            test_num_det_per_class_post=int(getattr(cfg.TEST, "NUM_DET_PER_CLASS_POST", 0) or 0),
+            test_nms_cross_class=float(getattr(cfg.TEST, "NMS_CROSS_CLASS", 0.0) or 0.0),
+            test_nms_with_mask_iou=float(getattr(cfg.TEST, "NMS_WITH_MASK_IOU", 0.0) or 0.0),
+            test_nms_small_box_iou=float(getattr(cfg.TEST, "NMS_SMALL_BOX_IOU", 0.0) or 0.0),
+            test_nms_small_box_score_threshold=float(getattr(cfg.TEST, "NMS_SMALL_BOX_SCORE_THRESHOLD", 0.0) or 0.0),
         )
 
 

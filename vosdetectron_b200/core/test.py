@@ -14,7 +14,7 @@ from .. import ops
 from ..config import get_cfg
 
 
-def box_results_with_nms_and_limit(scores, boxes, cfg=None):
+def box_results_with_nms_and_limit(scores, boxes, cfg=None, _per_class_limit=True):
     """Drop-in for lib/core/test.py:733-797: ``scores`` (R,K), ``boxes`` (R,4K) ndarrays (or CUDA tensors) ->
     ``(scores, boxes, cls_boxes)`` ndarrays, cls_boxes[j] = (n_j,5) [x1,y1,x2,y2,score].  One upload, four
     launches (threshold + sort per class, IoU bitmask, greedy reduce, over-all-classes limit), one download."""
@@ -40,7 +40,7 @@ def box_results_with_nms_and_limit(scores, boxes, cfg=None):
     for j in range(1, K):
         cls_boxes[j] = d[start:start + cc[j], :5].copy()
         start += int(cc[j])
-    if cfg.test_num_det_per_class > 0:                       # test.py:785-788
+    if _per_class_limit and cfg.test_num_det_per_class > 0:  # test.py:785-788 (the lib_vos copy has no such branch)
         for j in range(1, K):
             keep = np.argsort(-cls_boxes[j][:, -1])[:cfg.test_num_det_per_class]
             cls_boxes[j] = cls_boxes[j][keep, :]
@@ -71,6 +71,27 @@ def rle_encode(mask):
                 c |= 0x20
             out.append(chr(c + 48))
     return {'size': [int(h), int(w)], 'counts': ''.join(out)}
+
+
+def rle_counts_from_string(s):
+    """'counts' string of a COCO RLE -> list of run lengths (pycocotools common/maskApi.c rleFrString)."""
+    if isinstance(s, bytes):
+        s = s.decode('ascii')
+    counts, p, n = [], 0, len(s)
+    while p < n:
+        x, k, more = 0, 0, True
+        while more:
+            c = ord(s[p]) - 48
+            x |= (c & 0x1f) << (5 * k)
+            more = bool(c & 0x20)
+            p += 1
+            k += 1
+            if not more and (c & 0x10):
+                x |= -1 << (5 * k)
+        if len(counts) > 2:
+            x += counts[-2]
+        counts.append(x)
+    return counts
 
 
 def _class_order(cls_boxes, num_classes):

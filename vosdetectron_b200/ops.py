@@ -469,3 +469,48 @@ def pack_mask_bits_cuda(masks_u8):
     _bind(m)
     _lib.call("vosd_pack_mask_bits", _ptr(m), n, pixels, _ptr(out), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------- mask-IoU suppression
+def rle_to_bits_cuda(run_lists, pixels, device=None):
+    """COCO run lengths of R masks (list of int sequences, alternating 0-runs / 1-runs) -> packed
+    (R, ceil(pixels/32)*4) uint8 on the device, 1 bit per pixel in the RLE's column-major order."""
+    R = len(run_lists)
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    words = (int(pixels) + 31) // 32
+    out = torch.empty((R, words * 4), dtype=torch.uint8, device=dev)
+    if R == 0 or pixels == 0:
+        return out
+    counts = np.array([len(r) for r in run_lists], dtype=np.int32)
+    offsets = np.concatenate(([0], np.cumsum(counts[:-1], dtype=np.int64))).astype(np.int64)
+    flat = np.concatenate([np.asarray(r, dtype=np.int64) for r in run_lists]) if counts.sum() else np.zeros(1, np.int64)
+    if flat.min() < 0 or any(int(np.sum(r)) != int(pixels) for r in run_lists):
+        raise ValueError("run lengths must be non-negative and sum to the pixel count")
+    runs = torch.from_numpy(flat.astype(np.uint32).view(np.int32)).to(dev)
+    offs = torch.from_numpy(offsets).to(dev)        # named: a temporary would be recycled before the launch
+    cnts = torch.from_numpy(counts).to(dev)
+    _bind(out)
+    _lib.call("vosd_rle_to_bits", _ptr(runs), _ptr(offs), _ptr(cnts), R, int(pixels), _ptr(out), int(counts.max()),
+              _stream())
+    return out
+
+
+def mask_iou_nms_cuda(packed, order, iou_th):
+    """packed (R, bytes) uint8 bit masks, order (R) int32 (mask index per descending-score position, or None) ->
+    (removed (R) int32 per POSITION, num_keep (1) int32); vos_test.py:1001-1010 semantics."""
+    p = _need_cuda(packed, "packed", torch.uint8)
+    if p.dim() != 2:
+        raise ValueError("packed must be (R, bytes_per_mask)")
+    R, nb = int(p.shape[0]), int(p.shape[1])
+    if nb % 4:
+        p = torch.nn.functional.pad(p, (0, 4 - nb % 4)).contiguous()       # whole 32-bit words, zero padding bits
+        nb = int(p.shape[1])
+    o = None if order is None else _need_cuda(order, "order", torch.int32)
+    removed = torch.empty((max(R, 1),), dtype=torch.int32, device=p.device)
+    num = torch.empty((1,), dtype=torch.int32, device=p.device)
+    nbytes = _lib.load().vosd_mask_iou_nms_workspace_bytes(R)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=p.device)
+    _bind(p)
+    _lib.call("vosd_mask_iou_nms", _ptr(p), R, nb, _ptr(o), float(iou_th), _ptr(removed), _ptr(num), _ptr(ws), nbytes,
+              _stream())
+    return removed[:R], num

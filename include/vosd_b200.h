@@ -359,6 +359,19 @@ VOSD_API int vosd_rle_to_bits(const uint32_t* runs, const long long* run_offset,
                               int num_masks, long long pixels, uint8_t* out_packed, int max_run_count,
                               cudaStream_t stream);
 
+/* ------------------------------------------------------------------------------------ */
+/* bbox_overlaps ("next" row, SURVEY 8f rank 3: first piece of the training label         */
+/* assignment).  Replaces cython_bbox.bbox_overlaps (lib/utils/cython_bbox.pyx:32-73,     */
+/* bound at lib/utils/boxes.py:55) and the `.argmax(axis=1)` / `.max(axis=1)` that follow  */
+/* it in datasets/json_dataset.py:450-456 and roi_data/rpn.py:149-158.  fp32, the          */
+/* reference's operation order: bit-identical.                                             */
+/*   boxes (N,4), query_boxes (K,4) fp32, 16-byte aligned; overlaps (N,K) fp32 or NULL;    */
+/*   row_max (N) fp32 or NULL; row_argmax (N) int32 or NULL (first maximum, as np.argmax;  */
+/*   0 and 0.0 when K == 0).                                                               */
+/* ------------------------------------------------------------------------------------ */
+VOSD_API int vosd_bbox_overlaps(const float* boxes, int num_boxes, const float* query_boxes, int num_query,
+                                float* overlaps, float* row_max, int* row_argmax, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,3 +102,36 @@ def test_batch_rows_ties_and_capacity(orc, synth):
     z = torch.zeros((1, 50, K), device="cuda")
     d3, c3, cc3 = ops.box_results_cuda(z, torch.zeros((1, 50, 4 * K), device="cuda"), 0.05, 0.5, 20)
     assert int(c3[0]) == 0 and int(cc3.sum()) == 0
+
+
+def test_bbox_overlaps_bit_identical_to_cython_bbox(synth):
+    """vosd_bbox_overlaps against the reference's own cython_bbox (oracle/_ref, compiled from
+    lib/utils/cython_bbox.pyx): bit-identical matrix, np.argmax / np.max of it for the labels."""
+    import importlib.util
+    import os
+    from vosdetectron_b200 import ops
+    from vosdetectron_b200.utils import boxes as box_utils
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    so = [f for f in os.listdir(ref_dir) if f.startswith("cython_bbox")] if os.path.isdir(ref_dir) else []
+    if not so:
+        pytest.skip("oracle/_ref/cython_bbox*.so not built")
+    spec = importlib.util.spec_from_file_location("cython_bbox", os.path.join(ref_dir, so[0]))
+    cb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cb)
+    rs = np.random.RandomState(12)
+    for N, K in [(1, 1), (2000, 17), (513, 1500), (300, 0), (0, 5)]:
+        boxes = synth.random_rois(100 + N, max(N, 1), (800, 1344))[:N, 1:5].copy()
+        gts = synth.random_rois(200 + K, max(K, 1), (800, 1344), smin=30)[:K, 1:5].copy()
+        if N > 10 and K > 3:
+            boxes[:5] = gts[:1]                         # exact matches (overlap 1.0) and ties across duplicated gts
+            gts[2] = gts[1]
+            boxes[7, 2] = boxes[7, 0] - 3.0             # negative width
+        want = cb.bbox_overlaps(boxes, gts)
+        got = box_utils.bbox_overlaps(boxes, gts)
+        assert got.dtype == np.float32 and got.shape == (N, K) and np.array_equal(got, want)
+        if N and K:
+            _, mx, am = ops.bbox_overlaps_cuda(torch.from_numpy(boxes).cuda(), torch.from_numpy(gts).cuda(), want_matrix=False)
+            assert np.array_equal(mx.cpu().numpy(), want.max(axis=1))
+            assert np.array_equal(am.cpu().numpy(), want.argmax(axis=1))
+    with pytest.raises(ValueError):
+        box_utils.bbox_overlaps(np.zeros((1, 4)), np.zeros((1, 4), np.float32))

@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/.."
 tag=$1; shift
 mkdir -p gpurun_ab/obj_$tag
-for f in api roialign proposals collect paste flow_align mask_nms; do
+for f in api roialign proposals collect paste flow_align mask_nms overlaps; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden "$@" \
        -c vosdetectron_b200/csrc/$f.cu -o gpurun_ab/obj_$tag/$f.o &
 done

@@ -6,9 +6,14 @@
 #include <vector>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 __global__ void k(const __grid_constant__ CUtensorMap tm, const CUtensorMap* gtm, const float* feat, int c0, int c1, int c2, int bytes, float* out, int n, int variant) {
+    // (variant >= 10: same as variant - 10 with the destination rounded up to 1024 bytes)
     extern __shared__ __align__(1024) unsigned char dyn[];
     __shared__ __align__(8) unsigned long long bar;
-    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(&bar), dst = (unsigned)__cvta_generic_to_shared(dyn);
+    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(&bar);
+    unsigned dst = (unsigned)__cvta_generic_to_shared(dyn);
+    if (threadIdx.x == 0) printf("dyn smem address 0x%x (mod 1024 = %u, mod 128 = %u)\n", dst, dst & 1023u, dst & 127u);
+    if (variant >= 10) { dst = (dst + 1023u) & ~1023u; variant -= 10; }      // force a 1024-byte aligned destination
+    const unsigned char* src_s = dyn + (dst - (unsigned)__cvta_generic_to_shared(dyn));
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_s) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -46,7 +51,7 @@ __global__ void k(const __grid_constant__ CUtensorMap tm, const CUtensorMap* gtm
                          :: "r"(dst), "l"(feat), "r"(bytes), "r"(bar_s) : "memory");
     }
     asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" :: "r"(bar_s), "r"(0) : "memory");
-    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = reinterpret_cast<float*>(dyn)[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = reinterpret_cast<const float*>(src_s)[i];
 }
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -77,9 +82,11 @@ int main(int argc, char** argv) {
     if (rc) return 0;
     const int n = bx * b1 * b2;
     float* out; CK(cudaMalloc(&out, n * 4));
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 4 + 1024));
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 4 + 2048));
     CUtensorMap* gtm; CK(cudaMalloc(&gtm, sizeof(tm))); CK(cudaMemcpy(gtm, &tm, sizeof(tm), cudaMemcpyHostToDevice));
-    k<<<1, 128, n * 4 + 1024>>>(tm, gtm, feat, 5, 2, 3, n * 4, out, n, variant);
+    const int cx = argc > 7 ? atoi(argv[7]) : 5;
+    printf("x coordinate %d (start offset %d bytes)\n", cx, cx * 4);
+    k<<<1, 128, n * 4 + 2048>>>(tm, gtm, feat, cx, 2, 3, n * 4, out, n, variant);
     CK(cudaDeviceSynchronize());
     std::vector<float> o(n); CK(cudaMemcpy(o.data(), out, n * 4, cudaMemcpyDeviceToHost));
     printf("first: %.1f %.1f %.1f | row1: %.1f | plane1: %.1f\n", o[0], o[1], o[2], o[bx], o[bx * b1]);

@@ -58,7 +58,7 @@ def install_reference_aliases(legacy_model_roi_align=True):
         'modeling.collect_and_distribute_fpn_rpn_proposals':
             ('.modeling.collect_and_distribute_fpn_rpn_proposals',
              ['collect', 'distribute', 'CollectAndDistributeFpnRpnProposalsOp']),
-        'utils.boxes': ('.utils.boxes', ['nms']),
+        'utils.boxes': ('.utils.boxes', ['nms', 'bbox_overlaps']),
         'core.test': ('.core.test', ['segm_results']),
         # lib_vos/tools/vos_test.py is imported as the top-level module `vos_test` (infer_davis_sequential.py:27)
         'vos_test': ('.core.vos_test', ['segm_results', 'box_results_with_nms_and_limit', 'nms_with_mask_iou']),

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvosd_b200.so")
-SOURCES = ["api.cu", "roialign.cu", "proposals.cu", "collect.cu", "paste.cu", "flow_align.cu", "mask_nms.cu"]
+SOURCES = ["api.cu", "roialign.cu", "proposals.cu", "collect.cu", "paste.cu", "flow_align.cu", "mask_nms.cu", "overlaps.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

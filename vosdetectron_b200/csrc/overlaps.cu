@@ -1,0 +1,80 @@
+// bbox_overlaps (first piece of the training label assignment).
+//
+// Reference: lib/utils/cython_bbox.pyx:32-73 (bound as box_utils.bbox_overlaps, lib/utils/boxes.py:55); callers on
+// the training path: datasets/json_dataset.py:450-456 (proposal -> gt overlaps, then .argmax(axis=1) / .max(axis=1)),
+// roi_data/rpn.py:149-158 (anchor -> gt overlaps, row and column maxima), roi_data/mask_rcnn.py:58.
+//
+// fp32 arithmetic in the reference's operation order (C floats, no fused multiply-add on baseline x86-64): a pair
+// overlaps only if iw > 0 and ih > 0, widths use the "+ 1" convention.  One thread per box row, query boxes in shared
+// memory; the row maximum / first arg-maximum (NumPy argmax tie rule) come out of the same pass, so the (N,K) matrix
+// need not be written at all when only the labels are wanted.
+#include "common.cuh"
+
+namespace vosd {
+namespace {
+
+constexpr int kQueryTile = 1024;    // query boxes per shared-memory tile
+
+__global__ void __launch_bounds__(256) bbox_overlaps_kernel(const float4* __restrict__ boxes, int N,
+                                                            const float4* __restrict__ query, int K,
+                                                            float* __restrict__ overlaps, float* __restrict__ row_max,
+                                                            int* __restrict__ row_argmax) {
+    __shared__ float4 q[kQueryTile];
+    __shared__ float qarea[kQueryTile];
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N) b = boxes[n];
+    const float barea = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+    float best = -1.f;          // overlaps are >= 0: the first column wins ties, like np.argmax
+    int best_k = 0;
+    for (int k0 = 0; k0 < K; k0 += kQueryTile) {
+        const int kt = min(kQueryTile, K - k0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kt; i += blockDim.x) {
+            const float4 v = query[k0 + i];
+            q[i] = v;
+            qarea[i] = __fmul_rn(__fadd_rn(__fsub_rn(v.z, v.x), 1.f), __fadd_rn(__fsub_rn(v.w, v.y), 1.f));   // :49-52
+        }
+        __syncthreads();
+        if (n >= N) continue;
+        for (int i = 0; i < kt; ++i) {
+            const float4 v = q[i];
+            float o = 0.f;
+            const float iw = __fadd_rn(__fsub_rn(fminf(b.z, v.z), fmaxf(b.x, v.x)), 1.f);                     // :54-57
+            if (iw > 0.f) {
+                const float ih = __fadd_rn(__fsub_rn(fminf(b.w, v.w), fmaxf(b.y, v.y)), 1.f);                 // :59-62
+                if (ih > 0.f) {
+                    const float inter = __fmul_rn(iw, ih);
+                    const float ua = __fsub_rn(__fadd_rn(barea, qarea[i]), inter);                            // :64-68
+                    o = __fdiv_rn(inter, ua);                                                                  // :69
+                }
+            }
+            if (overlaps) overlaps[(size_t)n * K + k0 + i] = o;
+            if (o > best) {
+                best = o;
+                best_k = k0 + i;
+            }
+        }
+    }
+    if (n < N) {
+        if (row_max) row_max[n] = K > 0 ? best : 0.f;
+        if (row_argmax) row_argmax[n] = best_k;
+    }
+}
+
+}  // namespace
+}  // namespace vosd
+
+extern "C" int vosd_bbox_overlaps(const float* boxes, int num_boxes, const float* query_boxes, int num_query,
+                                  float* overlaps, float* row_max, int* row_argmax, cudaStream_t stream) {
+    using namespace vosd;
+    if (num_boxes < 0 || num_query < 0) return VOSD_ERR_BAD_SHAPE;
+    if (num_boxes == 0) return VOSD_OK;
+    if (!boxes || (num_query && !query_boxes)) return VOSD_ERR_BAD_ARG;
+    if (!aligned16(boxes) || (num_query && !aligned16(query_boxes))) return VOSD_ERR_BAD_ARG;
+    bbox_overlaps_kernel<<<ceil_div(num_boxes, 256), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(boxes), num_boxes, reinterpret_cast<const float4*>(query_boxes), num_query,
+        overlaps, row_max, row_argmax);
+    count_launch();
+    return check_launch();
+}

@@ -514,3 +514,20 @@ def mask_iou_nms_cuda(packed, order, iou_th):
     _lib.call("vosd_mask_iou_nms", _ptr(p), R, nb, _ptr(o), float(iou_th), _ptr(removed), _ptr(num), _ptr(ws), nbytes,
               _stream())
     return removed[:R], num
+
+
+# ----------------------------------------------------------------------------- bbox_overlaps
+def bbox_overlaps_cuda(boxes, query_boxes, want_matrix=True):
+    """boxes (N,4), query_boxes (K,4) on the device -> (overlaps (N,K) or None, row_max (N), row_argmax (N) int32);
+    cython_bbox.pyx:32-73 arithmetic, np.argmax tie rule."""
+    b = _need_cuda(boxes, "boxes")
+    q = _need_cuda(query_boxes, "query_boxes")
+    if b.dim() != 2 or b.size(1) != 4 or q.dim() != 2 or q.size(1) != 4:
+        raise ValueError("boxes must be (N,4) and query_boxes (K,4)")
+    N, K = int(b.size(0)), int(q.size(0))
+    ov = torch.zeros((N, K), dtype=torch.float32, device=b.device) if want_matrix else None
+    mx = torch.zeros((N,), dtype=torch.float32, device=b.device)
+    am = torch.zeros((N,), dtype=torch.int32, device=b.device)
+    _bind(b)
+    _lib.call("vosd_bbox_overlaps", _ptr(b), N, _ptr(q), K, _ptr(ov), _ptr(mx), _ptr(am), _stream())
+    return ov, mx, am

@@ -6,6 +6,9 @@
 in, int64 ndarray of kept indices (ascending) out, ``[]`` for empty input.  One H2D copy in,
 one D2H copy out; the work is done by the bitmask kernels of csrc/proposals.cu.
 ``nms_cuda`` is the tensor-in / tensor-out variant that stays on the device.
+
+``bbox_overlaps(boxes, query_boxes)`` replaces cython_bbox.bbox_overlaps (boxes.py:55); ``ops.bbox_overlaps_cuda``
+also returns the row maxima / arg-maxima the label assignment takes next (json_dataset.py:453-456).
 """
 import numpy as np
 import torch
@@ -22,6 +25,19 @@ def nms(dets, thresh):
     keep, num = ops.nms_cuda(d, thresh)
     n = int(num.item())
     return keep[:n].cpu().numpy()
+
+
+def bbox_overlaps(boxes, query_boxes):
+    """cython_bbox.bbox_overlaps (cython_bbox.pyx:32-73; boxes.py:55) with the reference's ndarray signature:
+    (N,4) x (K,4) float32 -> (N,K) float32."""
+    if boxes.dtype != np.float32 or query_boxes.dtype != np.float32:
+        raise ValueError("Buffer dtype mismatch, expected 'float32'")        # what the typed Cython signature raises
+    N, K = boxes.shape[0], query_boxes.shape[0]
+    if N == 0 or K == 0:
+        return np.zeros((N, K), dtype=np.float32)
+    b = torch.from_numpy(np.ascontiguousarray(boxes)).cuda()
+    q = torch.from_numpy(np.ascontiguousarray(query_boxes)).cuda()
+    return ops.bbox_overlaps_cuda(b, q)[0].cpu().numpy()
 
 
 def bbox_transform(boxes, deltas, weights=(1.0, 1.0, 1.0, 1.0)):

@@ -307,7 +307,9 @@ VOSD_API int vosd_pack_mask_bits(const uint8_t* masks, int num_masks, long long 
 /* the fp32 sum differs (the reference's atomics are unordered as well).                  */
 /* bottomdiff / flowdiff are ACCUMULATED into; FlowAlignFunction.backward zero-fills them */
 /* (functions/flow_align.py:41-43): pass zero_init != 0 to have the library clear them on */
-/* `stream`.  N*C*H*W must be < 2^31 (the reference indexes with int).                     */
+/* `stream`.  N*C*H*W must be < 2^31 (the reference indexes with int).  flowdiff == NULL:  */
+/* the flow gradient is not wanted (flow from a frozen estimator); its tap loads and        */
+/* arithmetic (:95-112) are skipped.                                                       */
 /* ------------------------------------------------------------------------------------ */
 VOSD_API int vosd_flow_align_fwd(int batches, int height, int width, int channels, const float* bottom,
                                  const float* flow, float* top, cudaStream_t stream);
@@ -363,8 +365,9 @@ VOSD_API int vosd_rle_to_bits(const uint32_t* runs, const long long* run_offset,
 /* bbox_overlaps ("next" row, SURVEY 8f rank 3: first piece of the training label         */
 /* assignment).  Replaces cython_bbox.bbox_overlaps (lib/utils/cython_bbox.pyx:32-73,     */
 /* bound at lib/utils/boxes.py:55) and the `.argmax(axis=1)` / `.max(axis=1)` that follow  */
-/* it in datasets/json_dataset.py:450-456 and roi_data/rpn.py:149-158.  fp32, the          */
-/* reference's operation order: bit-identical.                                             */
+/* it in datasets/json_dataset.py:450-456 and roi_data/rpn.py:149-158.  The arithmetic of   */
+/* the compiled .pyx (areas and union in float64, products and the division in float32):    */
+/* bit-identical.                                                                          */
 /*   boxes (N,4), query_boxes (K,4) fp32, 16-byte aligned; overlaps (N,K) fp32 or NULL;    */
 /*   row_max (N) fp32 or NULL; row_argmax (N) int32 or NULL (first maximum, as np.argmax;  */
 /*   0 and 0.0 when K == 0).                                                               */

@@ -124,6 +124,24 @@ def test_backward_vs_reference_kernel_and_oracle(case, refk, orc, synth, exact_m
         assert bool(((ref == 0) == (mine == 0)).all()) or float((mine[ref == 0]).abs().max()) == 0.0
 
 
+def test_backward_without_flow_gradient(refk, synth):
+    """flowdiff == NULL: same feature gradient (the tap loads / dx / dy arithmetic are compiled out)."""
+    from vosdetectron_b200 import ops
+    from vosdetectron_b200.vos_model.flow_align.functions.flow_align import FlowAlignFunction
+    f, fl, g = make(synth, 61, 2, 24, 40, 56, "smooth", 2.0)
+    gf, gfl = ops.flow_align_backward(g, f, fl, want_flow_grad=False)
+    assert gfl is None
+    rf, _ = refk.bwd(g, f, fl)
+    ok, err, scale = close(gf, rf)
+    assert ok, (err, scale)
+    gfs, gfls = ops.flow_align_ml_backward([g], [f], [fl], want_flow_grad=False)
+    assert gfls is None and close(gfs[0], rf)[0]
+    f2 = f.clone().requires_grad_(True)
+    out = FlowAlignFunction.apply(f2, fl)              # flow does not require grad
+    out.backward(g)
+    assert close(f2.grad, rf)[0]
+
+
 def test_forward_fast_variant_within_1e5(refk, synth):
     from vosdetectron_b200 import _lib, ops
     f, fl, _ = make(synth, 17, 2, 32, 48, 84, "smooth", 2.0)

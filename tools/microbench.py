@@ -264,6 +264,25 @@ def main():
                 report(out, "REFERENCE_flowalign_bwd_5lvl_%dframes" % B, timer, ref_b, alg_b, {"elements": elems})
 
 
+    # ---------------- yardsticks: what the memory system gives plain fill / copy kernels of the same sizes ----------------
+    if want("yard"):
+        fill = torch.empty(410 << 20, dtype=torch.uint8, device="cuda")           # the paste output of 10 frames
+        report(out, "YARDSTICK_memset_410MB (cudaMemsetAsync via torch.zero_)", timer, lambda: fill.zero_(), fill.numel())
+        a = torch.empty(353 << 20, dtype=torch.uint8, device="cuda")              # FlowAlign forward: read 353 MB, write 353 MB
+        b = torch.empty_like(a)
+        report(out, "YARDSTICK_copy_353MB_read+353MB_write (torch.copy_)", timer, lambda: b.copy_(a), 2 * a.numel())
+        if want("flow") or True:
+            from vosdetectron_b200 import _lib as _l
+            shapes = [synth.level_shape(synth.DAVIS_BLOB, l) for l in synth.FPN_LEVELS]
+            feats = [torch.randn((4, 256, h, w), device="cuda") for h, w in shapes]
+            flows = [cu(synth.flow_field(4000 + i, 4, h, w, "smooth", 2.0)) for i, (h, w) in enumerate(shapes)]
+            grads = [torch.randn_like(f) for f in feats]
+            elems = sum(f.numel() for f in feats)
+            report(out, "flowalign_bwd_feature_grad_only_5lvl_4frames", timer,
+                   lambda: ops.flow_align_ml_backward(grads, feats, flows, want_flow_grad=False),
+                   2 * elems * 4 + sum(f.numel() for f in flows) * 4, {"elements": elems})
+
+
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump({"peak_gbs_measured": PEAK, "gpu": torch.cuda.get_device_name(0), "results": out}, open(args.out, "w"), indent=1)
 

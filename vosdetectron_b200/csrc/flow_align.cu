@@ -327,7 +327,7 @@ __device__ __forceinline__ FlowGrad flow_grad(float g, float f1, float f2, float
     return o;
 }
 
-template <bool ALU>
+template <bool ALU, bool WANT_FLOW>
 __global__ void __launch_bounds__(kFlowThreads, VOSD_FLOW_MINB_BWD) flow_align_bwd_kernel(const __grid_constant__ FlowArgs a) {
     constexpr int kFlowRows = kFlowRowsBwd;
     const FlowTile t = decode_tile(a);
@@ -383,10 +383,14 @@ __global__ void __launch_bounds__(kFlowThreads, VOSD_FLOW_MINB_BWD) flow_align_b
     auto fetch = [&](float (&b)[kFlowRows][5], const float* p, const float* q) {
 #pragma unroll
         for (int r = 0; r < kFlowRows; ++r) {
-            b[r][0] = __ldg(p + ld[r]);
-            b[r][1] = __ldg(p + ld[r] + 1);
-            b[r][2] = __ldg(p + ld[r] + W);
-            b[r][3] = __ldg(p + ld[r] + W + 1);
+            if (WANT_FLOW) {                              // the taps only feed the flow gradient
+                b[r][0] = __ldg(p + ld[r]);
+                b[r][1] = __ldg(p + ld[r] + 1);
+                b[r][2] = __ldg(p + ld[r] + W);
+                b[r][3] = __ldg(p + ld[r] + W + 1);
+            } else {
+                b[r][0] = b[r][1] = b[r][2] = b[r][3] = 0.f;
+            }
             b[r][4] = __ldcs(q + ldg[r]);
         }
     };
@@ -404,8 +408,10 @@ __global__ void __launch_bounds__(kFlowThreads, VOSD_FLOW_MINB_BWD) flow_align_b
                 FlowGrad v = ALU ? flow_grad(b[r][4], b[r][0], b[r][1], b[r][2], b[r][3], hr[r], wr[r], fac[r])
                                  : flow_grad_ref(b[r][4], b[r][0], b[r][1], b[r][2], b[r][3], hr[r], wr[r]);
                 if (off[r] < 0) v.a1 = v.a2 = v.a3 = v.a4 = v.dx = v.dy = 0.f;
-                gx[r] += __fmul_rn(b[r][4], v.dx);               // :111-112, summed over the chunk first
-                gy[r] += __fmul_rn(b[r][4], v.dy);
+                if (WANT_FLOW) {
+                    gx[r] += __fmul_rn(b[r][4], v.dx);           // :111-112, summed over the chunk first
+                    gy[r] += __fmul_rn(b[r][4], v.dy);
+                }
                 if (r > 0 && !((vm >> r) & 1u) && off[r - 1] >= 0) {   // previous row's bottom pair stands alone
                     red_add(d + off[r - 1] + W, pl);
                     red_add(d + off[r - 1] + W + 1, pr);
@@ -434,10 +440,10 @@ __global__ void __launch_bounds__(kFlowThreads, VOSD_FLOW_MINB_BWD) flow_align_b
     auto prefetch = [&](const float* p, const float* q) {
 #pragma unroll
         for (int r = 0; r < kFlowRows; ++r) {
-            prefetch_l2(p + ld[r]);
+            if (WANT_FLOW) prefetch_l2(p + ld[r]);
             prefetch_l2(q + ldg[r]);
         }
-        prefetch_l2(p + ld[kFlowRows - 1] + W);
+        if (WANT_FLOW) prefetch_l2(p + ld[kFlowRows - 1] + W);
     };
     fetch(cur, base, td);
     int c = c0;
@@ -456,6 +462,7 @@ __global__ void __launch_bounds__(kFlowThreads, VOSD_FLOW_MINB_BWD) flow_align_b
     }
     if (c < c1) scatter(cur, bd);
     // flow gradient: one reduction per (pixel, channel chunk) instead of one per channel
+    if (!WANT_FLOW) return;
     float* fd = L.out1 + (size_t)t.n * 2 * plane;
 #pragma unroll
     for (int r = 0; r < kFlowRows; ++r)
@@ -532,33 +539,47 @@ int flow_fwd(int num_levels, int batches, int channels, const int* level_h, cons
 int flow_bwd(int num_levels, int batches, int channels, const int* level_h, const int* level_w,
              const float* const* topdiff, const float* const* bottom, const float* const* flow,
              float* const* bottomdiff, float* const* flowdiff, int zero_init, cudaStream_t stream) {
-    if (num_levels > 0 && (!level_h || !level_w || !topdiff || !bottom || !flow || !bottomdiff || !flowdiff))
+    if (num_levels > 0 && (!level_h || !level_w || !topdiff || !bottom || !flow || !bottomdiff))
         return VOSD_ERR_BAD_ARG;
+    // flowdiff == NULL (the table, or every entry): the flow gradient is not wanted -- the tap loads, their
+    // conversions and the dx / dy arithmetic (:95-112) are compiled out
+    bool want_flow = flowdiff != nullptr;
+    if (want_flow) {
+        int have = 0, live = 0;                       // empty levels carry no pointers at all
+        for (int l = 0; l < num_levels; ++l) {
+            if ((long long)level_h[l] * level_w[l] * batches == 0) continue;
+            ++live;
+            have += flowdiff[l] != nullptr;
+        }
+        if (have == 0) want_flow = false;
+        else if (have != live) return VOSD_ERR_BAD_ARG;
+    }
     FlowArgs a = {};
     const long long grid = plan(a, kFlowRowsBwd, num_levels, batches, channels, level_h, level_w);
     if (grid < 0) return (int)grid;
     for (int l = 0; l < num_levels; ++l) {
         const size_t plane = (size_t)level_h[l] * level_w[l];
-        if (plane && batches && (!flowdiff[l] || (channels && (!topdiff[l] || !bottom[l] || !flow[l] || !bottomdiff[l]))))
+        if (plane && batches && channels && (!topdiff[l] || !bottom[l] || !flow[l] || !bottomdiff[l]))
             return VOSD_ERR_BAD_ARG;
         a.lv[l].topdiff = topdiff[l];
         a.lv[l].bottom = bottom[l];
         a.lv[l].flow = flow[l];
         a.lv[l].out0 = bottomdiff[l];
-        a.lv[l].out1 = flowdiff[l];
+        a.lv[l].out1 = want_flow ? flowdiff[l] : nullptr;
         if (zero_init && plane && batches) {
             // FlowAlignFunction.backward zero-fills both gradients itself (functions/flow_align.py:41-43)
             if (channels && cudaMemsetAsync(bottomdiff[l], 0, plane * batches * channels * sizeof(float), stream) != cudaSuccess)
                 return VOSD_ERR_LAUNCH;
-            if (cudaMemsetAsync(flowdiff[l], 0, plane * batches * 2 * sizeof(float), stream) != cudaSuccess)
+            if (want_flow && cudaMemsetAsync(flowdiff[l], 0, plane * batches * 2 * sizeof(float), stream) != cudaSuccess)
                 return VOSD_ERR_LAUNCH;
         }
     }
     if (grid == 0) return VOSD_OK;
-    if (g_flow_fast.load(std::memory_order_relaxed) == kFlowExactAlu)
-        flow_align_bwd_kernel<true><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a);
-    else
-        flow_align_bwd_kernel<false><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a);
+    const bool alu = g_flow_fast.load(std::memory_order_relaxed) == kFlowExactAlu;
+    if (alu && want_flow) flow_align_bwd_kernel<true, true><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a);
+    else if (alu) flow_align_bwd_kernel<true, false><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a);
+    else if (want_flow) flow_align_bwd_kernel<false, true><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a);
+    else flow_align_bwd_kernel<false, false><<<(unsigned)grid, kFlowThreads, 0, stream>>>(a);
     count_launch();
     return check_launch();
 }

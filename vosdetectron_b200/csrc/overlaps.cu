@@ -4,10 +4,12 @@
 // the training path: datasets/json_dataset.py:450-456 (proposal -> gt overlaps, then .argmax(axis=1) / .max(axis=1)),
 // roi_data/rpn.py:149-158 (anchor -> gt overlaps, row and column maxima), roi_data/mask_rcnn.py:58.
 //
-// fp32 arithmetic in the reference's operation order (C floats, no fused multiply-add on baseline x86-64): a pair
-// overlaps only if iw > 0 and ih > 0, widths use the "+ 1" convention.  One thread per box row, query boxes in shared
-// memory; the row maximum / first arg-maximum (NumPy argmax tie rule) come out of the same pass, so the (N,K) matrix
-// need not be written at all when only the labels are wanted.
+// Arithmetic as compiled from the .pyx: Cython types the literal in `x2 - x1 + 1` as the double 1.0, so widths,
+// heights and the areas are formed in float64 (`box_area` and `iw`, `ih` are rounded to their float32 variables, the
+// union `ua = float(area_n + box_area - iw * ih)` is summed in float64 and rounded once), `iw * ih` and the final
+// division are float32; no fused multiply-add (baseline x86-64).  A pair overlaps only if iw > 0 and ih > 0.
+// One thread per box row, query boxes in shared memory; the row maximum / first arg-maximum (NumPy argmax tie
+// rule) come out of the same pass, so the (N,K) matrix need not be written at all when only the labels are wanted.
 #include "common.cuh"
 
 namespace vosd {
@@ -24,7 +26,8 @@ __global__ void __launch_bounds__(256) bbox_overlaps_kernel(const float4* __rest
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n < N) b = boxes[n];
-    const float barea = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+    // area of box n in float64 (exact: two 25-bit factors), cython_bbox.pyx:65-66
+    const double barea = __dmul_rn((double)__fsub_rn(b.z, b.x) + 1.0, (double)__fsub_rn(b.w, b.y) + 1.0);
     float best = -1.f;          // overlaps are >= 0: the first column wins ties, like np.argmax
     int best_k = 0;
     for (int k0 = 0; k0 < K; k0 += kQueryTile) {
@@ -33,19 +36,19 @@ __global__ void __launch_bounds__(256) bbox_overlaps_kernel(const float4* __rest
         for (int i = threadIdx.x; i < kt; i += blockDim.x) {
             const float4 v = query[k0 + i];
             q[i] = v;
-            qarea[i] = __fmul_rn(__fadd_rn(__fsub_rn(v.z, v.x), 1.f), __fadd_rn(__fsub_rn(v.w, v.y), 1.f));   // :49-52
+            qarea[i] = (float)__dmul_rn((double)__fsub_rn(v.z, v.x) + 1.0, (double)__fsub_rn(v.w, v.y) + 1.0);  // :49-52
         }
         __syncthreads();
         if (n >= N) continue;
         for (int i = 0; i < kt; ++i) {
             const float4 v = q[i];
             float o = 0.f;
-            const float iw = __fadd_rn(__fsub_rn(fminf(b.z, v.z), fmaxf(b.x, v.x)), 1.f);                     // :54-57
+            const float iw = (float)((double)__fsub_rn(fminf(b.z, v.z), fmaxf(b.x, v.x)) + 1.0);             // :54-57
             if (iw > 0.f) {
-                const float ih = __fadd_rn(__fsub_rn(fminf(b.w, v.w), fmaxf(b.y, v.y)), 1.f);                 // :59-62
+                const float ih = (float)((double)__fsub_rn(fminf(b.w, v.w), fmaxf(b.y, v.y)) + 1.0);         // :59-62
                 if (ih > 0.f) {
                     const float inter = __fmul_rn(iw, ih);
-                    const float ua = __fsub_rn(__fadd_rn(barea, qarea[i]), inter);                            // :64-68
+                    const float ua = (float)__dsub_rn(__dadd_rn(barea, (double)qarea[i]), (double)inter);    // :64-68
                     o = __fdiv_rn(inter, ua);                                                                  // :69
                 }
             }

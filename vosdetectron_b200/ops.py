@@ -129,16 +129,17 @@ def flow_align_forward(features, flows):
     return out
 
 
-def flow_align_backward(grad_output, features, flows):
-    """-> (grad_feature, grad_flow); flow_align_cuda_kernel.cu:57-117.  Both gradients are cleared on the
-    stream by the library (zero_init=1)."""
+def flow_align_backward(grad_output, features, flows, want_flow_grad=True):
+    """-> (grad_feature, grad_flow or None); flow_align_cuda_kernel.cu:57-117.  The gradients are cleared on the
+    stream by the library (zero_init=1).  ``want_flow_grad=False`` skips the flow gradient (and the tap loads and
+    arithmetic that only feed it)."""
     f, fl = _flow_pair(features, flows)
     g = _need_cuda(grad_output, "grad_output")
     if g.shape != f.shape:
         raise ValueError("grad_output %s does not match features %s" % (tuple(g.shape), tuple(f.shape)))
     N, C, H, W = f.shape
     gf = torch.empty_like(f)
-    gfl = torch.empty_like(fl)
+    gfl = torch.empty_like(fl) if want_flow_grad else None
     _bind(f)
     _lib.call("vosd_flow_align_bwd", N, H, W, C, _ptr(g), _ptr(f), _ptr(fl), _ptr(gf), _ptr(gfl), 1, _stream())
     return gf, gfl
@@ -167,20 +168,21 @@ def flow_align_ml_forward(level_features, level_flows):
     return outs
 
 
-def flow_align_ml_backward(level_grads, level_features, level_flows):
+def flow_align_ml_backward(level_grads, level_features, level_flows, want_flow_grad=True):
     pairs = [_flow_pair(f, fl) for f, fl in zip(level_features, level_flows)]
     if not pairs:
         return [], []
     grads = [_need_cuda(g, "grad_output") for g in level_grads]
     N, C = pairs[0][0].shape[:2]
     gfs = [torch.empty_like(f) for f, _ in pairs]
-    gfls = [torch.empty_like(fl) for _, fl in pairs]
+    gfls = [torch.empty_like(fl) for _, fl in pairs] if want_flow_grad else None
     L = len(pairs)
     hs = (ctypes.c_int * L)(*[int(f.shape[2]) for f, _ in pairs])
     ws = (ctypes.c_int * L)(*[int(f.shape[3]) for f, _ in pairs])
     _bind(pairs[0][0])
     _lib.call("vosd_flow_align_ml_bwd", L, N, C, hs, ws, _ptr_table(grads), _ptr_table([f for f, _ in pairs]),
-              _ptr_table([fl for _, fl in pairs]), _ptr_table(gfs), _ptr_table(gfls), 1, _stream())
+              _ptr_table([fl for _, fl in pairs]), _ptr_table(gfs), None if gfls is None else _ptr_table(gfls), 1,
+              _stream())
     return gfs, gfls
 
 

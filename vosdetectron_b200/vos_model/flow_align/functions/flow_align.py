@@ -25,8 +25,10 @@ class FlowAlignFunction(Function):
         features, flows = ctx.saved_tensors
         if not grad_output.is_cuda:
             raise NotImplementedError("FlowAlign backward needs CUDA tensors")
-        grad_feature, grad_flow = ops.flow_align_backward(grad_output.contiguous(), features, flows)
-        return grad_feature, grad_flow
+        # a flow that does not require grad (a frozen estimator's output) skips the flow-gradient half of the kernel
+        grad_feature, grad_flow = ops.flow_align_backward(grad_output.contiguous(), features, flows,
+                                                          want_flow_grad=ctx.needs_input_grad[1])
+        return (grad_feature if ctx.needs_input_grad[0] else None), grad_flow
 
 
 class _FlowAlignML(Function):
@@ -44,8 +46,9 @@ class _FlowAlignML(Function):
         L = ctx.num_levels
         feats, flows = ctx.saved_tensors[:L], ctx.saved_tensors[L:]
         grads = [g.contiguous() if g is not None else torch.zeros_like(f) for g, f in zip(grads, feats)]
-        gfs, gfls = ops.flow_align_ml_backward(grads, feats, flows)
-        return (None,) + tuple(gfs) + tuple(gfls)
+        want_flow = any(ctx.needs_input_grad[1 + L:])
+        gfs, gfls = ops.flow_align_ml_backward(grads, feats, flows, want_flow_grad=want_flow)
+        return (None,) + tuple(gfs) + (tuple(gfls) if gfls is not None else (None,) * L)
 
 
 def flow_align_multilevel(level_features, level_flows):

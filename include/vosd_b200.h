@@ -101,6 +101,19 @@ VOSD_API int vosd_roialign_ml_fwd(const float* const* level_data, const int* lev
                          int num_rois, const float* rois, const int* roi_level,
                          const int* out_index, float* top_data, cudaStream_t stream);
 
+/* The same forward for CHANNELS-LAST maps: level_data[l] points to a (N, H_l, W_l, C) fp32 array (what a
+ * torch.channels_last tensor of logical shape (N,C,H_l,W_l) holds), 16-byte aligned; top_data stays (R,C,ph,pw).
+ * Tensor-mode TMA loads (32 channels x <= 32 texels x 1 row per box) land in shared memory in the layout the
+ * consumer reads, so no warp stages or transposes anything.  Same summation order and
+ * parity gate as the default NCHW kernel.  Supported: sampling_ratio == 2, aligned_width in {7, 14, 28},
+ * channels % 32 == 0 (every head of the reference); anything else returns VOSD_ERR_UNSUPPORTED and the caller uses
+ * vosd_roialign_ml_fwd on NCHW maps.  batch_size = N (bounds of the tensor maps). */
+VOSD_API int vosd_roialign_ml_fwd_nhwc(const float* const* level_data, const int* level_h, const int* level_w,
+                                       const float* level_scale, int num_levels, int batch_size, int channels,
+                                       int aligned_height, int aligned_width, int sampling_ratio,
+                                       int num_rois, const float* rois, const int* roi_level,
+                                       const int* out_index, float* top_data, cudaStream_t stream);
+
 /* Test hook selecting the RoIAlign kernel family, so every path stays covered by the parity tests:
  *   0 = default (separable warp-specialised forward where sampling_ratio == 2, pooled width 7/14/28 and
  *       C % 32 == 0, else the staged forward; record-based atomic-scatter backward),

@@ -43,6 +43,9 @@ SIGNATURES = {
     "vosd_roialign_ml_fwd": (ctypes.c_int, [ctypes.POINTER(vp), c_int_p, c_int_p, c_float_p, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             vp, vp, vp, vp, vp]),
+    "vosd_roialign_ml_fwd_nhwc": (ctypes.c_int, [ctypes.POINTER(vp), c_int_p, c_int_p, c_float_p, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int, vp, vp, vp, vp, vp]),
     "vosd_roialign_ml_bwd": (ctypes.c_int, [vp, ctypes.POINTER(vp), c_int_p, c_int_p, c_float_p, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, vp, vp, vp, ctypes.c_int, vp]),

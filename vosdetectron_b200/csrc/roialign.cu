@@ -1,6 +1,7 @@
 // Multi-level RoIAlign forward / backward for sm_100a.
 // Reference: lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.cu:65-121 (fwd), :195-270 (bwd),
 // driven per FPN level by lib/modeling/model_builder.py:262-303.
+#include <cstring>
 #include "common.cuh"
 #include "roialign_math.cuh"
 
@@ -1179,6 +1180,7 @@ bwd_tile_kernel(const __grid_constant__ LevelTable lv, const __grid_constant__ B
 
 }  // namespace vosd
 #include "roialign_sep.cuh"
+#include "roialign_nhwc.cuh"
 namespace vosd {
 
 // test hook (vosd_debug_force_generic): 0 = default (separable forward where it applies, record-based backward), 1 = generic kernels
@@ -1404,6 +1406,76 @@ extern "C" int vosd_roialign_ml_fwd(const float* const* level_data, const int* l
     if (num_levels > 1 && !roi_level && num_rois > 0) return VOSD_ERR_BAD_ARG;
     return ml_fwd(t, channels, aligned_height, aligned_width, sampling_ratio, num_rois, rois,
                   roi_level, out_index, top_data, stream);
+}
+
+// ---------------------------------------------------------------------------------------
+// Channels-last forward (roialign_nhwc.cuh): tensor maps are encoded per call on the host stack.
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static const EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+template <int T>
+static int launch_nhwc(const NhwcMaps& maps, const LevelTable& t, int channels, int ph, int num_rois,
+                       const float* rois, const int* roi_level, const int* out_index, float* top, cudaStream_t stream) {
+    const size_t dyn = (size_t)kNhwcWarps * kNhwcRingBytes;
+    if (cudaFuncSetAttribute(roialign_fwd_nhwc<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
+        return VOSD_ERR_LAUNCH;
+    dim3 grid(num_rois, ceil_div(channels / kSlab, kNhwcWarps / T), ceil_div(ph, 7));
+    roialign_fwd_nhwc<T><<<grid, kNhwcThreads, dyn, stream>>>(maps, t, channels, ph, rois, roi_level, out_index, top);
+    count_launch();
+    return check_launch();
+}
+
+extern "C" int vosd_roialign_ml_fwd_nhwc(const float* const* level_data, const int* level_h, const int* level_w,
+                                         const float* level_scale, int num_levels, int batch_size, int channels,
+                                         int aligned_height, int aligned_width, int sampling_ratio,
+                                         int num_rois, const float* rois, const int* roi_level,
+                                         const int* out_index, float* top_data, cudaStream_t stream) {
+    LevelTable t;
+    int rc = fill_table(t, level_data, level_h, level_w, level_scale, num_levels);
+    if (rc) return rc;
+    if (num_levels > 1 && !roi_level && num_rois > 0) return VOSD_ERR_BAD_ARG;
+    if (channels <= 0 || aligned_height <= 0 || aligned_width <= 0 || num_rois < 0 || batch_size <= 0) return VOSD_ERR_BAD_SHAPE;
+    if (sampling_ratio != 2 || (aligned_width != 7 && aligned_width != 14 && aligned_width != 28) || channels % kSlab ||
+        ceil_div(aligned_height, 7) > 65535 || ceil_div(channels / kSlab, 2) > 65535)
+        return VOSD_ERR_UNSUPPORTED;            // the caller falls back to the NCHW entry point
+    if (num_rois == 0) return VOSD_OK;
+    if (!rois || !top_data) return VOSD_ERR_BAD_ARG;
+    const EncodeTiledFn enc = encode_tiled();
+    if (!enc) return VOSD_ERR_UNSUPPORTED;
+    NhwcMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int l = 0; l < num_levels; l++) {
+        if (!aligned16(level_data[l])) return VOSD_ERR_BAD_ARG;
+        const cuuint64_t C = (cuuint64_t)channels, W = (cuuint64_t)level_w[l], H = (cuuint64_t)level_h[l];
+        const cuuint64_t dims[4] = {C, W, H, (cuuint64_t)batch_size};
+        const cuuint64_t strides[3] = {C * 4, W * C * 4, H * W * C * 4};
+        const cuuint32_t es[4] = {1, 1, 1, 1};
+        for (int b = 0; b < kNhwcBoxes; b++) {
+            const cuuint32_t box[4] = {(cuuint32_t)kSlab, (cuuint32_t)(8 * (b + 1)), 1, 1};
+            if (enc(&maps.m[l][b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(level_data[l]), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return VOSD_ERR_BAD_SHAPE;
+        }
+    }
+    switch (aligned_width / 7) {
+        case 1: return launch_nhwc<1>(maps, t, channels, aligned_height, num_rois, rois, roi_level, out_index, top_data, stream);
+        case 2: return launch_nhwc<2>(maps, t, channels, aligned_height, num_rois, rois, roi_level, out_index, top_data, stream);
+        default: return launch_nhwc<4>(maps, t, channels, aligned_height, num_rois, rois, roi_level, out_index, top_data, stream);
+    }
 }
 
 extern "C" int vosd_roialign_ml_bwd(const float* top_diff, float* const* level_diff, const int* level_h,

@@ -37,8 +37,24 @@ def _bind(t):
 
 
 # ----------------------------------------------------------------------------- RoIAlign
+def _is_channels_last(t):
+    """(N,C,H,W) tensor whose memory order is N,H,W,C (torch.channels_last) and not also plain contiguous."""
+    return (isinstance(t, torch.Tensor) and t.is_cuda and t.dim() == 4 and t.dtype == torch.float32
+            and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous())
+
+
+def _nhwc_supported(C, aligned_width, sampling_ratio):
+    return int(sampling_ratio) == 2 and int(aligned_width) in (7, 14, 28) and C % 32 == 0
+
+
 def roi_align_forward(features, rois, aligned_height, aligned_width, spatial_scale, sampling_ratio):
-    """(N,C,H,W) x (R,5) -> (R,C,ph,pw); roi_align_kernel.cu:65-121 semantics."""
+    """(N,C,H,W) x (R,5) -> (R,C,ph,pw); roi_align_kernel.cu:65-121 semantics.  Channels-last features take the
+    TMA-fed kernel (no layout conversion) where it applies."""
+    if _is_channels_last(features) and _nhwc_supported(features.shape[1], aligned_width, sampling_ratio):
+        r = _need_cuda(rois, "rois")
+        if r.dim() != 2 or r.size(1) != 5:
+            raise ValueError("rois must be (R,5)")
+        return roi_align_ml_forward([features], [spatial_scale], r, None, aligned_height, aligned_width, sampling_ratio)
     f = _need_cuda(features, "features")
     r = _need_cuda(rois, "rois")
     if r.dim() != 2 or r.size(1) != 5:
@@ -76,13 +92,27 @@ def _level_arrays(tensors, scales):
 
 def roi_align_ml_forward(level_features, level_scales, rois, roi_level, aligned_height, aligned_width,
                          sampling_ratio, out_index=None):
-    """All FPN levels in one launch.  ``level_features[k]`` is the map ``roi_level == k`` reads."""
-    feats = [_need_cuda(f, "level_features[%d]" % i) for i, f in enumerate(level_features)]
+    """All FPN levels in one launch.  ``level_features[k]`` is the map ``roi_level == k`` reads.
+    If every level is a channels-last tensor (memory order N,H,W,C) and the head is one of the reference's
+    (sampling_ratio 2, pooled width 7/14/28, C % 32 == 0) the TMA-fed channels-last kernel runs on the maps as
+    they are; otherwise the maps are used in (or converted to) the reference's NCHW order."""
     r = _need_cuda(rois, "rois")
-    lv = _need_cuda(roi_level, "roi_level", torch.int32)
+    lv = None if roi_level is None else _need_cuda(roi_level, "roi_level", torch.int32)
     oi = None if out_index is None else _need_cuda(out_index, "out_index", torch.int32)
-    C = feats[0].shape[1]
     R = r.size(0)
+    if (len(level_features) > 0 and all(_is_channels_last(f) for f in level_features)
+            and _nhwc_supported(level_features[0].shape[1], aligned_width, sampling_ratio)):
+        N, C = (int(v) for v in level_features[0].shape[:2])
+        if any(tuple(f.shape[:2]) != (N, C) for f in level_features):
+            raise ValueError("all levels must share batch size and channel count")
+        out = torch.empty((R, C, aligned_height, aligned_width), dtype=torch.float32, device=r.device)
+        ptrs, hs, ws, sc = _level_arrays(level_features, level_scales)
+        _bind(r)
+        _lib.call("vosd_roialign_ml_fwd_nhwc", ptrs, hs, ws, sc, len(level_features), N, C, int(aligned_height),
+                  int(aligned_width), int(sampling_ratio), R, _ptr(r), _ptr(lv), _ptr(oi), _ptr(out), _stream())
+        return out
+    feats = [_need_cuda(f, "level_features[%d]" % i) for i, f in enumerate(level_features)]
+    C = feats[0].shape[1]
     out = torch.empty((R, C, aligned_height, aligned_width), dtype=torch.float32, device=r.device)
     ptrs, hs, ws, sc = _level_arrays(feats, level_scales)
     _bind(r)

@@ -319,6 +319,8 @@ def gpu_arm(args, rank, world, local_rank):
         return t.pin_memory()
     h_rpn = {l: (pin(s), pin(d)) for l, (s, d) in host["rpn"].items()}
     h_feats = {l: pin(f) for l, f in host["feats"].items()}
+    if args.features_layout == "channels_last":
+        h_feats = {l: f.contiguous(memory_format=torch.channels_last).pin_memory() for l, f in h_feats.items()}
     h_info, h_boxes, h_cls = pin(host["im_info"]), pin(host["det_boxes"]), pin(host["det_cls"])
     # the mask head output the reference moves is (D,81,28,28); the API uploads what paste reads
     h_masks = pin(host["det_masks"])
@@ -429,6 +431,40 @@ def gpu_arm(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = world * B * e2e_steps / (e2e_ms / 1000.0)
+    # ---- the same device-resident step with the FPN maps in the OTHER memory order (single GPU only): the default
+    #      line is the reference's NCHW; torch.channels_last maps take the TMA-fed RoIAlign kernel.  Reported as an
+    #      extra key, never mixed into `value`.
+    alt = None
+    if world == 1:
+        alt_layout = "channels_last" if args.features_layout == "nchw" else "nchw"
+        keep = d_feats
+        if alt_layout == "channels_last":
+            d_feats = {l: f.contiguous(memory_format=torch.channels_last) for l, f in keep.items()}
+        else:
+            d_feats = {l: f.contiguous() for l, f in keep.items()}
+        torch.cuda.synchronize()
+        for _ in range(max(3, args.warmup)):
+            run_step(None)
+        torch.cuda.synchronize()
+        events.clear()
+        e0.record()
+        for _ in range(args.steps):
+            events.append([])
+            run_step(mark)
+        e1.record()
+        torch.cuda.synchronize()
+        alt_ms = e0.elapsed_time(e1)
+        alt_stage = {n: 0.0 for n in stage_names}
+        for ev in events:
+            for sid in {x[2] for x in ev}:
+                chain = [x for x in ev if x[2] == sid]
+                for (n0, a, _), (_, b, _) in zip(chain[:-1], chain[1:]):
+                    if n0 in alt_stage:
+                        alt_stage[n0] += a.elapsed_time(b)
+        alt = {"features_layout": alt_layout, "value": B * args.steps / (alt_ms / 1000.0), "unit": UNIT,
+               "ms_per_step": alt_ms / args.steps,
+               "stages_ms": {n: v / args.steps for n, v in alt_stage.items()}}
+        d_feats = keep
     clocks = sampler.stop()
 
     if rank != 0:
@@ -477,6 +513,7 @@ def gpu_arm(args, rank, world, local_rank):
                    "l2": "inputs larger than L2 (%.2f GB touched per step)" % (h2d_bytes / 1e9),
                    "streams": ("2: proposal chain on a high-priority stream beside mask RoIAlign + paste, joined before the box RoIAlign"
                                if pipe.overlap else "1"),
+                   "features_layout": args.features_layout,
                    "parallelism": "frame-sharded x%d%s" % (world, ", all-gather of dets + bit-packed masks per step" if world > 1 else "")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
@@ -487,6 +524,12 @@ def gpu_arm(args, rank, world, local_rank):
     }
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
+    if alt is not None:
+        # achieved bytes/s of the box RoIAlign with the maps in the other memory order (same algorithmic bytes)
+        if alt["stages_ms"].get("roialign_box"):
+            alt["roialign_box_gbs"] = alg["roialign_box"] / (alt["stages_ms"]["roialign_box"] * 1e-3) / 1e9
+            alt["roialign_box_frac"] = alt["roialign_box_gbs"] / peak
+        line["alt_layout"] = alt
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -501,6 +544,9 @@ def main():
     ap.add_argument("--frames-per-gpu", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run the mask chain behind the box chain on one stream")
+    ap.add_argument("--features-layout", default="nchw", choices=["nchw", "channels_last"],
+                    help="memory order of the synthetic FPN maps: the reference's NCHW (default) or torch.channels_last "
+                         "(N,H,W,C), which routes RoIAlign through the TMA-fed channels-last kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -283,6 +283,27 @@ def main():
                    2 * elems * 4 + sum(f.numel() for f in flows) * 4, {"elements": elems})
 
 
+    # ---------------- channels-last RoIAlign forward (TMA-fed) next to the NCHW kernels: the bench launch (10 frames) ----------------
+    if want("nhwc"):
+        B = 10
+        feats = synth.fpn_features(7000, synth.DAVIS_BLOB, B, lvls, 256)
+        fl = [cu(feats[l]) for l in lvls]
+        fl_cl = [f.contiguous(memory_format=torch.channels_last) for f in fl]
+        shapes = {l: feats[l].shape[2:] for l in lvls}
+        for R_per, res in ((1000, 7), (100, 14)):
+            rois_h = synth.random_rois(7001, R_per * B, synth.DAVIS_BLOB, B)
+            rois = cu(rois_h)
+            level, lc, order, restore = ops.distribute_cuda(rois)
+            lv0 = (level - 2).to(torch.int32)
+            touched = touched_texel_bytes(rois_h, level.cpu().numpy(), res, 2, shapes, 256)
+            alg = R_per * B * 256 * res * res * 4 + touched + 20 * R_per * B
+            a = report(out, "bench_roialign_fwd_%dx%d_%drois_nchw" % (res, res, R_per * B), timer,
+                       lambda: ops.roi_align_ml_forward(fl, scales, rois, lv0, res, res, 2), alg, {"rois": R_per * B})
+            b = report(out, "bench_roialign_fwd_%dx%d_%drois_channels_last_tma" % (res, res, R_per * B), timer,
+                       lambda: ops.roi_align_ml_forward(fl_cl, scales, rois, lv0, res, res, 2), alg, {"rois": R_per * B})
+            print("speedup channels-last / nchw: %.2fx" % (a["ms_cold_median"] / b["ms_cold_median"]), flush=True)
+
+
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump({"peak_gbs_measured": PEAK, "gpu": torch.cuda.get_device_name(0), "results": out}, open(args.out, "w"), indent=1)
 

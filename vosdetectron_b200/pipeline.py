@@ -230,7 +230,9 @@ class HostPipeline:
             return {k: HostPipeline._like(v, device) for k, v in x.items()}
         if isinstance(x, (tuple, list)):
             return tuple(HostPipeline._like(v, device) for v in x)
-        return torch.empty(x.shape, dtype=x.dtype, device=device)
+        cl = x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+        return torch.empty(x.shape, dtype=x.dtype, device=device,
+                           memory_format=torch.channels_last if cl else torch.contiguous_format)
 
     @staticmethod
     def _copy(dst, src):

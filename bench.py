@@ -303,9 +303,13 @@ def gpu_arm(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+    # "NCCL version ..." banner there even with NCCL_DEBUG_FILE set), so fd 1 is pointed at stderr for the whole run
+    # and the JSON line goes to a private duplicate of the original stdout.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL's own log lines (the "NCCL version ..." banner under NCCL_DEBUG=VERSION/INFO) go to stderr: stdout
-        # carries exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B = args.frames_per_gpu
@@ -530,7 +534,9 @@ def gpu_arm(args, rank, world, local_rank):
             alt["roialign_box_gbs"] = alg["roialign_box"] / (alt["stages_ms"]["roialign_box"] * 1e-3) / 1e9
             alt["roialign_box_frac"] = alt["roialign_box_gbs"] / peak
         line["alt_layout"] = alt
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
     if world > 1:
         dist.destroy_process_group()
 

@@ -1455,6 +1455,7 @@ extern "C" int vosd_roialign_ml_fwd_nhwc(const float* const* level_data, const i
     if (!rois || !top_data) return VOSD_ERR_BAD_ARG;
     const EncodeTiledFn enc = encode_tiled();
     if (!enc) return VOSD_ERR_UNSUPPORTED;
+    if (num_levels > 4) return VOSD_ERR_UNSUPPORTED;    // NhwcMaps holds the 4 RoI levels of an FPN
     NhwcMaps maps;
     memset(&maps, 0, sizeof(maps));
     for (int l = 0; l < num_levels; l++) {
@@ -1464,7 +1465,7 @@ extern "C" int vosd_roialign_ml_fwd_nhwc(const float* const* level_data, const i
         const cuuint64_t strides[3] = {C * 4, W * C * 4, H * W * C * 4};
         const cuuint32_t es[4] = {1, 1, 1, 1};
         for (int b = 0; b < kNhwcBoxes; b++) {
-            const cuuint32_t box[4] = {(cuuint32_t)kSlab, (cuuint32_t)(8 * (b + 1)), 1, 1};
+            const cuuint32_t box[4] = {(cuuint32_t)kSlab, (cuuint32_t)(kNhwcBoxStep * (b + 1)), 1, 1};
             if (enc(&maps.m[l][b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(level_data[l]), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)

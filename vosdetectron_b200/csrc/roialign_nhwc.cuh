@@ -20,15 +20,29 @@
 
 namespace vosd {
 
+// Tuning knobs (A/B builds, tools/ab_build.sh): ring bytes per warp, CTAs per SM, box-width step in texels.
+#ifndef VOSD_NHWC_RING
+#define VOSD_NHWC_RING 12288
+#endif
+#ifndef VOSD_NHWC_MINB
+#define VOSD_NHWC_MINB 2
+#endif
+#ifndef VOSD_NHWC_PFDIST
+#define VOSD_NHWC_PFDIST 148        // > 0: L2-prefetch the footprint of the RoI this many CTAs ahead (A/B: -6 %)
+#endif
+#ifndef VOSD_NHWC_BOXSTEP
+#define VOSD_NHWC_BOXSTEP 8
+#endif
 constexpr int kNhwcWarps = 8;
 constexpr int kNhwcThreads = 32 * kNhwcWarps;
-constexpr int kNhwcRingBytes = 12288;                  // per warp: 3 slots of 32 texels .. 12 slots of 8 texels
+constexpr int kNhwcRingBytes = VOSD_NHWC_RING;         // per warp: 3 slots of 32 texels .. 12 slots of 8 texels at 12 KB
 constexpr int kNhwcTexelBytes = kSlab * 4;             // 128: one texel of a slab
-constexpr int kNhwcBoxes = 4;                          // box widths 8, 16, 24, 32 texels
-constexpr int kNhwcMaxSlots = 12;
+constexpr int kNhwcBoxStep = VOSD_NHWC_BOXSTEP;        // box widths kNhwcBoxStep, 2 * kNhwcBoxStep, ... 32 texels
+constexpr int kNhwcBoxes = 32 / kNhwcBoxStep;
+constexpr int kNhwcMaxSlots = kNhwcRingBytes / (kNhwcBoxStep * kNhwcTexelBytes);
 
 struct NhwcMaps {
-    CUtensorMap m[VOSD_MAX_LEVELS][kNhwcBoxes];        // [level][box width / 8 - 1]
+    CUtensorMap m[4][kNhwcBoxes];                      // [level][box width / kNhwcBoxStep - 1]; FPN RoI levels: <= 4
 };
 
 __device__ __forceinline__ float lds_off128(unsigned a) {
@@ -44,9 +58,12 @@ __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map
                  :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 :: "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 struct NhwcShared {
-    Tap ytab[16];                 // sample rows of this CTA's 7 output rows
-    Tap xtab[64];                 // all sample columns (2 * PW <= 56)
     float wy[kSepMaxRows * kSepWyStride];
     int xoff[28][2];              // per output column: byte offset (texel * 128) of the low tap of its two samples
     float xw[28][4];              // h0, l0, h1, l1 (0 for an invalid sample)
@@ -55,7 +72,7 @@ struct NhwcShared {
 
 // grid = (RoIs, slab groups of 8 / T, groups of 7 output rows), block = 256, dynamic smem = 8 rings (1024-aligned).
 template <int T>
-__global__ void __launch_bounds__(kNhwcThreads, 2)
+__global__ void __launch_bounds__(kNhwcThreads, VOSD_NHWC_MINB)
 roialign_fwd_nhwc(const __grid_constant__ NhwcMaps maps, const __grid_constant__ LevelTable lv, int channels,
                   int pooled_h, const float* __restrict__ rois, const int* __restrict__ roi_level,
                   const int* __restrict__ out_index, float* __restrict__ top) {
@@ -78,32 +95,35 @@ roialign_fwd_nhwc(const __grid_constant__ NhwcMaps maps, const __grid_constant__
     const int H = lv.h[level], W = lv.w[level];
     const RoiGeom g = roi_geometry(rois + 5 * (size_t)n, lv.scale[level], pooled_h, PW, 2);
     const int row = out_index ? __ldg(out_index + n) : n;
-    if (tid < 2 * nph) {
-        const int sy = 2 * ph_begin + tid;
-        const AxisTap t = axis_tap(sample_coord(g.start_h, g.bin_h, sy >> 1, sy & 1, 2), H);
-        sh.ytab[tid] = Tap{t.valid ? t.low : -1, t.high, t.l, t.h};
-    } else if (tid >= 64 && tid < 64 + 2 * PW) {
-        const int k = tid - 64;
+    const int sub = warp % T, team = warp / T;
+
+    // Every warp owns its barriers and derives the footprint in registers (lanes = samples, shuffles), so its first
+    // TMA loads leave before any CTA-wide barrier: the per-CTA cold start is the load latency alone.
+    if (lane == 0) {
+        for (int k = 0; k < kNhwcMaxSlots; k++) mbar_init((unsigned)__cvta_generic_to_shared(&sh.full[warp][k]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // the x tap of sample column k, with the "clamped to the last column" rewrite the consumer relies on
+    auto x_tap = [&](int k) {
         const AxisTap t = axis_tap(sample_coord(g.start_w, g.bin_w, k >> 1, k & 1, 2), W);
         Tap e = Tap{t.valid ? t.low : -1, t.high, t.l, t.h};
         // a sample clamped to the last column becomes (W-2, W-1) with weights (0, 1): the high tap is always "next texel"
         if (t.valid && t.low == t.high && W >= 2) e = Tap{W - 2, W - 1, 1.f, 0.f};
-        sh.xtab[k] = e;
-    } else if (tid >= 128 && tid < 128 + kNhwcWarps * kNhwcMaxSlots) {
-        mbar_init((unsigned)__cvta_generic_to_shared(&sh.full[0][0]) + 8u * (unsigned)(tid - 128), 1);
-    }
-    for (int i = tid; i < kSepMaxRows * kSepWyStride; i += kNhwcThreads) sh.wy[i] = 0.f;
-    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-
+        return e;
+    };
+    auto y_tap = [&](int k) {                           // sample row k of this CTA's output rows
+        const int sy = 2 * ph_begin + k;
+        const AxisTap t = axis_tap(sample_coord(g.start_h, g.bin_h, sy >> 1, sy & 1, 2), H);
+        return Tap{t.valid ? t.low : -1, t.high, t.l, t.h};
+    };
     // footprint: rows shared, one column extent per group of 7 output columns ("half")
-    const int sub = warp % T, team = warp / T;
     int xlo_h[T], tw_h[T];
     int y_lo, th;
     {
         int lo2 = 1 << 30, hi2 = -1;
         if (lane < 2 * nph) {
-            const Tap t = sh.ytab[lane];
+            const Tap t = y_tap(lane);
             if (t.low >= 0) { lo2 = t.low; hi2 = t.high; }
         }
 #pragma unroll
@@ -112,11 +132,12 @@ roialign_fwd_nhwc(const __grid_constant__ NhwcMaps maps, const __grid_constant__
             hi2 = max(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
         }
         y_lo = lo2; th = hi2 - lo2 + 1;
+        // lanes 0..13 of quarter q hold the taps of half q (T <= 2: one pass; T == 4: 14 * 4 = 56 samples, two passes)
 #pragma unroll
         for (int h = 0; h < T; h++) {
             int lo = 1 << 30, hi = -1;
             if (lane < 14) {
-                const Tap t = sh.xtab[14 * h + lane];
+                const Tap t = x_tap(14 * h + lane);
                 if (t.low >= 0) { lo = t.low; hi = t.high; }
             }
 #pragma unroll
@@ -145,28 +166,51 @@ roialign_fwd_nhwc(const __grid_constant__ NhwcMaps maps, const __grid_constant__
         return;
     }
     if (tw_max > 32 || th > kSepMaxRows || W < 2) {
-        // footprint beyond the ring: direct gather, the reference's arithmetic element by element (lanes = channels)
+        // Footprint beyond the ring (~8 % of the synthetic RoIs): direct gather with the reference's arithmetic,
+        // element by element.  Lanes = channels (every tap is one 128-byte line), the 28 + 14 sample taps come from
+        // tables built once per CTA, and the results leave through the (idle) ring memory as coalesced stores.
+        __shared__ Tap gy[2 * NPH], gx[2 * PW];
+        if (tid < 2 * nph) {
+            gy[tid] = y_tap(tid);
+        } else if (tid >= 64 && tid < 64 + 2 * PW) {
+            const int k = tid - 64;
+            const AxisTap t = axis_tap(sample_coord(g.start_w, g.bin_w, k >> 1, k & 1, 2), W);
+            gx[k] = Tap{t.valid ? t.low : -1, t.high, t.l, t.h};
+        }
+        __syncthreads();
+        const int nch = nslab * kSlab;
+        const int ostride = group_bins | 1;
+        float* obuf = reinterpret_cast<float*>(nhwc_dyn);            // nch * ostride floats <= 8 rings
         const float* fbase = lv.data[level] + (size_t)g.batch * H * W * channels + (size_t)slab0 * kSlab;
-        for (int e = tid; e < nslab * kSlab * group_bins; e += kNhwcThreads) {
-            const int c = e % (nslab * kSlab), b = e / (nslab * kSlab);
-            const int ph = ph_begin + b / PW, pw = b % PW;
-            const float* d = fbase + c;
-            float acc = 0.f;
-            for (int iy = 0; iy < 2; iy++) {
-                const AxisTap ty = axis_tap(sample_coord(g.start_h, g.bin_h, ph, iy, 2), H);
-                for (int ix = 0; ix < 2; ix++) {
-                    const AxisTap tx = axis_tap(sample_coord(g.start_w, g.bin_w, pw, ix, 2), W);
-                    float val = 0.f;
-                    if (ty.valid && tx.valid)
-                        val = bilinear_value(ty.h, ty.l, tx.h, tx.l,
-                                             __ldg(d + ((size_t)ty.low * W + tx.low) * channels),
-                                             __ldg(d + ((size_t)ty.low * W + tx.high) * channels),
-                                             __ldg(d + ((size_t)ty.high * W + tx.low) * channels),
-                                             __ldg(d + ((size_t)ty.high * W + tx.high) * channels));
-                    acc = __fadd_rn(acc, val);
+        for (int b = 0; b < group_bins; b++) {
+            const int pr = b / PW, pw = b - pr * PW;
+            const Tap ty0 = gy[2 * pr], ty1 = gy[2 * pr + 1], tx0 = gx[2 * pw], tx1 = gx[2 * pw + 1];
+            for (int c = tid; c < nch; c += kNhwcThreads) {
+                const float* d = fbase + c;
+                float acc = 0.f;
+#pragma unroll
+                for (int iy = 0; iy < 2; iy++) {
+                    const Tap ty = iy ? ty1 : ty0;
+#pragma unroll
+                    for (int ix = 0; ix < 2; ix++) {
+                        const Tap tx = ix ? tx1 : tx0;
+                        float val = 0.f;
+                        if (ty.low >= 0 && tx.low >= 0)
+                            val = bilinear_value(ty.h, ty.l, tx.h, tx.l,
+                                                 __ldg(d + ((size_t)ty.low * W + tx.low) * channels),
+                                                 __ldg(d + ((size_t)ty.low * W + tx.high) * channels),
+                                                 __ldg(d + ((size_t)ty.high * W + tx.low) * channels),
+                                                 __ldg(d + ((size_t)ty.high * W + tx.high) * channels));
+                        acc = __fadd_rn(acc, val);
+                    }
                 }
+                obuf[c * ostride + b] = __fmul_rn(acc, 0.25f);
             }
-            __stcs(out_roi + (size_t)c * bins + b, __fmul_rn(acc, 0.25f));
+        }
+        __syncthreads();
+        for (int e = tid; e < nch * group_bins; e += kNhwcThreads) {
+            const int c = e / group_bins, b = e - c * group_bins;
+            __stcs(out_roi + (size_t)c * bins + b, obuf[c * ostride + b]);
         }
         return;
     }
@@ -178,9 +222,9 @@ roialign_fwd_nhwc(const __grid_constant__ NhwcMaps maps, const __grid_constant__
     const bool half_empty = htw <= 0;                   // no valid sample column in this half: its outputs are 0
     const int th_my = half_empty ? 0 : th;
     if (half_empty) { hx = 0; htw = 2; }
-    const int bsel = (htw + 7) / 8 - 1;                 // 0..3
-    const int slot_bytes = (bsel + 1) * 8 * kNhwcTexelBytes;
-    const int NS = kNhwcRingBytes / slot_bytes;         // 12, 6, 4, 3
+    const int bsel = (htw + kNhwcBoxStep - 1) / kNhwcBoxStep - 1;
+    const int slot_bytes = (bsel + 1) * kNhwcBoxStep * kNhwcTexelBytes;
+    const int NS = kNhwcRingBytes / slot_bytes;         // 12, 6, 4, 3 at 12 KB / step 8
     const unsigned dyn_s = (unsigned)__cvta_generic_to_shared(nhwc_dyn);
     if (dyn_s & 127u) __trap();                         // TMA destinations must be 128-byte aligned
     const unsigned ring_s = dyn_s + (unsigned)warp * kNhwcRingBytes;
@@ -196,8 +240,41 @@ roialign_fwd_nhwc(const __grid_constant__ NhwcMaps maps, const __grid_constant__
             tma_load_4d(ring_s + (unsigned)(y * slot_bytes), map, s * kSlab, hx, y_lo + y, g.batch, full_s + 8u * (unsigned)y);
         }
     }
+    if (VOSD_NHWC_PFDIST > 0 && live) {
+        // L2 prefetch of this warp's slab of the footprint of RoI n + VOSD_NHWC_PFDIST (same row group): by the time
+        // that CTA starts, its first TMA loads hit L2.  Geometry recomputed in registers, lanes = texel rows.
+        const int n2 = n + VOSD_NHWC_PFDIST;
+        if (n2 < (int)gridDim.x) {
+            const int level2 = roi_level ? __ldg(roi_level + n2) : 0;
+            const int H2 = lv.h[level2], W2 = lv.w[level2];
+            const RoiGeom g2 = roi_geometry(rois + 5 * (size_t)n2, lv.scale[level2], pooled_h, PW, 2);
+            int lo = 1 << 30, hi = -1, xl = 1 << 30, xh = -1;
+            if (lane < 2 * nph) {
+                const int sy = 2 * ph_begin + lane;
+                const AxisTap t = axis_tap(sample_coord(g2.start_h, g2.bin_h, sy >> 1, sy & 1, 2), H2);
+                if (t.valid) { lo = t.low; hi = t.high; }
+            }
+            if (lane < 14) {
+                const int k = 14 * sub + lane;
+                const AxisTap t = axis_tap(sample_coord(g2.start_w, g2.bin_w, k >> 1, k & 1, 2), W2);
+                if (t.valid) { xl = t.low; xh = t.high; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+                xl = min(xl, __shfl_xor_sync(0xffffffffu, xl, o));
+                xh = max(xh, __shfl_xor_sync(0xffffffffu, xh, o));
+            }
+            const int tw2 = xh - xl + 1, th2 = hi - lo + 1;
+            if (tw2 > 0 && tw2 <= 32 && th2 > 0 && th2 <= kSepMaxRows) {
+                const CUtensorMap* map2 = &maps.m[level2][(tw2 + kNhwcBoxStep - 1) / kNhwcBoxStep - 1];
+                for (int y = lane; y < th2; y += 32) tma_prefetch_4d(map2, s * kSlab, min(xl, W2 - 2 < 0 ? 0 : xl), lo + y, g2.batch);
+            }
+        }
+    }
     if (tid < PW) {
-        const Tap t0 = sh.xtab[2 * tid], t1 = sh.xtab[2 * tid + 1];
+        const Tap t0 = x_tap(2 * tid), t1 = x_tap(2 * tid + 1);
         int ox = 0;
 #pragma unroll
         for (int h = 0; h < T; h++) if (h == tid / 7) ox = tw_h[h] > 0 ? xlo_h[h] : 0;
@@ -205,14 +282,18 @@ roialign_fwd_nhwc(const __grid_constant__ NhwcMaps maps, const __grid_constant__
         sh.xoff[tid][1] = t1.low >= 0 ? (t1.low - ox) * kNhwcTexelBytes : 0;
         sh.xw[tid][0] = t0.low >= 0 ? t0.h : 0.f; sh.xw[tid][1] = t0.low >= 0 ? t0.l : 0.f;
         sh.xw[tid][2] = t1.low >= 0 ? t1.h : 0.f; sh.xw[tid][3] = t1.low >= 0 ? t1.l : 0.f;
-    } else if (tid >= 32 && tid < 32 + nph) {
+    } else if (tid >= 32 && tid < 32 + NPH) {
+        // thread = output row pr: it owns column pr of Wy (zero fill + its two sample rows; 0.25 = 1 / count, exact)
         const int pr = tid - 32;
+        for (int y = 0; y < th; y++) sh.wy[y * kSepWyStride + pr] = 0.f;
+        if (pr < nph) {
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const Tap t = sh.ytab[2 * pr + k];
-            if (t.low >= 0) {
-                sh.wy[(t.low - y_lo) * kSepWyStride + pr] += 0.25f * t.h;
-                if (t.high != t.low) sh.wy[(t.high - y_lo) * kSepWyStride + pr] += 0.25f * t.l;
+            for (int k = 0; k < 2; k++) {
+                const Tap t = y_tap(2 * pr + k);
+                if (t.low >= 0) {
+                    sh.wy[(t.low - y_lo) * kSepWyStride + pr] += 0.25f * t.h;
+                    if (t.high != t.low) sh.wy[(t.high - y_lo) * kSepWyStride + pr] += 0.25f * t.l;
+                }
             }
         }
     }

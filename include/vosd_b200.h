@@ -388,6 +388,20 @@ VOSD_API int vosd_rle_to_bits(const uint32_t* runs, const long long* run_offset,
 VOSD_API int vosd_bbox_overlaps(const float* boxes, int num_boxes, const float* query_boxes, int num_query,
                                 float* overlaps, float* row_max, int* row_argmax, cudaStream_t stream);
 
+/* Box regression targets of the label assignment (rank 3, second piece): _compute_targets +      */
+/* _expand_bbox_targets (lib/roi_data/fast_rcnn.py:216-260; bbox_transform_inv                     */
+/* lib/utils/boxes.py:208-239) + bbox_outside_weights (:206-208) in one launch.                    */
+/*   ex_rois, gt_rois (n,4) fp32, 16-byte aligned: sampled RoIs and the gt box each is assigned to; */
+/*   labels (n) int32; weights HOST float[4] = MODEL.BBOX_REG_WEIGHTS; class_agnostic != 0:         */
+/*   MODEL.CLS_AGNOSTIC_BBOX_REG (2 regression classes, labels clipped to 1).                       */
+/*   bbox_targets, inside_weights, outside_weights (n, 4*K') fp32, K' = 2 or num_classes; every     */
+/*   element is written (outside_weights may be NULL).  fp32 in NumPy's operation order; the two    */
+/*   logarithms are logf (<= 1 ulp from NumPy's float32 log).                                       */
+VOSD_API int vosd_bbox_targets(const float* ex_rois, const float* gt_rois, const int* labels, int num_rois,
+                               int num_classes, int class_agnostic, const float* weights /*host*/,
+                               float* bbox_targets, float* inside_weights, float* outside_weights,
+                               cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -568,5 +568,41 @@ def nms_with_mask_iou(cls_boxes, cls_segms, num_classes, iou_th=0.9, max_per_cla
     return out_b, out_s
 
 
+
+# --------------------------------------------------------------------------- #
+# (f3) label assignment pieces: bbox_overlaps is the reference's own cython_bbox (oracle/_ref);
+# bbox_transform_inv lib/utils/boxes.py:208-239, _compute_targets / _expand_bbox_targets
+# lib/roi_data/fast_rcnn.py:216-260, outside weights :206-208
+# --------------------------------------------------------------------------- #
+def bbox_transform_inv(boxes, gt_boxes, weights=(1.0, 1.0, 1.0, 1.0)):
+    ex_widths = boxes[:, 2] - boxes[:, 0] + 1.0
+    ex_heights = boxes[:, 3] - boxes[:, 1] + 1.0
+    ex_ctr_x = boxes[:, 0] + 0.5 * ex_widths
+    ex_ctr_y = boxes[:, 1] + 0.5 * ex_heights
+    gt_widths = gt_boxes[:, 2] - gt_boxes[:, 0] + 1.0
+    gt_heights = gt_boxes[:, 3] - gt_boxes[:, 1] + 1.0
+    gt_ctr_x = gt_boxes[:, 0] + 0.5 * gt_widths
+    gt_ctr_y = gt_boxes[:, 1] + 0.5 * gt_heights
+    wx, wy, ww, wh = weights
+    return np.vstack((wx * (gt_ctr_x - ex_ctr_x) / ex_widths, wy * (gt_ctr_y - ex_ctr_y) / ex_heights,
+                      ww * np.log(gt_widths / ex_widths), wh * np.log(gt_heights / ex_heights))).transpose()
+
+
+def bbox_targets(ex_rois, gt_rois, labels, num_classes, weights=(10., 10., 5., 5.), class_agnostic=False):
+    t = bbox_transform_inv(ex_rois, gt_rois, weights).astype(np.float32, copy=False)
+    clss = np.asarray(labels).copy()
+    K = num_classes
+    if class_agnostic:
+        K = 2
+        clss = clss.clip(max=1)
+    targets = np.zeros((clss.size, 4 * K), dtype=np.float32)
+    inside = np.zeros_like(targets)
+    for i in np.where(clss > 0)[0]:
+        c = int(clss[i])
+        targets[i, 4 * c:4 * c + 4] = t[i]
+        inside[i, 4 * c:4 * c + 4] = 1.0
+    return targets, inside, np.array(inside > 0, dtype=np.float32)
+
+
 def num_threads():
     return lib().orc_num_threads()

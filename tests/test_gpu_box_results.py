@@ -135,3 +135,24 @@ def test_bbox_overlaps_bit_identical_to_cython_bbox(synth):
             assert np.array_equal(am.cpu().numpy(), want.argmax(axis=1))
     with pytest.raises(ValueError):
         box_utils.bbox_overlaps(np.zeros((1, 4)), np.zeros((1, 4), np.float32))
+
+
+def test_bbox_targets_against_reference_outputs(golden):
+    """vosd_bbox_targets against lib/roi_data/fast_rcnn.py's own outputs: zeros / weights / class columns exact,
+    dx, dy bit-identical (fp32 NumPy order), dw, dh within 2 ulp-ish (logf vs NumPy's float32 log): rtol 1e-6 + 1e-7."""
+    from vosdetectron_b200 import ops
+    g = golden("bbox_targets")
+    ex, gt = torch.from_numpy(g["ex"]).cuda(), torch.from_numpy(g["gt"]).cuda()
+    lb = torch.from_numpy(g["labels"]).cuda()
+    for tag, agn in (("k", False), ("a", True)):
+        t, w, o = (x.cpu().numpy() for x in ops.bbox_targets_cuda(ex, gt, lb, int(g["num_classes"]), class_agnostic=agn))
+        rt = g["targets_" + tag]
+        assert t.shape == rt.shape and np.array_equal(w, g["inside_" + tag]) and np.array_equal(o, g["outside_" + tag])
+        assert np.array_equal(t == 0, rt == 0)
+        hit = g["inside_" + tag] > 0
+        cols = np.arange(rt.shape[1])[None, :].repeat(rt.shape[0], 0) % 4
+        xy = hit & (cols < 2)
+        assert np.array_equal(t[xy], rt[xy])
+        assert np.allclose(t[hit], rt[hit], rtol=1e-6, atol=1e-7)
+    e = ops.bbox_targets_cuda(ex[:0], gt[:0], lb[:0], 9)
+    assert e[0].shape == (0, 36)

@@ -255,3 +255,12 @@ def test_nms_with_mask_iou_golden(orc, golden):
         got = np.vstack([np.vstack(c) for c in ob if len(c)])
         assert np.array_equal(got, g["mout_boxes_" + tag])
         assert [s['counts'] for sl in os_ for s in sl] == [str(c) for c in g["mout_counts_" + tag]]
+
+
+def test_bbox_targets_golden(orc, golden):
+    """_compute_targets + _expand_bbox_targets (lib/roi_data/fast_rcnn.py:216-260) against the reference's outputs."""
+    g = golden("bbox_targets")
+    for tag, agn in (("k", False), ("a", True)):
+        t, w, o = orc.bbox_targets(g["ex"], g["gt"], g["labels"], int(g["num_classes"]), class_agnostic=agn)
+        assert np.array_equal(t, g["targets_" + tag]) and np.array_equal(w, g["inside_" + tag])
+        assert np.array_equal(o, g["outside_" + tag])

@@ -81,3 +81,65 @@ extern "C" int vosd_bbox_overlaps(const float* boxes, int num_boxes, const float
     count_launch();
     return check_launch();
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Box regression targets of the training label assignment:
+//   _compute_targets      lib/roi_data/fast_rcnn.py:216-229  -> box_utils.bbox_transform_inv (lib/utils/boxes.py:208-239)
+//   _expand_bbox_targets  lib/roi_data/fast_rcnn.py:232-260  (4-of-4K expansion, inside weights 1 on the label's class)
+//   bbox_outside_weights = (bbox_inside_weights > 0)          lib/roi_data/fast_rcnn.py:206-208
+// fp32 in NumPy's operation order (widths with + 1, centres, weights multiplied before the division, log of the
+// ratio); one thread per RoI row writes the whole 4K-wide row (zeros + its four targets): every byte is written.
+// ---------------------------------------------------------------------------------------------------------
+namespace vosd {
+namespace {
+
+__global__ void __launch_bounds__(256) bbox_targets_kernel(const float4* __restrict__ ex, const float4* __restrict__ gt,
+                                                           const int* __restrict__ labels, int n, int K, int agnostic,
+                                                           float wx, float wy, float ww, float wh,
+                                                           float* __restrict__ targets, float* __restrict__ inside,
+                                                           float* __restrict__ outside) {
+    // one warp per row: lanes stride over the 4K columns (coalesced zero fill), lane 0 derives the four targets
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= n) return;
+    int cls = labels[row];
+    if (agnostic) cls = min(cls, 1);                                     // clss.clip(max=1), :246-249
+    const float4 b = ex[row], g = gt[row];
+    const float ew = __fadd_rn(__fsub_rn(b.z, b.x), 1.f), eh = __fadd_rn(__fsub_rn(b.w, b.y), 1.f);     // boxes.py:221-222
+    const float ecx = __fadd_rn(b.x, __fmul_rn(0.5f, ew)), ecy = __fadd_rn(b.y, __fmul_rn(0.5f, eh));   // :223-224
+    const float gw = __fadd_rn(__fsub_rn(g.z, g.x), 1.f), gh = __fadd_rn(__fsub_rn(g.w, g.y), 1.f);     // :226-227
+    const float gcx = __fadd_rn(g.x, __fmul_rn(0.5f, gw)), gcy = __fadd_rn(g.y, __fmul_rn(0.5f, gh));   // :228-229
+    float t[4];
+    t[0] = __fdiv_rn(__fmul_rn(wx, __fsub_rn(gcx, ecx)), ew);                                           // :232
+    t[1] = __fdiv_rn(__fmul_rn(wy, __fsub_rn(gcy, ecy)), eh);                                           // :233
+    t[2] = __fmul_rn(ww, logf(__fdiv_rn(gw, ew)));                                                       // :234
+    t[3] = __fmul_rn(wh, logf(__fdiv_rn(gh, eh)));                                                       // :235
+    const size_t base = (size_t)row * 4 * K;
+    for (int c = lane; c < 4 * K; c += 32) {
+        const bool hit = cls > 0 && cls < K && (c >> 2) == cls;          // inds = where(clss > 0), :253-259
+        const float v = hit ? t[c & 3] : 0.f;
+        targets[base + c] = v;
+        inside[base + c] = hit ? 1.f : 0.f;
+        if (outside) outside[base + c] = hit ? 1.f : 0.f;
+    }
+}
+
+}  // namespace
+}  // namespace vosd
+
+extern "C" int vosd_bbox_targets(const float* ex_rois, const float* gt_rois, const int* labels, int num_rois,
+                                 int num_classes, int class_agnostic, const float* weights /*host*/,
+                                 float* bbox_targets, float* inside_weights, float* outside_weights,
+                                 cudaStream_t stream) {
+    using namespace vosd;
+    if (num_rois < 0 || num_classes < 1) return VOSD_ERR_BAD_SHAPE;
+    if (num_rois == 0) return VOSD_OK;
+    if (!ex_rois || !gt_rois || !labels || !weights || !bbox_targets || !inside_weights) return VOSD_ERR_BAD_ARG;
+    if (!aligned16(ex_rois) || !aligned16(gt_rois)) return VOSD_ERR_BAD_ARG;
+    const int K = class_agnostic ? 2 : num_classes;                      // :244-247
+    bbox_targets_kernel<<<ceil_div(num_rois * 32, 256), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(ex_rois), reinterpret_cast<const float4*>(gt_rois), labels, num_rois, K,
+        class_agnostic ? 1 : 0, weights[0], weights[1], weights[2], weights[3], bbox_targets, inside_weights,
+        outside_weights);
+    count_launch();
+    return check_launch();
+}

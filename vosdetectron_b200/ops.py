@@ -563,3 +563,21 @@ def bbox_overlaps_cuda(boxes, query_boxes, want_matrix=True):
     _bind(b)
     _lib.call("vosd_bbox_overlaps", _ptr(b), N, _ptr(q), K, _ptr(ov), _ptr(mx), _ptr(am), _stream())
     return ov, mx, am
+
+
+def bbox_targets_cuda(ex_rois, gt_rois, labels, num_classes, weights=(10.0, 10.0, 5.0, 5.0), class_agnostic=False):
+    """Sampled RoIs (n,4), their assigned gt boxes (n,4), labels (n) int32 -> (bbox_targets, bbox_inside_weights,
+    bbox_outside_weights), each (n, 4*K): fast_rcnn.py:216-260 + :206-208 in one launch."""
+    e = _need_cuda(ex_rois, "ex_rois")
+    g = _need_cuda(gt_rois, "gt_rois")
+    lb = _need_cuda(labels, "labels", torch.int32)
+    if e.dim() != 2 or e.size(1) != 4 or g.shape != e.shape or lb.shape != (e.size(0),):
+        raise ValueError("ex_rois / gt_rois must be (n,4) and labels (n)")
+    n = int(e.size(0))
+    K = 2 if class_agnostic else int(num_classes)
+    outs = [torch.empty((n, 4 * K), dtype=torch.float32, device=e.device) for _ in range(3)]
+    w = (ctypes.c_float * 4)(*[float(v) for v in weights])
+    _bind(e)
+    _lib.call("vosd_bbox_targets", _ptr(e), _ptr(g), _ptr(lb), n, int(num_classes), int(bool(class_agnostic)), w,
+              _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _stream())
+    return tuple(outs)

@@ -340,7 +340,7 @@ def gpu_arm(args, rank, world, local_rank):
     torch.cuda.synchronize()
 
     stage_names = ["proposals", "collect_distribute", "join_wait", "roialign_box", "mask_rois", "roialign_mask", "paste"]
-    pipe.overlap = not args.no_overlap
+    pipe.overlap = "full" if args.full_overlap else (not args.no_overlap)
     pipe.packed_masks = world > 1          # all-gather payload, written by the paste kernel itself
     events = []
 
@@ -550,6 +550,8 @@ def main():
     ap.add_argument("--frames-per-gpu", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run the mask chain behind the box chain on one stream")
+    ap.add_argument("--full-overlap", action="store_true",
+                    help="experiment: box RoIAlign on the proposal stream, concurrent with mask RoIAlign + paste")
     ap.add_argument("--features-layout", default="nchw", choices=["nchw", "channels_last"],
                     help="memory order of the synthetic FPN maps: the reference's NCHW (default) or torch.channels_last "
                          "(N,H,W,C), which routes RoIAlign through the TMA-fed channels-last kernel")

@@ -126,6 +126,12 @@ class RegionPipeline:
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 prop, level = proposal_chain()
+                if overlap == "full":
+                    # experiment: the box RoIAlign follows the proposals on the side stream, beside mask RoIAlign + paste
+                    post = prop["rois"].shape[1]
+                    mark("roialign_box")
+                    box_feats = self.roi_features(feats, prop["rois"].view(B * post, 5), level, self.box_resolution)
+                    mark("end")
             # No record_stream on the side stream's tensors: it would park every freed block behind an event and
             # make the caching allocator cudaMalloc fresh outputs each step.  Reuse is safe without it: the blocks
             # are only re-allocated by the side stream, whose next use starts with wait_stream(main) above.
@@ -135,11 +141,12 @@ class RegionPipeline:
             main.wait_stream(side)
         else:
             prop, level = proposal_chain()
-        post = prop["rois"].shape[1]
-        rois = prop["rois"].view(B * post, 5)
-        mark("roialign_box")
-        box_feats = self.roi_features(feats, rois, level, self.box_resolution)
-        mark("end")
+        if overlap != "full":
+            post = prop["rois"].shape[1]
+            rois = prop["rois"].view(B * post, 5)
+            mark("roialign_box")
+            box_feats = self.roi_features(feats, rois, level, self.box_resolution)
+            mark("end")
         if not overlap:
             mask_rois, mlevel, mask_feats, pasted, packed = self._mask_branch(feats, det_boxes, det_cls, det_masks,
                                                                       frame_hw, im_scale, mark)

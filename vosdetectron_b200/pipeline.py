@@ -127,7 +127,8 @@ class RegionPipeline:
             with torch.cuda.stream(side):
                 prop, level = proposal_chain()
                 if overlap == "full":
-                    # experiment: the box RoIAlign follows the proposals on the side stream, beside mask RoIAlign + paste
+                    # the box RoIAlign follows the proposals on the side stream, beside mask RoIAlign + paste
+                    # (bench: 1.296 -> 1.212 ms per step; with overlap=True both chains join first and it runs alone)
                     post = prop["rois"].shape[1]
                     mark("roialign_box")
                     box_feats = self.roi_features(feats, prop["rois"].view(B * post, 5), level, self.box_resolution)

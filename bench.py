@@ -339,21 +339,37 @@ def gpu_arm(args, rank, world, local_rank):
     d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks = upload()
     torch.cuda.synchronize()
 
-    stage_names = ["proposals", "collect_distribute", "join_wait", "roialign_box", "mask_rois", "roialign_mask", "paste"]
+    stage_names = ["proposals", "collect_distribute", "join_wait", "roialign_box", "paste_rle", "mask_rois", "roialign_mask", "paste"]
     pipe.overlap = False if args.no_overlap else (True if args.join_overlap else "full")
-    pipe.packed_masks = world > 1          # all-gather payload, written by the paste kernel itself
+    # all-gather payload of the sharded clip: the 1-bit-per-pixel masks the paste kernel writes itself (default), or
+    # COCO RLE strings from the fused paste -> RLE kernel (--gather-rle: 50x fewer bytes, but the extra kernel costs
+    # more than the gather saves: 2 GPUs 1.44 vs 1.34 ms, 4 GPUs 1.51 vs 1.40 ms, 8 GPUs 1.93 vs 1.71 ms per step)
+    pipe.packed_masks = False if world == 1 else ("rle" if args.gather_rle else True)
     events = []
 
     pending = []          # all-gathers in flight (N > 1): they overlap the next step's kernels
 
-    def run_step(mark=None):
-        out = pipe.step(d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks, frame_hw, im_scale, mark=mark)
+    graph = {"g": None, "out": None, "launches": 0}
+
+    def run_step(mark=None, replay=False):
+        if replay and graph["g"] is not None:
+            graph["g"].replay()
+            out = graph["out"]
+        else:
+            out = pipe.step(d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks, frame_hw, im_scale, mark=mark)
         if world > 1:
             while len(pending) > 1:                       # at most two gathers outstanding
                 for w in pending.pop(0)[2]:
                     w.wait()
             dets = torch.cat([d_boxes, d_cls.unsqueeze(-1).float(), torch.ones_like(d_cls).unsqueeze(-1).float()], dim=2)
-            pending.append(all_gather_frames(dets, out["masks_packed"], async_op=True))
+            if out["masks_packed"] is not None:
+                payload = out["masks_packed"].clone() if (replay and graph["g"] is not None) else out["masks_packed"]
+                pending.append(all_gather_frames(dets, payload, async_op=True))
+            else:
+                r = out["masks_rle"]                      # record = box, class, score, RLE offset / length in the arena
+                rec = torch.cat([dets, r["str_offset"].view(B, -1, 1).float(), r["str_len"].view(B, -1, 1).float()], dim=2)
+                chars = r["chars"].clone() if (replay and graph["g"] is not None) else r["chars"]
+                pending.append(all_gather_frames(rec, chars.view(B, -1), async_op=True))
         return out
 
     def drain():
@@ -377,20 +393,54 @@ def gpu_arm(args, rank, world, local_rank):
         e.record()              # on the current stream: the mask chain marks its own (second) stream
         events[-1].append((name, e, torch.cuda.current_stream().cuda_stream))
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # The step is a fixed sequence of ~10 kernel launches and ~50 small tensor ops on static shapes: captured once
+    # as a CUDA graph (both streams, fork / join included) it costs one launch per step.  That matters at N > 1,
+    # where 8 Python processes share the host cores and the eager step becomes launch-bound (1.21 ms on 1 GPU,
+    # 1.71 ms on 8).  Any capture failure falls back to the eager step.
+    if not args.no_cuda_graph:
+        try:
+            torch.cuda.synchronize()
+            l0 = _lib.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                g_out = pipe.step(d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks, frame_hw, im_scale, mark=None)
+            graph.update(g=g, out=g_out, launches=_lib.launch_count() - l0)
+            for _ in range(3):
+                run_step(replay=True)
+            drain()
+            torch.cuda.synchronize()
+        except Exception as exc:  # noqa: BLE001
+            print("CUDA graph capture failed (%s: %s); timing the eager step" % (type(exc).__name__, str(exc)[:200]),
+                  file=sys.stderr)
+            graph.update(g=None, out=None, launches=0)
+            torch.cuda.synchronize()
+    barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None     # one nvidia-smi poller per job, not per rank
+    if sampler:
+        sampler.start()
     launches0 = _lib.launch_count()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         events.append([])
-        out = run_step(mark)
+        out = run_step(mark, replay=True)
     drain()               # every gather of the timed steps has completed before the closing event
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
+    if graph["g"] is not None:
+        launches = graph["launches"] * args.steps      # replayed launches do not pass through the host counter
+        # stage durations: CUDA events cannot be read inside a replayed graph, so the same K steps run once more
+        # eagerly with the per-stage marks (this pass is not part of `value`)
+        events.clear()
+        for _ in range(args.steps):
+            events.append([])
+            out = run_step(mark)
+        drain()
+        torch.cuda.synchronize()
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -469,7 +519,7 @@ def gpu_arm(args, rank, world, local_rank):
                "ms_per_step": alt_ms / args.steps,
                "stages_ms": {n: v / args.steps for n, v in alt_stage.items()}}
         d_feats = keep
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
 
     if rank != 0:
         if world > 1:
@@ -524,12 +574,14 @@ def gpu_arm(args, rank, world, local_rank):
                                "2: proposals -> collect -> box RoIAlign on a high-priority stream beside mask RoIAlign + paste "
                                "(stage durations of concurrent kernels overlap)"),
                    "features_layout": args.features_layout,
-                   "parallelism": "frame-sharded x%d%s" % (world, ", all-gather of dets + bit-packed masks per step" if world > 1 else "")},
+                   "cuda_graph": ("the timed region replays a CUDA graph of the step; stage durations from an eager pass "
+                                  "of the same steps" if graph["g"] is not None else "off (eager step)"),
+                   "parallelism": "frame-sharded x%d%s" % (world, (", all-gather of dets + %s per step" % ("COCO RLE strings (fused paste -> RLE kernel)" if args.gather_rle else "bit-packed masks")) if world > 1 else "")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": int(launches),
-        "launches_per_step_expected": STEP_LAUNCHES,
+        "launches_per_step_expected": STEP_LAUNCHES + (1 if pipe.packed_masks == "rle" else 0),
         "roofline": roofline,
     }
     if cpu_baseline is not None:
@@ -556,6 +608,9 @@ def main():
     ap.add_argument("--frames-per-gpu", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run the mask chain behind the box chain on one stream")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="time the eager step instead of a CUDA-graph replay of it")
+    ap.add_argument("--gather-rle", action="store_true",
+                    help="N > 1: all-gather COCO RLE strings (fused paste -> RLE kernel) instead of 1-bit-per-pixel masks")
     ap.add_argument("--join-overlap", action="store_true",
                     help="join the two streams before the box RoIAlign (it then runs alone) instead of letting it run "
                          "on the proposal stream beside mask RoIAlign + paste (default)")

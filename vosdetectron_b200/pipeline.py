@@ -35,7 +35,12 @@ class RegionPipeline:
                         for l in self.rpn_levels}
         self._ws = None
         self.overlap = True
-        self.packed_masks = False      # step() also returns the bit-packed masks (frame-sharded clips)
+        # payload of a frame-sharded clip's all-gather, produced inside step(): False = none, True = 1 bit per pixel
+        # (written by the paste kernel itself), "rle" = COCO RLE strings (fused paste -> RLE kernel: what the reference
+        # ships between its per-GPU processes, ~1 KB per detection instead of 51 KB)
+        self.packed_masks = False
+        self._rle = None
+        self.rle_bytes_per_det = 4096  # capacity of the gathered string arena (average per detection)
         self._side = None
 
     # ---- stage 1: proposals -> top RoIs + FPN levels (rows of frame f are in group f) ----------
@@ -68,6 +73,18 @@ class RegionPipeline:
         paste of the mask-head output (segm_results, test.py:801-855)."""
         c = self.cfg
         B, D = det_boxes.shape[:2]
+        rle = None
+        if self.packed_masks == "rle":
+            # First kernel of this chain: the fused paste -> RLE kernel is latency-bound (one CTA per detection, the
+            # largest boxes are its tail), like the proposal chain that starts on the other stream at the same time,
+            # so the two share the GPU before the bandwidth-bound kernels arrive.
+            mark("paste_rle")
+            K0, M0 = det_masks.shape[2], det_masks.shape[3]
+            cap = B * D * self.rle_bytes_per_det
+            rle = ops.paste_rle_cuda(det_masks.view(B * D, K0, M0, M0),
+                                     det_cls.view(-1) if c.mrcnn_cls_specific_mask else None, det_boxes.view(B * D, 4),
+                                     frame_hw[0], frame_hw[1], c.mrcnn_thresh_binarize, run_capacity=cap // 2,
+                                     str_capacity=cap)
         mark("mask_rois")
         frame_idx = torch.arange(B, device=det_boxes.device, dtype=torch.float32).view(B, 1, 1).expand(B, D, 1)
         mask_rois = torch.cat([frame_idx, det_boxes * im_scale], dim=2).view(B * D, 5).contiguous()
@@ -78,7 +95,11 @@ class RegionPipeline:
         mark("paste")
         K, M = det_masks.shape[2], det_masks.shape[3]
         cls = det_cls.view(-1) if c.mrcnn_cls_specific_mask else None
-        if self.packed_masks:
+        if self.packed_masks == "rle":
+            pasted = ops.paste_masks_cuda(det_masks.view(B * D, K, M, M), cls, det_boxes.view(B * D, 4),
+                                          frame_hw[0], frame_hw[1], c.mrcnn_thresh_binarize)
+            packed = None
+        elif self.packed_masks:
             # the paste kernel also writes the 1-bit-per-pixel copy (the all-gather payload of a sharded clip)
             pasted, packed = ops.paste_masks_packed_cuda(det_masks.view(B * D, K, M, M), cls, det_boxes.view(B * D, 4),
                                                          frame_hw[0], frame_hw[1], c.mrcnn_thresh_binarize)
@@ -87,6 +108,7 @@ class RegionPipeline:
                                           frame_hw[0], frame_hw[1], c.mrcnn_thresh_binarize)
             packed = None
         mark("mask_end")
+        self._rle = rle
         return mask_rois, mlevel, mask_feats, pasted, packed
 
     def step(self, rpn, im_info, feats, det_boxes, det_cls, det_masks, frame_hw, im_scale, mark=None, overlap=None):
@@ -154,7 +176,9 @@ class RegionPipeline:
         return {"rois": prop["rois"], "roi_count": prop["count"], "roi_level": prop["level"],
                 "box_feats": box_feats, "mask_feats": mask_feats, "mask_rois": mask_rois, "mask_level": mlevel,
                 "masks": pasted.view(B, D, frame_hw[0], frame_hw[1]),
-                "masks_packed": None if packed is None else packed.view(B, D, -1)}
+                "masks_packed": None if packed is None else packed.view(B, D, -1),
+                # "rle" payload: chars (B, cap/B) uint8 arena slices are NOT per frame -- offsets index the whole arena
+                "masks_rle": self._rle}
 
 
 # Number of library kernels one RegionPipeline.step enqueues (counted, see bench.py):

@@ -312,6 +312,25 @@ def gpu_arm(args, rank, world, local_rank):
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+    # Pinned host buffers should live on the NUMA node the GPU hangs off (first touch): the e2e leg is PCIe-bound
+    # and measured 23 ms vs 36 ms per step depending on where the pages landed.  Best effort; silent if the
+    # container hides the topology.
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node >= 0:
+            cpus = set()
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= set(os.sched_getaffinity(0))
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                print("rank %d: host buffers and launches pinned to NUMA node %d (%d cpus)" % (rank, node, len(cpus)),
+                      file=sys.stderr)
+    except Exception:  # noqa: BLE001
+        pass
     B = args.frames_per_gpu
     host = make_host_inputs(B, 3000 + 100 * rank)
     pipe = RegionPipeline(RegionConfig())
@@ -435,12 +454,16 @@ def gpu_arm(args, rank, world, local_rank):
         launches = graph["launches"] * args.steps      # replayed launches do not pass through the host counter
         # stage durations: CUDA events cannot be read inside a replayed graph, so the same K steps run once more
         # eagerly with the per-stage marks (this pass is not part of `value`)
+        # ... with the two chains JOINED before the box RoIAlign, so each RoIAlign is timed alone on the GPU: the
+        # roofline figure is a property of the kernel, not of what happens to run beside it
         events.clear()
+        overlap_mode, pipe.overlap = pipe.overlap, (pipe.overlap if pipe.overlap is False else True)
         for _ in range(args.steps):
             events.append([])
             out = run_step(mark)
         drain()
         torch.cuda.synchronize()
+        pipe.overlap = overlap_mode
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -575,7 +598,8 @@ def gpu_arm(args, rank, world, local_rank):
                                "(stage durations of concurrent kernels overlap)"),
                    "features_layout": args.features_layout,
                    "cuda_graph": ("the timed region replays a CUDA graph of the step; stage durations from an eager pass "
-                                  "of the same steps" if graph["g"] is not None else "off (eager step)"),
+                                  "of the same steps with the chains joined before the box RoIAlign (each kernel alone)"
+                                  if graph["g"] is not None else "off (eager step)"),
                    "parallelism": "frame-sharded x%d%s" % (world, (", all-gather of dets + %s per step" % ("COCO RLE strings (fused paste -> RLE kernel)" if args.gather_rle else "bit-packed masks")) if world > 1 else "")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,

@@ -312,23 +312,35 @@ def gpu_arm(args, rank, world, local_rank):
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    # Pinned host buffers should live on the NUMA node the GPU hangs off (first touch): the e2e leg is PCIe-bound
-    # and measured 23 ms vs 36 ms per step depending on where the pages landed.  Best effort; silent if the
-    # container hides the topology.
+    # Pinned host buffers should live on the NUMA node the GPU hangs off: the e2e leg is PCIe-bound and measured
+    # 23 ms vs 36 ms per step depending on where the pages landed.  The container hides the topology
+    # (/sys/bus/pci/devices/*/numa_node = -1), so the placement is probed: pin a 64 MB buffer from each half of the
+    # allowed CPUs, time host->device copies, and keep the process on the faster half if it is clearly faster.
     try:
-        pr = torch.cuda.get_device_properties(dev)
-        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
-        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
-        if node >= 0:
-            cpus = set()
-            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-                lo, _, hi = part.partition("-")
-                cpus.update(range(int(lo), int(hi or lo) + 1))
-            cpus &= set(os.sched_getaffinity(0))
-            if cpus:
-                os.sched_setaffinity(0, cpus)
-                print("rank %d: host buffers and launches pinned to NUMA node %d (%d cpus)" % (rank, node, len(cpus)),
-                      file=sys.stderr)
+        allowed = sorted(os.sched_getaffinity(0))
+        if len(allowed) >= 4:
+            halves = [set(allowed[:len(allowed) // 2]), set(allowed[len(allowed) // 2:])]
+            rates = []
+            d_probe = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+            for h in halves:
+                os.sched_setaffinity(0, h)
+                h_probe = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+                h_probe.fill_(1)
+                for _ in range(2):
+                    d_probe.copy_(h_probe, non_blocking=True)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(8):
+                    d_probe.copy_(h_probe, non_blocking=True)
+                torch.cuda.synchronize()
+                rates.append(8 * 64 / 1024.0 / (time.perf_counter() - t0))
+                del h_probe
+            best = 0 if rates[0] >= rates[1] else 1
+            keep = halves[best] if rates[best] > 1.1 * rates[1 - best] else set(allowed)
+            os.sched_setaffinity(0, keep)
+            print("rank %d: H2D probe %.1f / %.1f GB/s from the two CPU halves -> %d cpus kept" % (rank, rates[0], rates[1], len(keep)),
+                  file=sys.stderr)
+            del d_probe
     except Exception:  # noqa: BLE001
         pass
     B = args.frames_per_gpu
@@ -456,8 +468,12 @@ def gpu_arm(args, rank, world, local_rank):
         # eagerly with the per-stage marks (this pass is not part of `value`)
         # ... with the two chains JOINED before the box RoIAlign, so each RoIAlign is timed alone on the GPU: the
         # roofline figure is a property of the kernel, not of what happens to run beside it
-        events.clear()
         overlap_mode, pipe.overlap = pipe.overlap, (pipe.overlap if pipe.overlap is False else True)
+        for _ in range(3):      # torch.cuda.graph() emptied the allocator cache: re-populate it outside the timed marks
+            run_step(None)
+        drain()
+        torch.cuda.synchronize()
+        events.clear()
         for _ in range(args.steps):
             events.append([])
             out = run_step(mark)

@@ -1,35 +1,47 @@
-"""Drop-in for lib/modeling/roi_xfrom/roi_align/modules/roi_align.py:6-45."""
-from torch.nn.functional import avg_pool2d, max_pool2d
-from torch.nn.modules.module import Module
+"""``nn.Module`` front ends of the RoIAlign op: drop-ins for the three classes of
+lib/modeling/roi_xfrom/roi_align/modules/roi_align.py:6-45 (same constructor arguments, same outputs).
+
+    RoIAlign(h, w, scale, sr)(features, rois)      -> (R, C, h, w)
+    RoIAlignAvg(h, w, scale, sr)(features, rois)   -> (R, C, h, w): pooled at (h+1) x (w+1), then a 2x2 stride-1 mean
+    RoIAlignMax(h, w, scale, sr)(features, rois)   -> (R, C, h, w): pooled at (h+1) x (w+1), then a 2x2 stride-1 max
+
+All three run the CUDA RoIAlign of this package (NCHW or channels-last features, see ops.roi_align_forward);
+the 2x2 reductions of the Avg / Max variants are plain torch pooling on the pooled (tiny) blob.
+"""
+import torch.nn.functional as F
+from torch import nn
 
 from ..functions.roi_align import RoIAlignFunction
 
 
-class _Base(Module):
+class _PooledRoIs(nn.Module):
+    """Holds the four hyper-parameters; ``pooled(features, rois, grow)`` samples a (h+grow) x (w+grow) grid."""
+
     def __init__(self, aligned_height, aligned_width, spatial_scale, sampling_ratio):
         super().__init__()
-        self.aligned_width = int(aligned_width)
-        self.aligned_height = int(aligned_height)
-        self.spatial_scale = float(spatial_scale)
-        self.sampling_ratio = int(sampling_ratio)
+        self.aligned_height, self.aligned_width = int(aligned_height), int(aligned_width)
+        self.spatial_scale, self.sampling_ratio = float(spatial_scale), int(sampling_ratio)
 
-    def _pool(self, features, rois, extra):
-        return RoIAlignFunction(self.aligned_height + extra, self.aligned_width + extra,
-                                self.spatial_scale, self.sampling_ratio)(features, rois)
+    def pooled(self, features, rois, grow=0):
+        op = RoIAlignFunction(self.aligned_height + grow, self.aligned_width + grow, self.spatial_scale,
+                              self.sampling_ratio)
+        return op(features, rois)
+
+    def extra_repr(self):
+        return "%dx%d, scale=%g, sampling_ratio=%d" % (self.aligned_height, self.aligned_width, self.spatial_scale,
+                                                       self.sampling_ratio)
 
 
-class RoIAlign(_Base):
+class RoIAlign(_PooledRoIs):
     def forward(self, features, rois):
-        return self._pool(features, rois, 0)
+        return self.pooled(features, rois)
 
 
-class RoIAlignAvg(_Base):
-    """(h+1)x(w+1) RoIAlign followed by a 2x2 stride-1 average (modules/roi_align.py:20-32)."""
-
+class RoIAlignAvg(_PooledRoIs):
     def forward(self, features, rois):
-        return avg_pool2d(self._pool(features, rois, 1), kernel_size=2, stride=1)
+        return F.avg_pool2d(self.pooled(features, rois, grow=1), kernel_size=2, stride=1)
 
 
-class RoIAlignMax(_Base):
+class RoIAlignMax(_PooledRoIs):
     def forward(self, features, rois):
-        return max_pool2d(self._pool(features, rois, 1), kernel_size=2, stride=1)
+        return F.max_pool2d(self.pooled(features, rois, grow=1), kernel_size=2, stride=1)

@@ -164,3 +164,20 @@ def test_reference_aliases_install():
     assert hasattr(mod, 'RoIAlignFunction')
     for n in names:
         sys.modules.pop(n, None)
+
+
+def test_rle_string_parser_matches_the_oracle(orc):
+    """core.test.rle_counts_from_string (host half of mask_util.decode in the nms_with_mask_iou mirror) against the
+    oracle's rleFrString restatement and its encoder, bytes or str input, negative differences included."""
+    from vosdetectron_b200.core import test as core_test
+    rs = np.random.RandomState(9)
+    for _ in range(50):
+        h, w = rs.randint(1, 40), rs.randint(1, 40)
+        m = (rs.rand(h, w) > rs.rand()).astype(np.uint8)
+        enc = orc.rle_encode(m)
+        counts = core_test.rle_counts_from_string(enc['counts'])
+        assert counts == orc.rle_from_string(enc['counts']) == orc.rle_counts_fast(m)
+        assert core_test.rle_counts_from_string(enc['counts'].encode('ascii')) == counts
+        assert core_test.rle_encode(m)['counts'] == enc['counts']
+    big = [5, 1000, 3, 2, 70000, 1]
+    assert core_test.rle_counts_from_string(orc.rle_to_string(big)) == big

@@ -311,6 +311,8 @@ def gpu_arm(args, rank, world, local_rank):
     os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if args.nccl_channels > 0:
+            os.environ["NCCL_MAX_NCHANNELS"] = str(args.nccl_channels)
         dist.init_process_group("nccl", device_id=dev)
     # Pinned host buffers should live on the NUMA node the GPU hangs off: the e2e leg is PCIe-bound and measured
     # 23 ms vs 36 ms per step depending on where the pages landed.  The container hides the topology
@@ -649,6 +651,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run the mask chain behind the box chain on one stream")
     ap.add_argument("--no-cuda-graph", action="store_true", help="time the eager step instead of a CUDA-graph replay of it")
+    ap.add_argument("--nccl-channels", type=int, default=0,
+                    help="N > 1 experiment: cap NCCL at this many channels (NCCL_MAX_NCHANNELS) so the all-gather holds fewer SMs")
     ap.add_argument("--gather-rle", action="store_true",
                     help="N > 1: all-gather COCO RLE strings (fused paste -> RLE kernel) instead of 1-bit-per-pixel masks")
     ap.add_argument("--join-overlap", action="store_true",

@@ -181,3 +181,52 @@ def test_rle_string_parser_matches_the_oracle(orc):
         assert core_test.rle_encode(m)['counts'] == enc['counts']
     big = [5, 1000, 3, 2, 70000, 1]
     assert core_test.rle_counts_from_string(orc.rle_to_string(big)) == big
+
+
+def test_argument_validation_of_the_next_row_entry_points(lib):
+    """Status codes of the round's new entry points, reachable without a GPU (validation precedes any CUDA call)."""
+    vp, ip, fp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float)
+    p = vp(256)
+    # FlowAlign: empty problems are no-ops, negative extents / missing pointers are errors, the int index limit holds
+    assert lib.vosd_flow_align_fwd(0, 8, 8, 4, None, None, None, None) == 0
+    assert lib.vosd_flow_align_fwd(2, 8, 8, 0, None, None, None, None) == 0
+    assert lib.vosd_flow_align_fwd(-1, 8, 8, 4, p, p, p, None) == -1
+    assert lib.vosd_flow_align_fwd(2, 8, 8, 4, None, p, p, None) == -2
+    assert lib.vosd_flow_align_fwd(64, 1024, 1024, 32, p, p, p, None) == -3           # N*C*H*W >= 2^31
+    assert lib.vosd_flow_align_bwd(2, 8, 8, 4, p, p, p, None, p, 0, None) == -2        # bottomdiff missing
+    assert lib.vosd_debug_flow_align_fast(0) in (0, 1, 2)
+    # mask-IoU suppression
+    assert lib.vosd_mask_iou_nms(None, -1, 64, None, 0.5, None, None, None, 0, None) == -1
+    assert lib.vosd_mask_iou_nms(p, 4, 64, None, 0.5, p, None, None, 0, None) == -2    # num_keep missing
+    assert lib.vosd_mask_iou_nms(p, 4, 62, None, 0.5, p, p, p, 1 << 20, None) == -2    # not whole 32-bit words
+    assert lib.vosd_mask_iou_nms(p, 5000, 64, None, 0.5, p, p, p, 1 << 30, None) == -3  # > 2048 masks
+    assert lib.vosd_mask_iou_nms(p, 8, 64, None, 0.5, p, p, None, 0, None) == -4       # workspace missing
+    assert lib.vosd_mask_iou_nms_workspace_bytes(100) >= 100 * 4 + 100 * 2 * 8
+    assert lib.vosd_rle_to_bits(None, None, None, 0, 100, None, 0, None) == 0
+    assert lib.vosd_rle_to_bits(p, p, p, 3, 100, p, 20000, None) == -3                 # > 12000 runs per mask
+    # label-assignment pieces
+    assert lib.vosd_bbox_overlaps(None, 0, None, 5, None, None, None, None) == 0
+    assert lib.vosd_bbox_overlaps(None, 4, p, 5, None, None, None, None) == -2
+    assert lib.vosd_bbox_overlaps(vp(260), 4, p, 5, None, None, None, None) == -2      # not 16-byte aligned
+    w = (ctypes.c_float * 4)(10, 10, 5, 5)
+    assert lib.vosd_bbox_targets(p, p, p, 0, 81, 0, w, p, p, None, None) == 0
+    assert lib.vosd_bbox_targets(p, p, p, 4, 0, 0, w, p, p, None, None) == -1
+    assert lib.vosd_bbox_targets(p, p, None, 4, 81, 0, w, p, p, None, None) == -2
+    # channels-last RoIAlign: heads outside the supported set are refused so that the caller takes the NCHW entry point
+    h, wd = (ctypes.c_int * 1)(50), (ctypes.c_int * 1)(84)
+    sc = (ctypes.c_float * 1)(0.0625)
+    data = (vp * 1)(256)
+    args = lambda C, pw, sr: (data, h, wd, sc, 1, 1, C, 7, pw, sr, 10, p, None, None, p, None)
+    assert lib.vosd_roialign_ml_fwd_nhwc(*args(256, 7, 0)) == -3                        # adaptive grid
+    assert lib.vosd_roialign_ml_fwd_nhwc(*args(48, 7, 2)) == -3                         # C % 32 != 0
+    assert lib.vosd_roialign_ml_fwd_nhwc(*args(256, 6, 2)) == -3                        # pooled width not 7 / 14 / 28
+    assert lib.vosd_roialign_ml_fwd_nhwc(*args(0, 7, 2)) == -1
+
+
+def test_channels_last_dispatch_predicates():
+    import torch
+    from vosdetectron_b200 import ops
+    x = torch.zeros((2, 64, 5, 7))
+    assert not ops._is_channels_last(x) and not ops._is_channels_last(x.contiguous(memory_format=torch.channels_last))  # CPU
+    assert ops._nhwc_supported(256, 7, 2) and ops._nhwc_supported(64, 28, 2)
+    assert not ops._nhwc_supported(48, 7, 2) and not ops._nhwc_supported(256, 7, 0) and not ops._nhwc_supported(256, 6, 2)

@@ -44,6 +44,54 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+def _worker_rle(rank, world, port, out_dir):
+    """The --gather-rle payload of bench.py: per-rank arena of COCO RLE strings + (offset, length) columns appended to
+    the detection records, gathered with the same all_gather_frames (async handles included)."""
+    import sys
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import region_oracle as orc
+    from vosdetectron_b200.core.test import rle_encode, rle_counts_from_string
+    from vosdetectron_b200.pipeline import shard_frames, all_gather_frames
+    dets, masks = _make_clip()
+    F, D, h, w = masks.shape
+    mine = shard_frames(F, world, rank)
+    cap = len(mine) * D * 256                              # fixed arena capacity per rank (bytes)
+    arena = np.zeros(cap, dtype=np.uint8)
+    rec = np.zeros((len(mine), D, 8), dtype=np.float32)
+    rec[:, :, :6] = dets[mine]
+    cur = 0
+    for i, f in enumerate(mine):
+        for d in range(D):
+            s = rle_encode(masks[f, d])['counts'].encode('ascii')
+            arena[cur:cur + len(s)] = np.frombuffer(s, dtype=np.uint8)
+            rec[i, d, 6], rec[i, d, 7] = cur, len(s)
+            cur += len(s)
+    assert cur <= cap
+    grec, garena, works = all_gather_frames(torch.from_numpy(rec), torch.from_numpy(arena).view(len(mine), -1), async_op=True)
+    for wk in works:
+        wk.wait()
+    ok = torch.equal(grec[:, :, :6], torch.from_numpy(dets))
+    per_rank = F // world
+    flat = garena.reshape(world, -1).numpy()               # rank r's arena = row r
+    for f in range(F):
+        r = f // per_rank
+        for d in range(D):
+            o, n = int(grec[f, d, 6]), int(grec[f, d, 7])
+            counts = rle_counts_from_string(flat[r, o:o + n].tobytes())
+            ok = ok and np.array_equal(orc.rle_decode(counts, h, w), masks[f, d])
+    open(os.path.join(out_dir, "rle%d" % rank), "w").write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_frame_sharded_rle_payload_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker_rle, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert open(tmp_path / "rle0").read() == "1" and open(tmp_path / "rle1").read() == "1"
+
+
 def test_frame_sharded_all_gather_world2(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)

@@ -230,3 +230,24 @@ def test_channels_last_dispatch_predicates():
     assert not ops._is_channels_last(x) and not ops._is_channels_last(x.contiguous(memory_format=torch.channels_last))  # CPU
     assert ops._nhwc_supported(256, 7, 2) and ops._nhwc_supported(64, 28, 2)
     assert not ops._nhwc_supported(48, 7, 2) and not ops._nhwc_supported(256, 7, 0) and not ops._nhwc_supported(256, 6, 2)
+
+
+def test_cffi_level_mirrors_import_and_reject_cpu_tensors():
+    """`_ext.roi_align` / `_ext.flow_align`: the entry points the reference's Function classes call, importable under
+    the reference's module names, refusing CPU tensors like everything else here."""
+    import sys
+    import torch
+    import vosdetectron_b200
+    names = vosdetectron_b200.install_reference_aliases()
+    assert 'modeling.roi_xfrom.roi_align._ext.roi_align' in sys.modules and 'vos_model.flow_align._ext.flow_align' in sys.modules
+    # (the parent packages `modeling`, `vos_model` come from the reference tree when it is on sys.path)
+    ra = sys.modules['modeling.roi_xfrom.roi_align._ext.roi_align']
+    fa = sys.modules['vos_model.flow_align._ext.flow_align']
+    assert ra.__all__ == ["roi_align_forward_cuda", "roi_align_backward_cuda"]
+    assert fa.__all__ == ["flow_align_forward_cuda", "flow_align_backward_cuda"]
+    f, r = torch.zeros((1, 4, 8, 8)), torch.zeros((2, 5))
+    with pytest.raises(NotImplementedError):
+        ra.roi_align_forward_cuda(7, 7, 0.25, 2, f, r, torch.zeros((2, 4, 7, 7)))
+    with pytest.raises(NotImplementedError):
+        fa.flow_align_forward_cuda(f, torch.zeros((1, 2, 8, 8)), torch.zeros_like(f))
+    assert isinstance(names, list)

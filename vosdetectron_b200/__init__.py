@@ -48,6 +48,11 @@ def install_reference_aliases(legacy_model_roi_align=True):
     from .vos_model.flow_align.modules import flow_align as fa_mod
     put('vos_model.flow_align', fa_pkg)
     put('vos_model.flow_align.functions.flow_align', fa_fn)
+    # the cffi-level modules the reference's Function classes import (`from .._ext import roi_align / flow_align`)
+    from .modeling.roi_xfrom.roi_align._ext import roi_align as ra_ext
+    from .vos_model.flow_align._ext import flow_align as fa_ext
+    put('modeling.roi_xfrom.roi_align._ext.roi_align', ra_ext)
+    put('vos_model.flow_align._ext.flow_align', fa_ext)
     put('vos_model.flow_align.modules.flow_align', fa_mod)
     if legacy_model_roi_align:
         # lib/model/roi_align is the dead 3-argument variant with different maths

@@ -12,12 +12,16 @@ detections).  With 10 frames per GPU, 8 GPUs process the 80-frame DAVIS-shaped c
 per step; frames are sharded with no data-path collective, only the final all-gather of
 detections + bit-packed masks ("scaling": "weak").
 
-  value : frames/s, inputs resident in HBM, CUDA events around exactly K steps, max over ranks.
+  value : frames/s, inputs resident in HBM, CUDA events around exactly K steps, max over ranks.  The step is
+          captured once as a CUDA graph (both streams) and the timed region replays it (--no-cuda-graph: eager).
   e2e   : same metric through the host-buffer API (vosdetectron_b200.pipeline.HostPipeline): per step H2D of
           every input from pinned host memory and D2H of the step's results (rois, counts, pasted masks),
           all inside the timed region; uploads, kernels and downloads of consecutive steps overlap on 3 streams.
-  roofline : the dominant kernel of the step, algorithmic bytes / its mean launch duration
-          (CUDA events recorded on the launching stream inside the timed region).
+  roofline : the dominant kernel of the step (box RoIAlign: most algorithmic bytes), algorithmic bytes / its mean
+          launch duration from CUDA events on the launching stream -- taken in an eager pass of the same K steps right
+          after the graph-replayed timed region (events cannot be read inside a replayed graph), each RoIAlign alone.
+  alt_layout : the same device-resident step with the FPN maps in torch.channels_last memory order (TMA-fed
+          RoIAlign kernel); never mixed into `value` (N=1 only).
   cpu_baseline : the oracle port of the reference's CPU path on this box's host cores (N=1 only).
 `--impl reference` times that CPU path alone (the reference has no CPU RoIAlign at all --
 functions/roi_align.py:29-30 raises -- so its RoIAlign leg is the oracle's C restatement).

@@ -101,6 +101,23 @@ VOSD_API int vosd_roialign_ml_fwd(const float* const* level_data, const int* lev
                          int num_rois, const float* rois, const int* roi_level,
                          const int* out_index, float* top_data, cudaStream_t stream);
 
+/* The same forward with a caller-provided workspace: the DEFAULT forward of the Python wrappers.  For the heads of
+ * the reference (sampling_ratio == 2, aligned_width in {7, 14, 28}, channels % 32 == 0, <= 4 levels, 16-byte aligned
+ * maps) a plan kernel derives every RoI's sample taps once into the workspace and a persistent, TMA-fed kernel
+ * (csrc/roialign_rw.cuh) streams the footprint rows; every other configuration runs vosd_roialign_ml_fwd's kernels
+ * (workspace unused).  batch_size = N of the (N,C,H_l,W_l) maps (bounds of the tensor maps).  Same results contract as
+ * vosd_roialign_ml_fwd (within 1e-5 of the reference kernel); non-finite texels propagate as in the reference.
+ * The workspace must be 256-byte aligned and at least vosd_roialign_fwd_workspace_bytes(...) (level_h / level_w: HOST
+ * arrays); it is scratch, owned by the caller, and may be reused by the next call on the same stream. */
+VOSD_API size_t vosd_roialign_fwd_workspace_bytes(const int* level_h, const int* level_w, int num_levels, int batch_size,
+                                                  int channels, int aligned_height, int aligned_width, int num_rois);
+VOSD_API int vosd_roialign_ml_fwd_ws(const float* const* level_data, const int* level_h, const int* level_w,
+                                     const float* level_scale, int num_levels, int batch_size, int channels,
+                                     int aligned_height, int aligned_width, int sampling_ratio,
+                                     int num_rois, const float* rois, const int* roi_level,
+                                     const int* out_index, float* top_data,
+                                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 /* The same forward for CHANNELS-LAST maps: level_data[l] points to a (N, H_l, W_l, C) fp32 array (what a
  * torch.channels_last tensor of logical shape (N,C,H_l,W_l) holds), 16-byte aligned; top_data stays (R,C,ph,pw).
  * Tensor-mode TMA loads (32 channels x <= 32 texels x 1 row per box) land in shared memory in the layout the

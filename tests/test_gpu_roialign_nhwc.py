@@ -1,7 +1,8 @@
 """GPU parity: channels-last RoIAlign forward (TMA-fed, csrc/roialign_nhwc.cuh) through the C ABI against
   (i)  the reference kernel (oracle/_ref/libref_roialign.so) on the NCHW copy of the same features:
        |out - ref| <= 1e-5*|ref| + 1e-6*max|ref| (north_star: 1e-5 relative; same gate as the separable NCHW kernel);
-  (ii) the separable NCHW kernel of this library on the NCHW copy: same summation order -> BIT-identical."""
+  (ii) the separable NCHW kernel of this library (workspace-free entry point) on the NCHW copy: same summation
+       order -> BIT-identical."""
 import ctypes
 import os
 
@@ -32,6 +33,15 @@ def ref_fwd():
     return fwd
 
 
+def sep_forward(f, rois, res, scale):
+    """The separable NCHW kernel (csrc/roialign_sep.cuh) through the workspace-free entry point it sits behind."""
+    from vosdetectron_b200 import _lib, ops
+    out = torch.empty((rois.shape[0], f.shape[1], res, res), dtype=torch.float32, device=f.device)
+    _lib.call("vosd_roialign_fwd", ops._ptr(f), float(scale), rois.shape[0], f.shape[2], f.shape[3], f.shape[1], res, res, 2,
+              ops._ptr(rois), ops._ptr(out), ops._stream())
+    return out
+
+
 def gate(out, ref, what):
     tol = 1e-5 * ref.abs() + 1e-6 * float(ref.abs().max())
     err = (out - ref).abs()
@@ -52,7 +62,7 @@ def test_single_level_edge_and_random_rois(ref_fwd, synth, res):
     out = RoIAlignFunction(res, res, 0.125, 2)(f_cl, rois)            # the reference's call form, channels-last input
     assert out.shape == (rois.shape[0], C, res, res) and out.is_contiguous()
     gate(out, ref_fwd(f, rois, res, res, 0.125, 2), "vs reference kernel, res %d" % res)
-    nchw = ops.roi_align_forward(f, rois, res, res, 0.125, 2)         # separable NCHW kernel of this library
+    nchw = sep_forward(f, rois, res, 0.125)                           # separable NCHW kernel of this library
     assert torch.equal(out, nchw), "not bit-identical to the NCHW kernel: max |diff| %g" % float((out - nchw).abs().max())
 
 

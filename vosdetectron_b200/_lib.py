@@ -43,6 +43,10 @@ SIGNATURES = {
     "vosd_roialign_ml_fwd": (ctypes.c_int, [ctypes.POINTER(vp), c_int_p, c_int_p, c_float_p, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             vp, vp, vp, vp, vp]),
+    "vosd_roialign_fwd_workspace_bytes": (ctypes.c_size_t, [c_int_p, c_int_p] + [ctypes.c_int] * 6),
+    "vosd_roialign_ml_fwd_ws": (ctypes.c_int, [ctypes.POINTER(vp), c_int_p, c_int_p, c_float_p, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
     "vosd_roialign_ml_fwd_nhwc": (ctypes.c_int, [ctypes.POINTER(vp), c_int_p, c_int_p, c_float_p, ctypes.c_int,
                                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                  ctypes.c_int, vp, vp, vp, vp, vp]),

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "../../include/vosd_b200.h"
 
 namespace vosd {
@@ -9,8 +11,12 @@ namespace vosd {
 // Diagnostic launch counter (host side, relaxed atomic).
 void count_launch(int n = 1);
 
+// VOSD_B200_DEBUG=1 in the environment: the CUDA error string behind a VOSD_ERR_LAUNCH goes to stderr.
 inline int check_launch() {
-    return cudaGetLastError() == cudaSuccess ? VOSD_OK : VOSD_ERR_LAUNCH;
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return VOSD_OK;
+    if (getenv("VOSD_B200_DEBUG")) fprintf(stderr, "[vosd_b200] CUDA error: %s\n", cudaGetErrorString(e));
+    return VOSD_ERR_LAUNCH;
 }
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs

@@ -1181,6 +1181,7 @@ bwd_tile_kernel(const __grid_constant__ LevelTable lv, const __grid_constant__ B
 }  // namespace vosd
 #include "roialign_sep.cuh"
 #include "roialign_nhwc.cuh"
+#include "roialign_rw.cuh"
 namespace vosd {
 
 // test hook (vosd_debug_force_generic): 0 = default (separable forward where it applies, record-based backward), 1 = generic kernels
@@ -1477,6 +1478,111 @@ extern "C" int vosd_roialign_ml_fwd_nhwc(const float* const* level_data, const i
         case 2: return launch_nhwc<2>(maps, t, channels, aligned_height, num_rois, rois, roi_level, out_index, top_data, stream);
         default: return launch_nhwc<4>(maps, t, channels, aligned_height, num_rois, rois, roi_level, out_index, top_data, stream);
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Row-window forward (roialign_rw.cuh): plan kernel + persistent TMA-fed main kernel, caller-provided workspace.
+// ---------------------------------------------------------------------------------------
+static bool rw_applies(int channels, int ph, int pw, int sr) {
+    return g_force_generic == 0 && sr == 2 && (pw == 7 || pw == 14 || pw == 28) && ph > 0 && channels % kSlab == 0;
+}
+
+static long long rw_base_items(int ph, int pw, int num_rois) {
+    return (long long)num_rois * ((ph + 6) / 7) * (pw / 7);
+}
+
+static size_t rw_items_bytes(long long nbase) { return align_up((size_t)(2 * nbase + 4096) * sizeof(RwItem), 256); }
+
+extern "C" size_t vosd_roialign_fwd_workspace_bytes(const int* level_h, const int* level_w, int num_levels, int batch_size,
+                                                    int channels, int aligned_height, int aligned_width, int num_rois) {
+    if (!level_h || !level_w || num_levels < 1 || num_levels > 4 || batch_size <= 0 || channels <= 0 || num_rois < 0 ||
+        aligned_height <= 0 || aligned_width <= 0)
+        return 0;
+    size_t bytes = 256 + rw_items_bytes(rw_base_items(aligned_height, aligned_width, num_rois));
+    for (int l = 0; l < num_levels; l++)
+        if (level_w[l] % 4)
+            bytes += align_up((size_t)batch_size * channels * level_h[l] * ((level_w[l] + 3) & ~3) * sizeof(float), 256);
+    return bytes;
+}
+
+extern "C" int vosd_roialign_ml_fwd_ws(const float* const* level_data, const int* level_h, const int* level_w,
+                                       const float* level_scale, int num_levels, int batch_size, int channels,
+                                       int aligned_height, int aligned_width, int sampling_ratio,
+                                       int num_rois, const float* rois, const int* roi_level,
+                                       const int* out_index, float* top_data,
+                                       void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    LevelTable t;
+    int rc = fill_table(t, level_data, level_h, level_w, level_scale, num_levels);
+    if (rc) return rc;
+    if (num_levels > 1 && !roi_level && num_rois > 0) return VOSD_ERR_BAD_ARG;
+    if (channels <= 0 || aligned_height <= 0 || aligned_width <= 0 || num_rois < 0 || batch_size <= 0) return VOSD_ERR_BAD_SHAPE;
+    if (num_rois == 0) return VOSD_OK;
+    if (!rois || !top_data) return VOSD_ERR_BAD_ARG;
+    const EncodeTiledFn enc = encode_tiled();
+    bool use_rw = rw_applies(channels, aligned_height, aligned_width, sampling_ratio) && enc && num_levels <= 4 &&
+                  rw_base_items(aligned_height, aligned_width, num_rois) < (1ll << 27);
+    for (int l = 0; l < num_levels && use_rw; l++) use_rw = aligned16(level_data[l]);
+    if (!use_rw)
+        return ml_fwd(t, channels, aligned_height, aligned_width, sampling_ratio, num_rois, rois, roi_level, out_index,
+                      top_data, stream);
+    const size_t need = vosd_roialign_fwd_workspace_bytes(level_h, level_w, num_levels, batch_size, channels,
+                                                          aligned_height, aligned_width, num_rois);
+    if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255)) return VOSD_ERR_WORKSPACE;
+    const int nbase = (int)rw_base_items(aligned_height, aligned_width, num_rois);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    RwCounters* ctr = reinterpret_cast<RwCounters*>(ws);
+    RwItem* items = reinterpret_cast<RwItem*>(ws + 256);
+    unsigned char* pad_ws = ws + 256 + rw_items_bytes(nbase);
+    const int cap_extra = nbase + 4096;
+    // tensor maps over (W, H, N * C), box (BX, 1, 32); levels whose rows are not 16-byte multiples read a padded copy
+    RwMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int l = 0; l < num_levels; l++) {
+        const int W = level_w[l], H = level_h[l], Wp = (W + 3) & ~3;
+        const float* src = level_data[l];
+        if (Wp != W) {
+            float* dst = reinterpret_cast<float*>(pad_ws);
+            const long long rows = (long long)batch_size * channels * H;
+            roialign_rw_pad<<<grid_for(rows * Wp, 256), 256, 0, stream>>>(src, dst, W, Wp, rows);
+            count_launch();
+            pad_ws += align_up((size_t)rows * Wp * sizeof(float), 256);
+            src = dst;
+        }
+        const cuuint64_t dims[3] = {(cuuint64_t)Wp, (cuuint64_t)H, (cuuint64_t)batch_size * channels};
+        const cuuint64_t strides[2] = {(cuuint64_t)Wp * 4, (cuuint64_t)H * Wp * 4};
+        const cuuint32_t es[3] = {1, 1, 1};
+        for (int v = 0; v < kRwVariants; v++) {
+            const cuuint32_t box[3] = {(cuuint32_t)(12 + 8 * v), 1, (cuuint32_t)kSlab};
+            if (enc(&maps.m[l][v], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(src), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return VOSD_ERR_BAD_SHAPE;
+        }
+    }
+    if (cudaMemsetAsync(ctr, 0, sizeof(RwCounters), stream) != cudaSuccess) return VOSD_ERR_LAUNCH;
+    roialign_rw_plan<<<ceil_div(nbase, 64), 64, 0, stream>>>(t, channels, aligned_height, aligned_width, num_rois, rois,
+                                                              roi_level, out_index, items, nbase, cap_extra, ctr);
+    count_launch();
+    if (check_launch() != VOSD_OK) return VOSD_ERR_LAUNCH;
+    RwArgs a;
+    a.items = items; a.ctr = ctr; a.top = top_data; a.rois = rois;
+    a.nbase = nbase; a.cap_extra = cap_extra;
+    a.channels = channels; a.pooled_h = aligned_height; a.pooled_w = aligned_width;
+    // work unit = (item, slab range): >= ~8 units per warp, >= 2 slabs per unit
+    const int slabs_all = channels / kSlab;
+    int split_log2 = 0;
+    while ((1 << (split_log2 + 1)) * 2 <= slabs_all && ((long long)nbase << split_log2) < 8ll * kNumSMs * kRwWarps) split_log2++;
+    a.split_log2 = split_log2;
+    a.slabs_per_unit = ceil_div(slabs_all, 1 << split_log2);
+    a.top_aligned = aligned16(top_data) ? 1 : 0;
+    const size_t dyn = (size_t)kRwWarps * kRwWarpBytes;
+    if (cudaFuncSetAttribute(roialign_fwd_rw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
+        return check_launch() == VOSD_OK ? VOSD_ERR_LAUNCH : VOSD_ERR_LAUNCH;
+    const long long units = (long long)nbase << split_log2;
+    const int grid = (int)(units < (long long)kNumSMs * kRwWarps ? ceil_div((int)units, kRwWarps) : kNumSMs);
+    roialign_fwd_rw<<<grid, kRwThreads, dyn, stream>>>(maps, t, a);
+    count_launch();
+    return check_launch();
 }
 
 extern "C" int vosd_roialign_ml_bwd(const float* top_diff, float* const* level_diff, const int* level_h,

@@ -59,12 +59,7 @@ def roi_align_forward(features, rois, aligned_height, aligned_width, spatial_sca
     r = _need_cuda(rois, "rois")
     if r.dim() != 2 or r.size(1) != 5:
         raise ValueError("rois must be (R,5)")          # reference shim returns 0 here (roi_align_cuda.c:15-18)
-    N, C, H, W = f.shape
-    out = torch.empty((r.size(0), C, aligned_height, aligned_width), dtype=torch.float32, device=f.device)
-    _bind(f)
-    _lib.call("vosd_roialign_fwd", _ptr(f), float(spatial_scale), r.size(0), H, W, C,
-              int(aligned_height), int(aligned_width), int(sampling_ratio), _ptr(r), _ptr(out), _stream())
-    return out
+    return roi_align_ml_forward([f], [spatial_scale], r, None, aligned_height, aligned_width, sampling_ratio)
 
 
 def roi_align_backward(grad_output, rois, feature_size, aligned_height, aligned_width, spatial_scale,
@@ -112,10 +107,21 @@ def roi_align_ml_forward(level_features, level_scales, rois, roi_level, aligned_
                   int(aligned_width), int(sampling_ratio), R, _ptr(r), _ptr(lv), _ptr(oi), _ptr(out), _stream())
         return out
     feats = [_need_cuda(f, "level_features[%d]" % i) for i, f in enumerate(level_features)]
-    C = feats[0].shape[1]
+    N, C = (int(v) for v in feats[0].shape[:2])
+    if any(tuple(f.shape[:2]) != (N, C) for f in feats):
+        raise ValueError("all levels must share batch size and channel count")
     out = torch.empty((R, C, aligned_height, aligned_width), dtype=torch.float32, device=r.device)
     ptrs, hs, ws, sc = _level_arrays(feats, level_scales)
     _bind(r)
+    if len(feats) <= 4:
+        # default: plan kernel + persistent TMA-fed kernel; the scratch comes from the caching allocator
+        need = int(_lib.load().vosd_roialign_fwd_workspace_bytes(hs, ws, len(feats), N, C, int(aligned_height),
+                                                                 int(aligned_width), R))
+        wsp = torch.empty(max(need, 256), dtype=torch.uint8, device=r.device)
+        _lib.call("vosd_roialign_ml_fwd_ws", ptrs, hs, ws, sc, len(feats), N, C, int(aligned_height),
+                  int(aligned_width), int(sampling_ratio), R, _ptr(r), _ptr(lv), _ptr(oi), _ptr(out), _ptr(wsp),
+                  wsp.numel(), _stream())
+        return out
     _lib.call("vosd_roialign_ml_fwd", ptrs, hs, ws, sc, len(feats), C, int(aligned_height), int(aligned_width),
               int(sampling_ratio), R, _ptr(r), _ptr(lv), _ptr(oi), _ptr(out), _stream())
     return out

@@ -68,7 +68,7 @@ def test_single_level_edge_and_random_rois(ref_fwd, synth, res):
 
 def test_full_size_multilevel(ref_fwd, synth):
     """BASELINE config 2 at full size (1000 RoIs x 256 ch over P2-P5, 7x7 and 14x14), channels-last maps."""
-    from vosdetectron_b200 import ops
+    from vosdetectron_b200 import _lib, ops
     feats = synth.fpn_features(2000, synth.COCO_BLOB, 1, synth.ROI_LEVELS, 256)
     rois = torch.from_numpy(synth.random_rois(2001, 1000, synth.COCO_BLOB, 1)).cuda()
     fl = [torch.from_numpy(feats[l]).cuda() for l in synth.ROI_LEVELS]
@@ -85,7 +85,12 @@ def test_full_size_multilevel(ref_fwd, synth):
             if len(idx):
                 ref[idx] = ref_fwd(fl[i], rois[idx].contiguous(), res, res, sc[i], 2)
         gate(out, ref, "full size res %d" % res)
-        assert torch.equal(out, ops.roi_align_ml_forward(fl, sc, rois, lv, res, res, 2))
+        gate(ops.roi_align_ml_forward(fl, sc, rois, lv, res, res, 2), ref, "NCHW row-window kernel, res %d" % res)
+        sep = torch.empty_like(out)                      # the separable NCHW kernel: same summation order as channels-last
+        ptrs, hs, ws, scs = ops._level_arrays(fl, sc)
+        _lib.call("vosd_roialign_ml_fwd", ptrs, hs, ws, scs, len(fl), 256, res, res, 2, rois.shape[0], ops._ptr(rois), ops._ptr(lv),
+                  None, ops._ptr(sep), ops._stream())
+        assert torch.equal(out, sep)
         scattered = ops.roi_align_ml_forward(fl_cl, sc, rois, lv, res, res, 2, out_index=perm)
         assert torch.equal(scattered[perm.long()], out)
 

@@ -1560,7 +1560,7 @@ extern "C" int vosd_roialign_ml_fwd_ws(const float* const* level_data, const int
         }
     }
     if (cudaMemsetAsync(ctr, 0, sizeof(RwCounters), stream) != cudaSuccess) return VOSD_ERR_LAUNCH;
-    roialign_rw_plan<<<ceil_div(nbase, 64), 64, 0, stream>>>(t, channels, aligned_height, aligned_width, num_rois, rois,
+    roialign_rw_plan<<<ceil_div(nbase, 8), 128, 0, stream>>>(t, channels, aligned_height, aligned_width, num_rois, rois,
                                                               roi_level, out_index, items, nbase, cap_extra, ctr);
     count_launch();
     if (check_launch() != VOSD_OK) return VOSD_ERR_LAUNCH;

@@ -99,13 +99,11 @@ __device__ __forceinline__ void sts_zero2(unsigned a) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// PLAN: one thread per base block (RoI, group of 7 output rows, group of 7 output columns).
+// PLAN: one HALF-WARP per base block (RoI, group of 7 output rows, group of 7 output columns).  Lane k < 14 of
+// the half-warp holds y sample k and x sample k of the block (sample 2p + i: bin p, sub-sample i); extents, slot
+// checks and the record are formed with 16-wide shuffles, so a block costs ~300 warp-instructions spread over
+// 16 lanes instead of ~3000 serial ones.
 // ------------------------------------------------------------------------------------------------------
-struct RwAxis {            // the 14 samples of 7 bins along one axis
-    int low[14], high[14]; // low < 0: invalid
-    float l[14], h[14];
-};
-
 __device__ __forceinline__ int rw_variant_of(int need) { return need <= 12 ? RW_V12 : (need <= 20 ? RW_V20 : (need <= 28 ? RW_V28 : -1)); }
 __device__ __forceinline__ int rw_slots_of(int variant) { return variant == RW_V12 ? 4 : (variant == RW_V20 ? 3 : 2); }
 
@@ -120,92 +118,146 @@ __device__ __forceinline__ void rw_piece(int kind, int n, int k, int& b0, int& n
     else { b0 = k; nb = 1; }
 }
 
-// footprint of bins [b0, b0 + nb): extent over the valid samples; returns false if none
-__device__ __forceinline__ bool rw_extent(const RwAxis& a, int b0, int nb, int& lo, int& hi) {
-    lo = 1 << 30; hi = -1;
-    for (int k = 2 * b0; k < 2 * (b0 + nb); k++)
-        if (a.low[k] >= 0) { lo = min(lo, a.low[k]); hi = max(hi, a.high[k]); }
-    return hi >= 0;
-}
-
-// a piece (rows [p0, p0+np), columns [q0, q0+nq)) is executable by a row-window variant?  -> variant or -1
-__device__ int rw_eval(const RwAxis& ya, const RwAxis& xa, int p0, int np, int q0, int nq) {
-    int ylo, yhi, xlo, xhi;
-    const bool vy = rw_extent(ya, p0, np, ylo, yhi), vx = rw_extent(xa, q0, nq, xlo, xhi);
-    if (!vy || !vx) return RW_ZERO;
-    if (yhi - ylo + 1 > kRwMaxRows) return -1;
-    const int variant = rw_variant_of(xhi - (xlo & ~3) + 1);
-    if (variant < 0) return -1;
-    const int S = rw_slots_of(variant);
-    // output rows p and p + S share an accumulator slot: they must never be open at the same texel row
-    for (int p = p0; p + S < p0 + np; p++) {
-        int lo1, hi1, lo2, hi2;
-        if (rw_extent(ya, p, 1, lo1, hi1) && rw_extent(ya, p + S, 1, lo2, hi2) && lo2 <= hi1) return -1;
-    }
-    return variant;
-}
-
-__device__ void rw_write_item(RwItem* it, const RwAxis& ya, const RwAxis& xa, int variant, int p0, int np, int q0, int nq,
-                              int roi, int out_row, int plane0, int level, int ph_base, int pw_base) {
-    int ylo = 0, yhi = -1, xlo = 0, xhi = -1;
-    rw_extent(ya, p0, np, ylo, yhi);
-    rw_extent(xa, q0, nq, xlo, xhi);
-    const int x0 = xlo & ~3;
-    it->out_row = out_row; it->plane0 = plane0; it->level = level; it->variant = variant;
-    it->x0 = x0; it->y_lo = ylo; it->th = yhi - ylo + 1; it->roi = roi;
-    it->ph0 = ph_base + p0; it->nph = np; it->pw0 = pw_base + q0; it->npw = nq;
-    it->pad[0] = it->pad[1] = 0;
-    if (variant > RW_V28) { it->lastp1 = 0; return; }
-    const int BX = 12 + 8 * variant;
-    unsigned long long lastp1 = 0;
-    for (int p = 0; p < 7; p++) {
-        int lo, hi;
-        if (p < np && rw_extent(ya, p0 + p, 1, lo, hi)) lastp1 |= (unsigned long long)(hi - ylo + 1) << (8 * p);
-        for (int i = 0; i < 2; i++) {
-            Tap t = Tap{-1, -1, 0.f, 0.f};
-            const int k = 2 * (p0 + p) + i;
-            if (p < np && ya.low[k] >= 0) t = Tap{ya.low[k] - ylo, ya.high[k] - ylo, ya.l[k], ya.h[k]};
-            it->ytab[2 * p + i] = t;
-        }
-    }
-    it->lastp1 = lastp1;
-    for (int q = 0; q < 7; q++)
-        for (int i = 0; i < 2; i++) {
-            const int k = 2 * (q0 + q) + i;
-            const bool v = q < nq && xa.low[k] >= 0;
-            it->xoff[2 * q + i] = v ? 4 * (xa.low[k] - x0) : 4 * BX;        // invalid: the two zero cells behind the row
-            it->xw[4 * q + 2 * i] = v ? xa.h[k] : 0.f;
-            it->xw[4 * q + 2 * i + 1] = v ? xa.l[k] : 0.f;
-        }
-}
-
 // sample coordinate for the fixed 2x2 grid: x / 2 == x * 0.5 exactly, so this equals sample_coord(.., 2) bit for bit
 __device__ __forceinline__ float rw_sample_coord(float start, float bin, int p, int i) {
     return __fadd_rn(__fmaf_rn((float)p, bin, start), __fmul_rn(__fmul_rn((float)i + .5f, bin), 0.5f));
 }
 
-// slow path of the plan: blocks that have to be split (or go direct); everything through local-memory tables
-__device__ __noinline__ void rw_plan_split(RoiGeom g, int H, int W, int nphz, RwItem* items, int b, int nbase,
-                                           int cap_extra, RwCounters* ctr, int n, int out_row, int plane0, int level, int z, int hq) {
-    RwAxis ya, xa;                                      // recomputed here so that the caller's copies stay in registers
-    for (int k = 0; k < 14; k++) {
-        ya.low[k] = -1; ya.high[k] = -1; ya.l[k] = ya.h[k] = 0.f;
-        if (k < 2 * nphz) {
-            const int sy = 14 * z + k;
-            const AxisTap t = axis_tap(rw_sample_coord(g.start_h, g.bin_h, sy >> 1, sy & 1), H);
-            if (t.valid) { ya.low[k] = t.low; ya.high[k] = t.high; ya.l[k] = t.l; ya.h[k] = t.h; }
-        }
+__device__ __forceinline__ int hw_min(int v, unsigned m) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(m, v, o, 16));
+    return v;
+}
+__device__ __forceinline__ int hw_max(int v, unsigned m) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(m, v, o, 16));
+    return v;
+}
+
+struct RwLaneTaps {        // lane k of the half-warp: sample k along y and along x (low < 0: invalid / lane >= 14)
+    int ylow, yhigh, xlow, xhigh;
+    float yl, yh, xl, xh;
+    int pfirst, plast;     // extent of the lane's output row (both lanes of a pair hold it); plast < 0: no valid sample
+};
+
+// extents of the piece (rows [p0, p0 + np), columns [q0, q0 + nq)); all lanes of the half-warp get the same values
+__device__ __forceinline__ void rw_extents(const RwLaneTaps& t, int k, unsigned m, int p0, int np, int q0, int nq,
+                                           int& ylo, int& yhi, int& xlo, int& xhi) {
+    const bool iny = k >= 2 * p0 && k < 2 * (p0 + np) && t.ylow >= 0, inx = k >= 2 * q0 && k < 2 * (q0 + nq) && t.xlow >= 0;
+    ylo = hw_min(iny ? t.ylow : 1 << 30, m); yhi = hw_max(iny ? t.yhigh : -1, m);
+    xlo = hw_min(inx ? t.xlow : 1 << 30, m); xhi = hw_max(inx ? t.xhigh : -1, m);
+}
+
+// variant that can run the piece, RW_ZERO if it has no valid sample, -1 if none
+__device__ __forceinline__ int rw_eval(const RwLaneTaps& t, int k, unsigned m, int p0, int np, int q0, int nq) {
+    int ylo, yhi, xlo, xhi;
+    rw_extents(t, k, m, p0, np, q0, nq, ylo, yhi, xlo, xhi);
+    if (yhi < 0 || xhi < 0) return RW_ZERO;
+    if (yhi - ylo + 1 > kRwMaxRows) return -1;
+    const int variant = rw_variant_of(xhi - (xlo & ~3) + 1);
+    if (variant < 0) return -1;
+    const int S = rw_slots_of(variant);
+    // output rows p and p + S share an accumulator slot: they must never be open at the same texel row
+    const int other_first = __shfl_down_sync(m, t.pfirst, 2 * S, 16), other_last = __shfl_down_sync(m, t.plast, 2 * S, 16);
+    const int p = k >> 1;
+    const bool clash = k < 14 && p >= p0 && p + S < p0 + np && t.plast >= 0 && other_last >= 0 && other_first <= t.plast;
+    return hw_max(clash ? 1 : 0, m) ? -1 : variant;
+}
+
+// writes the record of the piece; called by the whole half-warp
+__device__ __forceinline__ void rw_write_item(RwItem* it, const RwLaneTaps& t, int k, unsigned m, int variant, int p0, int np, int q0,
+                                              int nq, int roi, int out_row, int plane0, int level, int ph_base, int pw_base) {
+    int ylo, yhi, xlo, xhi;
+    rw_extents(t, k, m, p0, np, q0, nq, ylo, yhi, xlo, xhi);
+    if (variant == RW_ZERO || variant == RW_DIRECT) { ylo = 0; yhi = -1; xlo = 0; }
+    const int x0 = xlo & ~3;
+    // lastp1: byte j = (last row of local output row j) + 1, relative to ylo; gathered from the even lanes
+    const int pl = __shfl_sync(m, t.plast, min(2 * (p0 + (k & 7)), 15), 16);
+    unsigned lo32 = 0, hi32 = 0;
+    if (variant <= RW_V28 && k < 7 && k < np && pl >= 0) {
+        const unsigned v = (unsigned)(pl - ylo + 1);
+        if (k < 4) lo32 = v << (8 * k); else hi32 = v << (8 * (k - 4));
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { lo32 |= __shfl_xor_sync(m, lo32, o, 16); hi32 |= __shfl_xor_sync(m, hi32, o, 16); }
+    int4* o = reinterpret_cast<int4*>(it);
+    if (k == 0) {
+        o[0] = make_int4(out_row, plane0, level, variant);
+        o[1] = make_int4(x0, ylo, yhi - ylo + 1, roi);
+        o[2] = make_int4(ph_base + p0, np, pw_base + q0, nq);
+        o[3] = make_int4((int)lo32, (int)hi32, 0, 0);
+    }
+    // ytab: local sample j <- lane 2 * p0 + j
+    {
+        const int src = min(2 * p0 + k, 15);
+        const int sl = __shfl_sync(m, t.ylow, src, 16), sh = __shfl_sync(m, t.yhigh, src, 16);
+        const float fl = __shfl_sync(m, t.yl, src, 16), fh = __shfl_sync(m, t.yh, src, 16);
+        const bool v = k < 2 * np && sl >= 0;
+        if (k < 14 && variant <= RW_V28)
+            o[4 + k] = make_int4(v ? sl - ylo : -1, v ? sh - ylo : -1, __float_as_int(fl), __float_as_int(fh));
+    }
+    // x taps: local sample j <- lane 2 * q0 + j
+    const int BX = 12 + 8 * variant;
+    const int srcx = min(2 * q0 + k, 15);
+    const int sxl = __shfl_sync(m, t.xlow, srcx, 16);
+    const float fxl = __shfl_sync(m, t.xl, srcx, 16), fxh = __shfl_sync(m, t.xh, srcx, 16);
+    const bool vx = k < 2 * nq && sxl >= 0;
+    const int my_off = vx ? 4 * (sxl - x0) : 4 * BX;          // invalid: the two zero cells behind a scratch row
+    const float my_h = vx ? fxh : 0.f, my_l = vx ? fxl : 0.f;
+    {
+        // xw[q] = (h, l) of samples 2q, 2q + 1: lane q < 7 collects from lanes 2q, 2q + 1
+        const int a = min(2 * k, 15), b = min(2 * k + 1, 15);
+        const float h0 = __shfl_sync(m, my_h, a, 16), l0 = __shfl_sync(m, my_l, a, 16);
+        const float h1 = __shfl_sync(m, my_h, b, 16), l1 = __shfl_sync(m, my_l, b, 16);
+        if (k < 7 && variant <= RW_V28)
+            o[18 + k] = make_int4(__float_as_int(h0), __float_as_int(l0), __float_as_int(h1), __float_as_int(l1));
+        // xoff: lane j < 4 collects the offsets of samples 4j .. 4j + 3
+        const int c0 = __shfl_sync(m, my_off, min(4 * k, 15), 16), c1 = __shfl_sync(m, my_off, min(4 * k + 1, 15), 16);
+        const int c2 = __shfl_sync(m, my_off, min(4 * k + 2, 15), 16), c3 = __shfl_sync(m, my_off, min(4 * k + 3, 15), 16);
+        if (k < 4 && variant <= RW_V28) o[25 + k] = make_int4(c0, c1, k == 3 ? 0 : c2, k == 3 ? 0 : c3);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+roialign_rw_plan(const __grid_constant__ LevelTable lv, int channels, int pooled_h, int pooled_w, int num_rois,
+                 const float* __restrict__ rois, const int* __restrict__ roi_level, const int* __restrict__ out_index,
+                 RwItem* __restrict__ items, int nbase, int cap_extra, RwCounters* __restrict__ ctr) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int k = threadIdx.x & 15;
+    const unsigned m = 0xffffu << (threadIdx.x & 16);          // this half of the warp
+    if (b >= nbase) return;                                     // half-warp uniform
+    const int T = pooled_w / 7, Z = (pooled_h + 6) / 7;
+    const int n = b / (Z * T), z = (b / T) % Z, hq = b % T;
+    const int level = roi_level ? __ldg(roi_level + n) : 0;
+    const int H = lv.h[level], W = lv.w[level];
+    const RoiGeom g = roi_geometry(rois + 5 * (size_t)n, lv.scale[level], pooled_h, pooled_w, 2);
+    const int out_row = out_index ? __ldg(out_index + n) : n;
+    const int nphz = min(7, pooled_h - 7 * z);
+    RwLaneTaps t;
+    t.ylow = t.yhigh = t.xlow = t.xhigh = -1; t.yl = t.yh = t.xl = t.xh = 0.f;
+    if (k < 2 * nphz) {
+        const int sy = 14 * z + k;
+        const AxisTap a = axis_tap(rw_sample_coord(g.start_h, g.bin_h, sy >> 1, sy & 1), H);
+        if (a.valid) { t.ylow = a.low; t.yhigh = a.high; t.yl = a.l; t.yh = a.h; }
+    }
+    if (k < 14) {
         const int sx = 14 * hq + k;
-        const AxisTap t = axis_tap(rw_sample_coord(g.start_w, g.bin_w, sx >> 1, sx & 1), W);
-        xa.low[k] = -1; xa.high[k] = -1; xa.l[k] = xa.h[k] = 0.f;
-        if (t.valid) {
-            xa.low[k] = t.low; xa.high[k] = t.high; xa.l[k] = t.l; xa.h[k] = t.h;
-            if (t.low == t.high && W >= 2) { xa.low[k] = W - 2; xa.high[k] = W - 1; xa.h[k] = 0.f; xa.l[k] = 1.f; }
+        const AxisTap a = axis_tap(rw_sample_coord(g.start_w, g.bin_w, sx >> 1, sx & 1), W);
+        if (a.valid) {
+            t.xlow = a.low; t.xhigh = a.high; t.xl = a.l; t.xh = a.h;
+            // a sample clamped to the last column (low == high == W-1, weights 1 / 0) becomes (W-2, W-1) with
+            // weights 0 / 1: same value, and the high tap is always "next column"
+            if (a.low == a.high && W >= 2) { t.xlow = W - 2; t.xhigh = W - 1; t.xh = 0.f; t.xl = 1.f; }
         }
     }
-    RwItem* base = items + b;
-    // split kinds in order of increasing piece count
-    const int kinds[12][2] = {{0, 0}, {1, 0}, {0, 1}, {2, 0}, {1, 1}, {2, 1}, {3, 0}, {0, 3}, {3, 1}, {1, 3}, {2, 3}, {3, 3}};
+    {
+        const int ol = __shfl_xor_sync(m, t.ylow, 1, 16), oh = __shfl_xor_sync(m, t.yhigh, 1, 16);
+        t.pfirst = min(t.ylow >= 0 ? t.ylow : 1 << 30, ol >= 0 ? ol : 1 << 30);
+        t.plast = max(t.ylow >= 0 ? t.yhigh : -1, ol >= 0 ? oh : -1);
+    }
+    const int plane0 = g.batch * channels;
+    // split kinds (rows, columns) in order of increasing piece count; the first one whose pieces all run is taken
+    const unsigned char kinds[12][2] = {{0, 0}, {1, 0}, {0, 1}, {2, 0}, {1, 1}, {2, 1}, {3, 0}, {0, 3}, {3, 1}, {1, 3}, {2, 3}, {3, 3}};
     int pk = -1, qk = -1;
     if (W >= 2) {
         for (int c = 0; c < 12 && pk < 0; c++) {
@@ -216,7 +268,7 @@ __device__ __noinline__ void rw_plan_split(RoiGeom g, int H, int W, int nphz, Rw
                     int p0, np, q0, nq;
                     rw_piece(kinds[c][0], nphz, i, p0, np);
                     rw_piece(kinds[c][1], 7, j, q0, nq);
-                    ok = rw_eval(ya, xa, p0, np, q0, nq) >= 0;
+                    ok = rw_eval(t, k, m, p0, np, q0, nq) >= 0;
                 }
             if (ok) { pk = kinds[c][0]; qk = kinds[c][1]; }
         }
@@ -224,146 +276,26 @@ __device__ __noinline__ void rw_plan_split(RoiGeom g, int H, int W, int nphz, Rw
     int cnt = pk < 0 ? 1 : rw_pieces(pk, nphz) * rw_pieces(qk, 7);
     int extra0 = 0;
     if (cnt > 1) {
-        extra0 = atomicAdd(&ctr->n_extra, cnt - 1);
+        if (k == 0) extra0 = atomicAdd(&ctr->n_extra, cnt - 1);
+        extra0 = __shfl_sync(m, extra0, 0, 16);
         if (extra0 + cnt - 1 > cap_extra) {
-            // no room for the pieces: the slots this thread owns are marked to be skipped, the block goes direct
-            for (int k = extra0; k < min(extra0 + cnt - 1, cap_extra); k++) items[nbase + k].variant = RW_SKIP;
+            // no room for the pieces: the slots this block owns are marked to be skipped, the block goes direct
+            for (int e = extra0 + k; e < min(extra0 + cnt - 1, cap_extra); e += 16) items[nbase + e].variant = RW_SKIP;
             pk = -1; cnt = 1;
         }
     }
     if (pk < 0) {
-        rw_write_item(base, ya, xa, RW_DIRECT, 0, nphz, 0, 7, n, out_row, plane0, level, 7 * z, 7 * hq);
+        rw_write_item(items + b, t, k, m, RW_DIRECT, 0, nphz, 0, 7, n, out_row, plane0, level, 7 * z, 7 * hq);
         return;
     }
     const int nq_ = rw_pieces(qk, 7);
-    for (int k = 0; k < cnt; k++) {
+    for (int e = 0; e < cnt; e++) {
         int p0, np, q0, nq;
-        rw_piece(pk, nphz, k / nq_, p0, np);
-        rw_piece(qk, 7, k % nq_, q0, nq);
-        RwItem* it = k == 0 ? base : items + nbase + extra0 + k - 1;
-        rw_write_item(it, ya, xa, rw_eval(ya, xa, p0, np, q0, nq), p0, np, q0, nq, n, out_row, plane0, level, 7 * z, 7 * hq);
+        rw_piece(pk, nphz, e / nq_, p0, np);
+        rw_piece(qk, 7, e % nq_, q0, nq);
+        RwItem* it = e == 0 ? items + b : items + nbase + extra0 + e - 1;
+        rw_write_item(it, t, k, m, rw_eval(t, k, m, p0, np, q0, nq), p0, np, q0, nq, n, out_row, plane0, level, 7 * z, 7 * hq);
     }
-}
-
-__global__ void __maxnreg__(232)
-roialign_rw_plan(const __grid_constant__ LevelTable lv, int channels, int pooled_h, int pooled_w, int num_rois,
-                 const float* __restrict__ rois, const int* __restrict__ roi_level, const int* __restrict__ out_index,
-                 RwItem* __restrict__ items, int nbase, int cap_extra, RwCounters* __restrict__ ctr) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nbase) return;
-    const int T = pooled_w / 7, Z = (pooled_h + 6) / 7;
-    const int n = b / (Z * T), z = (b / T) % Z, hq = b % T;
-    const int level = roi_level ? __ldg(roi_level + n) : 0;
-    const int H = lv.h[level], W = lv.w[level];
-    const RoiGeom g = roi_geometry(rois + 5 * (size_t)n, lv.scale[level], pooled_h, pooled_w, 2);
-    const int out_row = out_index ? __ldg(out_index + n) : n;
-    const int nphz = min(7, pooled_h - 7 * z);
-    // all loops below are fully unrolled with static indices: the tables live in registers on the common path
-    RwAxis ya, xa;
-    int ylo = 1 << 30, yhi = -1, xlo = 1 << 30, xhi = -1;
-#pragma unroll
-    for (int k = 0; k < 14; k++) {
-        ya.low[k] = -1; ya.high[k] = -1; ya.l[k] = ya.h[k] = 0.f;
-        if (k < 2 * nphz) {
-            const int sy = 14 * z + k;
-            const AxisTap t = axis_tap(rw_sample_coord(g.start_h, g.bin_h, sy >> 1, sy & 1), H);
-            if (t.valid) { ya.low[k] = t.low; ya.high[k] = t.high; ya.l[k] = t.l; ya.h[k] = t.h; ylo = min(ylo, t.low); yhi = max(yhi, t.high); }
-        }
-        const int sx = 14 * hq + k;
-        const AxisTap t = axis_tap(rw_sample_coord(g.start_w, g.bin_w, sx >> 1, sx & 1), W);
-        xa.low[k] = -1; xa.high[k] = -1; xa.l[k] = xa.h[k] = 0.f;
-        if (t.valid) {
-            xa.low[k] = t.low; xa.high[k] = t.high; xa.l[k] = t.l; xa.h[k] = t.h;
-            // a sample clamped to the last column (low == high == W-1, weights 1 / 0) becomes (W-2, W-1) with
-            // weights 0 / 1: same value, and the high tap is always "next column"
-            if (t.low == t.high && W >= 2) { xa.low[k] = W - 2; xa.high[k] = W - 1; xa.h[k] = 0.f; xa.l[k] = 1.f; }
-            xlo = min(xlo, xa.low[k]); xhi = max(xhi, xa.high[k]);
-        }
-    }
-    const int plane0 = g.batch * channels;
-    // ---- common paths: the whole 7 x 7 block is one item, or (too many output rows open at once) three items of
-    //      3 + 2 + 2 output rows over the same columns
-    int variant = -1;
-    if (yhi < 0 || xhi < 0) variant = RW_ZERO;
-    else if (W >= 2) variant = rw_variant_of(xhi - (xlo & ~3) + 1);
-    int first[7], last[7];
-#pragma unroll
-    for (int p = 0; p < 7; p++) {
-        first[p] = 1 << 30; last[p] = -1;
-#pragma unroll
-        for (int i = 0; i < 2; i++)
-            if (ya.low[2 * p + i] >= 0) { first[p] = min(first[p], ya.low[2 * p + i]); last[p] = max(last[p], ya.high[2 * p + i]); }
-    }
-    bool whole = variant >= 0 && yhi - ylo + 1 <= kRwMaxRows;
-    if (whole && variant <= RW_V28) {
-        // output rows p and p + S share an accumulator slot: they must never be open at the same texel row
-        const int S = rw_slots_of(variant);
-#pragma unroll
-        for (int p = 0; p < 7; p++) {
-            if (p + 2 < 7 && S == 2) whole = whole && !(last[p] >= 0 && last[p + 2] >= 0 && first[p + 2] <= last[p]);
-            if (p + 3 < 7 && S == 3) whole = whole && !(last[p] >= 0 && last[p + 3] >= 0 && first[p + 3] <= last[p]);
-            if (p + 4 < 7 && S == 4) whole = whole && !(last[p] >= 0 && last[p + 4] >= 0 && first[p + 4] <= last[p]);
-        }
-    }
-    const int x0 = xlo & ~3;
-    // writes the item of output rows [P0, P0 + NP) (static: the tables stay in registers)
-    auto emit = [&](RwItem* it, auto P0c, auto NPc) {
-        constexpr int P0 = decltype(P0c)::value, NP = decltype(NPc)::value;
-        int lo = 1 << 30, hi = -1;
-        unsigned long long lastp1 = 0;
-#pragma unroll
-        for (int p = 0; p < NP; p++)
-            if (last[P0 + p] >= 0) { lo = min(lo, first[P0 + p]); hi = max(hi, last[P0 + p]); }
-#pragma unroll
-        for (int p = 0; p < NP; p++)
-            if (last[P0 + p] >= 0) lastp1 |= (unsigned long long)(last[P0 + p] - lo + 1) << (8 * p);
-        const int var = hi < 0 ? RW_ZERO : variant;
-        int4* o = reinterpret_cast<int4*>(it);
-        o[0] = make_int4(out_row, plane0, level, var);
-        o[1] = make_int4(x0, hi < 0 ? 0 : lo, hi < 0 ? 0 : hi - lo + 1, n);
-        o[2] = make_int4(7 * z + P0, min(NP, nphz - P0), 7 * hq, 7);
-        o[3] = make_int4((int)(unsigned)lastp1, (int)(unsigned)(lastp1 >> 32), 0, 0);
-        if (var == RW_ZERO) return;
-        const int BX = 12 + 8 * var;
-#pragma unroll
-        for (int k = 0; k < 14; k++) {
-            const bool v = k < 2 * NP && ya.low[(2 * P0 + k) % 14] >= 0;
-            o[4 + k] = make_int4(v ? ya.low[(2 * P0 + k) % 14] - lo : -1, v ? ya.high[(2 * P0 + k) % 14] - lo : -1,
-                                 __float_as_int(ya.l[(2 * P0 + k) % 14]), __float_as_int(ya.h[(2 * P0 + k) % 14]));
-        }
-#pragma unroll
-        for (int q = 0; q < 7; q++) {
-            const bool v0 = xa.low[2 * q] >= 0, v1 = xa.low[2 * q + 1] >= 0;
-            o[18 + q] = make_int4(__float_as_int(v0 ? xa.h[2 * q] : 0.f), __float_as_int(v0 ? xa.l[2 * q] : 0.f),
-                                  __float_as_int(v1 ? xa.h[2 * q + 1] : 0.f), __float_as_int(v1 ? xa.l[2 * q + 1] : 0.f));
-        }
-        int xo[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) xo[k] = k < 14 ? (xa.low[k] >= 0 ? 4 * (xa.low[k] - x0) : 4 * BX) : 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) o[25 + k] = make_int4(xo[4 * k], xo[4 * k + 1], xo[4 * k + 2], xo[4 * k + 3]);
-    };
-    using std::integral_constant;
-    if (whole) {
-        emit(items + b, integral_constant<int, 0>(), integral_constant<int, 7>());
-        return;
-    }
-    if (variant >= 0 && variant <= RW_V28 && nphz == 7 && yhi - ylo + 1 <= kRwMaxRows) {
-        // 3 + 2 + 2 output rows: at most S >= 2 rows share ... every piece has <= 3 rows, so slots never collide for
-        // S >= 3; for S == 2 (28-texel boxes) rows p and p + 2 of the 3-row piece must not overlap
-        const bool ok3 = rw_slots_of(variant) >= 3 || !(last[0] >= 0 && last[2] >= 0 && first[2] <= last[0]);
-        if (ok3) {
-            const int e0 = atomicAdd(&ctr->n_extra, 2);
-            if (e0 + 2 <= cap_extra) {
-                emit(items + b, integral_constant<int, 0>(), integral_constant<int, 3>());
-                emit(items + nbase + e0, integral_constant<int, 3>(), integral_constant<int, 2>());
-                emit(items + nbase + e0 + 1, integral_constant<int, 5>(), integral_constant<int, 2>());
-                return;
-            }
-            if (e0 < cap_extra) items[nbase + e0].variant = RW_SKIP;
-        }
-    }
-    rw_plan_split(g, H, W, nphz, items, b, nbase, cap_extra, ctr, n, out_row, plane0, level, z, hq);
 }
 
 // Copy of a level whose row pitch is not a multiple of 16 bytes into a zero-padded one (tensor maps need it).

@@ -482,6 +482,9 @@ def gpu_arm(args, rank, world, local_rank):
         events.clear()
         for _ in range(args.steps):
             events.append([])
+            # the eager step is host-bound (~60 tensor ops + 12 launches): a ~2 ms device-side sleep in front of it lets
+            # the host enqueue the whole step first, so the marks bracket kernels, not launch gaps
+            torch.cuda._sleep(4_000_000)
             out = run_step(mark)
         drain()
         torch.cuda.synchronize()

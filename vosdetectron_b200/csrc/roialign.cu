@@ -1576,8 +1576,10 @@ extern "C" int vosd_roialign_ml_fwd_ws(const float* const* level_data, const int
     a.slabs_per_unit = ceil_div(slabs_all, 1 << split_log2);
     a.top_aligned = aligned16(top_data) ? 1 : 0;
     const size_t dyn = (size_t)kRwWarps * kRwWarpBytes;
-    if (cudaFuncSetAttribute(roialign_fwd_rw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
-        return check_launch() == VOSD_OK ? VOSD_ERR_LAUNCH : VOSD_ERR_LAUNCH;
+    if (cudaFuncSetAttribute(roialign_fwd_rw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) {
+        check_launch();
+        return VOSD_ERR_LAUNCH;
+    }
     const long long units = (long long)nbase << split_log2;
     const int grid = (int)(units < (long long)kNumSMs * kRwWarps ? ceil_div((int)units, kRwWarps) : kNumSMs);
     roialign_fwd_rw<<<grid, kRwThreads, dyn, stream>>>(maps, t, a);

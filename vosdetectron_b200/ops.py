@@ -76,6 +76,21 @@ def roi_align_backward(grad_output, rois, feature_size, aligned_height, aligned_
     return gi
 
 
+# Scratch of the workspace entry points: one grow-only buffer per (device, stream), so that two calls in flight on
+# different streams never share one and a CUDA graph captured after the first call sees a fixed address.
+_WORKSPACES = {}
+
+
+def _workspace(device, nbytes):
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = buf
+    return buf
+
+
 def _level_arrays(tensors, scales):
     L = len(tensors)
     ptrs = (vp * L)(*[t.data_ptr() for t in tensors])
@@ -117,7 +132,7 @@ def roi_align_ml_forward(level_features, level_scales, rois, roi_level, aligned_
         # default: plan kernel + persistent TMA-fed kernel; the scratch comes from the caching allocator
         need = int(_lib.load().vosd_roialign_fwd_workspace_bytes(hs, ws, len(feats), N, C, int(aligned_height),
                                                                  int(aligned_width), R))
-        wsp = torch.empty(max(need, 256), dtype=torch.uint8, device=r.device)
+        wsp = _workspace(r.device, max(need, 256))
         _lib.call("vosd_roialign_ml_fwd_ws", ptrs, hs, ws, sc, len(feats), N, C, int(aligned_height),
                   int(aligned_width), int(sampling_ratio), R, _ptr(r), _ptr(lv), _ptr(oi), _ptr(out), _ptr(wsp),
                   wsp.numel(), _stream())

@@ -289,6 +289,165 @@ def touched_texel_bytes(rois, levels, res, sr, shapes, channels):
     return total
 
 
+# ------------------------------------------------------------------------------------------
+# BASELINE config 4: training step (2 frames / GPU): TRAIN 2000/2000 proposals, collect over the minibatch,
+# box RoIAlign 1024 x 256 x 7 x 7 and mask RoIAlign 256 x 256 x 14 x 14, forward AND backward
+# ------------------------------------------------------------------------------------------
+CFG4_IM_INFO = [[800.0, 1333.0, 1.6667], [800.0, 1067.0, 1.25]]     # train-style per-image true sizes
+CFG4_BOX_ROIS, CFG4_MASK_ROIS = 1024, 256
+
+
+def cfg4_train_step(dev, steps, warmup, seed=4000, with_ref=True):
+    """One GPU's training step of the region path on a COCO-shaped minibatch of 2 frames.  The label assignment
+    between collect and RoIAlign (sampling 512 RoIs per image, fg subset for the mask head) is outside this library:
+    the step takes the first 1024 collected RoIs for the box head and the first 256 of them for the mask head.
+    Returns ms per step, per-stage ms (CUDA events, a device-side sleep in front of every step keeps launch gaps out),
+    the roofline of both RoIAlign backward launches and the unmodified reference kernel (oracle/_ref) timed on the
+    same RoIs in the same run, driven like roi_feature_transform / RoIAlignFunction.backward (one launch per level)."""
+    import ctypes
+    import torch
+    from vosdetectron_b200 import ops, synth
+    from vosdetectron_b200.config import RegionConfig
+    from vosdetectron_b200.pipeline import RegionPipeline
+    blob, B = synth.COCO_BLOB, 2
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    r = synth.rpn_outputs(seed, blob, B)
+    rpn = {l: (cu(r[l][0]), cu(r[l][1])) for l in synth.FPN_LEVELS}
+    feats_h = synth.fpn_features(seed + 1, blob, B, synth.ROI_LEVELS, C_FPN)
+    feats = {l: cu(feats_h[l]) for l in synth.ROI_LEVELS}
+    im_info = cu(np.asarray(CFG4_IM_INFO, np.float32))
+    pipe = RegionPipeline(RegionConfig(), training=True)
+    fl = [feats[l] for l in synth.ROI_LEVELS]
+    sc = [1.0 / 2 ** l for l in synth.ROI_LEVELS]
+    shapes = [tuple(f.shape) for f in fl]
+    gen = torch.Generator(device="cpu").manual_seed(seed + 2)
+    top_box = torch.randn((CFG4_BOX_ROIS, C_FPN, 7, 7), generator=gen).to(dev)
+    top_mask = torch.randn((CFG4_MASK_ROIS, C_FPN, 14, 14), generator=gen).to(dev)
+    names = ["proposals", "collect_distribute", "sample_rois", "roialign_box_fwd", "roialign_box_bwd", "roialign_mask_fwd",
+             "roialign_mask_bwd", "end"]
+
+    def step(mark):
+        mark("proposals")
+        prop = pipe.proposals(rpn, im_info, images_per_group=B, mark=mark)
+        mark("sample_rois")
+        rois = prop["rois"].view(-1, 5)[:CFG4_BOX_ROIS].contiguous()
+        lv = (ops.distribute_cuda(rois)[0] - 2).to(torch.int32)
+        mrois, mlv = rois[:CFG4_MASK_ROIS].contiguous(), lv[:CFG4_MASK_ROIS].contiguous()
+        mark("roialign_box_fwd")
+        bf = ops.roi_align_ml_forward(fl, sc, rois, lv, 7, 7, 2)
+        mark("roialign_box_bwd")
+        gb = ops.roi_align_ml_backward(top_box, shapes, sc, rois, lv, 7, 7, 2)
+        mark("roialign_mask_fwd")
+        mf = ops.roi_align_ml_forward(fl, sc, mrois, mlv, 14, 14, 2)
+        mark("roialign_mask_bwd")
+        gm = ops.roi_align_ml_backward(top_mask, shapes, sc, mrois, mlv, 14, 14, 2)
+        mark("end")
+        return rois, lv, bf, gb, mf, gm
+
+    for _ in range(max(3, warmup)):
+        out = step(lambda n: None)
+    torch.cuda.synchronize()
+    # value: K steps back to back
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = step(lambda n: None)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / steps
+    # stage pass
+    evs = []
+
+    def mark(n):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        evs[-1].append((n, e))
+    for _ in range(steps):
+        evs.append([])
+        torch.cuda._sleep(6_000_000)
+        out = step(mark)
+    torch.cuda.synchronize()
+    stage = {n: 0.0 for n in names[:-1]}
+    for ev in evs:
+        for (n0, a), (_, b) in zip(ev[:-1], ev[1:]):
+            if n0 in stage:
+                stage[n0] += a.elapsed_time(b) / steps
+    rois, lv = out[0], out[1]
+    map_bytes = sum(int(np.prod(s)) * 4 for s in shapes)
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:  # noqa: BLE001
+        pass
+    alg_bwd = {"roialign_box_bwd": top_box.numel() * 4 + map_bytes, "roialign_mask_bwd": top_mask.numel() * 4 + map_bytes}
+    lv_full = (lv + 2).cpu().numpy()
+    lshape = {l: tuple(feats[l].shape[2:]) for l in synth.ROI_LEVELS}
+    alg_fwd = {"roialign_box_fwd": top_box.numel() * 4 + 20 * CFG4_BOX_ROIS
+               + touched_texel_bytes(rois.cpu().numpy(), lv_full, 7, 2, lshape, C_FPN),
+               "roialign_mask_fwd": top_mask.numel() * 4 + 20 * CFG4_MASK_ROIS
+               + touched_texel_bytes(rois[:CFG4_MASK_ROIS].cpu().numpy(), lv_full[:CFG4_MASK_ROIS], 14, 2, lshape, C_FPN)}
+    roof = {}
+    for k, bts in list(alg_bwd.items()) + list(alg_fwd.items()):
+        gbs = bts / (stage[k] * 1e-3) / 1e9 if stage[k] > 0 else None
+        roof[k] = {"ms": stage[k], "algorithmic_bytes": int(bts), "gbs": gbs, "frac": None if gbs is None else gbs / peak}
+    res = {"workload": "cfg4 training step: 2 frames/GPU (blob 800x1344), TRAIN 2000/2000 proposals + collect over the "
+                       "minibatch, box RoIAlign 1024x256x7x7 and mask RoIAlign 256x256x14x14 forward + backward "
+                       "(label assignment outside the library: first 1024 / 256 collected RoIs)",
+           "value": B * 1000.0 / ms_step, "unit": UNIT, "ms_per_step": ms_step, "frames_per_gpu": B,
+           "stages_ms": stage, "roofline": roof, "peak": peak,
+           "bwd_bytes_rule": "read top_diff once + write every gradient texel once (SURVEY 8d cfg 4)"}
+    # ---- the unmodified reference kernel on the same RoIs, driven like the reference's per-level loop
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_roialign.so")
+    if with_ref and os.path.exists(so):
+        lib = ctypes.CDLL(so)
+        vp = ctypes.c_void_p
+        lib.ROIAlignForwardLaucher.argtypes = [vp, ctypes.c_float] + [ctypes.c_int] * 7 + [vp, vp, vp]
+        lib.ROIAlignBackwardLaucher.argtypes = [vp, ctypes.c_float] + [ctypes.c_int] * 8 + [vp, vp, vp]
+        st = torch.cuda.current_stream().cuda_stream
+
+        def ref_pass(rr, ll, top, res_):
+            idx = [torch.nonzero(ll == i).flatten() for i in range(len(fl))]
+            per = [rr[i].contiguous() for i in idx]
+            tops = [top[i].contiguous() for i in idx]
+            outs, grads = [], []
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            for i, f in enumerate(fl):                     # forward: one launch per level + cat + restore
+                o = torch.zeros((per[i].shape[0], C_FPN, res_, res_), device=dev)
+                if per[i].shape[0]:
+                    lib.ROIAlignForwardLaucher(f.data_ptr(), sc[i], per[i].shape[0], f.shape[2], f.shape[3], C_FPN, res_, res_, 2,
+                                               per[i].data_ptr(), o.data_ptr(), st)
+                outs.append(o)
+            shuffled = torch.cat(outs)
+            restore = torch.argsort(torch.cat(idx))
+            _ = shuffled[restore]
+            b.record()
+            for i, f in enumerate(fl):                     # backward: zero-filled maps + one launch per level
+                g = torch.zeros_like(f)
+                if per[i].shape[0]:
+                    lib.ROIAlignBackwardLaucher(tops[i].data_ptr(), sc[i], f.shape[0], per[i].shape[0], f.shape[2], f.shape[3],
+                                                C_FPN, res_, res_, 2, per[i].data_ptr(), g.data_ptr(), st)
+                grads.append(g)
+            c.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b), b.elapsed_time(c)
+        ref = {}
+        for name, rr, ll, top, res_ in (("box", rois, lv, top_box, 7),
+                                        ("mask", rois[:CFG4_MASK_ROIS], lv[:CFG4_MASK_ROIS], top_mask, 14)):
+            for _ in range(2):
+                ref_pass(rr, ll, top, res_)
+            ts = []
+            for _ in range(max(5, steps // 2)):
+                torch.cuda._sleep(4_000_000)
+                ts.append(ref_pass(rr, ll, top, res_))
+            ref["roialign_%s_fwd_ms" % name] = float(np.median([t[0] for t in ts]))
+            ref["roialign_%s_bwd_ms" % name] = float(np.median([t[1] for t in ts]))
+        ref["how"] = ("oracle/_ref/libref_roialign.so = the unmodified roi_align_kernel.cu built for sm_100a; per-level launches + "
+                      "cat + restore (forward), zero-filled maps + per-level launches (backward), as the reference drives it")
+        res["ref_gpu_kernel"] = ref
+    return res
+
+
 def gpu_arm(args, rank, world, local_rank):
     # CPU baseline first (fork-based pool before any CUDA context exists in this process)
     cpu_baseline = None
@@ -567,6 +726,12 @@ def gpu_arm(args, rank, world, local_rank):
                "ms_per_step": alt_ms / args.steps,
                "stages_ms": {n: v / args.steps for n, v in alt_stage.items()}}
         d_feats = keep
+    train = None
+    if world == 1:
+        try:
+            train = cfg4_train_step(dev, max(5, min(args.steps, 20)), args.warmup)
+        except Exception as exc:  # noqa: BLE001
+            print("cfg4 training-step leg failed (%s: %s)" % (type(exc).__name__, str(exc)[:300]), file=sys.stderr)
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -635,6 +800,8 @@ def gpu_arm(args, rank, world, local_rank):
     }
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
+    if train is not None:
+        line["train_step_cfg4"] = train
     if alt is not None:
         # achieved bytes/s of the box RoIAlign with the maps in the other memory order (same algorithmic bytes)
         if alt["stages_ms"].get("roialign_box"):

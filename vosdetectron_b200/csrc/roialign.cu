@@ -996,189 +996,8 @@ roialign_bwd_records(const __grid_constant__ LevelTable lv, int channels, int po
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// Tile-owner backward ("write once"): the gradient maps are cut into 16x32-texel tiles; a CTA owns one
-// tile x 32-channel slab, accumulates in shared memory the contributions of EVERY RoI whose footprint
-// overlaps the tile, and then writes the tile to HBM with plain coalesced stores.  No global atomics, no
-// memset (every texel is written exactly once: zero or sum), deterministic summation order, and the
-// reduction traffic drops from 16 L2 atomics per output element to shared-memory read-modify-writes.
-//   K_a bwd_prep_kernel : per RoI, the per-axis tap tables (same arithmetic as forward) + texel extents
-//   K_b bwd_bin_kernel  : per tile, the ordered list of RoIs overlapping it (block-wide stable compaction)
-//   K_c bwd_tile_kernel : per (tile, slab chunk): lanes = channels, each warp owns 2 tile rows -> plain RMW
-// Every addend is computed exactly like the reference's (top * (wy*wx)) / count.
-// ---------------------------------------------------------------------------------------
-constexpr int kTileH = 16, kTileW = 32;       // kTileH * kTileW == kTileWords
-
-struct BwdTiling {
-    int tiles_y[VOSD_MAX_LEVELS], tiles_x[VOSD_MAX_LEVELS], base[VOSD_MAX_LEVELS + 1];   // base: first tile id of a level
-    int num_levels, batch;
-};
-struct __align__(16) BwdRoiInfo { int level, batch, y0, y1, x0, x1, gh, gw; };   // extents inclusive; y1 < y0: empty
-
-// K_a.  grid = R, block = 128.
-__global__ void __launch_bounds__(128)
-bwd_prep_kernel(const __grid_constant__ LevelTable lv, int pooled_h, int pooled_w, int sampling_ratio,
-                const float* __restrict__ rois, const int* __restrict__ roi_level, int ny, int nx,
-                BwdRoiInfo* __restrict__ info, Tap* __restrict__ ytabs, Tap* __restrict__ xtabs) {
-    const int n = blockIdx.x, tid = threadIdx.x;
-    const int l = roi_level ? roi_level[n] : 0;
-    const int H = lv.h[l], W = lv.w[l];
-    const RoiGeom g = roi_geometry(rois + 5 * (size_t)n, lv.scale[l], pooled_h, pooled_w, sampling_ratio);
-    __shared__ Tap sy[kMaxTaps], sx[kMaxTaps];
-    if (tid < ny) {
-        const AxisTap t = axis_tap(sample_coord(g.start_h, g.bin_h, tid / g.grid_h, tid % g.grid_h, g.grid_h), H);
-        sy[tid] = Tap{t.valid ? t.low : -1, t.high, t.l, t.h};
-        ytabs[(size_t)n * ny + tid] = sy[tid];
-    } else if (tid >= 64 && tid < 64 + nx) {
-        const int k = tid - 64;
-        const AxisTap t = axis_tap(sample_coord(g.start_w, g.bin_w, k / g.grid_w, k % g.grid_w, g.grid_w), W);
-        sx[k] = Tap{t.valid ? t.low : -1, t.high, t.l, t.h};
-        xtabs[(size_t)n * nx + k] = sx[k];
-    }
-    __syncthreads();
-    if (tid == 0) {
-        BwdRoiInfo r;
-        r.level = l; r.batch = g.batch; r.gh = g.grid_h; r.gw = g.grid_w;
-        r.y0 = 1 << 30; r.y1 = -1; r.x0 = 1 << 30; r.x1 = -1;
-        for (int k = 0; k < ny; k++) if (sy[k].low >= 0) { r.y0 = min(r.y0, sy[k].low); r.y1 = max(r.y1, sy[k].high); }
-        for (int k = 0; k < nx; k++) if (sx[k].low >= 0) { r.x0 = min(r.x0, sx[k].low); r.x1 = max(r.x1, sx[k].high); }
-        if (r.x1 < r.x0) { r.y0 = 1 << 30; r.y1 = -1; }          // no valid column: contributes nothing
-        info[n] = r;
-    }
-}
-
-// K_b.  grid = tiles, block = 256.  list[tile*cap ..] = RoIs overlapping the tile, ascending RoI index.
-__global__ void __launch_bounds__(256)
-bwd_bin_kernel(const __grid_constant__ BwdTiling tl, const BwdRoiInfo* __restrict__ info, int num_rois, int cap,
-               int* __restrict__ list, int* __restrict__ list_count) {
-    const int tile = blockIdx.x;
-    int l = 0;
-    while (l + 1 < tl.num_levels && tile >= tl.base[l + 1]) l++;
-    const int rel = tile - tl.base[l];
-    const int per_img = tl.tiles_y[l] * tl.tiles_x[l];
-    const int img = rel / per_img, ty = (rel % per_img) / tl.tiles_x[l], tx = rel % tl.tiles_x[l];
-    const int y0 = ty * kTileH, y1 = y0 + kTileH - 1, x0 = tx * kTileW, x1 = x0 + kTileW - 1;
-    __shared__ int warp_cnt[8];
-    __shared__ int base_s;
-    if (threadIdx.x == 0) base_s = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int n0 = 0; n0 < num_rois; n0 += 256) {
-        const int n = n0 + threadIdx.x;
-        bool hit = false;
-        if (n < num_rois) {
-            const BwdRoiInfo r = info[n];
-            hit = r.level == l && r.batch == img && r.y1 >= y0 && r.y0 <= y1 && r.x1 >= x0 && r.x0 <= x1;
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) warp_cnt[warp] = __popc(bal);
-        __syncthreads();
-        int off = base_s;
-        for (int w = 0; w < warp; w++) off += warp_cnt[w];
-        if (hit) list[(size_t)tile * cap + off + __popc(bal & ((1u << lane) - 1u))] = n;
-        __syncthreads();
-        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += warp_cnt[w]; base_s += t; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) list_count[tile] = base_s;
-}
-
-// K_c.  grid = (tiles, slab chunks), block = 256, dyn smem = acc tile + gbuf + tables.
-__global__ void __launch_bounds__(256, 2)
-bwd_tile_kernel(const __grid_constant__ LevelTable lv, const __grid_constant__ BwdTiling tl, int channels,
-                int pooled_h, int pooled_w, int ny, int nx, int slabs_per_cta, int gstride,
-                const BwdRoiInfo* __restrict__ info, const Tap* __restrict__ ytabs, const Tap* __restrict__ xtabs,
-                const int* __restrict__ list, const int* __restrict__ list_count, int cap,
-                const int* __restrict__ out_index, const float* __restrict__ top_diff) {
-    extern __shared__ __align__(16) unsigned char dyn_t[];
-    float* acc = reinterpret_cast<float*>(dyn_t);                                   // [32][512], word (t ^ c)
-    float* gbuf = acc + kSlab * kTileWords;                                         // [32][gstride]
-    Tap* ytab = reinterpret_cast<Tap*>(gbuf + kSlab * gstride);                     // [ny]
-    Tap* xtab = ytab + kMaxTaps;                                                    // [nx]
-
-    const int tile = blockIdx.x;
-    int l = 0;
-    while (l + 1 < tl.num_levels && tile >= tl.base[l + 1]) l++;
-    const int rel = tile - tl.base[l];
-    const int per_img = tl.tiles_y[l] * tl.tiles_x[l];
-    const int img = rel / per_img, ty = (rel % per_img) / tl.tiles_x[l], tx = rel % tl.tiles_x[l];
-    const int H = lv.h[l], W = lv.w[l];
-    const int y0 = ty * kTileH, x0 = tx * kTileW;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bins = pooled_h * pooled_w;
-    const int nroi = list_count[tile];
-    const int* my = list + (size_t)tile * cap;
-    float* accl = acc + lane * kTileWords;
-    const float* gl = gbuf + lane * gstride;
-    const size_t plane = (size_t)H * W;
-
-    for (int k = 0; k < slabs_per_cta; k++) {
-        const int c0 = (blockIdx.y * slabs_per_cta + k) * kSlab;
-        if (c0 >= channels) break;
-        const int nch = min(kSlab, channels - c0);
-        for (int i = tid; i < kSlab * kTileWords; i += 256) acc[i] = 0.f;
-        for (int j = 0; j < nroi; j++) {
-            const int n = my[j];
-            const BwdRoiInfo ri = info[n];
-            __syncthreads();                                    // previous RoI done with gbuf / tables (and acc zeroed)
-            // top_diff of this RoI for the slab -> gbuf[c][bin]; its tap tables -> shared memory
-            const int row = out_index ? out_index[n] : n;
-            const float* tsrc = top_diff + ((size_t)row * channels + c0) * bins;
-            for (int e = tid; e < nch * bins; e += 256) {
-                const int c = e / bins;
-                gbuf[c * gstride + (e - c * bins)] = __ldg(tsrc + e);
-            }
-            if (tid < ny) ytab[tid] = ytabs[(size_t)n * ny + tid];
-            else if (tid >= 64 && tid < 64 + nx) xtab[tid - 64] = xtabs[(size_t)n * nx + tid - 64];
-            __syncthreads();
-            const int gh = ri.gh, gw = ri.gw;
-            const int icount = gh * gw;
-            const bool pow2 = (icount & (icount - 1)) == 0;
-            const float count = (float)icount, inv_count = 1.0f / count;
-            // each warp owns tile rows warp and warp + 8: plain read-modify-write, no atomics
-            for (int rr = warp; rr < kTileH; rr += 8) {
-                const int y = y0 + rr;
-                for (int sy = 0; sy < ny; sy++) {
-                    const Tap t = ytab[sy];
-                    if (t.low < 0 || (t.low != y && t.high != y)) continue;          // uniform
-                    const int binrow = (sy / gh) * pooled_w;
-                    for (int half = 0; half < 2; half++) {
-                        if ((half == 0 ? t.low : t.high) != y) continue;
-                        const float wy = half == 0 ? t.h : t.l;
-                        for (int sx = 0; sx < nx; sx++) {
-                            const Tap u = xtab[sx];
-                            if (u.low < 0) continue;
-                            const int xl = u.low - x0, xh = u.high - x0;
-                            if (xh < 0 || xl >= kTileW) continue;
-                            const float tv = gl[binrow + sx / gw];
-                            if (xl >= 0) {
-                                const float a = __fmul_rn(tv, __fmul_rn(wy, u.h));
-                                const int i = (rr * kTileW + xl) ^ lane;
-                                accl[i] = __fadd_rn(accl[i], pow2 ? __fmul_rn(a, inv_count) : __fdiv_rn(a, count));
-                            }
-                            if (xh < kTileW) {
-                                const float a = __fmul_rn(tv, __fmul_rn(wy, u.l));
-                                const int i = (rr * kTileW + xh) ^ lane;
-                                accl[i] = __fadd_rn(accl[i], pow2 ? __fmul_rn(a, inv_count) : __fdiv_rn(a, count));
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // write the finished tile: lanes along x, one coalesced 128-byte row per (channel, tile row)
-        float* dst = lv.data[l] + ((size_t)img * channels + c0) * plane;
-        for (int e = warp; e < nch * kTileH; e += 8) {
-            const int c = e / kTileH, rr = e - c * kTileH;
-            const int y = y0 + rr, x = x0 + lane;
-            if (y < H && x < W) dst[(size_t)c * plane + (size_t)y * W + x] = acc[c * kTileWords + ((rr * kTileW + lane) ^ c)];
-        }
-        __syncthreads();
-    }
-}
-
 }  // namespace vosd
+
 #include "roialign_sep.cuh"
 #include "roialign_nhwc.cuh"
 #include "roialign_rw.cuh"

@@ -21,7 +21,8 @@
 //     R[pw] = sum of 4 taps wx * V[x]  ->  obuf[c][ph][pw]  ->  one bulk store per slab (7x7 head).
 //   Per (RoI, slab) with the bench's 12x12-texel footprints: ~1100 instructions and ~480 LSU wavefronts.
 // Non-finite features propagate exactly as in the reference: a texel enters a bin iff it is one of the 4 taps of a
-// valid sample of that bin (zero weights included: a tap with weight 0 is stored as -0.0f, which still multiplies).
+// valid sample of that bin (zero weights included: a tap with weight 0 is stored as -0.0f, which still multiplies;
+// tests/test_gpu_ext_shims.py::test_non_finite_texels_follow_the_reference).
 #pragma once
 #include <cuda.h>
 #include <type_traits>
@@ -397,8 +398,14 @@ __device__ __forceinline__ void rw_process(const RwArgs& a, const CUtensorMap* m
             if (t.low >= 0) {
                 const unsigned sl = (unsigned)(lane % S);
                 const unsigned al = wrow_s + 4u * ((unsigned)t.low * SW + sl), ah = wrow_s + 4u * ((unsigned)t.high * SW + sl);
-                sts_f32(al, lds_off(al) + 0.25f * t.h);
-                if (t.high != t.low) sts_f32(ah, lds_off(ah) + 0.25f * t.l);
+                // a tap whose weight is zero is stored as -0.0f: "entered, still multiplies" (the reference multiplies all
+                // four taps of a valid sample, so 0 * NaN reaches the bin there too); +0.0f = the row does not enter the slot
+                float v = lds_off(al) + 0.25f * t.h;
+                sts_f32(al, v == 0.f ? -0.f : v);
+                if (t.high != t.low) {
+                    v = lds_off(ah) + 0.25f * t.l;
+                    sts_f32(ah, v == 0.f ? -0.f : v);
+                }
             }
         }
         __syncwarp();
@@ -464,12 +471,14 @@ __device__ __forceinline__ void rw_process(const RwArgs& a, const CUtensorMap* m
                 if (++fr == th) { fr = 0; fs++; }
             }
             if (++slot == NS) slot = 0;
-            // every slot, every row: rows that do not enter a slot carry weight 0 (no branch, no mask)
+            // a row enters a slot iff its table entry is not +0.0f (warp-uniform: every lane reads the same word)
 #pragma unroll
             for (int s = 0; s < S; s++) {
-                const float2 w2 = make_float2(w[s], w[s]);
+                if (__float_as_uint(w[s]) != 0u) {
+                    const float2 w2 = make_float2(w[s], w[s]);
 #pragma unroll
-                for (int x = 0; x < BX / 2; x++) V[s][x] = __ffma2_rn(w2, f[x], V[s][x]);
+                    for (int x = 0; x < BX / 2; x++) V[s][x] = __ffma2_rn(w2, f[x], V[s][x]);
+                }
             }
             // ---- output rows whose last texel row this was (or that have no valid sample at all)
             while (p < nph && nxt <= r + 1) {

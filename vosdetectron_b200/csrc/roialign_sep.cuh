@@ -584,7 +584,9 @@ roialign_bwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
     for (int i = tid; i < 32 * 8 * T; i += kSepThreads) sh.ax[i] = 0.f;
     // 7x7 head: the first slab's top_diff (32 * 49 contiguous floats per team) is requested before anything
     // else, so its latency hides behind the setup
-    if (T == 1 && pooled_h == NPH && warp < kSepWarps) {
+    // (16-byte cp.async: only when top_diff is 16-byte aligned; a 4-byte aligned pointer takes the scalar fetch below)
+    const bool td_aligned = (reinterpret_cast<uintptr_t>(top_diff) & 15) == 0;
+    if (T == 1 && pooled_h == NPH && td_aligned && warp < kSepWarps) {
         const int s_first = blockIdx.y * slabs_per_cta + warp;
         if (s_first < channels / kSlab && s_first < (blockIdx.y + 1) * slabs_per_cta) {
             const float* src = top_diff + ((size_t)row * channels + (size_t)s_first * kSlab) * bins;
@@ -783,7 +785,7 @@ roialign_bwd_sep(const __grid_constant__ LevelTable lv, int channels, int pooled
     const unsigned wy_s = (unsigned)__cvta_generic_to_shared(sh.wy);
     const unsigned ax_s = (unsigned)__cvta_generic_to_shared(sh.ax) + 32u * (unsigned)sub;
     const int run = nph * PW;
-    const bool contiguous = T == 1 && pooled_h == NPH;  // 7x7 head: a slab's top_diff is 32 * 49 contiguous floats
+    const bool contiguous = T == 1 && pooled_h == NPH && td_aligned;  // 7x7 head: a slab's top_diff is 32 * 49 contiguous floats
     // top_diff of slab s -> ibuf[buf][c][bin]
     auto fetch = [&](int s, int buf, bool async) {
         const float* src = top_roi + (size_t)(s - slab0) * kSlab * bins;

@@ -30,10 +30,10 @@ def roi_align_forward_cuda(aligned_height, aligned_width, spatial_scale, samplin
     if rois.dim() != 2 or rois.size(1) != 5:
         return 0                                                    # roi_align_cuda.c:15-18
     N, C, H, W = features.size()
-    _lib.call("vosd_set_device", features.device.index)
-    _lib.call("vosd_roialign_fwd", _p(features), float(spatial_scale), rois.size(0), H, W, C, int(aligned_height),
-              int(aligned_width), int(sampling_ratio), _p(rois), _p(output),
-              ctypes.c_void_p(torch.cuda.current_stream(features.device).cuda_stream))
+    with torch.cuda.device(features.device):                     # the caller's current device is restored on exit
+        _lib.call("vosd_roialign_fwd", _p(features), float(spatial_scale), rois.size(0), H, W, C, int(aligned_height),
+                  int(aligned_width), int(sampling_ratio), _p(rois), _p(output),
+                  ctypes.c_void_p(torch.cuda.current_stream(features.device).cuda_stream))
     return 1
 
 
@@ -42,8 +42,8 @@ def roi_align_backward_cuda(aligned_height, aligned_width, spatial_scale, sampli
     if rois.dim() != 2 or rois.size(1) != 5:
         return 0                                                    # roi_align_cuda.c:51-54
     N, C, H, W = bottom_grad.size()
-    _lib.call("vosd_set_device", top_grad.device.index)
-    _lib.call("vosd_roialign_bwd", _p(top_grad), float(spatial_scale), N, rois.size(0), H, W, C, int(aligned_height),
-              int(aligned_width), int(sampling_ratio), _p(rois), _p(bottom_grad), 0,      # 0: the caller zero-filled
-              ctypes.c_void_p(torch.cuda.current_stream(top_grad.device).cuda_stream))
+    with torch.cuda.device(top_grad.device):                     # the caller's current device is restored on exit
+        _lib.call("vosd_roialign_bwd", _p(top_grad), float(spatial_scale), N, rois.size(0), H, W, C, int(aligned_height),
+                  int(aligned_width), int(sampling_ratio), _p(rois), _p(bottom_grad), 0,      # 0: the caller zero-filled
+                  ctypes.c_void_p(torch.cuda.current_stream(top_grad.device).cuda_stream))
     return 1

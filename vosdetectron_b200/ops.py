@@ -32,8 +32,11 @@ def _need_cuda(t, name, dtype=torch.float32):
     return t.contiguous()
 
 
-def _bind(t):
-    _lib.call("vosd_set_device", t.device.index if t.device.index is not None else torch.cuda.current_device())
+def _on(t):
+    """Context of a library call: the tensor's device is current (for torch AND for the library's CUDA runtime: both
+    read cudaGetDevice), so `_stream()` is the current stream OF THAT DEVICE, and the caller's device is restored on
+    exit.  Tensors on a non-current GPU therefore launch on their own device behind their own producer."""
+    return torch.cuda.device(t.device)
 
 
 # ----------------------------------------------------------------------------- RoIAlign
@@ -70,10 +73,10 @@ def roi_align_backward(grad_output, rois, feature_size, aligned_height, aligned_
     r = _need_cuda(rois, "rois")
     N, C, H, W = (int(v) for v in feature_size)
     gi = torch.empty((N, C, H, W), dtype=torch.float32, device=g.device)
-    _bind(g)
-    _lib.call("vosd_roialign_bwd", _ptr(g), float(spatial_scale), N, r.size(0), H, W, C,
-              int(aligned_height), int(aligned_width), int(sampling_ratio), _ptr(r), _ptr(gi), 1, _stream())
-    return gi
+    with _on(g):
+        _lib.call("vosd_roialign_bwd", _ptr(g), float(spatial_scale), N, r.size(0), H, W, C,
+                  int(aligned_height), int(aligned_width), int(sampling_ratio), _ptr(r), _ptr(gi), 1, _stream())
+        return gi
 
 
 # Scratch of the workspace entry points: one grow-only buffer per (device, stream), so that two calls in flight on
@@ -117,44 +120,44 @@ def roi_align_ml_forward(level_features, level_scales, rois, roi_level, aligned_
             raise ValueError("all levels must share batch size and channel count")
         out = torch.empty((R, C, aligned_height, aligned_width), dtype=torch.float32, device=r.device)
         ptrs, hs, ws, sc = _level_arrays(level_features, level_scales)
-        _bind(r)
-        _lib.call("vosd_roialign_ml_fwd_nhwc", ptrs, hs, ws, sc, len(level_features), N, C, int(aligned_height),
-                  int(aligned_width), int(sampling_ratio), R, _ptr(r), _ptr(lv), _ptr(oi), _ptr(out), _stream())
-        return out
+        with _on(r):
+            _lib.call("vosd_roialign_ml_fwd_nhwc", ptrs, hs, ws, sc, len(level_features), N, C, int(aligned_height),
+                      int(aligned_width), int(sampling_ratio), R, _ptr(r), _ptr(lv), _ptr(oi), _ptr(out), _stream())
+            return out
     feats = [_need_cuda(f, "level_features[%d]" % i) for i, f in enumerate(level_features)]
     N, C = (int(v) for v in feats[0].shape[:2])
     if any(tuple(f.shape[:2]) != (N, C) for f in feats):
         raise ValueError("all levels must share batch size and channel count")
     out = torch.empty((R, C, aligned_height, aligned_width), dtype=torch.float32, device=r.device)
     ptrs, hs, ws, sc = _level_arrays(feats, level_scales)
-    _bind(r)
-    if len(feats) <= 4:
-        # default: plan kernel + persistent TMA-fed kernel; the scratch comes from the caching allocator
-        need = int(_lib.load().vosd_roialign_fwd_workspace_bytes(hs, ws, len(feats), N, C, int(aligned_height),
-                                                                 int(aligned_width), R))
-        wsp = _workspace(r.device, max(need, 256))
-        _lib.call("vosd_roialign_ml_fwd_ws", ptrs, hs, ws, sc, len(feats), N, C, int(aligned_height),
-                  int(aligned_width), int(sampling_ratio), R, _ptr(r), _ptr(lv), _ptr(oi), _ptr(out), _ptr(wsp),
-                  wsp.numel(), _stream())
+    with _on(r):
+        if len(feats) <= 4:
+            # default: plan kernel + persistent TMA-fed kernel; the scratch comes from the caching allocator
+            need = int(_lib.load().vosd_roialign_fwd_workspace_bytes(hs, ws, len(feats), N, C, int(aligned_height),
+                                                                     int(aligned_width), R))
+            wsp = _workspace(r.device, max(need, 256))
+            _lib.call("vosd_roialign_ml_fwd_ws", ptrs, hs, ws, sc, len(feats), N, C, int(aligned_height),
+                      int(aligned_width), int(sampling_ratio), R, _ptr(r), _ptr(lv), _ptr(oi), _ptr(out), _ptr(wsp),
+                      wsp.numel(), _stream())
+            return out
+        _lib.call("vosd_roialign_ml_fwd", ptrs, hs, ws, sc, len(feats), C, int(aligned_height), int(aligned_width),
+                  int(sampling_ratio), R, _ptr(r), _ptr(lv), _ptr(oi), _ptr(out), _stream())
         return out
-    _lib.call("vosd_roialign_ml_fwd", ptrs, hs, ws, sc, len(feats), C, int(aligned_height), int(aligned_width),
-              int(sampling_ratio), R, _ptr(r), _ptr(lv), _ptr(oi), _ptr(out), _stream())
-    return out
 
 
 def roi_align_ml_backward(grad_output, level_shapes, level_scales, rois, roi_level, aligned_height,
                           aligned_width, sampling_ratio, out_index=None):
     g = _need_cuda(grad_output, "grad_output")
     r = _need_cuda(rois, "rois")
-    lv = _need_cuda(roi_level, "roi_level", torch.int32)
+    lv = None if roi_level is None else _need_cuda(roi_level, "roi_level", torch.int32)
     oi = None if out_index is None else _need_cuda(out_index, "out_index", torch.int32)
     grads = [torch.empty(tuple(int(v) for v in s), dtype=torch.float32, device=g.device) for s in level_shapes]
     N, C = grads[0].shape[:2]
     ptrs, hs, ws, sc = _level_arrays(grads, level_scales)
-    _bind(g)
-    _lib.call("vosd_roialign_ml_bwd", _ptr(g), ptrs, hs, ws, sc, len(grads), N, C, int(aligned_height),
-              int(aligned_width), int(sampling_ratio), r.size(0), _ptr(r), _ptr(lv), _ptr(oi), 1, _stream())
-    return grads
+    with _on(g):
+        _lib.call("vosd_roialign_ml_bwd", _ptr(g), ptrs, hs, ws, sc, len(grads), N, C, int(aligned_height),
+                  int(aligned_width), int(sampling_ratio), r.size(0), _ptr(r), _ptr(lv), _ptr(oi), 1, _stream())
+        return grads
 
 
 # ----------------------------------------------------------------------------- FlowAlign
@@ -175,9 +178,9 @@ def flow_align_forward(features, flows):
     f, fl = _flow_pair(features, flows)
     N, C, H, W = f.shape
     out = torch.empty_like(f)
-    _bind(f)
-    _lib.call("vosd_flow_align_fwd", N, H, W, C, _ptr(f), _ptr(fl), _ptr(out), _stream())
-    return out
+    with _on(f):
+        _lib.call("vosd_flow_align_fwd", N, H, W, C, _ptr(f), _ptr(fl), _ptr(out), _stream())
+        return out
 
 
 def flow_align_backward(grad_output, features, flows, want_flow_grad=True):
@@ -191,9 +194,9 @@ def flow_align_backward(grad_output, features, flows, want_flow_grad=True):
     N, C, H, W = f.shape
     gf = torch.empty_like(f)
     gfl = torch.empty_like(fl) if want_flow_grad else None
-    _bind(f)
-    _lib.call("vosd_flow_align_bwd", N, H, W, C, _ptr(g), _ptr(f), _ptr(fl), _ptr(gf), _ptr(gfl), 1, _stream())
-    return gf, gfl
+    with _on(f):
+        _lib.call("vosd_flow_align_bwd", N, H, W, C, _ptr(g), _ptr(f), _ptr(fl), _ptr(gf), _ptr(gfl), 1, _stream())
+        return gf, gfl
 
 
 def _ptr_table(tensors):
@@ -213,10 +216,10 @@ def flow_align_ml_forward(level_features, level_flows):
     L = len(pairs)
     hs = (ctypes.c_int * L)(*[int(f.shape[2]) for f, _ in pairs])
     ws = (ctypes.c_int * L)(*[int(f.shape[3]) for f, _ in pairs])
-    _bind(pairs[0][0])
-    _lib.call("vosd_flow_align_ml_fwd", L, N, C, hs, ws, _ptr_table([f for f, _ in pairs]),
-              _ptr_table([fl for _, fl in pairs]), _ptr_table(outs), _stream())
-    return outs
+    with _on(pairs[0][0]):
+        _lib.call("vosd_flow_align_ml_fwd", L, N, C, hs, ws, _ptr_table([f for f, _ in pairs]),
+                  _ptr_table([fl for _, fl in pairs]), _ptr_table(outs), _stream())
+        return outs
 
 
 def flow_align_ml_backward(level_grads, level_features, level_flows, want_flow_grad=True):
@@ -230,11 +233,11 @@ def flow_align_ml_backward(level_grads, level_features, level_flows, want_flow_g
     L = len(pairs)
     hs = (ctypes.c_int * L)(*[int(f.shape[2]) for f, _ in pairs])
     ws = (ctypes.c_int * L)(*[int(f.shape[3]) for f, _ in pairs])
-    _bind(pairs[0][0])
-    _lib.call("vosd_flow_align_ml_bwd", L, N, C, hs, ws, _ptr_table(grads), _ptr_table([f for f, _ in pairs]),
-              _ptr_table([fl for _, fl in pairs]), _ptr_table(gfs), None if gfls is None else _ptr_table(gfls), 1,
-              _stream())
-    return gfs, gfls
+    with _on(pairs[0][0]):
+        _lib.call("vosd_flow_align_ml_bwd", L, N, C, hs, ws, _ptr_table(grads), _ptr_table([f for f, _ in pairs]),
+                  _ptr_table([fl for _, fl in pairs]), _ptr_table(gfs), None if gfls is None else _ptr_table(gfls), 1,
+                  _stream())
+        return gfs, gfls
 
 
 # ----------------------------------------------------------------------------- proposals
@@ -283,11 +286,11 @@ def generate_proposals_cuda(level_inputs, im_info, pre_nms_topN, post_nms_topN, 
     rois = torch.zeros((L, N, cap, 5), dtype=torch.float32, device=dev)
     probs = torch.zeros((L, N, cap), dtype=torch.float32, device=dev)
     count = torch.empty((L, N), dtype=torch.int32, device=dev)
-    _bind(info)
-    _lib.call("vosd_generate_proposals", arr, L, N, _ptr(info), int(pre_nms_topN), int(post_nms_topN),
-              float(nms_thresh), float(min_size), _ptr(rois), _ptr(probs), _ptr(count),
-              _ptr(workspace), workspace.numel(), _stream())
-    return rois, probs, count
+    with _on(info):
+        _lib.call("vosd_generate_proposals", arr, L, N, _ptr(info), int(pre_nms_topN), int(post_nms_topN),
+                  float(nms_thresh), float(min_size), _ptr(rois), _ptr(probs), _ptr(count),
+                  _ptr(workspace), workspace.numel(), _stream())
+        return rois, probs, count
 
 
 def decode_anchors_cuda(deltas, anchors, feat_stride, im_info):
@@ -304,18 +307,18 @@ def decode_anchors_cuda(deltas, anchors, feat_stride, im_info):
     for k, v in enumerate(np.ascontiguousarray(anchors, dtype=np.float64).ravel()):
         lvl[0].anchors[k] = v
     out = torch.empty((N, H * W * A, 4), dtype=torch.float32, device=dl.device)
-    _bind(dl)
-    _lib.call("vosd_decode_anchors", lvl, N, _ptr(info), _ptr(out), _stream())
-    return out
+    with _on(dl):
+        _lib.call("vosd_decode_anchors", lvl, N, _ptr(info), _ptr(out), _stream())
+        return out
 
 
 def any_nan_cuda(t):
     """Device int32 flag tensor (1 element): 1 if any NaN (generate_proposals.py:62-63)."""
     x = _need_cuda(t, "tensor")
     flag = torch.zeros(1, dtype=torch.int32, device=x.device)
-    _bind(x)
-    _lib.call("vosd_any_nan", _ptr(x), x.numel(), _ptr(flag), _stream())
-    return flag
+    with _on(x):
+        _lib.call("vosd_any_nan", _ptr(x), x.numel(), _ptr(flag), _stream())
+        return flag
 
 
 # ----------------------------------------------------------------------------- NMS
@@ -330,9 +333,9 @@ def nms_cuda(dets, thresh):
     num = torch.empty(1, dtype=torch.int32, device=d.device)
     nbytes = _lib.load().vosd_nms_workspace_bytes(n)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=d.device)
-    _bind(d)
-    _lib.call("vosd_nms", _ptr(d), n, float(np.float32(thresh)), _ptr(keep), _ptr(num), _ptr(ws), nbytes, _stream())
-    return keep, num
+    with _on(d):
+        _lib.call("vosd_nms", _ptr(d), n, float(np.float32(thresh)), _ptr(keep), _ptr(num), _ptr(ws), nbytes, _stream())
+        return keep, num
 
 
 # ----------------------------------------------------------------------------- collect / distribute
@@ -355,12 +358,12 @@ def collect_distribute_cuda(rois, probs, count, post_nms_topN, images_per_group=
         "order": torch.zeros((G, post), dtype=torch.int32, device=dev),
         "restore": torch.zeros((G, post), dtype=torch.int32, device=dev),
     }
-    _bind(r)
-    _lib.call("vosd_collect_distribute", _ptr(r), _ptr(p), _ptr(c), L, N, cap, int(images_per_group), post,
-              int(k_min), int(k_max), float(canonical_scale), int(canonical_level),
-              _ptr(out["rois"]), _ptr(out["count"]), _ptr(out["level"]), _ptr(out["level_count"]),
-              _ptr(out["order"]), _ptr(out["restore"]), None, 0, _stream())
-    return out
+    with _on(r):
+        _lib.call("vosd_collect_distribute", _ptr(r), _ptr(p), _ptr(c), L, N, cap, int(images_per_group), post,
+                  int(k_min), int(k_max), float(canonical_scale), int(canonical_level),
+                  _ptr(out["rois"]), _ptr(out["count"]), _ptr(out["level"]), _ptr(out["level_count"]),
+                  _ptr(out["order"]), _ptr(out["restore"]), None, 0, _stream())
+        return out
 
 
 def distribute_cuda(rois, k_min=2, k_max=5, canonical_scale=224.0, canonical_level=4):
@@ -372,10 +375,10 @@ def distribute_cuda(rois, k_min=2, k_max=5, canonical_scale=224.0, canonical_lev
     lc = torch.empty(k_max - k_min + 1, dtype=torch.int32, device=dev)
     order = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
     restore = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
-    _bind(r)
-    _lib.call("vosd_distribute", _ptr(r), R, int(k_min), int(k_max), float(canonical_scale), int(canonical_level),
-              _ptr(level), _ptr(lc), _ptr(order), _ptr(restore), _stream())
-    return level[:R], lc, order[:R], restore[:R]
+    with _on(r):
+        _lib.call("vosd_distribute", _ptr(r), R, int(k_min), int(k_max), float(canonical_scale), int(canonical_level),
+                  _ptr(level), _ptr(lc), _ptr(order), _ptr(restore), _stream())
+        return level[:R], lc, order[:R], restore[:R]
 
 
 # ----------------------------------------------------------------------------- box head post-processing
@@ -389,9 +392,9 @@ def bbox_transform_cuda(boxes, deltas, weights=(1.0, 1.0, 1.0, 1.0), clip_hw=Non
     out = torch.empty_like(d)
     w = (ctypes.c_float * 4)(*[float(x) for x in weights])
     ch, cw = (float(clip_hw[0]), float(clip_hw[1])) if clip_hw is not None else (-1.0, -1.0)
-    _bind(b)
-    _lib.call("vosd_bbox_transform", _ptr(b), _ptr(d), b.size(0), d.size(1) // 4, w, ch, cw, _ptr(out), _stream())
-    return out
+    with _on(b):
+        _lib.call("vosd_bbox_transform", _ptr(b), _ptr(d), b.size(0), d.size(1) // 4, w, ch, cw, _ptr(out), _stream())
+        return out
 
 
 def box_results_cuda(scores, boxes, score_thresh=0.05, nms_thresh=0.3, max_per_image=100, rows=None, cap=None):
@@ -411,12 +414,12 @@ def box_results_cuda(scores, boxes, score_thresh=0.05, nms_thresh=0.3, max_per_i
     count = torch.empty((N,), dtype=torch.int32, device=dev)
     cls_count = torch.empty((N, K), dtype=torch.int32, device=dev)
     r = None if rows is None else _need_cuda(rows, "rows", torch.int32)
-    _bind(s)
-    nbytes = int(_lib.load().vosd_box_results_workspace_bytes(N, R, K))
-    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-    _lib.call("vosd_box_results", _ptr(s), _ptr(b), _ptr(r), N, R, K, float(score_thresh), float(nms_thresh),
-              int(max_per_image), cap, _ptr(dets), _ptr(count), _ptr(cls_count), _ptr(ws), nbytes, _stream())
-    return dets, count, cls_count
+    with _on(s):
+        nbytes = int(_lib.load().vosd_box_results_workspace_bytes(N, R, K))
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        _lib.call("vosd_box_results", _ptr(s), _ptr(b), _ptr(r), N, R, K, float(score_thresh), float(nms_thresh),
+                  int(max_per_image), cap, _ptr(dets), _ptr(count), _ptr(cls_count), _ptr(ws), nbytes, _stream())
+        return dets, count, cls_count
 
 
 # ----------------------------------------------------------------------------- paste
@@ -431,10 +434,10 @@ def paste_masks_cuda(masks, cls, ref_boxes, im_h, im_w, thresh=0.5, want_prob=Fa
         raise ValueError("masks must be (R,K,M,M) and ref_boxes (R,4)")
     out = torch.empty((R, im_h, im_w), dtype=torch.uint8, device=m.device)
     prob = torch.empty((R, im_h, im_w), dtype=torch.float32, device=m.device) if want_prob else None
-    _bind(m)
-    _lib.call("vosd_paste_masks", _ptr(m), _ptr(c), _ptr(b), R, K, M, int(im_h), int(im_w), float(thresh),
-              _ptr(out), _ptr(prob), _stream())
-    return (out, prob) if want_prob else out
+    with _on(m):
+        _lib.call("vosd_paste_masks", _ptr(m), _ptr(c), _ptr(b), R, K, M, int(im_h), int(im_w), float(thresh),
+                  _ptr(out), _ptr(prob), _stream())
+        return (out, prob) if want_prob else out
 
 
 def paste_masks_packed_cuda(masks, cls, ref_boxes, im_h, im_w, thresh=0.5, want_dense=True):
@@ -448,10 +451,10 @@ def paste_masks_packed_cuda(masks, cls, ref_boxes, im_h, im_w, thresh=0.5, want_
         raise ValueError("masks must be (R,K,M,M) and ref_boxes (R,4)")
     out = torch.empty((R, im_h, im_w), dtype=torch.uint8, device=m.device) if want_dense else None
     packed = torch.empty((R, (im_h * im_w + 7) // 8), dtype=torch.uint8, device=m.device)
-    _bind(m)
-    _lib.call("vosd_paste_masks_packed", _ptr(m), _ptr(c), _ptr(b), R, K, M, int(im_h), int(im_w), float(thresh),
-              _ptr(out), _ptr(packed), _stream())
-    return out, packed
+    with _on(m):
+        _lib.call("vosd_paste_masks_packed", _ptr(m), _ptr(c), _ptr(b), R, K, M, int(im_h), int(im_w), float(thresh),
+                  _ptr(out), _ptr(packed), _stream())
+        return out, packed
 
 
 def paste_rle_cuda(masks, cls, ref_boxes, im_h, im_w, thresh=0.5, run_capacity=None, str_capacity=None):
@@ -481,12 +484,12 @@ def paste_rle_cuda(masks, cls, ref_boxes, im_h, im_w, thresh=0.5, run_capacity=N
         "str_len": torch.empty(R, dtype=torch.int32, device=dev),
         "status": torch.empty(R, dtype=torch.int32, device=dev),
     }
-    _bind(m)
-    _lib.call("vosd_paste_rle", _ptr(m), _ptr(c), _ptr(b), R, K, M, int(im_h), int(im_w), float(thresh),
-              _ptr(out["runs"]), int(run_capacity), _ptr(out["chars"]), int(str_capacity), _ptr(out["cursors"]),
-              _ptr(out["run_offset"]), _ptr(out["run_count"]), _ptr(out["str_offset"]), _ptr(out["str_len"]),
-              _ptr(out["status"]), _stream())
-    return out
+    with _on(m):
+        _lib.call("vosd_paste_rle", _ptr(m), _ptr(c), _ptr(b), R, K, M, int(im_h), int(im_w), float(thresh),
+                  _ptr(out["runs"]), int(run_capacity), _ptr(out["chars"]), int(str_capacity), _ptr(out["cursors"]),
+                  _ptr(out["run_offset"]), _ptr(out["run_count"]), _ptr(out["str_offset"]), _ptr(out["str_len"]),
+                  _ptr(out["status"]), _stream())
+        return out
 
 
 def rle_results(masks, cls, ref_boxes, im_h, im_w, thresh=0.5):
@@ -519,9 +522,9 @@ def pack_mask_bits_cuda(masks_u8):
     for v in lead:
         n *= int(v)
     out = torch.empty(tuple(lead) + ((pixels + 7) // 8,), dtype=torch.uint8, device=m.device)
-    _bind(m)
-    _lib.call("vosd_pack_mask_bits", _ptr(m), n, pixels, _ptr(out), _stream())
-    return out
+    with _on(m):
+        _lib.call("vosd_pack_mask_bits", _ptr(m), n, pixels, _ptr(out), _stream())
+        return out
 
 
 # ----------------------------------------------------------------------------- mask-IoU suppression
@@ -542,10 +545,10 @@ def rle_to_bits_cuda(run_lists, pixels, device=None):
     runs = torch.from_numpy(flat.astype(np.uint32).view(np.int32)).to(dev)
     offs = torch.from_numpy(offsets).to(dev)        # named: a temporary would be recycled before the launch
     cnts = torch.from_numpy(counts).to(dev)
-    _bind(out)
-    _lib.call("vosd_rle_to_bits", _ptr(runs), _ptr(offs), _ptr(cnts), R, int(pixels), _ptr(out), int(counts.max()),
-              _stream())
-    return out
+    with _on(out):
+        _lib.call("vosd_rle_to_bits", _ptr(runs), _ptr(offs), _ptr(cnts), R, int(pixels), _ptr(out), int(counts.max()),
+                  _stream())
+        return out
 
 
 def mask_iou_nms_cuda(packed, order, iou_th):
@@ -563,10 +566,10 @@ def mask_iou_nms_cuda(packed, order, iou_th):
     num = torch.empty((1,), dtype=torch.int32, device=p.device)
     nbytes = _lib.load().vosd_mask_iou_nms_workspace_bytes(R)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=p.device)
-    _bind(p)
-    _lib.call("vosd_mask_iou_nms", _ptr(p), R, nb, _ptr(o), float(iou_th), _ptr(removed), _ptr(num), _ptr(ws), nbytes,
-              _stream())
-    return removed[:R], num
+    with _on(p):
+        _lib.call("vosd_mask_iou_nms", _ptr(p), R, nb, _ptr(o), float(iou_th), _ptr(removed), _ptr(num), _ptr(ws), nbytes,
+                  _stream())
+        return removed[:R], num
 
 
 # ----------------------------------------------------------------------------- bbox_overlaps
@@ -581,9 +584,9 @@ def bbox_overlaps_cuda(boxes, query_boxes, want_matrix=True):
     ov = torch.zeros((N, K), dtype=torch.float32, device=b.device) if want_matrix else None
     mx = torch.zeros((N,), dtype=torch.float32, device=b.device)
     am = torch.zeros((N,), dtype=torch.int32, device=b.device)
-    _bind(b)
-    _lib.call("vosd_bbox_overlaps", _ptr(b), N, _ptr(q), K, _ptr(ov), _ptr(mx), _ptr(am), _stream())
-    return ov, mx, am
+    with _on(b):
+        _lib.call("vosd_bbox_overlaps", _ptr(b), N, _ptr(q), K, _ptr(ov), _ptr(mx), _ptr(am), _stream())
+        return ov, mx, am
 
 
 def bbox_targets_cuda(ex_rois, gt_rois, labels, num_classes, weights=(10.0, 10.0, 5.0, 5.0), class_agnostic=False):
@@ -598,7 +601,7 @@ def bbox_targets_cuda(ex_rois, gt_rois, labels, num_classes, weights=(10.0, 10.0
     K = 2 if class_agnostic else int(num_classes)
     outs = [torch.empty((n, 4 * K), dtype=torch.float32, device=e.device) for _ in range(3)]
     w = (ctypes.c_float * 4)(*[float(v) for v in weights])
-    _bind(e)
-    _lib.call("vosd_bbox_targets", _ptr(e), _ptr(g), _ptr(lb), n, int(num_classes), int(bool(class_agnostic)), w,
-              _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _stream())
-    return tuple(outs)
+    with _on(e):
+        _lib.call("vosd_bbox_targets", _ptr(e), _ptr(g), _ptr(lb), n, int(num_classes), int(bool(class_agnostic)), w,
+                  _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _stream())
+        return tuple(outs)

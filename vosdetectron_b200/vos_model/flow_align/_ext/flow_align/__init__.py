@@ -32,8 +32,8 @@ def flow_align_forward_cuda(bottom, flow, top):
     N, C, H, W = bottom.size()                                      # flow_align_cuda.c:14-17
     if tuple(flow.size()) != (N, 2, H, W) or tuple(top.size()) != (N, C, H, W):
         raise ValueError("flow must be (N,2,H,W) and top (N,C,H,W)")     # the reference would read out of bounds
-    _lib.call("vosd_set_device", bottom.device.index)
-    _lib.call("vosd_flow_align_fwd", N, H, W, C, _p(bottom), _p(flow), _p(top), _stream(bottom))
+    with torch.cuda.device(bottom.device):                     # the caller's current device is restored on exit
+        _lib.call("vosd_flow_align_fwd", N, H, W, C, _p(bottom), _p(flow), _p(top), _stream(bottom))
     return 1
 
 
@@ -43,7 +43,7 @@ def flow_align_backward_cuda(top_grad, bottom, flow, bottom_grad, flow_grad):
     if tuple(bottom.size()) != (N, C, H, W) or tuple(flow.size()) != (N, 2, H, W) or \
             tuple(bottom_grad.size()) != (N, C, H, W) or tuple(flow_grad.size()) != (N, 2, H, W):
         raise ValueError("inconsistent shapes")
-    _lib.call("vosd_set_device", top_grad.device.index)
-    _lib.call("vosd_flow_align_bwd", N, H, W, C, _p(top_grad), _p(bottom), _p(flow), _p(bottom_grad), _p(flow_grad), 0,
-              _stream(top_grad))                                    # 0: the caller zero-filled both gradients
+    with torch.cuda.device(top_grad.device):                     # the caller's current device is restored on exit
+        _lib.call("vosd_flow_align_bwd", N, H, W, C, _p(top_grad), _p(bottom), _p(flow), _p(bottom_grad), _p(flow_grad), 0,
+                  _stream(top_grad))                                    # 0: the caller zero-filled both gradients
     return 1

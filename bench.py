@@ -462,7 +462,7 @@ def gpu_arm(args, rank, world, local_rank):
     import torch.distributed as dist
     from vosdetectron_b200 import _lib, synth
     from vosdetectron_b200.config import RegionConfig
-    from vosdetectron_b200.pipeline import RegionPipeline, STEP_LAUNCHES, all_gather_frames, pack_mask_bits
+    from vosdetectron_b200.pipeline import FrameGather, RegionPipeline, STEP_LAUNCHES, all_gather_frames, pack_mask_bits
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -547,6 +547,8 @@ def gpu_arm(args, rank, world, local_rank):
 
     graph = {"g": None, "out": None, "launches": 0}
 
+    fg = {"g": None}      # FrameGather of the bit-packed payload (copy-engine peer pushes; NCCL if unavailable)
+
     def run_step(mark=None, replay=False):
         if replay and graph["g"] is not None:
             graph["g"].replay()
@@ -554,14 +556,24 @@ def gpu_arm(args, rank, world, local_rank):
         else:
             out = pipe.step(d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks, frame_hw, im_scale, mark=mark)
         if world > 1:
-            while len(pending) > 1:                       # at most two gathers outstanding
-                for w in pending.pop(0)[2]:
-                    w.wait()
             dets = torch.cat([d_boxes, d_cls.unsqueeze(-1).float(), torch.ones_like(d_cls).unsqueeze(-1).float()], dim=2)
             if out["masks_packed"] is not None:
-                payload = out["masks_packed"].clone() if (replay and graph["g"] is not None) else out["masks_packed"]
-                pending.append(all_gather_frames(dets, payload, async_op=True))
+                if fg["g"] is None:
+                    fg["g"] = FrameGather(dets.shape, dets.dtype, out["masks_packed"].shape, out["masks_packed"].dtype, dev,
+                                          transport=args.gather_transport)
+                    print("rank %d: frame gather transport = %s%s" % (rank, fg["g"].transport,
+                          "" if fg["g"].why is None else " (copy-engine path unavailable: %s)" % fg["g"].why), file=sys.stderr)
+                g_ = fg["g"]
+                while len(pending) >= g_.slots:                # the slot about to be reused
+                    g_.finish(pending.pop(0)[3])
+                payload = out["masks_packed"]
+                if g_.transport != "ce" and replay and graph["g"] is not None:
+                    payload = payload.clone()                  # NCCL reads it after the next replay has started
+                pending.append((None, None, [], g_.start(dets, payload)))
             else:
+                while len(pending) > 1:                       # at most two gathers outstanding
+                    for w in pending.pop(0)[2]:
+                        w.wait()
                 r = out["masks_rle"]                      # record = box, class, score, RLE offset / length in the arena
                 rec = torch.cat([dets, r["str_offset"].view(B, -1, 1).float(), r["str_len"].view(B, -1, 1).float()], dim=2)
                 chars = r["chars"].clone() if (replay and graph["g"] is not None) else r["chars"]
@@ -570,8 +582,11 @@ def gpu_arm(args, rank, world, local_rank):
 
     def drain():
         while pending:
-            for w in pending.pop(0)[2]:
+            p_ = pending.pop(0)
+            for w in p_[2]:
                 w.wait()
+            if len(p_) > 3:
+                fg["g"].finish(p_[3])
 
     def barrier():
         if world > 1:
@@ -673,15 +688,29 @@ def gpu_arm(args, rank, world, local_rank):
         slot = hp.submit(host_batch)
     hp.synchronize()
     res = hp.results(slot)
-    d2h_bytes = sum(res[k].numel() * res[k].element_size() for k in ("rois", "roi_count", "masks"))
+    d2h_bytes = sum(res[k].numel() * res[k].element_size() for k in ("rois", "roi_count", "masks_packed"))
+    # bytes that really cross PCIe per step: every input, but ONE class channel of each detection's (K,M,M) mask
+    h2d_bytes_e2e = h2d_bytes - h_masks.numel() * h_masks.element_size() + h_masks.numel() // h_masks.shape[2] * h_masks.element_size()
     barrier()
     e2e_steps = max(4, min(args.steps, 12))
     e0.record()
     hp.s_h2d.wait_event(e0)
+    e2e_pending = []
     for _ in range(e2e_steps):
-        hp.submit(host_batch)
-        if world > 1:
-            pass    # the all-gather of the device-resident arm is not repeated here: e2e measures the host API
+        slot = hp.submit(host_batch)
+        if world > 1 and fg["g"] is not None:
+            # the sharded clip's exchange is part of the end-to-end step: gather this batch's records + packed masks
+            with torch.cuda.stream(hp.s_cmp):
+                while len(e2e_pending) >= fg["g"].slots:
+                    fg["g"].finish(e2e_pending.pop(0))
+                o_ = hp.dev_out[slot]
+                dets = torch.cat([hp.dev[slot]["det_boxes"], hp.dev[slot]["det_cls"].unsqueeze(-1).float(),
+                                  torch.ones_like(hp.dev[slot]["det_cls"]).unsqueeze(-1).float()], dim=2)
+                e2e_pending.append(fg["g"].start(dets, o_["masks_packed"]))
+    if world > 1 and fg["g"] is not None:
+        with torch.cuda.stream(hp.s_cmp):
+            while e2e_pending:
+                fg["g"].finish(e2e_pending.pop(0))
     for s_ in (hp.s_h2d, hp.s_cmp, hp.s_d2h):
         torch.cuda.current_stream().wait_stream(s_)
     e1.record()
@@ -790,10 +819,15 @@ def gpu_arm(args, rank, world, local_rank):
                    "cuda_graph": ("the timed region replays a CUDA graph of the step; stage durations from an eager pass "
                                   "of the same steps with the chains joined before the box RoIAlign (each kernel alone)"
                                   if graph["g"] is not None else "off (eager step)"),
-                   "parallelism": "frame-sharded x%d%s" % (world, (", all-gather of dets + %s per step" % ("COCO RLE strings (fused paste -> RLE kernel)" if args.gather_rle else "bit-packed masks")) if world > 1 else "")},
+                   "parallelism": "frame-sharded x%d%s" % (world, (", all-gather of dets + %s per step%s" % (
+                       "COCO RLE strings (fused paste -> RLE kernel)" if args.gather_rle else "bit-packed masks",
+                       "" if fg["g"] is None else " [%s]" % ("copy-engine peer pushes over NVLink (symmetric memory), no SMs"
+                                                             if fg["g"].transport == "ce" else "NCCL all_gather_into_tensor"))) if world > 1 else "")},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes_e2e, "d2h_bytes_per_step": d2h_bytes,
+                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                "what": "HostPipeline: pinned host inputs -> H2D (class channel of every detection mask gathered on the host "
+                        "inside the timed region) -> step -> D2H of rois, counts and the 1-bit-per-pixel pasted masks"},
         "gpu_launches": int(launches),
         "launches_per_step_expected": STEP_LAUNCHES + (1 if pipe.packed_masks == "rle" else 0),
         "roofline": roofline,
@@ -827,6 +861,9 @@ def main():
     ap.add_argument("--no-cuda-graph", action="store_true", help="time the eager step instead of a CUDA-graph replay of it")
     ap.add_argument("--nccl-channels", type=int, default=0,
                     help="N > 1 experiment: cap NCCL at this many channels (NCCL_MAX_NCHANNELS) so the all-gather holds fewer SMs")
+    ap.add_argument("--gather-transport", default="auto", choices=["auto", "ce", "nccl"],
+                    help="N > 1: exchange of the packed masks -- copy-engine peer pushes over symmetric memory (auto: when "
+                         "available) or NCCL all_gather_into_tensor")
     ap.add_argument("--gather-rle", action="store_true",
                     help="N > 1: all-gather COCO RLE strings (fused paste -> RLE kernel) instead of 1-bit-per-pixel masks")
     ap.add_argument("--join-overlap", action="store_true",

@@ -96,3 +96,40 @@ def test_frame_sharded_all_gather_world2(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert open(tmp_path / "ok0").read() == "1" and open(tmp_path / "ok1").read() == "1"
+
+
+def _worker_clip(rank, world, port, out_dir):
+    """run_clip (the frame-sharded clip driver) on CPU: 3 batches of 2 frames per rank through a stand-in step,
+    gathered with two rotating slots; the result must be the clip in (batch, rank, frame) order on every rank."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vosdetectron_b200.pipeline import FrameGather, pack_mask_bits, run_clip, unpack_mask_bits
+    nb, fr, D, h, w = 3, 2, 3, 11, 13
+    dets, masks = _make_clip(frames=nb * world * fr, D=D, h=h, w=w)
+    # frame f of the clip = batch f // (world * fr), rank (f // fr) % world
+    mine = [[b * world * fr + rank * fr + i for i in range(fr)] for b in range(nb)]
+    batches = [{"frames": idx} for idx in mine]
+    calls = []
+
+    def step_fn(batch):
+        calls.append(tuple(batch["frames"]))
+        return {"masks_packed": pack_mask_bits(torch.from_numpy(masks[batch["frames"]]))}
+
+    def records_fn(batch, out):
+        return torch.from_numpy(dets[batch["frames"]]), out["masks_packed"]
+
+    gd, gm = run_clip(batches, step_fn, records_fn)
+    ok = len(calls) == nb and torch.equal(gd, torch.from_numpy(dets))
+    ok = ok and torch.equal(unpack_mask_bits(gm, h, w), torch.from_numpy(masks))
+    # a single-rank gather is the identity and allocates nothing symmetric
+    g1 = FrameGather((fr, D, 6), torch.float32, (fr, D, 4), torch.uint8, "cpu", transport="nccl")
+    ok = ok and g1.transport == "nccl"
+    open(os.path.join(out_dir, "clip%d" % rank), "w").write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_run_clip_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker_clip, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert open(tmp_path / "clip0").read() == "1" and open(tmp_path / "clip1").read() == "1"

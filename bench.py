@@ -514,9 +514,26 @@ def gpu_arm(args, rank, world, local_rank):
     frame_hw, im_scale = synth.DAVIS_FRAME, synth.DAVIS_SCALE
 
     # pinned host buffers (e2e) and device-resident copies (value)
+    wc_keep = []
+
     def pin(a):
-        t = torch.from_numpy(np.ascontiguousarray(a))
-        return t.pin_memory()
+        a = np.ascontiguousarray(a)
+        if args.wc_pinned:
+            # write-combined pinned memory (cudaHostAllocWriteCombined): the device's PCIe reads do not snoop the CPU
+            # caches; the host only ever writes these input buffers
+            import ctypes
+            rt = ctypes.CDLL("libcudart.so")
+            ptr = ctypes.c_void_p()
+            if rt.cudaHostAlloc(ctypes.byref(ptr), ctypes.c_size_t(max(a.nbytes, 16)), ctypes.c_uint(0x04)) != 0:
+                raise RuntimeError("cudaHostAlloc(write-combined) failed")
+            buf = (ctypes.c_uint8 * max(a.nbytes, 16)).from_address(ptr.value)
+            arr = np.frombuffer(buf, dtype=a.dtype, count=a.size).reshape(a.shape)
+            arr[...] = a
+            wc_keep.append(buf)
+            t = torch.from_numpy(arr)
+            assert t.is_pinned()
+            return t
+        return torch.from_numpy(a).pin_memory()
     h_rpn = {l: (pin(s), pin(d)) for l, (s, d) in host["rpn"].items()}
     h_feats = {l: pin(f) for l, f in host["feats"].items()}
     if args.features_layout == "channels_last":
@@ -861,6 +878,8 @@ def main():
     ap.add_argument("--no-cuda-graph", action="store_true", help="time the eager step instead of a CUDA-graph replay of it")
     ap.add_argument("--nccl-channels", type=int, default=0,
                     help="N > 1 experiment: cap NCCL at this many channels (NCCL_MAX_NCHANNELS) so the all-gather holds fewer SMs")
+    ap.add_argument("--wc-pinned", action="store_true",
+                    help="experiment: write-combined pinned host input buffers for the e2e leg")
     ap.add_argument("--gather-transport", default="auto", choices=["auto", "ce", "nccl"],
                     help="N > 1: exchange of the packed masks -- copy-engine peer pushes over symmetric memory (auto: when "
                          "available) or NCCL all_gather_into_tensor")

@@ -8,7 +8,8 @@
  *   - plain pointers + explicit sizes + cudaStream_t, no framework types;
  *   - the caller allocates outputs and the opaque workspace (size from the matching
  *     *_workspace_bytes()); no hidden cudaMalloc, no hidden synchronisation, no global
- *     mutable state: calls are re-entrant and only enqueue work on `stream`;
+ *     mutable state (the two vosd_debug_* test hooks only act in processes that export
+ *     VOSD_B200_TEST_HOOKS=1): calls are re-entrant and only enqueue work on `stream`;
  *   - return value: VOSD_OK (0) or a negative vosd_status -- never exit()
  *     (the reference launchers print and exit(-1), roi_align_kernel.cu:135-139,283-287);
  *   - there is no CPU implementation behind any entry point.
@@ -136,7 +137,8 @@ VOSD_API int vosd_roialign_ml_fwd_nhwc(const float* const* level_data, const int
  *       C % 32 == 0, else the staged forward; record-based atomic-scatter backward),
  *   1 = generic un-staged kernels everywhere (also the in-kernel fallback for oversize RoIs),
  *   2 = staged kernels everywhere (bit-exact forward; adds the staged backward).
- * Returns the previous setting.  Process-wide; not for production use. */
+ * Returns the previous setting.  Takes effect ONLY in processes that export VOSD_B200_TEST_HOOKS=1 (the test suite
+ * does); elsewhere it is a no-op, so a production process has no mutable library state. */
 VOSD_API int vosd_debug_force_generic(int on);
 
 /* level_diff[l] (N,C,H_l,W_l) accumulated into (zero_init as above, needs batch_size). */
@@ -363,7 +365,8 @@ VOSD_API int vosd_flow_align_ml_bwd(int num_levels, int batches, int channels, c
 /*   2 = the same double-precision operation sequence with the float->double widenings done as bit shuffles  */
 /*       on the ALU pipe (bit-identical; non-finite taps take the expression as written; measured slower),   */
 /*   1 = plain fp32 bilinear weights in the forward (NOT bit-identical, |err| <= 1e-6 relative).             */
-/* Returns the previous setting.  Process-wide; not for production use. */
+/* Returns the previous setting.  Takes effect only with VOSD_B200_TEST_HOOKS=1 in the environment (see
+ * vosd_debug_force_generic); a no-op elsewhere. */
 VOSD_API int vosd_debug_flow_align_fast(int on);
 
 /* ------------------------------------------------------------------------------------ */

@@ -8,6 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+os.environ.setdefault("VOSD_B200_TEST_HOOKS", "1")      # vosd_debug_* (kernel-family selection) only act with this set
 
 
 def pytest_configure(config):

@@ -11,6 +11,8 @@ roi_feature_transform (one launch per level + cat + index_select).  This script 
 tooling, not the product path; it loads oracle/_ref only as the comparison arm.
 """
 import argparse
+import os
+os.environ.setdefault("VOSD_B200_TEST_HOOKS", "1")
 import ctypes
 import json
 import os

@@ -54,9 +54,18 @@ struct CollectKeys {
     int N, cap, ipg, img0;
     // j enumerates (level, image-in-group, slot) -- the reference's concatenation order
     __device__ __forceinline__ uint64_t operator()(int j) const {
-        const int slot = j % cap;
-        const int s = j / cap;
-        const int l = s / ipg, img = img0 + (s - l * ipg);
+        // j / cap and s / ipg through fp32 (exact here: j < 2^22, and (j + 0.5) / cap stays >= 0.5 / cap away from every
+        // integer, far more than the rounding error of the division); a handful of instructions instead of ~40
+        int s, l;
+        if (j < (1 << 22)) {
+            s = __float2int_rd(__fdividef((float)j + 0.5f, (float)cap));
+            l = __float2int_rd(__fdividef((float)s + 0.5f, (float)ipg));
+        } else {
+            s = j / cap;
+            l = s / ipg;
+        }
+        const int slot = j - s * cap;
+        const int img = img0 + (s - l * ipg);
         if (slot >= count[l * N + img]) return 0;
         const float p = __ldg(probs + ((size_t)l * N + img) * cap + slot);
         return ((uint64_t)float_to_ordered(p) << 32) | (uint64_t)(0xffffffffu - (uint32_t)j);

@@ -19,6 +19,13 @@ inline int check_launch() {
     return VOSD_ERR_LAUNCH;
 }
 
+// The vosd_debug_* entry points (kernel-family selection for the parity tests) only take effect in processes that
+// export VOSD_B200_TEST_HOOKS=1 (tests/conftest.py, tools/): a production process has no mutable library state.
+inline bool test_hooks_enabled() {
+    const char* e = getenv("VOSD_B200_TEST_HOOKS");
+    return e && e[0] == '1';
+}
+
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -214,12 +214,9 @@ extern "C" int vosd_box_results(const float* scores, const float* boxes, const i
         dim3 grid(L.words, L.words, L.segs);
         nms_mask_kernel<<<grid, 64, 0, stream>>>(wb, count, R, L.words, nms_thresh, mask);
     }
-    if (L.words <= 32)
-        nms_reduce_warp_kernel<<<L.segs, 32, 0, stream>>>(wb, nullptr, count, R, L.words, mask, use_mask, 0, 2, 1, R,
-                                                          nullptr, nullptr, nullptr, orig, flag);
-    else
-        nms_reduce_kernel<<<L.segs, 32, 0, stream>>>(wb, nullptr, count, R, L.words, mask, use_mask, 0, 2, 1, R,
-                                                     nullptr, nullptr, nullptr, orig, flag);
+    if (launch_nms_reduce(L.segs, R, L.words, wb, nullptr, count, mask, use_mask, 0, 2, 1, R, nullptr, nullptr, nullptr, orig, flag,
+                          stream) != cudaSuccess)
+        return VOSD_ERR_LAUNCH;
     det_limit_kernel<<<N, kSelThreads, (size_t)K * sizeof(int), stream>>>(scores, boxes, flag, R, K, max_per_image, cap,
                                                                           out_dets, out_count, out_cls_count);
     count_launch(use_mask ? 4 : 3);

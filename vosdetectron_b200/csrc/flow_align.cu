@@ -613,5 +613,6 @@ extern "C" int vosd_flow_align_ml_bwd(int num_levels, int batches, int channels,
 }
 
 extern "C" int vosd_debug_flow_align_fast(int on) {
+    if (!vosd::test_hooks_enabled()) return vosd::g_flow_fast.load(std::memory_order_relaxed);
     return vosd::g_flow_fast.exchange(on, std::memory_order_relaxed);
 }

@@ -107,7 +107,8 @@ struct RpnKeys {
     const float* s;   // scores of one image at one level, (A, H*W)
     int A, HW;
     __device__ __forceinline__ uint64_t operator()(int j) const {
-        const int a = j / HW;
+        // j / HW through fp32 (exact for j < 2^22: (j + 0.5) / HW stays >= 0.5 / HW away from every integer)
+        const int a = j < (1 << 22) ? __float2int_rd(__fdividef((float)j + 0.5f, (float)HW)) : j / HW;
         const uint32_t flat = (uint32_t)(j - a * HW) * (uint32_t)A + (uint32_t)a;   // (h, w, a) order
         return ((uint64_t)float_to_ordered(__ldg(s + j)) << 32) | (uint64_t)(0xffffffffu - flat);
     }
@@ -117,7 +118,10 @@ struct RpnKeys {
 // planes are streamed by 8 SMs at once, histograms meet in distributed shared memory, rank 0
 // sorts the survivors and decodes them.  grid = segments * kTopkCluster, block = 1024,
 // dyn smem = sort_cap * 8.
-constexpr int kTopkCluster = 8;
+#ifndef VOSD_TOPK_CLUSTER
+#define VOSD_TOPK_CLUSTER 4
+#endif
+constexpr int kTopkCluster = VOSD_TOPK_CLUSTER;
 __global__ void __cluster_dims__(kTopkCluster, 1, 1) __launch_bounds__(kSelThreads, 1)
 topk_decode_kernel(const __grid_constant__ RpnParams p, const float* __restrict__ im_info,
                    float4* __restrict__ ws_boxes, float* __restrict__ ws_scores,
@@ -360,6 +364,134 @@ nms_reduce_warp_kernel(const float4* __restrict__ boxes, const float* __restrict
     if (lane == 0 && out_count) out_count[seg] = min(kept_total, limit);
 }
 
+// K3, CTA-wide path for segments whose whole bitmask fits shared memory (rows * words * 8 bytes <= 128 KB, i.e. up to
+// 1024 boxes: the TEST-mode RPN segments and the per-class segments of the box head).  The one-warp kernels above are
+// bound by the latency of their global loads (~1.5 us per 64-box chunk); here 512 threads first copy the segment's upper
+// triangle into shared memory in one coalesced sweep, warp 0 then resolves chunk after chunk from shared memory (64
+// dependent steps per chunk on the diagonal word, then lanes = later words OR the survivors' rows), and all threads
+// emit the kept boxes.  Same result as the warp kernels bit for bit (the greedy order is the same).
+constexpr int kNmsCtaThreads = 512;
+constexpr int kNmsCtaMaxWords = 16;
+__global__ void __launch_bounds__(kNmsCtaThreads)
+nms_reduce_cta_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                      const int* __restrict__ count, int seg_stride, int words_per_row,
+                      const unsigned long long* __restrict__ mask, int use_mask, int post, int mode,
+                      int num_images, int cap, float* __restrict__ out_rois, float* __restrict__ out_probs,
+                      int* __restrict__ out_count, const int* __restrict__ orig_index,
+                      int* __restrict__ keep_flag) {
+    extern __shared__ __align__(16) unsigned long long sm_mask[];       // [n][nblk]
+    __shared__ unsigned long long kept_w[kNmsCtaMaxWords];
+    __shared__ int kept_prefix[kNmsCtaMaxWords + 1];
+    const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int n = count[seg];
+    const int nblk = (n + 63) / 64;
+    const float4* b = boxes + (size_t)seg * seg_stride;
+    const float* sc = scores ? scores + (size_t)seg * seg_stride : nullptr;
+    const unsigned long long* mrow = mask + (size_t)seg * seg_stride * words_per_row;
+    const int limit = post > 0 ? post : n;
+    const float img = (float)(seg % num_images);
+    if (mode == 2) { orig_index += (size_t)seg * seg_stride; keep_flag += (size_t)seg * seg_stride; }   // per-segment flags
+    if (use_mask) {
+        // only words w >= i / 64 of row i were written by nms_mask_kernel (upper triangle)
+        for (int idx = tid; idx < n * nblk; idx += kNmsCtaThreads) {
+            const int i = idx / nblk, w = idx - i * nblk;
+            sm_mask[idx] = w >= (i >> 6) ? mrow[(size_t)i * words_per_row + w] : 0ull;
+        }
+    }
+    __shared__ unsigned long long removed[kNmsCtaMaxWords];
+    __shared__ unsigned long long kept_now;
+    __shared__ int kept_sofar;
+    if (tid < kNmsCtaMaxWords) removed[tid] = 0;
+    if (tid == 0) kept_sofar = 0;
+    __syncthreads();
+    const int w_of = tid % kNmsCtaMaxWords, g_of = tid / kNmsCtaMaxWords;      // OR phase: thread = (later word, row group)
+    for (int c = 0; c < nblk; c++) {
+        const int i0 = c * 64;
+        const int nin = min(64, n - i0);
+        if (tid < 32) {
+            // warp 0: the chunk against itself, 64 dependent steps on the diagonal word (shared-memory broadcasts)
+            unsigned long long kept = nin < 64 ? (1ull << nin) - 1ull : ~0ull;
+            const int before = kept_sofar;
+            if (before >= limit) kept = 0;           // everything after the first `limit` survivors is dropped anyway
+            else if (use_mask) {
+                // Greedy result of the chunk = the unique fixpoint of K = alive & ~OR(rows of K): bit t of the right-hand
+                // side only depends on bits < t of K (rows are upper-triangular), so iterating from K = alive fixes at least
+                // one more leading bit per round and usually converges in a few rounds (the depth of the suppression
+                // chains) instead of 64 dependent steps.  Lane L holds the diagonal words of boxes L and L + 32.
+                const unsigned long long alive = ~removed[c] & kept;
+                const unsigned long long* dcol = sm_mask + (size_t)i0 * nblk + c;
+                const unsigned long long d0 = lane < nin ? dcol[(size_t)lane * nblk] : 0ull;
+                const unsigned long long d1 = lane + 32 < nin ? dcol[(size_t)(lane + 32) * nblk] : 0ull;
+                kept = alive;
+                for (int round = 0; round < 65; round++) {
+                    const unsigned long long sup = (((kept >> lane) & 1ull) ? d0 : 0ull) | (((kept >> (lane + 32)) & 1ull) ? d1 : 0ull);
+                    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)sup);
+                    const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(sup >> 32));
+                    const unsigned long long next = alive & ~(((unsigned long long)hi << 32) | lo);
+                    if (next == kept) break;
+                    kept = next;
+                }
+            }
+            if (lane == 0) { kept_w[c] = kept; kept_prefix[c] = before; kept_now = kept; kept_sofar = before + __popcll(kept); }
+        }
+        __syncthreads();
+        if (use_mask && c + 1 < nblk) {
+            // all threads: OR the survivors' rows into the removed words of the later chunks
+            const unsigned long long kept = kept_now;
+            if (w_of > c && w_of < nblk) {
+                unsigned long long acc = 0;
+                for (int t = g_of; t < nin; t += kNmsCtaThreads / kNmsCtaMaxWords)
+                    if ((kept >> t) & 1ull) acc |= sm_mask[(size_t)(i0 + t) * nblk + w_of];
+                if (acc) atomicOr(&removed[w_of], acc);
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        kept_prefix[nblk] = kept_sofar;
+        if (out_count) out_count[seg] = min(kept_sofar, limit);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kNmsCtaThreads) {
+        const int c = i >> 6, t = i & 63;
+        const unsigned long long kept = kept_w[c];
+        if ((kept >> t) & 1ull) {
+            const int pos = kept_prefix[c] + __popcll(kept & ((1ull << t) - 1ull));
+            if (pos < limit) {
+                if (mode == 0) {
+                    const float4 v = b[i];
+                    float* o = out_rois + ((size_t)seg * cap + pos) * 5;
+                    o[0] = img; o[1] = v.x; o[2] = v.y; o[3] = v.z; o[4] = v.w;
+                    out_probs[(size_t)seg * cap + pos] = sc[i];
+                } else {
+                    keep_flag[orig_index[i]] = 1;
+                }
+            }
+        }
+    }
+}
+
+// dispatch of K3 (host): CTA-wide kernel when the segment's bitmask fits 128 KB of shared memory
+static inline cudaError_t launch_nms_reduce(int segs, int seg_stride, int words, const float4* boxes, const float* scores,
+                                            const int* count, const unsigned long long* mask, int use_mask, int post, int mode,
+                                            int num_images, int cap, float* out_rois, float* out_probs, int* out_count,
+                                            const int* orig_index, int* keep_flag, cudaStream_t stream) {
+    const size_t dyn = (size_t)seg_stride * words * sizeof(unsigned long long);
+    if (words <= kNmsCtaMaxWords && dyn <= 128 * 1024 && seg_stride >= 128) {
+        cudaError_t e = cudaFuncSetAttribute(nms_reduce_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+        nms_reduce_cta_kernel<<<segs, kNmsCtaThreads, dyn, stream>>>(boxes, scores, count, seg_stride, words, mask, use_mask, post, mode,
+                                                                   num_images, cap, out_rois, out_probs, out_count, orig_index, keep_flag);
+    } else if (words <= 32) {
+        nms_reduce_warp_kernel<<<segs, 32, 0, stream>>>(boxes, scores, count, seg_stride, words, mask, use_mask, post, mode, num_images,
+                                                        cap, out_rois, out_probs, out_count, orig_index, keep_flag);
+    } else {
+        nms_reduce_kernel<<<segs, 32, 0, stream>>>(boxes, scores, count, seg_stride, words, mask, use_mask, post, mode, num_images, cap,
+                                                   out_rois, out_probs, out_count, orig_index, keep_flag);
+    }
+    return cudaSuccess;
+}
+
 // ------------------------------------------------------------------------------------
 // Streaming decode of every anchor of a level (coalesced plane reads, 16-byte stores).
 // grid-stride over (image, position); each thread handles all A anchors of one position.
@@ -552,14 +684,9 @@ extern "C" int vosd_generate_proposals(const vosd_rpn_level* levels, int num_lev
         nms_mask_kernel<<<grid, 64, 0, stream>>>(ws_boxes, ws_count, lay.M, lay.words, nms_thresh, ws_mask);
         count_launch();
     }
-    if (lay.words <= 32)
-        nms_reduce_warp_kernel<<<lay.S, 32, 0, stream>>>(ws_boxes, ws_scores, ws_count, lay.M, lay.words, ws_mask,
-                                                         use_mask, use_mask ? post_nms_topN : 0, 0, num_images, lay.cap,
-                                                         out_rois, out_probs, out_count, nullptr, nullptr);
-    else
-        nms_reduce_kernel<<<lay.S, 32, 0, stream>>>(ws_boxes, ws_scores, ws_count, lay.M, lay.words, ws_mask,
-                                                    use_mask, use_mask ? post_nms_topN : 0, 0, num_images, lay.cap,
-                                                    out_rois, out_probs, out_count, nullptr, nullptr);
+    if (launch_nms_reduce(lay.S, lay.M, lay.words, ws_boxes, ws_scores, ws_count, ws_mask, use_mask, use_mask ? post_nms_topN : 0, 0,
+                          num_images, lay.cap, out_rois, out_probs, out_count, nullptr, nullptr, stream) != cudaSuccess)
+        return VOSD_ERR_LAUNCH;
     count_launch();
     return check_launch();
 }
@@ -636,12 +763,9 @@ extern "C" int vosd_nms(const float* dets, int n, float thresh, int64_t* keep, i
     nms_sort_kernel<<<1, kSelThreads, dyn, stream>>>(dets, n, P, boxes, orig, count, flag);
     dim3 grid(L.words, L.words, 1);
     nms_mask_kernel<<<grid, 64, 0, stream>>>(boxes, count, n, L.words, thresh, mask);
-    if (L.words <= 32)
-        nms_reduce_warp_kernel<<<1, 32, 0, stream>>>(boxes, nullptr, count, n, L.words, mask, 1, 0, 1, 1, n,
-                                                     nullptr, nullptr, nullptr, orig, flag);
-    else
-        nms_reduce_kernel<<<1, 32, 0, stream>>>(boxes, nullptr, count, n, L.words, mask, 1, 0, 1, 1, n,
-                                                nullptr, nullptr, nullptr, orig, flag);
+    if (launch_nms_reduce(1, n, L.words, boxes, nullptr, count, mask, 1, 0, 1, 1, n, nullptr, nullptr, nullptr, orig, flag, stream) !=
+        cudaSuccess)
+        return VOSD_ERR_LAUNCH;
     compact_flags_kernel<<<1, kSelThreads, 0, stream>>>(flag, n, reinterpret_cast<long long*>(keep), num_keep);
     count_launch(4);
     return check_launch();

@@ -1423,6 +1423,7 @@ extern "C" int vosd_roialign_ml_bwd(const float* top_diff, float* const* level_d
 // Test hook: route RoIAlign through the generic (un-staged) kernels so both paths stay covered.
 extern "C" VOSD_API int vosd_debug_force_generic(int on) {
     const int old = g_force_generic;
+    if (!test_hooks_enabled()) return old;          // production processes cannot change the kernel family
     g_force_generic = on;
     return old;
 }

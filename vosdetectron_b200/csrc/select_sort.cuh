@@ -14,6 +14,7 @@ namespace vosd {
 constexpr int kSelThreads = 1024;
 constexpr int kRadixBits = 11;
 constexpr int kBins = 1 << kRadixBits;     // 2048 bins, two per thread
+constexpr int kKeyBatch = 8;               // keys fetched per thread before they are consumed
 
 struct SelectShared {
     int hist[kBins];
@@ -69,9 +70,15 @@ __device__ void radix_select(const KeyFn& key_at, int n, int m, SelectShared& sh
         const uint32_t dmask = (1u << bits) - 1u;
         for (int b = threadIdx.x; b < kBins; b += kSelThreads) sh.hist[b] = 0;
         __syncthreads();
-        for (int j = threadIdx.x; j < n; j += kSelThreads) {
-            const uint64_t k = key_at(j);
-            if (k != 0 && (k & mask) == prefix) atomicAdd(&sh.hist[(uint32_t)(k >> shift) & dmask], 1);
+        // kKeyBatch keys per thread are fetched before the first atomic: the loads of a batch are in flight together
+        // (one key per iteration exposes the full L2 latency per key: the passes were bound by it)
+        for (int j = threadIdx.x; j < n; j += kKeyBatch * kSelThreads) {
+            uint64_t kb[kKeyBatch];
+#pragma unroll
+            for (int u = 0; u < kKeyBatch; u++) kb[u] = j + u * kSelThreads < n ? key_at(j + u * kSelThreads) : 0;
+#pragma unroll
+            for (int u = 0; u < kKeyBatch; u++)
+                if (kb[u] != 0 && (kb[u] & mask) == prefix) atomicAdd(&sh.hist[(uint32_t)(kb[u] >> shift) & dmask], 1);
         }
         __syncthreads();
         // descending suffix scan: thread t owns bins (kBins-1-2t) and (kBins-2-2t)
@@ -124,12 +131,16 @@ __device__ int select_and_sort(const KeyFn& key_at, int n, int n_valid, int m, u
     if (take == 0) return 0;
     uint64_t mask = 0, prefix = 0;
     if (take < n_valid) radix_select(key_at, n, take, sh, mask, prefix);
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const uint64_t k = key_at(j);
-        if (k != 0 && (k & mask) >= prefix) {
-            const int pos = atomicAdd(&sh.counter, 1);
-            if (pos < P) keys_out[pos] = k;
-        }
+    for (int j = threadIdx.x; j < n; j += kKeyBatch * blockDim.x) {
+        uint64_t kb[kKeyBatch];
+#pragma unroll
+        for (int u = 0; u < kKeyBatch; u++) kb[u] = j + u * (int)blockDim.x < n ? key_at(j + u * (int)blockDim.x) : 0;
+#pragma unroll
+        for (int u = 0; u < kKeyBatch; u++)
+            if (kb[u] != 0 && (kb[u] & mask) >= prefix) {
+                const int pos = atomicAdd(&sh.counter, 1);
+                if (pos < P) keys_out[pos] = kb[u];
+            }
     }
     __syncthreads();
     bitonic_sort_desc(keys_out, P);
@@ -166,9 +177,13 @@ __device__ void radix_select_cluster(cooperative_groups::cluster_group& cluster,
         int* h = sh.hist[buf];
         for (int b = threadIdx.x; b < kBins; b += kSelThreads) h[b] = 0;
         __syncthreads();
-        for (int j = j0 + threadIdx.x; j < j1; j += kSelThreads) {
-            const uint64_t k = key_at(j);
-            if (k != 0 && (k & mask) == prefix) atomicAdd(&h[(uint32_t)(k >> shift) & dmask], 1);
+        for (int j = j0 + threadIdx.x; j < j1; j += kKeyBatch * kSelThreads) {
+            uint64_t kb[kKeyBatch];
+#pragma unroll
+            for (int u = 0; u < kKeyBatch; u++) kb[u] = j + u * kSelThreads < j1 ? key_at(j + u * kSelThreads) : 0;
+#pragma unroll
+            for (int u = 0; u < kKeyBatch; u++)
+                if (kb[u] != 0 && (kb[u] & mask) == prefix) atomicAdd(&h[(uint32_t)(kb[u] >> shift) & dmask], 1);
         }
         cluster.sync();
         const int b0 = kBins - 1 - 2 * threadIdx.x, b1 = b0 - 1;
@@ -210,12 +225,16 @@ __device__ int select_and_sort_cluster(cooperative_groups::cluster_group& cluste
     __syncthreads();
     uint64_t mask = 0, prefix = 0;
     if (take < n) radix_select_cluster(cluster, key_at, j0, j1, take, sh, mask, prefix);
-    for (int j = j0 + threadIdx.x; j < j1; j += kSelThreads) {
-        const uint64_t k = key_at(j);
-        if (k != 0 && (k & mask) >= prefix) {
-            const int pos = atomicAdd(&sh.counter, 1);
-            if (pos < P) keys_out[pos] = k;
-        }
+    for (int j = j0 + threadIdx.x; j < j1; j += kKeyBatch * kSelThreads) {
+        uint64_t kb[kKeyBatch];
+#pragma unroll
+        for (int u = 0; u < kKeyBatch; u++) kb[u] = j + u * kSelThreads < j1 ? key_at(j + u * kSelThreads) : 0;
+#pragma unroll
+        for (int u = 0; u < kKeyBatch; u++)
+            if (kb[u] != 0 && (kb[u] & mask) >= prefix) {
+                const int pos = atomicAdd(&sh.counter, 1);
+                if (pos < P) keys_out[pos] = kb[u];
+            }
     }
     cluster.sync();                                   // every slice collected, counters final
     if (rank == 0) {

@@ -422,6 +422,21 @@ VOSD_API int vosd_bbox_targets(const float* ex_rois, const float* gt_rois, const
                                float* bbox_targets, float* inside_weights, float* outside_weights,
                                cudaStream_t stream);
 
+/* Sampling of the training RoIs (rank 3, third piece): the index selection of _sample_rois                */
+/* (lib/roi_data/fast_rcnn.py:132-160) for every image of the minibatch in one launch.                     */
+/*   max_overlaps, keys (num_images, stride) fp32: max overlap of every box of the image's roidb entry     */
+/*   (gt rows included) and ONE UNIFORM RANDOM KEY per box; num_boxes (num_images) int32 valid boxes.      */
+/*   RNG contract: npr.choice(inds, size, replace=False) of the reference = the `size` candidates with the */
+/*   smallest keys, in ascending key order (ties: lower index first) -- reproducible, and the same         */
+/*   distribution as the reference's permutation draw.  Foreground candidates: max_overlaps >= fg_thresh,  */
+/*   at most fg_rois_per_image = round(FG_FRACTION * BATCH_SIZE_PER_IM); background: bg_thresh_lo <=       */
+/*   max_overlaps < bg_thresh_hi, filling up to rois_per_image.                                            */
+/*   keep_inds (num_images, rois_per_image) int32: foreground picks, then background picks, -1 beyond      */
+/*   num_keep; num_fg, num_keep (num_images) int32.  rois_per_image <= VOSD_MAX_TOPK.                      */
+VOSD_API int vosd_sample_rois(const float* max_overlaps, const float* keys, const int* num_boxes, int num_images, int stride,
+                              int rois_per_image, int fg_rois_per_image, float fg_thresh, float bg_thresh_hi,
+                              float bg_thresh_lo, int* keep_inds, int* num_fg, int* num_keep, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

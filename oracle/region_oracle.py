@@ -604,5 +604,114 @@ def bbox_targets(ex_rois, gt_rois, labels, num_classes, weights=(10., 10., 5., 5
     return targets, inside, np.array(inside > 0, dtype=np.float32)
 
 
+# --------------------------------------------------------------------------- #
+# (f3 / a11) label assignment: add_proposals (datasets/json_dataset.py:413-427 -> _merge_proposal_boxes_into_roidb
+# :429-490, _add_class_assignments :513-532), _sample_rois (roi_data/fast_rcnn.py:132-213), add_fast_rcnn_blobs
+# (:108-129), _add_multilevel_rois (:262-290), the mask_rois / roi_has_mask part of add_mask_rcnn_blobs
+# (roi_data/mask_rcnn.py:34-102).  RNG contract: one uniform key per box; "npr.choice(inds, size, replace=False)" =
+# the `size` candidates with the smallest keys in ascending key order (ties: lower index first).
+# --------------------------------------------------------------------------- #
+def bbox_overlaps(boxes, query):
+    """utils.cython_bbox.bbox_overlaps: the reference's own compiled .pyx when oracle/_ref has it, else its restatement
+    (float64 areas / union, float32 products -- see csrc/overlaps.cu)."""
+    boxes = np.ascontiguousarray(boxes, np.float32)
+    query = np.ascontiguousarray(query, np.float32)
+    try:
+        import ref_harness
+        mod = ref_harness._load_ext("cython_bbox", "cython_bbox")
+        return mod.bbox_overlaps(boxes, query)
+    except Exception:  # noqa: BLE001
+        pass
+    N, K = boxes.shape[0], query.shape[0]
+    out = np.zeros((N, K), np.float32)
+    for k in range(K):
+        qa = np.float32((query[k, 2] - query[k, 0] + 1) * (query[k, 3] - query[k, 1] + 1))
+        for n in range(N):
+            iw = np.float32(min(boxes[n, 2], query[k, 2]) - max(boxes[n, 0], query[k, 0]) + 1)
+            if iw > 0:
+                ih = np.float32(min(boxes[n, 3], query[k, 3]) - max(boxes[n, 1], query[k, 1]) + 1)
+                if ih > 0:
+                    ua = np.float32(np.float32((boxes[n, 2] - boxes[n, 0] + 1) * (boxes[n, 3] - boxes[n, 1] + 1)) + qa - iw * ih)
+                    out[n, k] = iw * ih / ua
+    return out
+
+
+def add_proposals(gt_boxes, gt_classes, rois, im_scale, batch_idx):
+    """One image of add_proposals: returns (boxes, max_overlaps, max_classes, box_to_gt_ind_map) of the roidb entry
+    after the merge: the G ground-truth rows first, then the image's proposals in original-image coordinates."""
+    gt_boxes = np.asarray(gt_boxes, np.float32)
+    gt_classes = np.asarray(gt_classes, np.int32)
+    G = gt_boxes.shape[0]
+    inv = np.float32(1.) / np.float32(im_scale)
+    props = (rois[rois[:, 0] == batch_idx, 1:] * inv).astype(np.float32)
+    n = props.shape[0]
+    mx = np.zeros(n, np.float32)
+    cls = np.zeros(n, np.int32)
+    b2g = -np.ones(n, np.int32)
+    if G > 0 and n > 0:
+        ov = bbox_overlaps(props, gt_boxes)
+        am, m = ov.argmax(axis=1), ov.max(axis=1)
+        pos = m > 0
+        mx[pos], cls[pos], b2g[pos] = m[pos], gt_classes[am[pos]], am[pos].astype(np.int32)
+    return (np.concatenate([gt_boxes, props]), np.concatenate([np.ones(G, np.float32), mx]),
+            np.concatenate([gt_classes, cls]), np.concatenate([np.arange(G, dtype=np.int32), b2g]))
+
+
+def choice_by_keys(inds, size, keys):
+    inds = np.asarray(inds)
+    return inds[np.argsort(keys[inds], kind='stable')[:int(size)]]
+
+
+def sample_rois(boxes, max_overlaps, max_classes, box_to_gt, gt_boxes, keys, im_scale, batch_idx, num_classes,
+                rois_per_image=512, fg_fraction=0.25, fg_thresh=0.5, bg_hi=0.5, bg_lo=0.0,
+                weights=(10., 10., 5., 5.)):
+    """_sample_rois for one image -> dict(labels_int32, rois, bbox_targets, bbox_inside_weights, bbox_outside_weights,
+    keep_inds, num_fg)."""
+    fg_per = int(np.round(fg_fraction * rois_per_image))
+    fg = np.where(max_overlaps >= fg_thresh)[0]
+    nfg = min(fg_per, fg.size)
+    if fg.size > 0:
+        fg = choice_by_keys(fg, nfg, keys)
+    bg = np.where((max_overlaps < bg_hi) & (max_overlaps >= bg_lo))[0]
+    nbg = min(rois_per_image - nfg, bg.size)
+    if bg.size > 0:
+        bg = choice_by_keys(bg, nbg, keys)
+    keep = np.append(fg, bg).astype(np.int64)
+    labels = max_classes[keep].copy()
+    labels[nfg:] = 0
+    sb = boxes[keep]
+    gt_assign = box_to_gt[keep]
+    t, iw, ow = bbox_targets(sb, np.asarray(gt_boxes, np.float32)[gt_assign, :], labels, num_classes, weights)
+    rois = np.hstack((batch_idx * np.ones((sb.shape[0], 1), np.float32), sb * np.float32(im_scale))).astype(np.float32)
+    return {"labels_int32": labels.astype(np.int32), "rois": rois, "bbox_targets": t, "bbox_inside_weights": iw,
+            "bbox_outside_weights": ow, "keep_inds": keep, "num_fg": nfg, "sampled_boxes": sb}
+
+
+def mask_rois_of(sample, im_scale, batch_idx):
+    """mask_rois / roi_has_mask_int32 of add_mask_rcnn_blobs (the masks_int32 rasterisation is pycocotools': not here)."""
+    labels = sample["labels_int32"]
+    fg = np.where(labels > 0)[0]
+    has = (labels > 0).astype(np.int32)
+    if fg.size > 0:
+        rf = sample["sampled_boxes"][fg].copy()
+    else:
+        rf = sample["sampled_boxes"][np.where(labels == 0)[0][0]].reshape((1, -1)).copy()
+        has[0] = 1
+    rf = rf * np.float32(im_scale)
+    return np.hstack((batch_idx * np.ones((rf.shape[0], 1), np.float32), rf)).astype(np.float32), has
+
+
+def add_fast_rcnn_blobs(samples, k_min=2, k_max=5, mask_rois=None):
+    """Concatenation over the minibatch + _add_multilevel_rois."""
+    blobs = {k: np.concatenate([s[k] for s in samples]) for k in
+             ("labels_int32", "rois", "bbox_targets", "bbox_inside_weights", "bbox_outside_weights")}
+    blobs.update({k: v for k, v in distribute(blobs["rois"], k_min, k_max, 'rois').items() if k != 'rois'})
+    if mask_rois is not None:
+        blobs["mask_rois"] = np.concatenate([m[0] for m in mask_rois])
+        blobs["roi_has_mask_int32"] = np.concatenate([m[1] for m in mask_rois])
+        blobs.update({k: v for k, v in distribute(blobs["mask_rois"], k_min, k_max, 'mask_rois').items() if k != 'mask_rois'})
+    return blobs
+
+
 def num_threads():
     return lib().orc_num_threads()

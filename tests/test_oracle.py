@@ -264,3 +264,26 @@ def test_bbox_targets_golden(orc, golden):
         t, w, o = orc.bbox_targets(g["ex"], g["gt"], g["labels"], int(g["num_classes"]), class_agnostic=agn)
         assert np.array_equal(t, g["targets_" + tag]) and np.array_equal(w, g["inside_" + tag])
         assert np.array_equal(o, g["outside_" + tag])
+
+
+def test_label_assignment_oracle_reproduces_the_reference(orc, golden):
+    """add_proposals + _sample_rois + add_fast_rcnn_blobs (+ mask_rois) restated in oracle/region_oracle.py against
+    tests/golden/labels.npz, produced by the unmodified reference under the key-based RNG contract."""
+    g = golden("labels")
+    K, scales = int(g["num_classes"]), g["im_scales"]
+    samples, mrois = [], []
+    for i in range(2):
+        boxes, mo, mc, b2g = orc.add_proposals(g["gt_boxes%d" % i], g["gt_classes%d" % i], g["rpn_rois"], scales[i], i)
+        assert np.array_equal(boxes, g["boxes%d" % i]) and np.array_equal(mo, g["max_overlaps%d" % i])
+        assert np.array_equal(mc, g["max_classes%d" % i]) and np.array_equal(b2g, g["box_to_gt%d" % i])
+        s = orc.sample_rois(boxes, mo, mc, b2g, g["gt_boxes%d" % i], g["keys%d" % i], scales[i], i, K)
+        samples.append(s)
+        mrois.append(orc.mask_rois_of(s, scales[i], i))
+    blobs = orc.add_fast_rcnn_blobs(samples, mask_rois=mrois)
+    for k in ("labels_int32", "rois", "bbox_targets", "bbox_inside_weights", "bbox_outside_weights", "rois_fpn2", "rois_fpn3",
+              "rois_fpn4", "rois_fpn5", "rois_idx_restore_int32"):
+        assert np.array_equal(blobs[k], g[k]), k
+        assert np.array_equal(blobs[k], g["m_" + k]), k
+    for k in ("mask_rois", "roi_has_mask_int32", "mask_rois_fpn2", "mask_rois_fpn3", "mask_rois_fpn4", "mask_rois_fpn5",
+              "mask_rois_idx_restore_int32"):
+        assert np.array_equal(blobs[k], g["m_" + k]), k

@@ -94,6 +94,8 @@ SIGNATURES = {
     "vosd_rle_to_bits": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_longlong, vp, ctypes.c_int, vp]),
     "vosd_bbox_overlaps": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, vp, vp]),
     "vosd_bbox_targets": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, vp, vp, vp, vp]),
+    "vosd_sample_rois": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                        ctypes.c_float, ctypes.c_float, vp, vp, vp, vp]),
     "vosd_paste_masks": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_float, vp, vp, vp]),
 }

@@ -49,6 +49,14 @@ class RegionConfig:
     test_soft_nms: bool = False
     test_bbox_vote: bool = False
     bbox_reg_weights: tuple = (10.0, 10.0, 5.0, 5.0)
+    # TRAIN.* / MODEL.* read by the label assignment (config.py:99-127; roi_data/fast_rcnn.py:132-213)
+    train_batch_size_per_im: int = 512
+    train_fg_fraction: float = 0.25
+    train_fg_thresh: float = 0.5
+    train_bg_thresh_hi: float = 0.5
+    train_bg_thresh_lo: float = 0.0
+    cls_agnostic_bbox_reg: bool = False
+    mask_on: bool = False
     # lib_vos extras of box_results_with_nms_and_limit / nms_with_mask_iou (config.py:948-953)
     test_num_det_per_class_pre: int = 0
     test_num_det_per_class_post: int = 0
@@ -90,6 +98,14 @@ class RegionConfig:
             test_num_det_per_class=int(getattr(cfg.TEST, "NUM_DET_PER_CLASS", 0) or 0),
             test_soft_nms=bool(cfg.TEST.SOFT_NMS.ENABLED), test_bbox_vote=bool(cfg.TEST.BBOX_VOTE.ENABLED),
             bbox_reg_weights=tuple(float(x) for x in cfg.MODEL.BBOX_REG_WEIGHTS),
+            # label-assignment knobs: a partial cfg (inference only) keeps the reference's defaults (config.py:99-127)
+            train_batch_size_per_im=int(getattr(cfg.TRAIN, "BATCH_SIZE_PER_IM", 512)),
+            train_fg_fraction=float(getattr(cfg.TRAIN, "FG_FRACTION", 0.25)),
+            train_fg_thresh=float(getattr(cfg.TRAIN, "FG_THRESH", 0.5)),
+            train_bg_thresh_hi=float(getattr(cfg.TRAIN, "BG_THRESH_HI", 0.5)),
+            train_bg_thresh_lo=float(getattr(cfg.TRAIN, "BG_THRESH_LO", 0.0)),
+            cls_agnostic_bbox_reg=bool(getattr(cfg.MODEL, "CLS_AGNOSTIC_BBOX_REG", False)),
+            mask_on=bool(getattr(cfg.MODEL, "MASK_ON", False)),
             test_num_det_per_class_pre=int(getattr(cfg.TEST, "NUM_DET_PER_CLASS_PRE", 0) or 0),
             test_num_det_per_class_post=int(getattr(cfg.TEST, "NUM_DET_PER_CLASS_POST", 0) or 0),
             test_nms_cross_class=float(getattr(cfg.TEST, "NMS_CROSS_CLASS", 0.0) or 0.0),

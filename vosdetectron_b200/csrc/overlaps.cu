@@ -11,6 +11,7 @@
 // One thread per box row, query boxes in shared memory; the row maximum / first arg-maximum (NumPy argmax tie
 // rule) come out of the same pass, so the (N,K) matrix need not be written at all when only the labels are wanted.
 #include "common.cuh"
+#include "select_sort.cuh"
 
 namespace vosd {
 namespace {
@@ -140,6 +141,81 @@ extern "C" int vosd_bbox_targets(const float* ex_rois, const float* gt_rois, con
         reinterpret_cast<const float4*>(ex_rois), reinterpret_cast<const float4*>(gt_rois), labels, num_rois, K,
         class_agnostic ? 1 : 0, weights[0], weights[1], weights[2], weights[3], bbox_targets, inside_weights,
         outside_weights);
+    count_launch();
+    return check_launch();
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Sampling of the training RoIs: _sample_rois (lib/roi_data/fast_rcnn.py:132-160).  The reference draws
+// npr.choice(inds, size, replace=False) from NumPy's global generator; here the caller supplies one uniform key per
+// box and "choice" is the `size` candidates with the SMALLEST keys in ascending key order (ties: lower index first),
+// so the draw is reproducible, testable against the reference under the same contract, and the same distribution.
+// One CTA per image: count the candidates, radix-select + sort them by key (select_sort.cuh), foreground first.
+// ---------------------------------------------------------------------------------------------------------
+namespace vosd {
+namespace {
+
+struct SampleKeys {
+    const float* ov;
+    const float* keys;
+    float lo, hi;         // candidate: lo <= ov < hi  (foreground: lo = FG_THRESH, hi = +inf)
+    __device__ __forceinline__ bool cand(int j) const { const float v = __ldg(ov + j); return v >= lo && v < hi; }
+    __device__ __forceinline__ uint64_t operator()(int j) const {
+        if (!cand(j)) return 0;
+        return ((uint64_t)(~float_to_ordered(__ldg(keys + j))) << 32) | (uint64_t)(0xffffffffu - (uint32_t)j);
+    }
+};
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+sample_rois_kernel(const float* __restrict__ max_overlaps, const float* __restrict__ keys, const int* __restrict__ num_boxes,
+                   int stride, int rois_per_image, int fg_per_image, float fg_thresh, float bg_hi, float bg_lo, int P,
+                   int* __restrict__ keep_inds, int* __restrict__ num_fg, int* __restrict__ num_keep) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    uint64_t* sel = reinterpret_cast<uint64_t*>(dyn);
+    __shared__ SelectShared sh;
+    const int b = blockIdx.x;
+    const int n = num_boxes[b];
+    int* keep = keep_inds + (size_t)b * rois_per_image;
+    int written = 0, nfg = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        SampleKeys kf{max_overlaps + (size_t)b * stride, keys + (size_t)b * stride, pass == 0 ? fg_thresh : bg_lo,
+                      pass == 0 ? __int_as_float(0x7f800000) : bg_hi};
+        int cnt = 0;
+        for (int j0 = 0; j0 < n; j0 += kSelThreads) {
+            const int j = j0 + threadIdx.x;
+            cnt += __syncthreads_count(j < n && kf.cand(j));
+        }
+        const int want = min(pass == 0 ? fg_per_image : rois_per_image - nfg, cnt);
+        const int take = select_and_sort(kf, n, cnt, want, sel, P, sh);
+        for (int i = threadIdx.x; i < take; i += kSelThreads) keep[written + i] = (int)(0xffffffffu - (uint32_t)sel[i]);
+        __syncthreads();
+        if (pass == 0) nfg = take;
+        written += take;
+    }
+    for (int i = written + threadIdx.x; i < rois_per_image; i += kSelThreads) keep[i] = -1;
+    if (threadIdx.x == 0) { num_fg[b] = nfg; num_keep[b] = written; }
+}
+
+}  // namespace
+}  // namespace vosd
+
+extern "C" int vosd_sample_rois(const float* max_overlaps, const float* keys, const int* num_boxes, int num_images, int stride,
+                                int rois_per_image, int fg_rois_per_image, float fg_thresh, float bg_thresh_hi,
+                                float bg_thresh_lo, int* keep_inds, int* num_fg, int* num_keep, cudaStream_t stream) {
+    using namespace vosd;
+    if (num_images < 0 || stride < 0 || rois_per_image <= 0 || fg_rois_per_image < 0 || fg_rois_per_image > rois_per_image)
+        return VOSD_ERR_BAD_SHAPE;
+    if (num_images == 0) return VOSD_OK;
+    if (!max_overlaps || !keys || !num_boxes || !keep_inds || !num_fg || !num_keep) return VOSD_ERR_BAD_ARG;
+    if (rois_per_image > VOSD_MAX_TOPK) return VOSD_ERR_UNSUPPORTED;
+    const int P = next_pow2(rois_per_image);
+    const size_t dyn = (size_t)P * sizeof(uint64_t);
+    if (cudaFuncSetAttribute(sample_rois_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
+        return VOSD_ERR_LAUNCH;
+    sample_rois_kernel<<<num_images, kSelThreads, dyn, stream>>>(max_overlaps, keys, num_boxes, stride, rois_per_image,
+                                                                 fg_rois_per_image, fg_thresh, bg_thresh_hi, bg_thresh_lo, P,
+                                                                 keep_inds, num_fg, num_keep);
     count_launch();
     return check_launch();
 }

@@ -1,11 +1,11 @@
-"""Drop-in for lib/modeling/collect_and_distribute_fpn_rpn_proposals.py:18-138 (inference branch).
+"""Drop-in for lib/modeling/collect_and_distribute_fpn_rpn_proposals.py:18-138.
 
 ``collect(inputs, is_training)`` and ``distribute(rois, label_blobs)`` keep the reference's
 ndarray-in / dict-of-ndarray-out signatures; the top-N, the level map and the per-level split
-run in csrc/collect.cu.  The training branch of the reference op (:57-82) goes on to label
-assignment and RoI sampling on the host (json_dataset.add_proposals,
-roi_data.fast_rcnn.add_fast_rcnn_blobs), which SURVEY.md section 8f lists as a "next" row; the
-op raises there instead of silently doing something else.
+run in csrc/collect.cu.  The training branch of the op (:57-82) goes through the mirrors of
+json_dataset.add_proposals and roi_data.fast_rcnn.add_fast_rcnn_blobs in this package (overlaps,
+sampling, regression targets and the FPN split on the device; see roi_data/fast_rcnn.py for the
+sampler's RNG contract).
 """
 import numpy as np
 import torch
@@ -89,10 +89,19 @@ class CollectAndDistributeFpnRpnProposalsOp(nn.Module):
         super().__init__()
         self._cfg = cfg
 
-    def forward(self, inputs, roidb, im_info):
-        if self.training:
-            raise NotImplementedError(
-                "training-time label assignment (add_proposals / add_fast_rcnn_blobs, "
-                "collect_and_distribute_fpn_rpn_proposals.py:57-82) is outside the region pipeline; "
-                "call collect() and feed the reference's roi_data code")
-        return collect_and_distribute(inputs, False, self._cfg)
+    def forward(self, inputs, roidb, im_info, rand_keys=None):
+        """Inference: distribute(collect(inputs)).  Training (:57-82): add_proposals on the roidb entries, then
+        add_fast_rcnn_blobs (sampling, regression targets, FPN split); ``rand_keys`` is the sampler's RNG contract
+        (roi_data/fast_rcnn.py), None = keys drawn from numpy's global generator."""
+        cfg = self._cfg or get_cfg()
+        if not self.training:
+            return collect_and_distribute(inputs, False, self._cfg)
+        from ..datasets import json_dataset
+        from ..roi_data import fast_rcnn
+        rois = collect(inputs, True, self._cfg)
+        info = im_info.detach().cpu().numpy() if isinstance(im_info, torch.Tensor) else np.asarray(im_info)
+        im_scales = info[:, 2]
+        json_dataset.add_proposals(roidb, rois, im_scales, crowd_thresh=0)
+        blobs = {k: [] for k in fast_rcnn.get_fast_rcnn_blob_names(True, cfg)}
+        fast_rcnn.add_fast_rcnn_blobs(blobs, im_scales, roidb, rand_keys, cfg)
+        return blobs

@@ -605,3 +605,42 @@ def bbox_targets_cuda(ex_rois, gt_rois, labels, num_classes, weights=(10.0, 10.0
         _lib.call("vosd_bbox_targets", _ptr(e), _ptr(g), _ptr(lb), n, int(num_classes), int(bool(class_agnostic)), w,
                   _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _stream())
         return tuple(outs)
+
+
+# ----------------------------------------------------------------------------- label assignment (training)
+def label_proposals_cuda(proposals, gt_boxes, gt_classes):
+    """One image of add_proposals (datasets/json_dataset.py:413-490 + _add_class_assignments :513-532) on the device:
+    proposals (n,4) in ORIGINAL-image coordinates, gt_boxes (G,4), gt_classes (G) int32 (> 0) ->
+    (max_overlaps (n) fp32, max_classes (n) int32, box_to_gt_ind_map (n) int32; 0 / 0 / -1 where nothing overlaps)."""
+    p = _need_cuda(proposals, "proposals")
+    n = int(p.size(0))
+    if gt_boxes is None or int(gt_boxes.size(0)) == 0 or n == 0:
+        return (torch.zeros(n, dtype=torch.float32, device=p.device), torch.zeros(n, dtype=torch.int32, device=p.device),
+                torch.full((n,), -1, dtype=torch.int32, device=p.device))
+    g = _need_cuda(gt_boxes, "gt_boxes")
+    c = _need_cuda(gt_classes, "gt_classes", torch.int32)
+    _, mx, am = bbox_overlaps_cuda(p, g, want_matrix=False)
+    pos = mx > 0
+    cls = torch.where(pos, c[am.long()], torch.zeros_like(am))
+    b2g = torch.where(pos, am, torch.full_like(am, -1))
+    return torch.where(pos, mx, torch.zeros_like(mx)), cls, b2g
+
+
+def sample_rois_cuda(max_overlaps, keys, num_boxes, rois_per_image, fg_rois_per_image, fg_thresh, bg_thresh_hi,
+                     bg_thresh_lo):
+    """Index selection of _sample_rois (fast_rcnn.py:132-160) for a minibatch in one launch; see vosd_sample_rois for the
+    key-based RNG contract.  max_overlaps, keys (B,N) fp32, num_boxes (B) int32 ->
+    (keep_inds (B, rois_per_image) int32 [-1 padded], num_fg (B), num_keep (B))."""
+    ov = _need_cuda(max_overlaps, "max_overlaps")
+    k = _need_cuda(keys, "keys")
+    nb = _need_cuda(num_boxes, "num_boxes", torch.int32)
+    if ov.dim() != 2 or k.shape != ov.shape or nb.shape != (ov.size(0),):
+        raise ValueError("max_overlaps / keys must be (B,N) and num_boxes (B)")
+    B, N = int(ov.size(0)), int(ov.size(1))
+    keep = torch.empty((B, int(rois_per_image)), dtype=torch.int32, device=ov.device)
+    nfg = torch.empty((B,), dtype=torch.int32, device=ov.device)
+    nkeep = torch.empty((B,), dtype=torch.int32, device=ov.device)
+    with _on(ov):
+        _lib.call("vosd_sample_rois", _ptr(ov), _ptr(k), _ptr(nb), B, N, int(rois_per_image), int(fg_rois_per_image),
+                  float(fg_thresh), float(bg_thresh_hi), float(bg_thresh_lo), _ptr(keep), _ptr(nfg), _ptr(nkeep), _stream())
+        return keep, nfg, nkeep

@@ -241,12 +241,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's kernel, from the committed
-# `ncu --set full` capture of this same bench command (10 frames / step); not measured live.
-NCU_TRAFFIC = {
-    "roialign_box": {"bytes": 315785216 + 459859712, "source": "profiles/r01_roialign_fwd_v3g_sep_ncu.txt"},
-    "roialign_mask": {"bytes": 663342848 + 195825408, "source": "profiles/r01_roialign_fwd_v3f_sep_box_mask_ncu.txt"},
-}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's kernel: not measurable inside a timed run
+# (ncu replays every kernel ~40 times), so it is read from the committed capture of the same launches
+# (profiles/r02_traffic.json, written next to the ncu summary it comes from, with the commit it was taken at).
+def _load_traffic():
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        return {k: {"bytes": v["bytes"], "source": "%s @ %s" % (v["source"], t.get("commit", "?"))}
+                for k, v in t.items() if isinstance(v, dict) and "bytes" in v}
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+NCU_TRAFFIC = _load_traffic()
 
 
 def touched_texel_bytes(rois, levels, res, sr, shapes, channels):

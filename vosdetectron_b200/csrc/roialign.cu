@@ -1362,7 +1362,9 @@ extern "C" int vosd_roialign_ml_fwd_ws(const float* const* level_data, const int
         if (Wp != W) {
             float* dst = reinterpret_cast<float*>(pad_ws);
             const long long rows = (long long)batch_size * channels * H;
-            roialign_rw_pad<<<grid_for(rows * Wp, 256), 256, 0, stream>>>(src, dst, W, Wp, rows);
+            const long long rb = (rows + 7) / 8;
+            dim3 pgrid(ceil_div(Wp / 4, 32), (unsigned)(rb < 65535 ? rb : 65535));
+            roialign_rw_pad<<<pgrid, dim3(32, 8), 0, stream>>>(src, dst, W, Wp, rows);
             count_launch();
             pad_ws += align_up((size_t)rows * Wp * sizeof(float), 256);
             src = dst;

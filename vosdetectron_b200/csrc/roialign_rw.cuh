@@ -300,13 +300,19 @@ roialign_rw_plan(const __grid_constant__ LevelTable lv, int channels, int pooled
 }
 
 // Copy of a level whose row pitch is not a multiple of 16 bytes into a zero-padded one (tensor maps need it).
+// grid = (ceil(Wp / 4 / 32) , rows / 8), block = (32, 8): a thread writes one aligned float4 of a row.
 __global__ void __launch_bounds__(256)
 roialign_rw_pad(const float* __restrict__ src, float* __restrict__ dst, int W, int Wp, long long rows) {
-    const long long total = rows * Wp;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / Wp;
-        const int x = (int)(i - r * Wp);
-        dst[i] = x < W ? __ldg(src + r * W + x) : 0.f;
+    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    if (x4 >= Wp) return;
+    for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8) {
+        const float* s = src + r * W;
+        float4 v;
+        v.x = x4 < W ? __ldg(s + x4) : 0.f;
+        v.y = x4 + 1 < W ? __ldg(s + x4 + 1) : 0.f;
+        v.z = x4 + 2 < W ? __ldg(s + x4 + 2) : 0.f;
+        v.w = x4 + 3 < W ? __ldg(s + x4 + 3) : 0.f;
+        *reinterpret_cast<float4*>(dst + r * Wp + x4) = v;
     }
 }
 
@@ -441,6 +447,7 @@ __device__ __forceinline__ void rw_process(const RwArgs& a, const CUtensorMap* m
         for (int x = 0; x < BX / 2; x++) V[s][x] = make_float2(0.f, 0.f);
 
     int slot = 0;
+    unsigned ready = 0;                                 // the next row's barrier phase is already known to be complete
     for (int sl = 0; sl < nslab; sl++) {
         if (full) {
             if (leader) bulk_store_wait_read();         // the previous slab's bulk store has read obuf
@@ -451,8 +458,14 @@ __device__ __forceinline__ void rw_process(const RwArgs& a, const CUtensorMap* m
         unsigned wrow_r = wrow_s;
         for (int r = 0; r < th; r++) {
             const unsigned slot_bar = bar_s + 8u * (unsigned)slot;
-            mbar_wait_guard(slot_bar, (phase >> slot) & 1u);
+            // the barrier test of THIS row was issued one row earlier (a try_wait costs ~90 cycles even when the phase
+            // has long completed); only a row whose early test failed spins here
+            if (!ready) mbar_wait_guard(slot_bar, (phase >> slot) & 1u);
             phase ^= 1u << slot;
+            {
+                const int nslot = slot + 1 == NS ? 0 : slot + 1;
+                ready = (sl * th + r + 1 < total) ? mbar_try_wait(bar_s + 8u * (unsigned)nslot, (phase >> nslot) & 1u) : 0u;
+            }
             const float4 wq = lds_v4(wrow_r);
             const float w[4] = {wq.x, wq.y, wq.z, wq.w};
             wrow_r += SW * 4;
@@ -498,12 +511,20 @@ __device__ __forceinline__ void rw_process(const RwArgs& a, const CUtensorMap* m
                         default: break;
                     }
                     // lanes only read back their own scratch row: no barrier needed
+                    // all 28 tap loads first (the asm loads are issued in program order: interleaving them with the FMAs and
+                    // stores of each column would serialise seven load -> FMA -> store round trips)
+                    float tp[28];
 #pragma unroll
                     for (int q = 0; q < 7; q++) {
-                        const float t0 = lds_off(xa[2 * q]), t1 = lds_f32_off4(xa[2 * q]), t2 = lds_off(xa[2 * q + 1]), t3 = lds_f32_off4(xa[2 * q + 1]);
-                        const float R = fmaf(xw[4 * q + 3], t3, fmaf(xw[4 * q + 2], t2, fmaf(xw[4 * q + 1], t1, xw[4 * q] * t0)));
-                        sts_f32(orow + 4u * q, R);
+                        tp[4 * q] = lds_off(xa[2 * q]); tp[4 * q + 1] = lds_f32_off4(xa[2 * q]);
+                        tp[4 * q + 2] = lds_off(xa[2 * q + 1]); tp[4 * q + 3] = lds_f32_off4(xa[2 * q + 1]);
                     }
+                    float R[7];
+#pragma unroll
+                    for (int q = 0; q < 7; q++)
+                        R[q] = fmaf(xw[4 * q + 3], tp[4 * q + 3], fmaf(xw[4 * q + 2], tp[4 * q + 2], fmaf(xw[4 * q + 1], tp[4 * q + 1], xw[4 * q] * tp[4 * q])));
+#pragma unroll
+                    for (int q = 0; q < 7; q++) sts_f32(orow + 4u * q, R[q]);
                 }
                 p++;
                 nxt = (int)((lastp1 >> (8 * p)) & 0xffu);

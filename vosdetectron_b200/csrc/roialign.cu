@@ -1356,16 +1356,18 @@ extern "C" int vosd_roialign_ml_fwd_ws(const float* const* level_data, const int
     // tensor maps over (W, H, N * C), box (BX, 1, 32); levels whose rows are not 16-byte multiples read a padded copy
     RwMaps maps;
     memset(&maps, 0, sizeof(maps));
+    RwPadJobs pj;
+    memset(&pj, 0, sizeof(pj));
+    long long pad_f4 = 0;
     for (int l = 0; l < num_levels; l++) {
         const int W = level_w[l], H = level_h[l], Wp = (W + 3) & ~3;
         const float* src = level_data[l];
         if (Wp != W) {
             float* dst = reinterpret_cast<float*>(pad_ws);
             const long long rows = (long long)batch_size * channels * H;
-            const long long rb = (rows + 7) / 8;
-            dim3 pgrid(ceil_div(Wp / 4, 32), (unsigned)(rb < 65535 ? rb : 65535));
-            roialign_rw_pad<<<pgrid, dim3(32, 8), 0, stream>>>(src, dst, W, Wp, rows);
-            count_launch();
+            pj.src[pj.n] = src; pj.dst[pj.n] = dst; pj.W[pj.n] = W; pj.Wp[pj.n] = Wp; pj.rows[pj.n] = rows;
+            pj.n++;
+            pad_f4 += rows * (Wp / 4);
             pad_ws += align_up((size_t)rows * Wp * sizeof(float), 256);
             src = dst;
         }
@@ -1381,8 +1383,12 @@ extern "C" int vosd_roialign_ml_fwd_ws(const float* const* level_data, const int
         }
     }
     if (cudaMemsetAsync(ctr, 0, sizeof(RwCounters), stream) != cudaSuccess) return VOSD_ERR_LAUNCH;
-    roialign_rw_plan<<<ceil_div(nbase, 8), 128, 0, stream>>>(t, channels, aligned_height, aligned_width, num_rois, rois,
-                                                              roi_level, out_index, items, nbase, cap_extra, ctr);
+    pj.plan_blocks = ceil_div(nbase, 8);
+    // padding copies ride in the same launch: ~8 float4 per thread, at most two blocks per SM beside the plan
+    long long pad_blocks = (pad_f4 + 128 * 8 - 1) / (128 * 8);
+    if (pad_blocks > 2 * kNumSMs) pad_blocks = 2 * kNumSMs;
+    roialign_rw_plan<<<pj.plan_blocks + (int)pad_blocks, 128, 0, stream>>>(t, pj, channels, aligned_height, aligned_width, num_rois,
+                                                                          rois, roi_level, out_index, items, nbase, cap_extra, ctr);
     count_launch();
     if (check_launch() != VOSD_OK) return VOSD_ERR_LAUNCH;
     RwArgs a;
@@ -1392,7 +1398,11 @@ extern "C" int vosd_roialign_ml_fwd_ws(const float* const* level_data, const int
     // work unit = (item, slab range): >= ~8 units per warp, >= 2 slabs per unit
     const int slabs_all = channels / kSlab;
     int split_log2 = 0;
-    while ((1 << (split_log2 + 1)) * 2 <= slabs_all && ((long long)nbase << split_log2) < 8ll * kNumSMs * kRwWarps) split_log2++;
+#ifndef VOSD_RW_UNITS_PER_WARP
+#define VOSD_RW_UNITS_PER_WARP 8
+#endif
+    while ((1 << (split_log2 + 1)) * 2 <= slabs_all && ((long long)nbase << split_log2) < (long long)VOSD_RW_UNITS_PER_WARP * kNumSMs * kRwWarps)
+        split_log2++;
     a.split_log2 = split_log2;
     a.slabs_per_unit = ceil_div(slabs_all, 1 << split_log2);
     a.top_aligned = aligned16(top_data) ? 1 : 0;

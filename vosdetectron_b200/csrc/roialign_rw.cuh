@@ -219,10 +219,47 @@ __device__ __forceinline__ void rw_write_item(RwItem* it, const RwLaneTaps& t, i
     }
 }
 
+// Levels whose row pitch is not a multiple of 16 bytes are copied into zero-padded buffers of the workspace (tensor maps
+// need 16-byte strides).  The copy rides in the plan launch: blocks beyond the plan's own do it (one aligned float4 of a
+// row per thread and step), so it costs no launch of its own and runs beside the plan.
+struct RwPadJobs {
+    const float* src[4];
+    float* dst[4];
+    int W[4], Wp[4];
+    long long rows[4];
+    int n;              // jobs
+    int plan_blocks;    // blocks [0, plan_blocks) plan, the rest pad
+};
+
+__device__ __forceinline__ void rw_pad_block(const RwPadJobs& pj, int blk, int nblk) {
+    for (int j = 0; j < pj.n; j++) {
+        const int q = pj.Wp[j] >> 2, W = pj.W[j], Wp = pj.Wp[j];
+        const long long total = pj.rows[j] * q;
+        const float* __restrict__ src = pj.src[j];
+        float* __restrict__ dst = pj.dst[j];
+        for (long long i = (long long)blk * blockDim.x + threadIdx.x; i < total; i += (long long)nblk * blockDim.x) {
+            const long long r = i / q;
+            const int x4 = (int)(i - r * q) * 4;
+            const float* s = src + r * W;
+            float4 v;
+            v.x = x4 < W ? __ldg(s + x4) : 0.f;
+            v.y = x4 + 1 < W ? __ldg(s + x4 + 1) : 0.f;
+            v.z = x4 + 2 < W ? __ldg(s + x4 + 2) : 0.f;
+            v.w = x4 + 3 < W ? __ldg(s + x4 + 3) : 0.f;
+            *reinterpret_cast<float4*>(dst + r * Wp + x4) = v;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
-roialign_rw_plan(const __grid_constant__ LevelTable lv, int channels, int pooled_h, int pooled_w, int num_rois,
-                 const float* __restrict__ rois, const int* __restrict__ roi_level, const int* __restrict__ out_index,
-                 RwItem* __restrict__ items, int nbase, int cap_extra, RwCounters* __restrict__ ctr) {
+roialign_rw_plan(const __grid_constant__ LevelTable lv, const __grid_constant__ RwPadJobs pj, int channels, int pooled_h,
+                 int pooled_w, int num_rois, const float* __restrict__ rois, const int* __restrict__ roi_level,
+                 const int* __restrict__ out_index, RwItem* __restrict__ items, int nbase, int cap_extra,
+                 RwCounters* __restrict__ ctr) {
+    if ((int)blockIdx.x >= pj.plan_blocks) {
+        rw_pad_block(pj, (int)blockIdx.x - pj.plan_blocks, (int)gridDim.x - pj.plan_blocks);
+        return;
+    }
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     const int k = threadIdx.x & 15;
     const unsigned m = 0xffffu << (threadIdx.x & 16);          // this half of the warp
@@ -296,23 +333,6 @@ roialign_rw_plan(const __grid_constant__ LevelTable lv, int channels, int pooled
         rw_piece(qk, 7, e % nq_, q0, nq);
         RwItem* it = e == 0 ? items + b : items + nbase + extra0 + e - 1;
         rw_write_item(it, t, k, m, rw_eval(t, k, m, p0, np, q0, nq), p0, np, q0, nq, n, out_row, plane0, level, 7 * z, 7 * hq);
-    }
-}
-
-// Copy of a level whose row pitch is not a multiple of 16 bytes into a zero-padded one (tensor maps need it).
-// grid = (ceil(Wp / 4 / 32) , rows / 8), block = (32, 8): a thread writes one aligned float4 of a row.
-__global__ void __launch_bounds__(256)
-roialign_rw_pad(const float* __restrict__ src, float* __restrict__ dst, int W, int Wp, long long rows) {
-    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    if (x4 >= Wp) return;
-    for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8) {
-        const float* s = src + r * W;
-        float4 v;
-        v.x = x4 < W ? __ldg(s + x4) : 0.f;
-        v.y = x4 + 1 < W ? __ldg(s + x4 + 1) : 0.f;
-        v.z = x4 + 2 < W ? __ldg(s + x4 + 2) : 0.f;
-        v.w = x4 + 3 < W ? __ldg(s + x4 + 3) : 0.f;
-        *reinterpret_cast<float4*>(dst + r * Wp + x4) = v;
     }
 }
 

@@ -569,14 +569,28 @@ def gpu_arm(args, rank, world, local_rank):
 
     pending = []          # all-gathers in flight (N > 1): they overlap the next step's kernels
 
-    graph = {"g": None, "out": None, "launches": 0}
+    graph = {"g": None, "out": None, "launches": 0, "alt": None, "n": 0}
 
     fg = {"g": None}      # FrameGather of the bit-packed payload (copy-engine peer pushes; NCCL if unavailable)
 
     def run_step(mark=None, replay=False):
+        direct = False
         if replay and graph["g"] is not None:
-            graph["g"].replay()
-            out = graph["out"]
+            if graph["alt"] is not None and fg["g"] is not None and fg["g"].transport == "ce":
+                # two captured graphs with their own output buffers take turns, so the gather can push straight from
+                # the step's packed masks (no staging copy between consecutive replays); before a graph is replayed
+                # again, the gather that still reads its outputs (two steps back) must be done
+                k = graph["n"] % 2
+                graph["n"] += 1
+                ev = graph["busy"][k]
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
+                (graph["g"] if k == 0 else graph["alt"][0]).replay()
+                out = graph["out"] if k == 0 else graph["alt"][1]
+                direct = True
+            else:
+                graph["g"].replay()
+                out = graph["out"]
         else:
             out = pipe.step(d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks, frame_hw, im_scale, mark=mark)
         if world > 1:
@@ -593,7 +607,10 @@ def gpu_arm(args, rank, world, local_rank):
                 payload = out["masks_packed"]
                 if g_.transport != "ce" and replay and graph["g"] is not None:
                     payload = payload.clone()                  # NCCL reads it after the next replay has started
-                pending.append((None, None, [], g_.start(dets, payload)))
+                slot_ = g_.start(dets, payload, stage=not direct)
+                if direct:
+                    graph["busy"][(graph["n"] - 1) % 2] = g_.done_event(slot_)
+                pending.append((None, None, [], slot_))
             else:
                 while len(pending) > 1:                       # at most two gathers outstanding
                     for w in pending.pop(0)[2]:
@@ -639,7 +656,12 @@ def gpu_arm(args, rank, world, local_rank):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 g_out = pipe.step(d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks, frame_hw, im_scale, mark=None)
-            graph.update(g=g, out=g_out, launches=_lib.launch_count() - l0)
+            graph.update(g=g, out=g_out, launches=_lib.launch_count() - l0, busy=[None, None])
+            if world > 1 and not args.gather_rle and args.gather_transport != "nccl":
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2):
+                    g2_out = pipe.step(d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks, frame_hw, im_scale, mark=None)
+                graph["alt"] = (g2, g2_out)
             for _ in range(3):
                 run_step(replay=True)
             drain()
@@ -682,7 +704,7 @@ def gpu_arm(args, rank, world, local_rank):
             events.append([])
             # the eager step is host-bound (~60 tensor ops + 12 launches): a ~2 ms device-side sleep in front of it lets
             # the host enqueue the whole step first, so the marks bracket kernels, not launch gaps
-            torch.cuda._sleep(4_000_000)
+            torch.cuda._sleep(4_000_000 * (1 + world // 2))    # the ranks share the host cores: longer head start at N > 1
             out = run_step(mark)
         drain()
         torch.cuda.synchronize()

@@ -363,7 +363,7 @@ class FrameGather:
         if int(err) != 0:
             raise RuntimeError("cuStreamWaitValue32 failed: %s" % err)
 
-    def _start_ce(self, dets, masks, slot):
+    def _start_ce(self, dets, masks, slot, stage=True):
         main = torch.cuda.current_stream(self.device)
         self.ev_ready[slot].record(main)
         self.seq[slot] += 1
@@ -374,10 +374,14 @@ class FrameGather:
         cs_h = self.cs.cuda_stream
         with torch.cuda.stream(self.cs):
             self.cs.wait_event(self.ev_ready[slot])
-            sd, sm = self.stage_d[slot], self.stage_m[slot]
-            sd.copy_(dets.contiguous().view(torch.uint8).view(-1), non_blocking=True)
-            sm.copy_(masks.contiguous().view(torch.uint8).view(-1), non_blocking=True)
-            self.ev_staged[slot].record(self.cs)          # the producer may overwrite dets / masks from here on
+            if stage:
+                sd, sm = self.stage_d[slot], self.stage_m[slot]
+                sd.copy_(dets.contiguous().view(torch.uint8).view(-1), non_blocking=True)
+                sm.copy_(masks.contiguous().view(torch.uint8).view(-1), non_blocking=True)
+                self.ev_staged[slot].record(self.cs)      # the producer may overwrite dets / masks from here on
+            else:
+                # pushed straight from the caller's tensors: they must stay untouched until done_event(slot)
+                sd, sm = dets.contiguous().view(torch.uint8).view(-1), masks.contiguous().view(torch.uint8).view(-1)
             for dst_d, dst_m, dst_flag, ack_addr in self.push[slot]:
                 if seq > 1:                                # that peer has read what I pushed into this slot last time
                     self._wait_flag(cs_h, ack_addr, seq - 1)
@@ -387,7 +391,8 @@ class FrameGather:
             for addr in self.wait_addr[slot]:              # every rank's payload has landed in my slot
                 self._wait_flag(cs_h, addr, seq)
             self.ev_done[slot].record(self.cs)
-        main.wait_event(self.ev_staged[slot])
+        if stage:
+            main.wait_event(self.ev_staged[slot])
 
     def _finish_ce(self, slot):
         """Views into the receive slot (no copy): valid until the slot is reused by the gather after next."""
@@ -410,9 +415,15 @@ class FrameGather:
             dst.copy_(val, non_blocking=True)
 
     # ---- public ---------------------------------------------------------------------------------
-    def start(self, dets, masks):
-        """Begin the gather of this batch (asynchronous).  dets / masks may be overwritten by work enqueued on the
-        current stream after this call returns."""
+    def done_event(self, slot):
+        """CUDA event recorded when the gather started in `slot` is complete (copy-engine transport), else None."""
+        return self.ev_done[slot] if (self.world > 1 and self.transport == "ce") else None
+
+    def start(self, dets, masks, stage=True):
+        """Begin the gather of this batch (asynchronous).  With ``stage`` (default) dets / masks may be overwritten by
+        work enqueued on the current stream after this call returns (they are copied to a staging buffer first, and the
+        current stream waits for that copy); ``stage=False`` pushes straight from the caller's tensors, which must then
+        stay untouched until ``done_event(slot)`` (a producer that alternates between two output buffers)."""
         slot = self.count % self.slots
         self.count += 1
         if self.world == 1:
@@ -421,7 +432,7 @@ class FrameGather:
             if self.seq[slot] > 0 and not self.released[slot]:
                 self._release_ce(slot)                     # whatever read the previous contents was enqueued before
             self.released[slot] = False
-            self._start_ce(dets, masks, slot)
+            self._start_ce(dets, masks, slot, stage)
         else:
             if self.works[slot] is not None:
                 for w in self.works[slot]:

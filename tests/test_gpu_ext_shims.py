@@ -171,3 +171,38 @@ def test_non_finite_texels_follow_the_reference(ref_ra, synth, res):
     assert torch.equal(~torch.isfinite(out), bad_ref)
     ok = ~bad_ref
     gate(torch.where(ok, out, torch.zeros_like(out)), torch.where(ok, ref, torch.zeros_like(ref)), "finite outputs")
+
+
+def test_channels_last_inputs_the_tma_kernel_does_not_take_use_the_nchw_kernel(synth):
+    """Channels-last maps the channels-last entry point answers VOSD_ERR_UNSUPPORTED for (five levels; a base that is
+    not 16-byte aligned) still come back from the GPU, through the NCHW kernel."""
+    from vosdetectron_b200 import ops
+    rois = torch.from_numpy(synth.random_rois(61, 80, synth.COCO_BLOB, 1)).cuda()
+    f = torch.from_numpy(synth.fpn_features(62, synth.COCO_BLOB, 1, (4,), 32)[4]).cuda()
+    ref = ops.roi_align_forward(f, rois, 7, 7, 1.0 / 16, 2)
+    # (a) five levels, every one channels-last; all RoIs read level 3
+    cl = [f.contiguous(memory_format=torch.channels_last) for _ in range(5)]
+    lv = torch.full((rois.shape[0],), 3, dtype=torch.int32, device="cuda")
+    out = ops.roi_align_ml_forward(cl, [1.0 / 16] * 5, rois, lv, 7, 7, 2)
+    gate(out, ref, "five channels-last levels")
+    # (b) channels-last view whose base is 4-byte aligned only
+    N, C, H, W = f.shape
+    buf = torch.empty(N * C * H * W + 1, dtype=torch.float32, device="cuda")
+    odd = buf[1:].view(N, H, W, C).permute(0, 3, 1, 2)
+    odd.copy_(f)
+    assert odd.data_ptr() % 16 != 0 and odd.is_contiguous(memory_format=torch.channels_last)
+    gate(ops.roi_align_forward(odd, rois, 7, 7, 1.0 / 16, 2), ref, "unaligned channels-last base")
+
+
+def test_flow_align_ml_backward_validates_its_lists():
+    from vosdetectron_b200 import ops
+    f = [torch.randn(1, 32, 16, 24, device="cuda"), torch.randn(1, 32, 8, 12, device="cuda")]
+    fl = [torch.zeros(1, 2, 16, 24, device="cuda"), torch.zeros(1, 2, 8, 12, device="cuda")]
+    g = [torch.ones_like(t) for t in f]
+    ops.flow_align_ml_backward(g, f, fl)
+    with pytest.raises(ValueError):
+        ops.flow_align_ml_backward(g[:1], f, fl)                  # short grad list
+    with pytest.raises(ValueError):
+        ops.flow_align_ml_backward([g[0], g[0]], f, fl)           # grad of the wrong level
+    with pytest.raises(ValueError):
+        ops.flow_align_ml_backward(g, [f[0], torch.randn(1, 16, 8, 12, device="cuda")], fl)   # channel mismatch

@@ -46,14 +46,17 @@ def _is_channels_last(t):
             and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous())
 
 
-def _nhwc_supported(C, aligned_width, sampling_ratio):
-    return int(sampling_ratio) == 2 and int(aligned_width) in (7, 14, 28) and C % 32 == 0
+def _nhwc_supported(C, aligned_width, sampling_ratio, levels=()):
+    """What vosd_roialign_ml_fwd_nhwc takes (it answers VOSD_ERR_UNSUPPORTED otherwise, include/vosd_b200.h): the
+    reference's heads, at most four levels, 16-byte aligned bases (the tensor maps need them)."""
+    return (int(sampling_ratio) == 2 and int(aligned_width) in (7, 14, 28) and C % 32 == 0 and len(levels) <= 4
+            and all(f.data_ptr() % 16 == 0 for f in levels))
 
 
 def roi_align_forward(features, rois, aligned_height, aligned_width, spatial_scale, sampling_ratio):
     """(N,C,H,W) x (R,5) -> (R,C,ph,pw); roi_align_kernel.cu:65-121 semantics.  Channels-last features take the
     TMA-fed kernel (no layout conversion) where it applies."""
-    if _is_channels_last(features) and _nhwc_supported(features.shape[1], aligned_width, sampling_ratio):
+    if _is_channels_last(features) and _nhwc_supported(features.shape[1], aligned_width, sampling_ratio, [features]):
         r = _need_cuda(rois, "rois")
         if r.dim() != 2 or r.size(1) != 5:
             raise ValueError("rois must be (R,5)")
@@ -114,16 +117,23 @@ def roi_align_ml_forward(level_features, level_scales, rois, roi_level, aligned_
     oi = None if out_index is None else _need_cuda(out_index, "out_index", torch.int32)
     R = r.size(0)
     if (len(level_features) > 0 and all(_is_channels_last(f) for f in level_features)
-            and _nhwc_supported(level_features[0].shape[1], aligned_width, sampling_ratio)):
+            and _nhwc_supported(level_features[0].shape[1], aligned_width, sampling_ratio, level_features)):
         N, C = (int(v) for v in level_features[0].shape[:2])
         if any(tuple(f.shape[:2]) != (N, C) for f in level_features):
             raise ValueError("all levels must share batch size and channel count")
         out = torch.empty((R, C, aligned_height, aligned_width), dtype=torch.float32, device=r.device)
         ptrs, hs, ws, sc = _level_arrays(level_features, level_scales)
         with _on(r):
-            _lib.call("vosd_roialign_ml_fwd_nhwc", ptrs, hs, ws, sc, len(level_features), N, C, int(aligned_height),
-                      int(aligned_width), int(sampling_ratio), R, _ptr(r), _ptr(lv), _ptr(oi), _ptr(out), _stream())
-            return out
+            try:
+                _lib.call("vosd_roialign_ml_fwd_nhwc", ptrs, hs, ws, sc, len(level_features), N, C,
+                          int(aligned_height), int(aligned_width), int(sampling_ratio), R, _ptr(r), _ptr(lv),
+                          _ptr(oi), _ptr(out), _stream())
+                return out
+            except _lib.VosdError as e:
+                # -3: a shape this kernel does not take (documented in the header: the caller uses the NCHW entry
+                # point, still on the GPU); anything else is an error
+                if e.status != -3:
+                    raise
     feats = [_need_cuda(f, "level_features[%d]" % i) for i, f in enumerate(level_features)]
     N, C = (int(v) for v in feats[0].shape[:2])
     if any(tuple(f.shape[:2]) != (N, C) for f in feats):
@@ -228,6 +238,13 @@ def flow_align_ml_backward(level_grads, level_features, level_flows, want_flow_g
         return [], []
     grads = [_need_cuda(g, "grad_output") for g in level_grads]
     N, C = pairs[0][0].shape[:2]
+    if any(f.shape[:2] != (N, C) for f, _ in pairs):
+        raise ValueError("all levels must share batch size and channel count")
+    if len(grads) != len(pairs) or len(level_features) != len(level_flows):
+        raise ValueError("one grad_output and one flow per level")
+    for k, (g, (f, _)) in enumerate(zip(grads, pairs)):
+        if g.shape != f.shape:
+            raise ValueError("grad_output[%d] %s does not match features %s" % (k, tuple(g.shape), tuple(f.shape)))
     gfs = [torch.empty_like(f) for f, _ in pairs]
     gfls = [torch.empty_like(fl) for _, fl in pairs] if want_flow_grad else None
     L = len(pairs)

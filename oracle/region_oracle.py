@@ -713,5 +713,85 @@ def add_fast_rcnn_blobs(samples, k_min=2, k_max=5, mask_rois=None):
     return blobs
 
 
+# --------------------------------------------------------------------------- #
+# (f3) RPN label assignment: get_field_of_anchors (roi_data/data_utils.py:50-102), _get_rpn_blobs
+# (roi_data/rpn.py:143-270).  RNG contract: npr.choice(fg_inds, size, replace=False) = the `size` candidates with the
+# smallest per-anchor keys (keys indexed by the anchor's position in the whole field); npr.randint(n, size=k) =
+# floor(u[:k] * n) of the image's uniforms u (float64 product).
+# --------------------------------------------------------------------------- #
+def field_of_anchors(stride, sizes, aspect_ratios, train_max_size, coarsest_stride=32):
+    """-> ((field*field*A, 4) float32 in (y, x, anchor) order, A, field)."""
+    cell = generate_anchors(stride=stride, sizes=sizes, aspect_ratios=aspect_ratios)
+    A = cell.shape[0]
+    field = int(np.ceil(coarsest_stride * np.ceil(train_max_size / float(coarsest_stride)) / float(stride)))
+    out = np.zeros((field, field, A, 4), np.float64)
+    for y in range(field):
+        for x in range(field):
+            out[y, x] = cell + np.array([x * stride, y * stride, x * stride, y * stride], np.float64)
+    return out.reshape(-1, 4).astype(np.float32), A, field
+
+
+def rpn_labels(im_height, im_width, all_anchors, gt_boxes, keys, rand_bg, batch=256, fg_fraction=0.5, pos=0.7,
+               neg=0.3, straddle=0):
+    """_get_rpn_blobs before the per-field split -> (labels (T) int32, bbox_targets, inside, outside weights (T,4))."""
+    T = all_anchors.shape[0]
+    if straddle >= 0:
+        ins = np.where((all_anchors[:, 0] >= -straddle) & (all_anchors[:, 1] >= -straddle)
+                       & (all_anchors[:, 2] < im_width + straddle) & (all_anchors[:, 3] < im_height + straddle))[0]
+    else:
+        ins = np.arange(T)
+    anchors = all_anchors[ins]
+    n = len(ins)
+    labels = np.full(n, -1, np.int32)
+    a2g_max = None
+    gt_boxes = np.asarray(gt_boxes, np.float32).reshape(-1, 4)
+    if len(gt_boxes) > 0:
+        ov = bbox_overlaps(anchors, gt_boxes)
+        a2g_arg = ov.argmax(axis=1)
+        a2g_max = ov[np.arange(n), a2g_arg]
+        g2a_max = ov.max(axis=0)
+        labels[np.where(ov == g2a_max)[0]] = 1
+        labels[a2g_max >= pos] = 1
+    num_fg = int(fg_fraction * batch)
+    fg = np.where(labels == 1)[0]
+    if len(fg) > num_fg:
+        drop = np.argsort(keys[ins[fg]], kind='stable')[:len(fg) - num_fg]
+        labels[fg[drop]] = -1
+    fg = np.where(labels == 1)[0]
+    num_bg = batch - int(np.sum(labels == 1))
+    bg = np.where(a2g_max < neg)[0] if a2g_max is not None else np.arange(n)
+    if len(bg) > num_bg:
+        posn = np.floor(np.asarray(rand_bg[:num_bg], np.float64) * len(bg)).astype(np.int64)
+        labels[bg[posn]] = 0
+    targets = np.zeros((n, 4), np.float32)
+    if len(fg) > 0:
+        targets[fg] = bbox_transform_inv(anchors[fg], gt_boxes[a2g_arg[fg]]).astype(np.float32, copy=False)
+    inside = np.zeros((n, 4), np.float32)
+    inside[labels == 1] = 1.0
+    outside = np.zeros((n, 4), np.float32)
+    n_ex = np.sum(labels >= 0)
+    if n_ex > 0:
+        outside[labels >= 0] = 1.0 / n_ex
+
+    def unmap(d, fill):
+        full = np.full((T,) + d.shape[1:], fill, d.dtype)
+        full[ins] = d
+        return full
+    return unmap(labels, -1), unmap(targets, 0), unmap(inside, 0), unmap(outside, 0)
+
+
+def rpn_blobs_split(fields, labels, targets, inside, outside):
+    """The per-field reshape of rpn.py:237-270; fields = [(A, field_size), ...]."""
+    out, s = [], 0
+    for A, F in fields:
+        e = s + F * F * A
+        out.append({"rpn_labels_int32_wide": labels[s:e].reshape(1, F, F, A).transpose(0, 3, 1, 2),
+                    "rpn_bbox_targets_wide": targets[s:e].reshape(1, F, F, 4 * A).transpose(0, 3, 1, 2),
+                    "rpn_bbox_inside_weights_wide": inside[s:e].reshape(1, F, F, 4 * A).transpose(0, 3, 1, 2),
+                    "rpn_bbox_outside_weights_wide": outside[s:e].reshape(1, F, F, 4 * A).transpose(0, 3, 1, 2)})
+        s = e
+    return out
+
+
 def num_threads():
     return lib().orc_num_threads()

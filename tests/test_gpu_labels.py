@@ -117,3 +117,85 @@ def test_training_branch_of_the_collect_op(golden):
     op.eval()
     ev = op(inputs, None, im_info)
     assert np.array_equal(ev["rois"], rois[:1000])           # TEST post_nms_topN = 1000 rows, score order
+
+
+# ----------------------------------------------------------------------------- RPN labels (roi_data/rpn.py)
+def _rpn_cfg(fpn, max_size=384):
+    from vosdetectron_b200.config import RegionConfig
+    c = RegionConfig()
+    c.fpn_on = c.multilevel_rpn = fpn
+    c.train_max_size = max_size
+    c.rpn_sizes = (32, 64, 128, 256)
+    return c
+
+
+def _rpn_roidb(g, tag):
+    n = int(g[tag + "n"])
+    roidb = [{"height": int(g["%shw%d" % (tag, i)][0]), "width": int(g["%shw%d" % (tag, i)][1]),
+              "boxes": g["%sboxes%d" % (tag, i)], "gt_classes": g["%sgt_classes%d" % (tag, i)],
+              "is_crowd": g["%sis_crowd%d" % (tag, i)]} for i in range(n)]
+    return (roidb, [float(s) for s in g[tag + "im_scales"]], [g["%skeys%d" % (tag, i)] for i in range(n)],
+            [g["%subg%d" % (tag, i)] for i in range(n)])
+
+
+@pytest.mark.parametrize("tag,fpn", [("fpn_", True), ("nogt_", True), ("single_", False)])
+def test_add_rpn_blobs_matches_the_reference(golden, tag, fpn):
+    """add_rpn_blobs / _get_rpn_blobs against tests/golden/rpn_labels.npz (unmodified reference, RNG contract of
+    roi_data/rpn.py): labels, weights and im_info bit-exact; regression targets rtol 1e-6 (logf vs NumPy's log)."""
+    from vosdetectron_b200.roi_data import rpn
+    g = golden("rpn_labels")
+    c = _rpn_cfg(fpn)
+    roidb, scales, keys, ubg = _rpn_roidb(g, tag)
+    names = rpn.get_rpn_blob_names(cfg=c)
+    blobs = {k: [] for k in names}
+    assert rpn.add_rpn_blobs(blobs, scales, roidb, rand_keys=keys, rand_bg=ubg, cfg=c)
+    assert set(names) == set(k[len(tag):] for k in g.files if k.startswith(tag + "rpn_") or k == tag + "im_info") | {"roidb"}
+    nfg = 0
+    for k in names:
+        if k == "roidb":
+            assert len(blobs[k]) == len(roidb) and all("boxes" in e and "height" not in e for e in blobs[k])
+            continue
+        ref = g[tag + k]
+        assert blobs[k].dtype == ref.dtype and blobs[k].shape == ref.shape, k
+        if "targets" in k:
+            assert np.allclose(blobs[k], ref, rtol=1e-6, atol=1e-7), k
+            assert np.array_equal(blobs[k] != 0, ref != 0), k
+        else:
+            assert np.array_equal(blobs[k], ref), k
+        if "labels" in k:
+            nfg += int((ref == 1).sum())
+    assert (nfg > 0) == (tag != "nogt_")
+
+
+def test_rpn_labels_full_field_against_the_oracle(orc, synth):
+    """The full training field (TRAIN.MAX_SIZE 1333: 451 143 anchors over five levels) against the restatement on
+    random gt boxes, plus the size-independent properties: at most RPN_BATCH_SIZE_PER_IM labelled anchors, at most
+    num_fg foreground, outside weights sum to 4 (one per coordinate), every labelled anchor inside the image."""
+    from vosdetectron_b200.roi_data import rpn
+    c = _rpn_cfg(True, 1333)
+    foas = rpn._fields(c)
+    anchors = np.concatenate([f.field_of_anchors for f in foas])
+    assert anchors.shape[0] == 451143
+    ref_anchors = np.concatenate([orc.field_of_anchors(2. ** l, (32 * 2. ** (l - 2),), (0.5, 1, 2), 1333)[0] for l in range(2, 7)])
+    assert np.array_equal(anchors, ref_anchors)
+    rs = np.random.RandomState(11)
+    h, w = 800., 1216.
+    for G in (1, 12, 60):
+        gt = synth.random_rois(100 + G, G, (int(h), int(w)), 1, smin=20, smax=500)[:, 1:5].astype(np.float32)
+        keys = rs.uniform(size=len(anchors)).astype(np.float32)
+        ubg = rs.uniform(size=256).astype(np.float32)
+        out = rpn._get_rpn_blobs(h, w, foas, anchors, gt, keys, ubg, cfg=c)
+        lab, tg, iw, ow = orc.rpn_labels(h, w, anchors, gt, keys, ubg)
+        ref = orc.rpn_blobs_split([(f.num_cell_anchors, f.field_size) for f in foas], lab, tg, iw, ow)
+        n_lab = n_fg = 0
+        osum = 0.0
+        for mine, r in zip(out, ref):
+            assert np.array_equal(mine["rpn_labels_int32_wide"], r["rpn_labels_int32_wide"])
+            assert np.array_equal(mine["rpn_bbox_inside_weights_wide"], r["rpn_bbox_inside_weights_wide"])
+            assert np.array_equal(mine["rpn_bbox_outside_weights_wide"], r["rpn_bbox_outside_weights_wide"])
+            assert np.allclose(mine["rpn_bbox_targets_wide"], r["rpn_bbox_targets_wide"], rtol=1e-6, atol=1e-7)
+            n_lab += int((mine["rpn_labels_int32_wide"] >= 0).sum())
+            n_fg += int((mine["rpn_labels_int32_wide"] == 1).sum())
+            osum += float(mine["rpn_bbox_outside_weights_wide"].astype(np.float64).sum())
+        assert 0 < n_lab <= 256 and n_fg <= 128
+        assert abs(osum - 4.0) < 1e-4

@@ -287,3 +287,37 @@ def test_label_assignment_oracle_reproduces_the_reference(orc, golden):
     for k in ("mask_rois", "roi_has_mask_int32", "mask_rois_fpn2", "mask_rois_fpn3", "mask_rois_fpn4", "mask_rois_fpn5",
               "mask_rois_idx_restore_int32"):
         assert np.array_equal(blobs[k], g["m_" + k]), k
+
+
+def _rpn_case(orc, g, tag, fields_spec):
+    """Re-run one case of tests/golden/rpn_labels.npz through the restatement -> dict of concatenated blobs."""
+    parts = [orc.field_of_anchors(st, sz, (0.5, 1, 2), 384) for st, sz in fields_spec]
+    anchors = np.concatenate([p[0] for p in parts])
+    fields = [(p[1], p[2]) for p in parts]
+    blobs = {}
+    for i in range(int(g[tag + "n"])):
+        s = g[tag + "im_scales"][i]
+        h, w = g["%shw%d" % (tag, i)]
+        keep = np.where((g["%sgt_classes%d" % (tag, i)] > 0) & (g["%sis_crowd%d" % (tag, i)] == 0))[0]
+        gt = g["%sboxes%d" % (tag, i)][keep] * s
+        lab = orc.rpn_labels(np.round(h * s), np.round(w * s), anchors, gt, g["%skeys%d" % (tag, i)], g["%subg%d" % (tag, i)])
+        for j, d in enumerate(orc.rpn_blobs_split(fields, *lab)):
+            for k, v in d.items():
+                blobs.setdefault(k + ("_fpn%d" % (j + 2) if len(fields) > 1 else ""), []).append(v)
+    return {k: np.concatenate(v) for k, v in blobs.items()}
+
+
+FPN_FIELDS = [(2. ** l, (32 * 2. ** (l - 2),)) for l in range(2, 7)]
+
+
+@pytest.mark.parametrize("tag,spec", [("fpn_", FPN_FIELDS), ("nogt_", FPN_FIELDS), ("single_", [(16, (32, 64, 128, 256))])])
+def test_rpn_label_oracle_reproduces_the_reference(orc, golden, tag, spec):
+    """_get_rpn_blobs restated in oracle/region_oracle.py against tests/golden/rpn_labels.npz (unmodified reference under
+    the RNG contract of vosdetectron_b200/roi_data/rpn.py): every blob bit-exact."""
+    g = golden("rpn_labels")
+    blobs = _rpn_case(orc, g, tag, spec)
+    assert blobs
+    for k, v in blobs.items():
+        ref = g[tag + k]
+        assert v.dtype == ref.dtype and v.shape == ref.shape, k
+        assert np.array_equal(v, ref), k

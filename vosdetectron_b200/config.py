@@ -57,6 +57,20 @@ class RegionConfig:
     train_bg_thresh_lo: float = 0.0
     cls_agnostic_bbox_reg: bool = False
     mask_on: bool = False
+    # TRAIN.RPN_* / RPN.* / FPN.* read by the RPN label assignment (config.py:48,118-145,666-709; roi_data/rpn.py)
+    fpn_on: bool = True
+    multilevel_rpn: bool = True
+    fpn_coarsest_stride: int = 32
+    train_max_size: int = 1333
+    train_rpn_positive_overlap: float = 0.7
+    train_rpn_negative_overlap: float = 0.3
+    train_rpn_fg_fraction: float = 0.5
+    train_rpn_batch_size_per_im: int = 256
+    train_rpn_straddle_thresh: float = 0
+    rpn_stride: int = 16
+    rpn_sizes: tuple = (64, 128, 256, 512)
+    rpn_single_aspect_ratios: tuple = (0.5, 1, 2)
+    identity_training: bool = False
     # lib_vos extras of box_results_with_nms_and_limit / nms_with_mask_iou (config.py:948-953)
     test_num_det_per_class_pre: int = 0
     test_num_det_per_class_post: int = 0
@@ -106,6 +120,18 @@ class RegionConfig:
             train_bg_thresh_lo=float(getattr(cfg.TRAIN, "BG_THRESH_LO", 0.0)),
             cls_agnostic_bbox_reg=bool(getattr(cfg.MODEL, "CLS_AGNOSTIC_BBOX_REG", False)),
             mask_on=bool(getattr(cfg.MODEL, "MASK_ON", False)),
+            fpn_on=bool(getattr(cfg.FPN, "FPN_ON", True)), multilevel_rpn=bool(getattr(cfg.FPN, "MULTILEVEL_RPN", True)),
+            fpn_coarsest_stride=int(getattr(cfg.FPN, "COARSEST_STRIDE", 32)),
+            train_max_size=int(getattr(cfg.TRAIN, "MAX_SIZE", 1333)),
+            train_rpn_positive_overlap=float(getattr(cfg.TRAIN, "RPN_POSITIVE_OVERLAP", 0.7)),
+            train_rpn_negative_overlap=float(getattr(cfg.TRAIN, "RPN_NEGATIVE_OVERLAP", 0.3)),
+            train_rpn_fg_fraction=float(getattr(cfg.TRAIN, "RPN_FG_FRACTION", 0.5)),
+            train_rpn_batch_size_per_im=int(getattr(cfg.TRAIN, "RPN_BATCH_SIZE_PER_IM", 256)),
+            train_rpn_straddle_thresh=float(getattr(cfg.TRAIN, "RPN_STRADDLE_THRESH", 0)),
+            rpn_stride=int(getattr(getattr(cfg, "RPN", None), "STRIDE", 16)),
+            rpn_sizes=tuple(getattr(getattr(cfg, "RPN", None), "SIZES", (64, 128, 256, 512))),
+            rpn_single_aspect_ratios=tuple(getattr(getattr(cfg, "RPN", None), "ASPECT_RATIOS", (0.5, 1, 2))),
+            identity_training=bool(getattr(cfg.MODEL, "IDENTITY_TRAINING", False)),
             test_num_det_per_class_pre=int(getattr(cfg.TEST, "NUM_DET_PER_CLASS_PRE", 0) or 0),
             test_num_det_per_class_post=int(getattr(cfg.TEST, "NUM_DET_PER_CLASS_POST", 0) or 0),
             test_nms_cross_class=float(getattr(cfg.TEST, "NMS_CROSS_CLASS", 0.0) or 0.0),

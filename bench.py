@@ -374,11 +374,12 @@ def cfg4_train_step(dev, steps, warmup, seed=4000, with_ref=True):
         torch.cuda._sleep(6_000_000)
         out = step(mark)
     torch.cuda.synchronize()
-    stage = {n: 0.0 for n in names[:-1]}
+    per = {n: [] for n in names[:-1]}
     for ev in evs:
         for (n0, a), (_, b) in zip(ev[:-1], ev[1:]):
-            if n0 in stage:
-                stage[n0] += a.elapsed_time(b) / steps
+            if n0 in per:
+                per[n0].append(a.elapsed_time(b))
+    stage = {n: float(np.median(v)) for n, v in per.items()}      # median over the steps
     rois, lv = out[0], out[1]
     map_bytes = sum(int(np.prod(s)) * 4 for s in shapes)
     peak = 6650.0
@@ -580,13 +581,13 @@ def gpu_arm(args, rank, world, local_rank):
                 # two captured graphs with their own output buffers take turns, so the gather can push straight from
                 # the step's packed masks (no staging copy between consecutive replays); before a graph is replayed
                 # again, the gather that still reads its outputs (two steps back) must be done
-                k = graph["n"] % 2
+                k = graph["n"] % (1 + len(graph["alt"]))
                 graph["n"] += 1
                 ev = graph["busy"][k]
                 if ev is not None:
                     torch.cuda.current_stream().wait_event(ev)
-                (graph["g"] if k == 0 else graph["alt"][0]).replay()
-                out = graph["out"] if k == 0 else graph["alt"][1]
+                (graph["g"] if k == 0 else graph["alt"][k - 1][0]).replay()
+                out = graph["out"] if k == 0 else graph["alt"][k - 1][1]
                 direct = True
             else:
                 graph["g"].replay()
@@ -598,7 +599,7 @@ def gpu_arm(args, rank, world, local_rank):
             if out["masks_packed"] is not None:
                 if fg["g"] is None:
                     fg["g"] = FrameGather(dets.shape, dets.dtype, out["masks_packed"].shape, out["masks_packed"].dtype, dev,
-                                          transport=args.gather_transport)
+                                          transport=args.gather_transport, slots=max(2, args.gather_slots))
                     print("rank %d: frame gather transport = %s%s" % (rank, fg["g"].transport,
                           "" if fg["g"].why is None else " (copy-engine path unavailable: %s)" % fg["g"].why), file=sys.stderr)
                 g_ = fg["g"]
@@ -609,7 +610,7 @@ def gpu_arm(args, rank, world, local_rank):
                     payload = payload.clone()                  # NCCL reads it after the next replay has started
                 slot_ = g_.start(dets, payload, stage=not direct)
                 if direct:
-                    graph["busy"][(graph["n"] - 1) % 2] = g_.done_event(slot_)
+                    graph["busy"][(graph["n"] - 1) % (1 + len(graph["alt"]))] = g_.done_event(slot_)
                 pending.append((None, None, [], slot_))
             else:
                 while len(pending) > 1:                       # at most two gathers outstanding
@@ -656,12 +657,19 @@ def gpu_arm(args, rank, world, local_rank):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 g_out = pipe.step(d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks, frame_hw, im_scale, mark=None)
-            graph.update(g=g, out=g_out, launches=_lib.launch_count() - l0, busy=[None, None])
+            nrot = max(2, args.gather_slots)
+            graph.update(g=g, out=g_out, launches=_lib.launch_count() - l0, busy=[None] * nrot)
             if world > 1 and not args.gather_rle and args.gather_transport != "nccl":
-                g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2):
-                    g2_out = pipe.step(d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks, frame_hw, im_scale, mark=None)
-                graph["alt"] = (g2, g2_out)
+                # as many captured copies of the step (each with its own outputs) as the gather has slots: the push of
+                # step i reads the outputs of copy i % slots, which is replayed again only after that push is done, so
+                # a rank that falls behind by a hiccup of up to (slots - 1) steps does not stall its peers
+                alts = []
+                for _ in range(nrot - 1):
+                    g2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g2):
+                        g2_out = pipe.step(d_rpn, d_info, d_feats, d_boxes, d_cls, d_masks, frame_hw, im_scale, mark=None)
+                    alts.append((g2, g2_out))
+                graph["alt"] = alts
             for _ in range(3):
                 run_step(replay=True)
             drain()
@@ -680,9 +688,11 @@ def gpu_arm(args, rank, world, local_rank):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host = time.perf_counter()
     for _ in range(args.steps):
         events.append([])
         out = run_step(mark, replay=True)
+    host_enqueue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps   # host time to enqueue one step (+ its gather)
     drain()               # every gather of the timed steps has completed before the closing event
     e1.record()
     barrier()
@@ -695,16 +705,22 @@ def gpu_arm(args, rank, world, local_rank):
         # ... with the two chains JOINED before the box RoIAlign, so each RoIAlign is timed alone on the GPU: the
         # roofline figure is a property of the kernel, not of what happens to run beside it
         overlap_mode, pipe.overlap = pipe.overlap, (pipe.overlap if pipe.overlap is False else True)
+        host_s = 0.0
         for _ in range(3):      # torch.cuda.graph() emptied the allocator cache: re-populate it outside the timed marks
+            torch.cuda.synchronize()
+            t_h = time.perf_counter()
             run_step(None)
+            host_s = max(host_s, time.perf_counter() - t_h)    # host time to ENQUEUE one eager step
         drain()
         torch.cuda.synchronize()
         events.clear()
+        # the eager step is host-bound (~60 tensor ops + 12 launches): a device-side sleep in front of it lets the host
+        # enqueue the whole step first, so the marks bracket kernels, not launch gaps.  Its length follows the measured
+        # enqueue time (a slower or shared host -- N ranks on one box -- needs a longer head start), at least 2 ms
+        sleep_cycles = int(min(max(0.002, 2.0 * host_s), 0.05) * 2.0e9)
         for _ in range(args.steps):
             events.append([])
-            # the eager step is host-bound (~60 tensor ops + 12 launches): a ~2 ms device-side sleep in front of it lets
-            # the host enqueue the whole step first, so the marks bracket kernels, not launch gaps
-            torch.cuda._sleep(4_000_000 * (1 + world // 2))    # the ranks share the host cores: longer head start at N > 1
+            torch.cuda._sleep(sleep_cycles)
             out = run_step(mark)
         drain()
         torch.cuda.synchronize()
@@ -716,14 +732,18 @@ def gpu_arm(args, rank, world, local_rank):
     value = world * B * args.steps / (ms / 1000.0)
 
     # stage duration = distance to the next mark on the SAME stream ("end" / "mask_end" close a chain)
-    stage_ms = {n: 0.0 for n in stage_names}
+    # (median over the K steps: one step whose launches the host delivered late does not move the figure)
+    per_step = {n: [] for n in stage_names}
     for ev in events:
+        acc = {n: 0.0 for n in stage_names}
         for sid in {x[2] for x in ev}:
             chain = [x for x in ev if x[2] == sid]
             for (n0, a, _), (_, b, _) in zip(chain[:-1], chain[1:]):
-                if n0 in stage_ms:
-                    stage_ms[n0] += a.elapsed_time(b)
-    stage_ms = {n: v / args.steps for n, v in stage_ms.items()}
+                if n0 in acc:
+                    acc[n0] += a.elapsed_time(b)
+        for n in stage_names:
+            per_step[n].append(acc[n])
+    stage_ms = {n: (float(np.median(v)) if v else 0.0) for n, v in per_step.items()}
 
     # ---- e2e: host buffers through HostPipeline (H2D + step + D2H per batch, 3 streams, 2 slots) ----
     from vosdetectron_b200.pipeline import HostPipeline
@@ -875,6 +895,7 @@ def gpu_arm(args, rank, world, local_rank):
                 "what": "HostPipeline: pinned host inputs -> H2D (class channel of every detection mask gathered on the host "
                         "inside the timed region) -> step -> D2H of rois, counts and the 1-bit-per-pixel pasted masks"},
         "gpu_launches": int(launches),
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "launches_per_step_expected": STEP_LAUNCHES + (1 if pipe.packed_masks == "rle" else 0),
         "roofline": roofline,
     }
@@ -912,6 +933,8 @@ def main():
     ap.add_argument("--gather-transport", default="auto", choices=["auto", "ce", "nccl"],
                     help="N > 1: exchange of the packed masks -- copy-engine peer pushes over symmetric memory (auto: when "
                          "available) or NCCL all_gather_into_tensor")
+    ap.add_argument("--gather-slots", type=int, default=4,
+                    help="N > 1: rotating slots of the frame gather = captured copies of the step (>= 2)")
     ap.add_argument("--gather-rle", action="store_true",
                     help="N > 1: all-gather COCO RLE strings (fused paste -> RLE kernel) instead of 1-bit-per-pixel masks")
     ap.add_argument("--join-overlap", action="store_true",

@@ -55,14 +55,18 @@ def test_generate_proposals_golden(golden, orc):
     _assert_rois_close(r, g["rois3_min16"])
 
 
-@pytest.mark.parametrize("pre,post", [(2000, 1000), (1000, 1000), (2000, 2000), (0, 300)])
+@pytest.mark.parametrize("pre,post", [(2000, 1000), (1000, 1000), (2000, 2000), (0, 300), (-1, 1000), (20000, 2000),
+                                      (30000, 0)])
 def test_generate_proposals_full_size_vs_oracle(synth, orc, pre, post):
-    """BASELINE config 1: 5 levels of an 800x1344 blob, A=3 (268 569 anchors / image)."""
+    """BASELINE config 1: 5 levels of an 800x1344 blob, A=3 (268 569 anchors / image).  pre <= 0 is the full argsort
+    branch (generate_proposals.py:131-132) on P3-P6: P3 sends all 50 400 boxes into NMS, beyond VOSD_MAX_TOPK, so the
+    call takes the streamed kernel (P2's 201 600 are left to the pre = 20 000 / 30 000 cases: the CPU oracle's NMS is
+    O(kept * n)); post = 0 returns every survivor of the 30 000."""
     from vosdetectron_b200 import ops
     N = 2
     rpn = synth.rpn_outputs(1000, synth.COCO_BLOB, N)
     im_info = np.array([[800, 1344, 1.6667], [800, 1067, 1.25]], dtype=np.float32)
-    lvls = [2, 3, 4, 5, 6] if pre > 0 else [5, 6]              # pre<=0: full sort, bounded by VOSD_MAX_TOPK
+    lvls = [2, 3, 4, 5, 6] if pre > 0 else [3, 4, 5, 6]
     rois, probs, count = ops.generate_proposals_cuda(_levels(orc, rpn, lvls), _cu(im_info), pre, post, 0.7, 0.0)
     for i, l in enumerate(lvls):
         ro, po = orc.generate_proposals(rpn[l][0], rpn[l][1], im_info, orc.fpn_anchors(l), 1. / 2 ** l,
@@ -81,9 +85,14 @@ def test_no_nms_branch_and_limits(synth, orc):
     r, p = _split(rois, probs, count, 0, 1)
     assert len(po) == 200 and np.array_equal(p, po)
     _assert_rois_close(r, ro)
-    big = synth.rpn_outputs(6, synth.COCO_BLOB, 1, levels=(2,))
-    with pytest.raises(_lib.VosdError):                        # full sort of P2 exceeds VOSD_MAX_TOPK
-        ops.generate_proposals_cuda(_levels(orc, big, [2]), _cu(im_info), 0, 50, 0.7, 0.0)
+    # no NMS on a segment longer than VOSD_MAX_TOPK (streamed kernel): the 20 000 best boxes in score order
+    big = synth.rpn_outputs(6, synth.COCO_BLOB, 1, levels=(3,))
+    im_big = np.array([[800, 1344, 1.0]], dtype=np.float32)
+    rois, probs, count = ops.generate_proposals_cuda(_levels(orc, big, [3]), _cu(im_big), 20000, 0, 0.0, 0.0)
+    ro, po = orc.generate_proposals(big[3][0], big[3][1], im_big, orc.fpn_anchors(3), 1. / 8, 20000, 0, 0.0, 0)
+    r, p = _split(rois, probs, count, 0, 1)
+    assert len(po) == 20000 and np.array_equal(p, po)
+    _assert_rois_close(r, ro)
 
 
 def test_decode_anchors_and_nan_guard(synth, orc):

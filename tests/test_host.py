@@ -50,7 +50,9 @@ def test_argument_validation_without_gpu(lib):
     assert lib.vosd_proposals_capacity(lv, 2, 2000, 0) == 2000
     one = ctypes.cast(ctypes.byref(lv[1]), ctypes.POINTER(RpnLevel))
     assert lib.vosd_proposals_capacity(one, 1, 2000, 1000) == 819                  # 13*21*3 < pre
-    assert lib.vosd_proposals_capacity(lv, 2, 0, 1000) == -3                       # full sort of P2 > MAX_TOPK
+    assert lib.vosd_proposals_capacity(lv, 2, 0, 1000) == 1000                     # full sort of P2: streamed kernel
+    assert lib.vosd_proposals_capacity(lv, 2, 0, 0) == 200 * 336 * 3
+    assert lib.vosd_generate_proposals_workspace_bytes(lv, 2, 1, 0, 1000) > 0
     lv[0].num_anchors = 17
     assert lib.vosd_proposals_capacity(lv, 2, 2000, 1000) == -3
     assert lib.vosd_generate_proposals_workspace_bytes(one, 1, 10, 2000, 1000) > 0

@@ -114,6 +114,24 @@ struct RpnKeys {
     }
 };
 
+// The proposal behind one ranked key: anchor of (h, w, a) shifted in fp64 (generate_proposals.py:69-89), decoded with
+// unit weights and clipped to the image; `score` gets the key's score.
+__device__ __forceinline__ float4 decode_ranked(const RpnLevelDev& L, const float* __restrict__ dl, int HW, uint64_t k,
+                                                double xform_clip, float im_h, float im_w, float& score) {
+    score = ordered_to_float((uint32_t)(k >> 32));
+    const uint32_t flat = 0xffffffffu - (uint32_t)k;
+    const int a = (int)(flat % (uint32_t)L.A);
+    const int pos = (int)(flat / (uint32_t)L.A);
+    const int h = pos / L.W, w = pos - h * L.W;
+    const double sx = __dmul_rn((double)w, L.stride), sy = __dmul_rn((double)h, L.stride);
+    const float ax1 = (float)__dadd_rn(L.anchors[4 * a + 0], sx), ay1 = (float)__dadd_rn(L.anchors[4 * a + 1], sy);
+    const float ax2 = (float)__dadd_rn(L.anchors[4 * a + 2], sx), ay2 = (float)__dadd_rn(L.anchors[4 * a + 3], sy);
+    const float* d = dl + (size_t)(4 * a) * HW + pos;
+    const float4 box = decode_box(ax1, ay1, ax2, ay2, __ldg(d), __ldg(d + HW), __ldg(d + 2 * HW), __ldg(d + 3 * HW),
+                                  1.f, 1.f, 1.f, 1.f, xform_clip);
+    return clip_box(box, im_h, im_w);
+}
+
 // K1.  One thread-block CLUSTER of kTopkCluster CTAs per (level, image) segment: the score
 // planes are streamed by 8 SMs at once, histograms meet in distributed shared memory, rank 0
 // sorts the survivors and decodes them.  grid = segments * kTopkCluster, block = 1024,
@@ -154,19 +172,7 @@ topk_decode_kernel(const __grid_constant__ RpnParams p, const float* __restrict_
         float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
         float score = 0.f;
         if (t < m) {
-            const uint64_t k = keys[t];
-            score = ordered_to_float((uint32_t)(k >> 32));
-            const uint32_t flat = 0xffffffffu - (uint32_t)k;
-            const int a = (int)(flat % (uint32_t)L.A);
-            const int pos = (int)(flat / (uint32_t)L.A);
-            const int h = pos / L.W, w = pos - h * L.W;
-            const double sx = __dmul_rn((double)w, L.stride), sy = __dmul_rn((double)h, L.stride);
-            const float ax1 = (float)__dadd_rn(L.anchors[4 * a + 0], sx), ay1 = (float)__dadd_rn(L.anchors[4 * a + 1], sy);
-            const float ax2 = (float)__dadd_rn(L.anchors[4 * a + 2], sx), ay2 = (float)__dadd_rn(L.anchors[4 * a + 3], sy);
-            const float* d = dl + (size_t)(4 * a) * HW + pos;
-            box = decode_box(ax1, ay1, ax2, ay2, __ldg(d), __ldg(d + HW), __ldg(d + 2 * HW), __ldg(d + 3 * HW),
-                             1.f, 1.f, 1.f, 1.f, p.xform_clip);
-            box = clip_box(box, im_h, im_w);
+            box = decode_ranked(L, dl, HW, keys[t], p.xform_clip, im_h, im_w, score);
             keep = keep_box(box, min_size, im_h, im_w);
         }
         int total;
@@ -471,6 +477,166 @@ nms_reduce_cta_kernel(const float4* __restrict__ boxes, const float* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------
+// Segments with more than VOSD_MAX_TOPK boxes entering NMS (pre_nms_topN <= 0 or > 16384 on a large level: the full
+// argsort branch of generate_proposals.py:131-132).  The n x n suppression bitmask of K2 would take gigabytes there, so
+// these calls run ONE streamed kernel instead, one CTA per segment:
+//   repeat: radix-select + sort the next 4096 best keys below the last one taken (a lazily produced full sort),
+//           decode them 1024 at a time, drop the boxes an already kept box suppresses (kept boxes are read back from
+//           the output), resolve the 1024 among themselves on a 1024 x 1024 bitmask in shared memory, append survivors;
+//   until post_nms_topN boxes are kept or the `take` best keys are consumed.
+// Same greedy order, same IoU arithmetic, same output layout as K1-K3.  Work is O(kept * n), memory O(1) per segment.
+// ------------------------------------------------------------------------------------
+constexpr int kStreamBatch = 4096;
+constexpr int kStreamWords = kSelThreads / 64;            // 16 mask words per row of a 1024-box step
+struct BoundedKeys {
+    RpnKeys base;
+    uint64_t bound;                                        // 0: no bound yet; else only keys < bound exist
+    __device__ __forceinline__ uint64_t operator()(int j) const {
+        const uint64_t k = base(j);
+        return (bound == 0ull || k < bound) ? k : 0ull;
+    }
+};
+constexpr size_t kStreamDyn = (size_t)kStreamBatch * 8 + (size_t)kSelThreads * kStreamWords * 8 + (size_t)kSelThreads * 20;
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+proposals_stream_kernel(const __grid_constant__ RpnParams p, const float* __restrict__ im_info, float nms_thresh, int post,
+                        int cap, float* __restrict__ out_rois, float* __restrict__ out_probs, int* __restrict__ out_count) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(dyn);                                            // [kStreamBatch]
+    unsigned long long* smask = reinterpret_cast<unsigned long long*>(dyn + (size_t)kStreamBatch * 8);   // [1024][16]
+    float4* cbox = reinterpret_cast<float4*>(dyn + (size_t)kStreamBatch * 8 + (size_t)kSelThreads * kStreamWords * 8);
+    float* carea = reinterpret_cast<float*>(cbox + kSelThreads);
+    float4* tile = reinterpret_cast<float4*>(smask);          // kept boxes of phase (a): the mask is built after it
+    float* tarea = reinterpret_cast<float*>(tile + kSelThreads);
+    __shared__ SelectShared sh;
+    __shared__ unsigned long long removed[kStreamWords], kept_w[kStreamWords];
+    __shared__ unsigned alive32[kSelThreads / 32];
+    __shared__ int kept_prefix[kStreamWords + 1];
+
+    const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int l = seg / p.num_images, img = seg - l * p.num_images;
+    const RpnLevelDev& L = p.lv[l];
+    const int HW = L.H * L.W;
+    const float im_h = im_info[img * 3 + 0], im_w = im_info[img * 3 + 1], im_s = im_info[img * 3 + 2];
+    const float min_size = __fmul_rn(p.min_size, im_s);
+    const float* __restrict__ dl = L.deltas + (size_t)img * 4 * L.n;
+    const bool use_nms = nms_thresh > 0.f;
+    const int limit = (use_nms && post > 0) ? min(post, cap) : cap;
+    float* rois = out_rois + (size_t)seg * cap * 5;
+    float* probs = out_probs + (size_t)seg * cap;
+
+    BoundedKeys kf{RpnKeys{L.scores + (size_t)img * L.n, L.A, HW}, 0ull};
+    int consumed = 0, kept_total = 0;
+    while (consumed < L.take && kept_total < limit) {
+        const int batch = min(kStreamBatch, L.take - consumed);
+        const int m = select_and_sort(kf, L.n, L.n - consumed, batch, keys, kStreamBatch, sh);
+        __syncthreads();
+        const uint64_t next_bound = keys[m - 1];
+        for (int c0 = 0; c0 < m && kept_total < limit; c0 += kSelThreads) {
+            const int t = c0 + tid;
+            float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+            float score = 0.f;
+            bool alive = false;
+            if (t < m) {
+                box = decode_ranked(L, dl, HW, keys[t], p.xform_clip, im_h, im_w, score);
+                alive = keep_box(box, min_size, im_h, im_w);
+            }
+            const float area = box_area(box);
+            cbox[tid] = box;
+            carea[tid] = area;
+            // (a) against the boxes kept so far
+            if (use_nms) {
+                for (int j0 = 0; j0 < kept_total; j0 += kSelThreads) {
+                    const int nj = min(kSelThreads, kept_total - j0);
+                    __syncthreads();
+                    if (tid < nj) {
+                        const float* r = rois + (size_t)(j0 + tid) * 5;
+                        const float4 kb = make_float4(r[1], r[2], r[3], r[4]);
+                        tile[tid] = kb;
+                        tarea[tid] = box_area(kb);
+                    }
+                    __syncthreads();
+                    if (alive)
+                        for (int j = 0; j < nj; j++)
+                            if (suppresses(tile[j], tarea[j], box, area, nms_thresh)) { alive = false; break; }
+                }
+            }
+            __syncthreads();                                  // tile reads done: the region becomes the bitmask
+            // (b) the step's boxes among themselves
+            const unsigned bal = __ballot_sync(0xffffffffu, alive);
+            if (lane == 0) alive32[tid >> 5] = bal;
+            if (use_nms) {
+                const int w0 = tid >> 6;
+                for (int w = 0; w < kStreamWords; w++) {
+                    unsigned long long bits = 0;
+                    if (alive && w >= w0) {
+                        const int jb = w * 64;
+                        for (int j = (w == w0 ? (tid & 63) + 1 : 0); j < 64; j++)
+                            if (suppresses(box, area, cbox[jb + j], carea[jb + j], nms_thresh)) bits |= 1ull << j;
+                    }
+                    smask[(size_t)tid * kStreamWords + w] = bits;
+                }
+            }
+            __syncthreads();
+            if (tid < kStreamWords) removed[tid] = ~((unsigned long long)alive32[2 * tid] | ((unsigned long long)alive32[2 * tid + 1] << 32));
+            __syncthreads();
+            for (int g = 0; g < kStreamWords; g++) {
+                if (tid < 32) {
+                    unsigned long long kept = ~removed[g];
+                    if (use_nms) {
+                        // greedy resolution of the 64 boxes of group g: the fixpoint of K = alive & ~OR(rows of K), as in K3
+                        const unsigned long long al = kept;
+                        const unsigned long long d0 = smask[(size_t)(g * 64 + lane) * kStreamWords + g];
+                        const unsigned long long d1 = smask[(size_t)(g * 64 + lane + 32) * kStreamWords + g];
+                        for (int round = 0; round < 65; round++) {
+                            const unsigned long long sup = (((kept >> lane) & 1ull) ? d0 : 0ull) | (((kept >> (lane + 32)) & 1ull) ? d1 : 0ull);
+                            const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)sup);
+                            const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(sup >> 32));
+                            const unsigned long long nx = al & ~(((unsigned long long)hi << 32) | lo);
+                            if (nx == kept) break;
+                            kept = nx;
+                        }
+                    }
+                    if (lane == 0) kept_w[g] = kept;
+                }
+                __syncthreads();
+                if (use_nms && g + 1 < kStreamWords) {
+                    const int w_of = tid % kStreamWords, t_of = tid / kStreamWords;         // (later word, box of the group)
+                    if (w_of > g && ((kept_w[g] >> t_of) & 1ull)) {
+                        const unsigned long long row = smask[(size_t)(g * 64 + t_of) * kStreamWords + w_of];
+                        if (row) atomicOr(&removed[w_of], row);
+                    }
+                    __syncthreads();
+                }
+            }
+            if (tid == 0) {
+                int acc = 0;
+                for (int g = 0; g < kStreamWords; g++) { kept_prefix[g] = acc; acc += __popcll(kept_w[g]); }
+                kept_prefix[kStreamWords] = acc;
+            }
+            __syncthreads();
+            {
+                const int g = tid >> 6, b = tid & 63;
+                const unsigned long long kw = kept_w[g];
+                if ((kw >> b) & 1ull) {
+                    const int pos = kept_total + kept_prefix[g] + __popcll(kw & ((1ull << b) - 1ull));
+                    if (pos < limit) {
+                        float* r = rois + (size_t)pos * 5;
+                        r[0] = (float)img; r[1] = box.x; r[2] = box.y; r[3] = box.z; r[4] = box.w;
+                        probs[pos] = score;
+                    }
+                }
+            }
+            kept_total += kept_prefix[kStreamWords];
+            __syncthreads();                                  // the appended rows are visible to phase (a) of the next step
+        }
+        consumed += m;
+        kf.bound = next_bound;
+    }
+    if (tid == 0) out_count[seg] = min(kept_total, limit);
+}
+
 // dispatch of K3 (host): CTA-wide kernel when the segment's bitmask fits 128 KB of shared memory
 static inline cudaError_t launch_nms_reduce(int segs, int seg_stride, int words, const float4* boxes, const float* scores,
                                             const int* count, const unsigned long long* mask, int use_mask, int post, int mode,
@@ -590,6 +756,7 @@ static int seg_take(const vosd_rpn_level& L, int pre) {
 
 struct PropLayout {
     int M, words, cap, S;
+    bool stream;          // some level sends more than VOSD_MAX_TOPK boxes into NMS: proposals_stream_kernel
     size_t off_boxes, off_scores, off_count, off_mask, total;
 };
 static int prop_layout(const vosd_rpn_level* levels, int num_levels, int num_images, int pre, int post,
@@ -603,10 +770,18 @@ static int prop_layout(const vosd_rpn_level* levels, int num_levels, int num_ima
         if (L.num_anchors > VOSD_MAX_ANCHORS) return VOSD_ERR_UNSUPPORTED;
         if ((long long)L.num_anchors * L.height * L.width > 0x7fffffffLL / 8) return VOSD_ERR_UNSUPPORTED;
         const int t = seg_take(L, pre);
-        if (t > VOSD_MAX_TOPK) return VOSD_ERR_UNSUPPORTED;
         M = t > M ? t : M;
     }
     lay.M = M;
+    lay.stream = M > VOSD_MAX_TOPK;
+    if (lay.stream) {
+        lay.words = 0;
+        lay.cap = post > 0 && post < M ? post : M;
+        lay.S = num_levels * num_images;
+        lay.off_boxes = lay.off_scores = lay.off_count = lay.off_mask = 0;
+        lay.total = 256;                      // the streamed kernel keeps its state in shared memory and in the outputs
+        return VOSD_OK;
+    }
     lay.words = (M + 63) / 64;
     lay.cap = post > 0 && post < M ? post : M;
     lay.S = num_levels * num_images;
@@ -673,6 +848,14 @@ extern "C" int vosd_generate_proposals(const vosd_rpn_level* levels, int num_lev
     // without NMS the reference keeps every filtered box (generate_proposals.py:159-166):
     // the caller must size the outputs with post_nms_topN = 0 in that case
     if (!(nms_thresh > 0.f) && lay.cap != lay.M) return VOSD_ERR_BAD_ARG;
+    if (lay.stream) {
+        if (cudaFuncSetAttribute(proposals_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamDyn) != cudaSuccess)
+            return VOSD_ERR_LAUNCH;
+        proposals_stream_kernel<<<lay.S, kSelThreads, kStreamDyn, stream>>>(p, im_info, nms_thresh, post_nms_topN, lay.cap,
+                                                                          out_rois, out_probs, out_count);
+        count_launch();
+        return check_launch();
+    }
     const size_t dyn = (size_t)p.sort_cap * sizeof(uint64_t);
     if (cudaFuncSetAttribute(topk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
         return VOSD_ERR_LAUNCH;

@@ -603,8 +603,14 @@ def gpu_arm(args, rank, world, local_rank):
                     print("rank %d: frame gather transport = %s%s" % (rank, fg["g"].transport,
                           "" if fg["g"].why is None else " (copy-engine path unavailable: %s)" % fg["g"].why), file=sys.stderr)
                 g_ = fg["g"]
-                while len(pending) >= g_.slots:                # the slot about to be reused
-                    g_.finish(pending.pop(0)[3])
+                # results are handed over (finish) and their slot given back to the senders (release) one step after
+                # the gather started -- not only when the slot is about to be reused: with > 2 slots every sender then
+                # holds its acknowledgement whole steps before it needs it
+                depth = 1 if (g_.slots > 2 and g_.transport == "ce") else g_.slots - 1
+                while len(pending) > depth:
+                    s_old = pending.pop(0)[3]
+                    g_.finish(s_old)
+                    g_.release(s_old)
                 payload = out["masks_packed"]
                 if g_.transport != "ce" and replay and graph["g"] is not None:
                     payload = payload.clone()                  # NCCL reads it after the next replay has started
@@ -933,8 +939,11 @@ def main():
     ap.add_argument("--gather-transport", default="auto", choices=["auto", "ce", "nccl"],
                     help="N > 1: exchange of the packed masks -- copy-engine peer pushes over symmetric memory (auto: when "
                          "available) or NCCL all_gather_into_tensor")
-    ap.add_argument("--gather-slots", type=int, default=4,
-                    help="N > 1: rotating slots of the frame gather = captured copies of the step (>= 2)")
+    ap.add_argument("--max-connections", type=int, default=0,
+                    help="experiment: CUDA_DEVICE_MAX_CONNECTIONS for the run (hardware work queues the streams map to)")
+    ap.add_argument("--gather-slots", type=int, default=2,
+                    help="N > 1: rotating slots of the frame gather = captured copies of the step (>= 2; measured at 8 GPUs: "
+                         "2 -> 74.2k, 3 -> 68.7k, 4 -> 66.5k frames/s, profiles/README.md)")
     ap.add_argument("--gather-rle", action="store_true",
                     help="N > 1: all-gather COCO RLE strings (fused paste -> RLE kernel) instead of 1-bit-per-pixel masks")
     ap.add_argument("--join-overlap", action="store_true",
@@ -944,6 +953,8 @@ def main():
                     help="memory order of the synthetic FPN maps: the reference's NCHW (default) or torch.channels_last "
                          "(N,H,W,C), which routes RoIAlign through the TMA-fed channels-last kernel")
     args = ap.parse_args()
+    if args.max_connections > 0:
+        os.environ["CUDA_DEVICE_MAX_CONNECTIONS"] = str(args.max_connections)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

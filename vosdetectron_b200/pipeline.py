@@ -415,6 +415,15 @@ class FrameGather:
             dst.copy_(val, non_blocking=True)
 
     # ---- public ---------------------------------------------------------------------------------
+    def release(self, slot):
+        """The caller has enqueued (on the current stream) every read of the results ``finish(slot)`` returned: tell the
+        senders now that the slot may be overwritten, instead of at the next ``start()`` that reuses it.  With more
+        than two slots this gives every sender its acknowledgement whole steps before it needs it, so a rank that runs
+        late does not hold up the pushes of the others."""
+        if self.world > 1 and self.transport == "ce" and self.seq[slot] > 0 and not self.released[slot]:
+            self._release_ce(slot)
+            self.released[slot] = True
+
     def done_event(self, slot):
         """CUDA event recorded when the gather started in `slot` is complete (copy-engine transport), else None."""
         return self.ev_done[slot] if (self.world > 1 and self.transport == "ce") else None

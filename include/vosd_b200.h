@@ -149,6 +149,19 @@ VOSD_API int vosd_roialign_ml_bwd(const float* top_diff, float* const* level_dif
                          int num_rois, const float* rois, const int* roi_level,
                          const int* out_index, int zero_init, cudaStream_t stream);
 
+/* Channels-last twin of vosd_roialign_ml_bwd: level_diff[l] is the gradient of a torch.channels_last map, i.e.  */
+/* (N, H_l, W_l, C) in memory; everything else as above (top_diff stays (R, C, ph, pw)).  One reduction per       */
+/* (texel, channel) of the footprint, 128-byte transactions (lanes = channels).  Heads of the reference only:     */
+/* sampling_ratio 2, pooled sizes multiples of 7, channels % 32 == 0; anything else VOSD_ERR_UNSUPPORTED (the      */
+/* caller converts and uses vosd_roialign_ml_bwd).  Replaces the same ROIAlignBackwardLaucher calls                */
+/* (roi_align_kernel.cu:195-290) for a channels-last backbone.                                                     */
+VOSD_API int vosd_roialign_ml_bwd_nhwc(const float* top_diff, float* const* level_diff, const int* level_h,
+                                       const int* level_w, const float* level_scale, int num_levels,
+                                       int batch_size, int channels,
+                                       int aligned_height, int aligned_width, int sampling_ratio,
+                                       int num_rois, const float* rois, const int* roi_level,
+                                       const int* out_index, int zero_init, cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------------ */
 /* RPN proposal generation for all (level, image) segments in one call.                   */
 /* Replaces GenerateProposalsOp.forward + proposals_for_one_image                         */

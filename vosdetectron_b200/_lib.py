@@ -53,6 +53,9 @@ SIGNATURES = {
     "vosd_roialign_ml_bwd": (ctypes.c_int, [vp, ctypes.POINTER(vp), c_int_p, c_int_p, c_float_p, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, vp, vp, vp, ctypes.c_int, vp]),
+    "vosd_roialign_ml_bwd_nhwc": (ctypes.c_int, [vp, ctypes.POINTER(vp), c_int_p, c_int_p, c_float_p, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int, vp, vp, vp, ctypes.c_int, vp]),
     "vosd_proposals_capacity": (ctypes.c_int, [ctypes.POINTER(RpnLevel), ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "vosd_generate_proposals_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(RpnLevel), ctypes.c_int,
                                                                   ctypes.c_int, ctypes.c_int, ctypes.c_int]),

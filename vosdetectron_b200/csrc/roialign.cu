@@ -1001,6 +1001,7 @@ roialign_bwd_records(const __grid_constant__ LevelTable lv, int channels, int po
 #include "roialign_sep.cuh"
 #include "roialign_nhwc.cuh"
 #include "roialign_rw.cuh"
+#include "roialign_nhwc_bwd.cuh"
 namespace vosd {
 
 // test hook (vosd_debug_force_generic): 0 = default (separable forward where it applies, record-based backward), 1 = generic kernels
@@ -1430,6 +1431,35 @@ extern "C" int vosd_roialign_ml_bwd(const float* top_diff, float* const* level_d
     if (num_levels > 1 && !roi_level && num_rois > 0) return VOSD_ERR_BAD_ARG;
     return ml_bwd(t, num_levels, batch_size, channels, aligned_height, aligned_width, sampling_ratio,
                   num_rois, rois, roi_level, out_index, top_diff, zero_init, stream);
+}
+
+// Channels-last gradient maps (roialign_nhwc_bwd.cuh): level_diff[l] is (N, H_l, W_l, C) in memory.
+extern "C" int vosd_roialign_ml_bwd_nhwc(const float* top_diff, float* const* level_diff, const int* level_h,
+                                         const int* level_w, const float* level_scale, int num_levels,
+                                         int batch_size, int channels,
+                                         int aligned_height, int aligned_width, int sampling_ratio,
+                                         int num_rois, const float* rois, const int* roi_level,
+                                         const int* out_index, int zero_init, cudaStream_t stream) {
+    LevelTable t;
+    int rc = fill_table(t, (const float* const*)level_diff, level_h, level_w, level_scale, num_levels);
+    if (rc) return rc;
+    if (channels <= 0 || aligned_height <= 0 || aligned_width <= 0 || num_rois < 0 || batch_size <= 0) return VOSD_ERR_BAD_SHAPE;
+    if (sampling_ratio != 2 || aligned_height % 7 || aligned_width % 7 || channels % 32) return VOSD_ERR_UNSUPPORTED;
+    const int bh = aligned_height / 7, bw = aligned_width / 7;
+    if (bh * bw > 65535) return VOSD_ERR_UNSUPPORTED;
+    if (num_levels > 1 && !roi_level && num_rois > 0) return VOSD_ERR_BAD_ARG;
+    if (zero_init) {
+        for (int l = 0; l < num_levels; l++)
+            if (cudaMemsetAsync(t.data[l], 0, sizeof(float) * (size_t)batch_size * channels * t.h[l] * t.w[l], stream) != cudaSuccess)
+                return VOSD_ERR_LAUNCH;
+    }
+    if (num_rois == 0) return VOSD_OK;
+    if (!rois || !top_diff) return VOSD_ERR_BAD_ARG;
+    dim3 grid(num_rois, bh * bw);
+    roialign_bwd_nhwc<<<grid, 32 * kNbWarps, 0, stream>>>(t, channels, aligned_height, aligned_width, bw, rois, roi_level,
+                                                          out_index, top_diff);
+    count_launch();
+    return check_launch();
 }
 
 // Test hook: route RoIAlign through the generic (un-staged) kernels so both paths stay covered.

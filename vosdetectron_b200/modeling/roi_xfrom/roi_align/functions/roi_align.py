@@ -17,6 +17,7 @@ class _RoIAlign(Function):
     def forward(ctx, features, rois, aligned_height, aligned_width, spatial_scale, sampling_ratio):
         ctx.params = (aligned_height, aligned_width, spatial_scale, sampling_ratio)
         ctx.feature_size = tuple(features.shape)
+        ctx.channels_last = ops._is_channels_last(features)      # the gradient comes back in the map's memory order
         ctx.save_for_backward(rois)
         return ops.roi_align_forward(features, rois, aligned_height, aligned_width, spatial_scale,
                                      sampling_ratio)
@@ -27,7 +28,8 @@ class _RoIAlign(Function):
         ah, aw, scale, sr = ctx.params
         if not grad_output.is_cuda:
             raise NotImplementedError("RoIAlign backward needs CUDA tensors")
-        grad_input = ops.roi_align_backward(grad_output.contiguous(), rois, ctx.feature_size, ah, aw, scale, sr)
+        grad_input = ops.roi_align_backward(grad_output.contiguous(), rois, ctx.feature_size, ah, aw, scale, sr,
+                                            channels_last=ctx.channels_last)
         return grad_input, None, None, None, None, None
 
 
@@ -55,6 +57,7 @@ class _RoIAlignML(Function):
                 *level_features):
         ctx.params = (aligned_height, aligned_width, sampling_ratio, tuple(scales))
         ctx.shapes = [tuple(f.shape) for f in level_features]
+        ctx.channels_last = len(level_features) > 0 and all(ops._is_channels_last(f) for f in level_features)
         ctx.save_for_backward(rois, roi_level, out_index if out_index is not None else torch.empty(0))
         ctx.has_index = out_index is not None
         return ops.roi_align_ml_forward(level_features, scales, rois, roi_level, aligned_height,
@@ -65,7 +68,8 @@ class _RoIAlignML(Function):
         rois, roi_level, out_index = ctx.saved_tensors
         ah, aw, sr, scales = ctx.params
         grads = ops.roi_align_ml_backward(grad_output.contiguous(), ctx.shapes, scales, rois, roi_level,
-                                          ah, aw, sr, out_index if ctx.has_index else None)
+                                          ah, aw, sr, out_index if ctx.has_index else None,
+                                          channels_last=ctx.channels_last)
         return (None, None, None, None, None, None, None) + tuple(grads)
 
 

@@ -69,9 +69,13 @@ def roi_align_forward(features, rois, aligned_height, aligned_width, spatial_sca
 
 
 def roi_align_backward(grad_output, rois, feature_size, aligned_height, aligned_width, spatial_scale,
-                       sampling_ratio):
+                       sampling_ratio, channels_last=False):
     """grad (R,C,ph,pw) -> (N,C,H,W); roi_align_kernel.cu:195-270 semantics.  The gradient map
-    is cleared on the stream by the library (zero_init=1), no separate fill kernel."""
+    is cleared on the stream by the library (zero_init=1), no separate fill kernel.  ``channels_last``: the gradient
+    comes back as a torch.channels_last tensor (see roi_align_ml_backward)."""
+    if channels_last:
+        return roi_align_ml_backward(grad_output, [feature_size], [spatial_scale], rois, None, aligned_height,
+                                     aligned_width, sampling_ratio, channels_last=True)[0]
     g = _need_cuda(grad_output, "grad_output")
     r = _need_cuda(rois, "rois")
     N, C, H, W = (int(v) for v in feature_size)
@@ -156,12 +160,29 @@ def roi_align_ml_forward(level_features, level_scales, rois, roi_level, aligned_
 
 
 def roi_align_ml_backward(grad_output, level_shapes, level_scales, rois, roi_level, aligned_height,
-                          aligned_width, sampling_ratio, out_index=None):
+                          aligned_width, sampling_ratio, out_index=None, channels_last=False):
+    """grad (R,C,ph,pw) -> one gradient map per level.  ``channels_last=True`` (the maps of the forward were
+    torch.channels_last tensors): the gradients are accumulated directly in that memory order by the channels-last
+    kernel (heads of the reference: sampling_ratio 2, pooled sizes multiples of 7, C % 32 == 0); other heads are
+    accumulated in NCHW order and converted."""
     g = _need_cuda(grad_output, "grad_output")
     r = _need_cuda(rois, "rois")
     lv = None if roi_level is None else _need_cuda(roi_level, "roi_level", torch.int32)
     oi = None if out_index is None else _need_cuda(out_index, "out_index", torch.int32)
-    grads = [torch.empty(tuple(int(v) for v in s), dtype=torch.float32, device=g.device) for s in level_shapes]
+    shapes = [tuple(int(v) for v in s) for s in level_shapes]
+    if channels_last:
+        N, C = shapes[0][:2]
+        if (int(sampling_ratio) == 2 and int(aligned_height) % 7 == 0 and int(aligned_width) % 7 == 0 and C % 32 == 0
+                and len(shapes) <= _lib.MAX_LEVELS):
+            grads = [torch.empty(s, dtype=torch.float32, device=g.device, memory_format=torch.channels_last) for s in shapes]
+            ptrs, hs, ws, sc = _level_arrays(grads, level_scales)
+            with _on(g):
+                _lib.call("vosd_roialign_ml_bwd_nhwc", _ptr(g), ptrs, hs, ws, sc, len(grads), N, C, int(aligned_height),
+                          int(aligned_width), int(sampling_ratio), r.size(0), _ptr(r), _ptr(lv), _ptr(oi), 1, _stream())
+                return grads
+        return [x.contiguous(memory_format=torch.channels_last)
+                for x in roi_align_ml_backward(g, shapes, level_scales, r, lv, aligned_height, aligned_width, sampling_ratio, oi)]
+    grads = [torch.empty(s, dtype=torch.float32, device=g.device) for s in shapes]
     N, C = grads[0].shape[:2]
     ptrs, hs, ws, sc = _level_arrays(grads, level_scales)
     with _on(g):

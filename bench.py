@@ -413,6 +413,22 @@ def cfg4_train_step(dev, steps, warmup, seed=4000, with_ref=True):
         lib.ROIAlignBackwardLaucher.argtypes = [vp, ctypes.c_float] + [ctypes.c_int] * 8 + [vp, vp, vp]
         st = torch.cuda.current_stream().cuda_stream
 
+        ref_out = {}
+
+        def ulp_hist(mine, theirs):
+            """Distance of the default forward to the reference kernel's output in units in the last place of the
+            reference value: counts of 0, 1, 2, 3, 4-15, >= 16 ulp (the default kernel re-associates the bilinear sum)."""
+            a_ = mine.contiguous().view(torch.int32).to(torch.int64)
+            b_ = theirs.contiguous().view(torch.int32).to(torch.int64)
+            a_ = torch.where(a_ < 0, -(a_ & 0x7fffffff), a_)              # sign-magnitude -> monotone integer line
+            b_ = torch.where(b_ < 0, -(b_ & 0x7fffffff), b_)
+            d = (a_ - b_).abs().flatten()
+            edges = [0, 1, 2, 3, 4, 16]
+            counts = [int(((d >= lo) & (d < hi)).sum()) for lo, hi in zip(edges, edges[1:] + [1 << 62])]
+            return {"ulp_0": counts[0], "ulp_1": counts[1], "ulp_2": counts[2], "ulp_3": counts[3], "ulp_4_15": counts[4],
+                    "ulp_ge_16": counts[5], "max_abs_err": float((mine - theirs).abs().max()),
+                    "max_abs_ref": float(theirs.abs().max())}
+
         def ref_pass(rr, ll, top, res_):
             idx = [torch.nonzero(ll == i).flatten() for i in range(len(fl))]
             per = [rr[i].contiguous() for i in idx]
@@ -428,7 +444,7 @@ def cfg4_train_step(dev, steps, warmup, seed=4000, with_ref=True):
                 outs.append(o)
             shuffled = torch.cat(outs)
             restore = torch.argsort(torch.cat(idx))
-            _ = shuffled[restore]
+            ref_out["fwd"] = shuffled[restore]
             b.record()
             for i, f in enumerate(fl):                     # backward: zero-filled maps + one launch per level
                 g = torch.zeros_like(f)
@@ -450,9 +466,29 @@ def cfg4_train_step(dev, steps, warmup, seed=4000, with_ref=True):
                 ts.append(ref_pass(rr, ll, top, res_))
             ref["roialign_%s_fwd_ms" % name] = float(np.median([t[0] for t in ts]))
             ref["roialign_%s_bwd_ms" % name] = float(np.median([t[1] for t in ts]))
+            ref["roialign_%s_fwd_vs_reference" % name] = ulp_hist(ops.roi_align_ml_forward(fl, sc, rr, ll, res_, res_, 2), ref_out["fwd"])
         ref["how"] = ("oracle/_ref/libref_roialign.so = the unmodified roi_align_kernel.cu built for sm_100a; per-level launches + "
                       "cat + restore (forward), zero-filled maps + per-level launches (backward), as the reference drives it")
         res["ref_gpu_kernel"] = ref
+    # the same two backward launches with the gradient maps in the OTHER memory order (torch.channels_last, the
+    # channels-last kernel): an extra key, not part of the step above
+    alt = {}
+    for name, top, rr, ll, pooled in (("roialign_box_bwd", top_box, rois, lv, 7),
+                                      ("roialign_mask_bwd", top_mask, rois[:CFG4_MASK_ROIS].contiguous(),
+                                       lv[:CFG4_MASK_ROIS].contiguous(), 14)):
+        ts = []
+        for i in range(max(5, steps // 2) + 2):
+            torch.cuda._sleep(4_000_000)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.roi_align_ml_backward(top, shapes, sc, rr, ll, pooled, pooled, 2, channels_last=True)
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(a.elapsed_time(b))
+        ms = float(np.median(ts))
+        alt[name] = {"ms": ms, "gbs": alg_bwd[name] / (ms * 1e-3) / 1e9, "frac": alg_bwd[name] / (ms * 1e-3) / 1e9 / peak}
+    res["alt_layout"] = {"features_layout": "channels_last", "roofline": alt}
     return res
 
 

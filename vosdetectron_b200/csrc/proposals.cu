@@ -28,9 +28,10 @@ __device__ __forceinline__ float4 decode_box(float ax1, float ay1, float ax2, fl
     const float bh = __fadd_rn(__fsub_rn(ay2, ay1), 1.0f);
     const float cx = __fadd_rn(ax1, __fmul_rn(0.5f, bw));
     const float cy = __fadd_rn(ay1, __fmul_rn(0.5f, bh));
-    const float dx = __fdiv_rn(d0, wx), dy = __fdiv_rn(d1, wy);
-    const double dw = fmin((double)__fdiv_rn(d2, ww), clip);
-    const double dh = fmin((double)__fdiv_rn(d3, wh), clip);
+    // (x / 1 is x exactly: the RPN decode passes unit weights as literals and skips four IEEE divisions per anchor)
+    const float dx = wx == 1.f ? d0 : __fdiv_rn(d0, wx), dy = wy == 1.f ? d1 : __fdiv_rn(d1, wy);
+    const double dw = fmin((double)(ww == 1.f ? d2 : __fdiv_rn(d2, ww)), clip);
+    const double dh = fmin((double)(wh == 1.f ? d3 : __fdiv_rn(d3, wh)), clip);
     const float pcx = __fadd_rn(__fmul_rn(dx, bw), cx);
     const float pcy = __fadd_rn(__fmul_rn(dy, bh), cy);
     const double pw = fmax(__dmul_rn(exp(dw), (double)bw), 1.0);
@@ -668,20 +669,23 @@ struct DecodeAllParams {
     double stride, clip;
     double anchors[4 * VOSD_MAX_ANCHORS];
 };
+// kA > 0: the anchor count is a compile-time constant (A = 3, every FPN level): the anchor loop unrolls and the double-
+// precision chains of the anchors of a position overlap; kA = 0: any A.
+template <int kA>
 __global__ void __launch_bounds__(256)
 decode_all_kernel(const __grid_constant__ DecodeAllParams p, const float* __restrict__ im_info, float4* __restrict__ out) {
+    // grid = (position blocks, images): no 64-bit division per position
     const int HW = p.H * p.W;
-    const long long total = (long long)p.N * HW;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int img = (int)(idx / HW);
-        const int pos = (int)(idx - (long long)img * HW);
+    const int img = blockIdx.y;
+    const float im_h = __ldg(im_info + img * 3), im_w = __ldg(im_info + img * 3 + 1);
+    for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < HW; pos += gridDim.x * blockDim.x) {
         const int h = pos / p.W, w = pos - h * p.W;
-        const float im_h = __ldg(im_info + img * 3), im_w = __ldg(im_info + img * 3 + 1);
         const double sx = __dmul_rn((double)w, p.stride), sy = __dmul_rn((double)h, p.stride);
         const float* d = p.deltas + (size_t)img * 4 * p.A * HW + pos;
-        float4* o = out + ((size_t)img * HW + pos) * p.A;
-        for (int a = 0; a < p.A; a++) {
+        const int A = kA > 0 ? kA : p.A;
+        float4* o = out + ((size_t)img * HW + pos) * A;
+#pragma unroll
+        for (int a = 0; a < A; a++) {
             const float ax1 = (float)__dadd_rn(p.anchors[4 * a + 0], sx), ay1 = (float)__dadd_rn(p.anchors[4 * a + 1], sy);
             const float ax2 = (float)__dadd_rn(p.anchors[4 * a + 2], sx), ay2 = (float)__dadd_rn(p.anchors[4 * a + 3], sy);
             const float* da = d + (size_t)(4 * a) * HW;
@@ -884,10 +888,12 @@ extern "C" int vosd_decode_anchors(const vosd_rpn_level* level, int num_images, 
     p.deltas = level->deltas; p.H = level->height; p.W = level->width; p.A = level->num_anchors; p.N = num_images;
     p.stride = level->feat_stride; p.clip = log(1000.0 / 16.0);
     for (int k = 0; k < 4 * p.A; k++) p.anchors[k] = level->anchors[k];
-    const long long total = (long long)num_images * p.H * p.W;
-    long long blocks = (total + 255) / 256;
-    if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
-    decode_all_kernel<<<(int)blocks, 256, 0, stream>>>(p, im_info, reinterpret_cast<float4*>(boxes));
+    if (num_images > 65535) return VOSD_ERR_UNSUPPORTED;
+    int blocks = ceil_div(p.H * p.W, 256);
+    const int cap = ceil_div(kNumSMs * 32, num_images);
+    if (blocks > cap) blocks = cap;
+    if (p.A == 3) decode_all_kernel<3><<<dim3(blocks, num_images), 256, 0, stream>>>(p, im_info, reinterpret_cast<float4*>(boxes));
+    else decode_all_kernel<0><<<dim3(blocks, num_images), 256, 0, stream>>>(p, im_info, reinterpret_cast<float4*>(boxes));
     count_launch();
     return check_launch();
 }

@@ -767,6 +767,21 @@ def gpu_arm(args, rank, world, local_rank):
         drain()
         torch.cuda.synchronize()
         pipe.overlap = overlap_mode
+        # the proposal chain with the GPU to itself (in the step it runs beside the mask RoIAlign, whose persistent CTAs
+        # hold every SM: the "proposals" stage above includes that wait)
+        alone = {"proposals": [], "collect_distribute": []}
+        for _ in range(max(5, args.steps // 2)):
+            torch.cuda._sleep(sleep_cycles)
+            evs_ = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            evs_[0].record()
+            pipe.proposals(d_rpn, d_info, mark=lambda n: evs_[1].record())
+            evs_[2].record()
+            torch.cuda.synchronize()
+            alone["proposals"].append(evs_[0].elapsed_time(evs_[1]))
+            alone["collect_distribute"].append(evs_[1].elapsed_time(evs_[2]))
+        stages_alone = {k: float(np.median(v)) for k, v in alone.items()}
+    if graph["g"] is None:
+        stages_alone = None
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -908,6 +923,7 @@ def gpu_arm(args, rank, world, local_rank):
                 "traffic": NCU_TRAFFIC.get(dom, {}).get("bytes"), "traffic_source": NCU_TRAFFIC.get(dom, {}).get("source"),
                 "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": stage_ms[dom],
                 "peak_source": peak_src,
+                "proposal_chain_alone_ms": stages_alone,
                 "stages": {k: {"ms": stage_ms[k], "algorithmic_bytes": alg.get(k),
                                "gbs": (alg[k] / (stage_ms[k] * 1e-3) / 1e9) if k in alg and stage_ms[k] > 0 else None}
                            for k in stage_ms}}

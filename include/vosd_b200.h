@@ -190,7 +190,11 @@ VOSD_API size_t vosd_generate_proposals_workspace_bytes(const vosd_rpn_level* le
  *   out_rois  (num_levels, N, cap, 5) fp32 [image, x1,y1,x2,y2] (rows >= count untouched = caller's fill);
  *   out_probs (num_levels, N, cap) fp32; out_count (num_levels, N) int32.
  *   nms_thresh <= 0 skips NMS (generate_proposals.py:159).  Ties between equal scores are
- *   ordered by lower flat (h,w,a) index first (the reference's order is unspecified).      */
+ *   ordered by lower flat (h,w,a) index first (the reference's order is unspecified).
+ *   Any pre_nms_topN: while at most VOSD_MAX_TOPK boxes of every level enter NMS the call is three launches (cluster
+ *   top-k + decode, IoU bitmask, greedy reduce); beyond that (pre_nms_topN <= 0 or > 16384 on a large level: the full
+ *   argsort branch, generate_proposals.py:131-132) one streamed kernel sorts lazily in batches and keeps the greedy
+ *   state in shared memory and in the outputs -- same results, O(kept * n) work, no n x n bitmask.                */
 VOSD_API int vosd_generate_proposals(const vosd_rpn_level* levels, int num_levels, int num_images,
                             const float* im_info, int pre_nms_topN, int post_nms_topN,
                             float nms_thresh, float min_size,

@@ -668,11 +668,19 @@ struct DecodeAllParams {
     int H, W, A, N;
     double stride, clip;
     double anchors[4 * VOSD_MAX_ANCHORS];
+    float fanchors[4 * VOSD_MAX_ANCHORS];     // kExact: the same anchors, exactly representable in fp32
+    float fstride;
 };
 // kA > 0: the anchor count is a compile-time constant (A = 3, every FPN level): the anchor loop unrolls and the double-
 // precision chains of the anchors of a position overlap; kA = 0: any A.
-template <int kA>
-__global__ void __launch_bounds__(256)
+// kExact: every anchor coordinate is a multiple of 0.5, the stride an integer and all shifted coordinates stay below
+// 2^22 (checked on the host), so "anchor + shift in fp64, rounded to fp32" (boxes.py:164) is an exact fp32 sum: the
+// four fp64 additions and conversions per anchor are skipped with identical bits.
+#ifndef VOSD_DECODE_MINB
+#define VOSD_DECODE_MINB 3
+#endif
+template <int kA, bool kExact>
+__global__ void __launch_bounds__(256, VOSD_DECODE_MINB)
 decode_all_kernel(const __grid_constant__ DecodeAllParams p, const float* __restrict__ im_info, float4* __restrict__ out) {
     // grid = (position blocks, images): no 64-bit division per position
     const int HW = p.H * p.W;
@@ -680,14 +688,21 @@ decode_all_kernel(const __grid_constant__ DecodeAllParams p, const float* __rest
     const float im_h = __ldg(im_info + img * 3), im_w = __ldg(im_info + img * 3 + 1);
     for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < HW; pos += gridDim.x * blockDim.x) {
         const int h = pos / p.W, w = pos - h * p.W;
-        const double sx = __dmul_rn((double)w, p.stride), sy = __dmul_rn((double)h, p.stride);
+        const double sx = kExact ? 0.0 : __dmul_rn((double)w, p.stride), sy = kExact ? 0.0 : __dmul_rn((double)h, p.stride);
+        const float fsx = __fmul_rn((float)w, p.fstride), fsy = __fmul_rn((float)h, p.fstride);
         const float* d = p.deltas + (size_t)img * 4 * p.A * HW + pos;
         const int A = kA > 0 ? kA : p.A;
         float4* o = out + ((size_t)img * HW + pos) * A;
 #pragma unroll
         for (int a = 0; a < A; a++) {
-            const float ax1 = (float)__dadd_rn(p.anchors[4 * a + 0], sx), ay1 = (float)__dadd_rn(p.anchors[4 * a + 1], sy);
-            const float ax2 = (float)__dadd_rn(p.anchors[4 * a + 2], sx), ay2 = (float)__dadd_rn(p.anchors[4 * a + 3], sy);
+            float ax1, ay1, ax2, ay2;
+            if (kExact) {
+                ax1 = __fadd_rn(p.fanchors[4 * a + 0], fsx); ay1 = __fadd_rn(p.fanchors[4 * a + 1], fsy);
+                ax2 = __fadd_rn(p.fanchors[4 * a + 2], fsx); ay2 = __fadd_rn(p.fanchors[4 * a + 3], fsy);
+            } else {
+                ax1 = (float)__dadd_rn(p.anchors[4 * a + 0], sx); ay1 = (float)__dadd_rn(p.anchors[4 * a + 1], sy);
+                ax2 = (float)__dadd_rn(p.anchors[4 * a + 2], sx); ay2 = (float)__dadd_rn(p.anchors[4 * a + 3], sy);
+            }
             const float* da = d + (size_t)(4 * a) * HW;
             float4 box = decode_box(ax1, ay1, ax2, ay2, __ldg(da), __ldg(da + HW), __ldg(da + 2 * HW),
                                     __ldg(da + 3 * HW), 1.f, 1.f, 1.f, 1.f, p.clip);
@@ -892,8 +907,18 @@ extern "C" int vosd_decode_anchors(const vosd_rpn_level* level, int num_images, 
     int blocks = ceil_div(p.H * p.W, 256);
     const int cap = ceil_div(kNumSMs * 32, num_images);
     if (blocks > cap) blocks = cap;
-    if (p.A == 3) decode_all_kernel<3><<<dim3(blocks, num_images), 256, 0, stream>>>(p, im_info, reinterpret_cast<float4*>(boxes));
-    else decode_all_kernel<0><<<dim3(blocks, num_images), 256, 0, stream>>>(p, im_info, reinterpret_cast<float4*>(boxes));
+    // exact fp32 shifts?  (half-integer anchors, integer stride, everything below 2^22)
+    bool exact = p.stride == floor(p.stride) && p.stride > 0 && p.stride * (double)(p.H > p.W ? p.H : p.W) < 4194304.0;
+    for (int k = 0; k < 4 * p.A; k++) {
+        exact = exact && 2.0 * p.anchors[k] == floor(2.0 * p.anchors[k]) && fabs(p.anchors[k]) < 4194304.0;
+        p.fanchors[k] = (float)p.anchors[k];
+    }
+    p.fstride = (float)p.stride;
+    const dim3 grid(blocks, num_images);
+    float4* out = reinterpret_cast<float4*>(boxes);
+    if (p.A == 3 && exact) decode_all_kernel<3, true><<<grid, 256, 0, stream>>>(p, im_info, out);
+    else if (p.A == 3) decode_all_kernel<3, false><<<grid, 256, 0, stream>>>(p, im_info, out);
+    else decode_all_kernel<0, false><<<grid, 256, 0, stream>>>(p, im_info, out);
     count_launch();
     return check_launch();
 }

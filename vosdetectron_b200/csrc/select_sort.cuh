@@ -101,8 +101,37 @@ __device__ void radix_select(const KeyFn& key_at, int n, int m, SelectShared& sh
     out_prefix = prefix;
 }
 
+// P == blockDim.x == 1024 (TEST-mode top-k and collect): one key per thread in a register; the 40 of the 55 stages
+// whose partner sits in the same warp (j < 32) are two shuffles each, only the 15 wider ones go through shared memory.
+__device__ __forceinline__ void bitonic_sort_desc_1024(uint64_t* keys) {
+    const int i = threadIdx.x;
+    uint64_t v = keys[i];
+    for (int k = 2; k <= 1024; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            uint64_t w;
+            if (j >= 32) {
+                __syncthreads();                    // the previous exchange has been read
+                keys[i] = v;
+                __syncthreads();
+                w = keys[i ^ j];
+            } else {
+                w = __shfl_xor_sync(0xffffffffu, v, j);
+            }
+            const bool keep_max = ((i & k) == 0) == ((i & j) == 0);
+            v = keep_max ? (v > w ? v : w) : (v < w ? v : w);
+        }
+    }
+    __syncthreads();
+    keys[i] = v;
+    __syncthreads();
+}
+
 // In-place bitonic sort of `P` (power of two) keys in shared memory, largest first.
 __device__ __forceinline__ void bitonic_sort_desc(uint64_t* keys, int P) {
+    if (P == 1024 && blockDim.x == 1024) {
+        bitonic_sort_desc_1024(keys);
+        return;
+    }
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = threadIdx.x; i < P; i += blockDim.x) {

@@ -235,6 +235,8 @@ VOSD_API int vosd_nms(const float* dets, int n, float thresh, int64_t* keep, int
 /*   order (G, post)         concat over levels of the indices assigned to each level      */
 /*                           (rois_fpnL = out_rois[order[level segment]]);                 */
 /*   restore (G, post)       rois_idx_restore_int32 = inverse permutation of order.        */
+/*   Rows >= out_count[g] of out_rois / out_level / order / restore are written as zeros   */
+/*   (the outputs need no clearing by the caller).                                         */
 /* ------------------------------------------------------------------------------------ */
 VOSD_API size_t vosd_collect_distribute_workspace_bytes(int num_levels, int num_images, int cap,
                                                int images_per_group, int post_nms_topN);

@@ -112,6 +112,15 @@ collect_distribute_kernel(const float* __restrict__ rois, const float* __restric
         lvl[t] = L;
         out_level[(size_t)g * post + t] = L;
     }
+    // rows beyond the group's count: zero boxes, level 0, identity-free zeros (the caller does not have to clear the
+    // outputs: six fill kernels less on the proposal chain of a step)
+    for (int t = take + threadIdx.x; t < post; t += kSelThreads) {
+        float* o = orow + (size_t)t * 5;
+        o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; o[3] = 0.f; o[4] = 0.f;
+        out_level[(size_t)g * post + t] = 0;
+        order[(size_t)g * post + t] = 0;
+        restore[(size_t)g * post + t] = 0;
+    }
     __syncthreads();
     split_by_level(lvl, take, k_min, k_max, order + (size_t)g * post, restore + (size_t)g * post,
                    level_count + (size_t)g * (k_max - k_min + 1), sh.warp_sums);

@@ -304,9 +304,11 @@ def make_rpn_levels(level_inputs):
 
 
 def generate_proposals_cuda(level_inputs, im_info, pre_nms_topN, post_nms_topN, nms_thresh, min_size,
-                            workspace=None):
+                            workspace=None, zero_fill=True):
     """All (level, image) segments in 3 launches.  Returns device tensors
-    rois (L,N,cap,5) [image,x1,y1,x2,y2], probs (L,N,cap), count (L,N) int32 (rows >= count are 0)."""
+    rois (L,N,cap,5) [image,x1,y1,x2,y2], probs (L,N,cap), count (L,N) int32 (rows >= count are 0; with
+    ``zero_fill=False`` they are uninitialised: two fill kernels less for a consumer that honours ``count``, like
+    collect_distribute_cuda)."""
     arr, keep = make_rpn_levels(level_inputs)
     L = len(level_inputs)
     N = keep[0].shape[0]
@@ -321,8 +323,9 @@ def generate_proposals_cuda(level_inputs, im_info, pre_nms_topN, post_nms_topN, 
     dev = info.device
     if workspace is None or workspace.numel() < nbytes:
         workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    rois = torch.zeros((L, N, cap, 5), dtype=torch.float32, device=dev)
-    probs = torch.zeros((L, N, cap), dtype=torch.float32, device=dev)
+    alloc = torch.zeros if zero_fill else torch.empty
+    rois = alloc((L, N, cap, 5), dtype=torch.float32, device=dev)
+    probs = alloc((L, N, cap), dtype=torch.float32, device=dev)
     count = torch.empty((L, N), dtype=torch.int32, device=dev)
     with _on(info):
         _lib.call("vosd_generate_proposals", arr, L, N, _ptr(info), int(pre_nms_topN), int(post_nms_topN),
@@ -389,12 +392,13 @@ def collect_distribute_cuda(rois, probs, count, post_nms_topN, images_per_group=
     dev = r.device
     post = int(post_nms_topN)
     out = {
-        "rois": torch.zeros((G, post, 5), dtype=torch.float32, device=dev),
+        # (the kernel writes every row: zeros beyond the group's count)
+        "rois": torch.empty((G, post, 5), dtype=torch.float32, device=dev),
         "count": torch.empty((G,), dtype=torch.int32, device=dev),
-        "level": torch.zeros((G, post), dtype=torch.int32, device=dev),
+        "level": torch.empty((G, post), dtype=torch.int32, device=dev),
         "level_count": torch.empty((G, k_max - k_min + 1), dtype=torch.int32, device=dev),
-        "order": torch.zeros((G, post), dtype=torch.int32, device=dev),
-        "restore": torch.zeros((G, post), dtype=torch.int32, device=dev),
+        "order": torch.empty((G, post), dtype=torch.int32, device=dev),
+        "restore": torch.empty((G, post), dtype=torch.int32, device=dev),
     }
     with _on(r):
         _lib.call("vosd_collect_distribute", _ptr(r), _ptr(p), _ptr(c), L, N, cap, int(images_per_group), post,

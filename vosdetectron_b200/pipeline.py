@@ -49,7 +49,7 @@ class RegionPipeline:
         m = self.cfg.mode(self.training)
         inputs = [(rpn[l][0], rpn[l][1], self.anchors[l], float(2 ** l)) for l in self.rpn_levels]
         rois, probs, count = ops.generate_proposals_cuda(inputs, im_info, m.pre_nms_topN, m.post_nms_topN,
-                                                         m.nms_thresh, m.min_size)
+                                                         m.nms_thresh, m.min_size, zero_fill=False)   # collect honours count
         if mark:
             mark("collect_distribute")
         c = self.cfg

@@ -100,6 +100,7 @@ struct RpnParams {
     int num_levels, num_images;
     int seg_stride;   // M: rows reserved per segment in the workspace
     int sort_cap;     // power of two >= M
+    int cand_cap;     // keys of the candidate buffer behind the sort buffer (per CTA)
     float min_size;
     double xform_clip;
 };
@@ -156,7 +157,8 @@ topk_decode_kernel(const __grid_constant__ RpnParams p, const float* __restrict_
     const int HW = L.H * L.W;
     RpnKeys kf{L.scores + (size_t)img * L.n, L.A, HW};
     const int P = next_pow2(L.take);
-    const int m = select_and_sort_cluster(cluster, kf, L.n, L.take, keys, P, sh);
+    uint64_t* cand = keys + p.sort_cap;                  // candidate keys of the threshold bin (select_sort.cuh)
+    const int m = select_and_sort_cluster(cluster, kf, L.n, L.take, keys, P, sh, cand, p.cand_cap);
     if (cluster.block_rank() != 0) return;
 
     const float im_h = im_info[img * 3 + 0], im_w = im_info[img * 3 + 1], im_s = im_info[img * 3 + 2];
@@ -875,7 +877,10 @@ extern "C" int vosd_generate_proposals(const vosd_rpn_level* levels, int num_lev
         count_launch();
         return check_launch();
     }
-    const size_t dyn = (size_t)p.sort_cap * sizeof(uint64_t);
+    // candidate buffer: what is left of ~200 KB behind the sort buffer, at most 16384 keys per CTA
+    long long cc = (200 * 1024 - (long long)p.sort_cap * 8) / 8;
+    p.cand_cap = (int)(cc < 0 ? 0 : (cc > 16384 ? 16384 : cc));
+    const size_t dyn = ((size_t)p.sort_cap + p.cand_cap) * sizeof(uint64_t);
     if (cudaFuncSetAttribute(topk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
         return VOSD_ERR_LAUNCH;
     topk_decode_kernel<<<lay.S * kTopkCluster, kSelThreads, dyn, stream>>>(p, im_info, ws_boxes, ws_scores, ws_count);

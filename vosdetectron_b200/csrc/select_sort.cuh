@@ -190,80 +190,132 @@ struct ClusterSelectShared {
     int found_above;
     int found_count;
     int counter;          // keys this CTA selected from its slice
+    int ncand;            // keys of this CTA's slice inside the threshold bin of the leading digit
 };
 
+// Cluster-wide select + sort.  On return rank 0 holds the `take` largest keys sorted descending in
+// its keys_out[0..take) (padded with 0 to P); the other ranks may exit.  All threads of all CTAs of
+// the cluster must call it.
+//
+// Scans of the score plane are what the kernel costs (every key is rebuilt from its score and index each time), so
+// only TWO of them touch global memory: the histogram of the leading digit, and a split scan that appends the keys
+// above the threshold bin to the output (they are selected whatever the later digits say) and the keys INSIDE the
+// threshold bin to `cand` (shared memory, `cap_cand` keys per CTA).  The remaining digits are resolved on `cand`
+// alone.  If the threshold bin of some CTA does not fit (a degenerate score distribution), every CTA of the cluster
+// falls back to rescanning its slice per digit, as before.  cap_cand == 0 disables the candidate buffer.
 template <class KeyFn>
-__device__ void radix_select_cluster(cooperative_groups::cluster_group& cluster, const KeyFn& key_at,
-                                     int j0, int j1, int m, ClusterSelectShared& sh,
-                                     uint64_t& out_mask, uint64_t& out_prefix) {
+__device__ int select_and_sort_cluster(cooperative_groups::cluster_group& cluster, const KeyFn& key_at,
+                                       int n, int m, uint64_t* keys_out, int P, ClusterSelectShared& sh,
+                                       uint64_t* cand = nullptr, int cap_cand = 0) {
+    const unsigned rank = cluster.block_rank(), nranks = cluster.num_blocks();
+    const int take = m < n ? m : n;
+    const int chunk = (n + (int)nranks - 1) / (int)nranks;
+    const int j0 = min(n, (int)rank * chunk), j1 = min(n, j0 + chunk);
+    if (threadIdx.x == 0) { sh.counter = 0; sh.ncand = 0; }
+    __syncthreads();
     uint64_t mask = 0, prefix = 0;
-    int need = m, shift = 64, buf = 0;
-    const unsigned nranks = cluster.num_blocks();
-    while (shift > 0) {
-        const int bits = shift >= kRadixBits ? kRadixBits : shift;
-        shift -= bits;
-        const uint32_t dmask = (1u << bits) - 1u;
-        int* h = sh.hist[buf];
-        for (int b = threadIdx.x; b < kBins; b += kSelThreads) h[b] = 0;
-        __syncthreads();
+    bool from_cand = false;                           // later digits are resolved on cand[] instead of the slice
+    if (take < n) {
+        int need = take, shift = 64, buf = 0;
+        bool first = true;
+        while (shift > 0) {
+            const int bits = shift >= kRadixBits ? kRadixBits : shift;
+            shift -= bits;
+            const uint32_t dmask = (1u << bits) - 1u;
+            int* h = sh.hist[buf];
+            for (int b = threadIdx.x; b < kBins; b += kSelThreads) h[b] = 0;
+            __syncthreads();
+            if (!from_cand) {
+                for (int j = j0 + threadIdx.x; j < j1; j += kKeyBatch * kSelThreads) {
+                    uint64_t kb[kKeyBatch];
+#pragma unroll
+                    for (int u = 0; u < kKeyBatch; u++) kb[u] = j + u * kSelThreads < j1 ? key_at(j + u * kSelThreads) : 0;
+#pragma unroll
+                    for (int u = 0; u < kKeyBatch; u++)
+                        if (kb[u] != 0 && (kb[u] & mask) == prefix) atomicAdd(&h[(uint32_t)(kb[u] >> shift) & dmask], 1);
+                }
+            } else {
+                const int nc = sh.ncand;
+                for (int i = threadIdx.x; i < nc; i += kSelThreads) {
+                    const uint64_t k = cand[i];
+                    if ((k & mask) == prefix) atomicAdd(&h[(uint32_t)(k >> shift) & dmask], 1);
+                }
+            }
+            cluster.sync();
+            const int b0 = kBins - 1 - 2 * threadIdx.x, b1 = b0 - 1;
+            int h0 = 0, h1 = 0;
+            for (unsigned r = 0; r < nranks; r++) {
+                const int* rh = cluster.map_shared_rank(h, r);
+                h0 += rh[b0];
+                h1 += rh[b1];
+            }
+            int total;
+            const int above0 = block_exclusive_scan(h0 + h1, sh.warp_sums, total);
+            const int above1 = above0 + h0;
+            if (above0 < need && need <= above0 + h0) { sh.found_bin = b0; sh.found_above = above0; sh.found_count = h0; }
+            if (above1 < need && need <= above1 + h1) { sh.found_bin = b1; sh.found_above = above1; sh.found_count = h1; }
+            __syncthreads();
+            need -= sh.found_above;
+            prefix |= (uint64_t)sh.found_bin << shift;
+            mask |= (uint64_t)dmask << shift;
+            const bool done = sh.found_count == need;
+            __syncthreads();
+            buf ^= 1;
+            if (done) break;
+            if (first && cap_cand > 0) {
+                // split scan (mask covers the leading digit only): above the threshold bin -> selected, inside -> candidate
+                for (int j = j0 + threadIdx.x; j < j1; j += kKeyBatch * kSelThreads) {
+                    uint64_t kb[kKeyBatch];
+#pragma unroll
+                    for (int u = 0; u < kKeyBatch; u++) kb[u] = j + u * kSelThreads < j1 ? key_at(j + u * kSelThreads) : 0;
+#pragma unroll
+                    for (int u = 0; u < kKeyBatch; u++) {
+                        if (kb[u] == 0) continue;
+                        const uint64_t top = kb[u] & mask;
+                        if (top > prefix) {
+                            const int pos = atomicAdd(&sh.counter, 1);
+                            if (pos < P) keys_out[pos] = kb[u];
+                        } else if (top == prefix) {
+                            const int c = atomicAdd(&sh.ncand, 1);
+                            if (c < cap_cand) cand[c] = kb[u];
+                        }
+                    }
+                }
+                cluster.sync();                        // every CTA's candidate count is final
+                bool fits = true;
+                for (unsigned r = 0; r < nranks; r++) fits = fits && *cluster.map_shared_rank(&sh.ncand, r) <= cap_cand;
+                if (fits) {
+                    from_cand = true;
+                } else {
+                    __syncthreads();
+                    if (threadIdx.x == 0) sh.counter = 0;   // nothing is collected yet on the rescan path
+                    __syncthreads();
+                }
+            }
+            first = false;
+        }
+    }
+    if (from_cand) {
+        const int nc = sh.ncand;
+        for (int i = threadIdx.x; i < nc; i += kSelThreads) {
+            const uint64_t k = cand[i];
+            if ((k & mask) >= prefix) {
+                const int pos = atomicAdd(&sh.counter, 1);
+                if (pos < P) keys_out[pos] = k;
+            }
+        }
+    } else {
         for (int j = j0 + threadIdx.x; j < j1; j += kKeyBatch * kSelThreads) {
             uint64_t kb[kKeyBatch];
 #pragma unroll
             for (int u = 0; u < kKeyBatch; u++) kb[u] = j + u * kSelThreads < j1 ? key_at(j + u * kSelThreads) : 0;
 #pragma unroll
             for (int u = 0; u < kKeyBatch; u++)
-                if (kb[u] != 0 && (kb[u] & mask) == prefix) atomicAdd(&h[(uint32_t)(kb[u] >> shift) & dmask], 1);
+                if (kb[u] != 0 && (kb[u] & mask) >= prefix) {
+                    const int pos = atomicAdd(&sh.counter, 1);
+                    if (pos < P) keys_out[pos] = kb[u];
+                }
         }
-        cluster.sync();
-        const int b0 = kBins - 1 - 2 * threadIdx.x, b1 = b0 - 1;
-        int h0 = 0, h1 = 0;
-        for (unsigned r = 0; r < nranks; r++) {
-            const int* rh = cluster.map_shared_rank(h, r);
-            h0 += rh[b0];
-            h1 += rh[b1];
-        }
-        int total;
-        const int above0 = block_exclusive_scan(h0 + h1, sh.warp_sums, total);
-        const int above1 = above0 + h0;
-        if (above0 < need && need <= above0 + h0) { sh.found_bin = b0; sh.found_above = above0; sh.found_count = h0; }
-        if (above1 < need && need <= above1 + h1) { sh.found_bin = b1; sh.found_above = above1; sh.found_count = h1; }
-        __syncthreads();
-        need -= sh.found_above;
-        prefix |= (uint64_t)sh.found_bin << shift;
-        mask |= (uint64_t)dmask << shift;
-        const bool done = sh.found_count == need;
-        __syncthreads();
-        buf ^= 1;
-        if (done) break;
-    }
-    out_mask = mask;
-    out_prefix = prefix;
-}
-
-// Cluster-wide select + sort.  On return rank 0 holds the `take` largest keys sorted descending in
-// its keys_out[0..take) (padded with 0 to P); the other ranks may exit.  All threads of all CTAs of
-// the cluster must call it.
-template <class KeyFn>
-__device__ int select_and_sort_cluster(cooperative_groups::cluster_group& cluster, const KeyFn& key_at,
-                                       int n, int m, uint64_t* keys_out, int P, ClusterSelectShared& sh) {
-    const unsigned rank = cluster.block_rank(), nranks = cluster.num_blocks();
-    const int take = m < n ? m : n;
-    const int chunk = (n + (int)nranks - 1) / (int)nranks;
-    const int j0 = min(n, (int)rank * chunk), j1 = min(n, j0 + chunk);
-    if (threadIdx.x == 0) sh.counter = 0;
-    __syncthreads();
-    uint64_t mask = 0, prefix = 0;
-    if (take < n) radix_select_cluster(cluster, key_at, j0, j1, take, sh, mask, prefix);
-    for (int j = j0 + threadIdx.x; j < j1; j += kKeyBatch * kSelThreads) {
-        uint64_t kb[kKeyBatch];
-#pragma unroll
-        for (int u = 0; u < kKeyBatch; u++) kb[u] = j + u * kSelThreads < j1 ? key_at(j + u * kSelThreads) : 0;
-#pragma unroll
-        for (int u = 0; u < kKeyBatch; u++)
-            if (kb[u] != 0 && (kb[u] & mask) >= prefix) {
-                const int pos = atomicAdd(&sh.counter, 1);
-                if (pos < P) keys_out[pos] = kb[u];
-            }
     }
     cluster.sync();                                   // every slice collected, counters final
     if (rank == 0) {

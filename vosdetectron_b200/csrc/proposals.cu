@@ -77,12 +77,19 @@ __device__ __forceinline__ bool suppresses(float4 a, float area_a, float4 b, flo
     float h = __fadd_rn(__fsub_rn(yy2, yy1), 1.f);
     w = 0.f >= w ? 0.f : w;
     h = 0.f >= h ? 0.f : h;
-    // disjoint boxes: inter = 0 and the union of two boxes (areas >= 1 by the +1 convention) is positive, so
-    // ovr = +0 < thresh for every thresh > 0 -- same decision as the division, without the division
-    if ((w == 0.f || h == 0.f) && thresh > 0.f && area_a > 0.f && area_b > 0.f) return false;
     const float inter = __fmul_rn(w, h);
-    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
-    return ovr >= thresh;
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    // The reference's decision is fl(inter / uni) >= thresh.  Two products decide all but the near-ties without the
+    // IEEE division (about a dozen instructions): with r = inter / uni exactly,
+    //   inter >= fl(fl(thresh * (1 + 2^-21)) * uni)  =>  r > thresh * (1 + 2^-22)  =>  fl(r) >= thresh   (rounding is monotone),
+    //   inter <= fl(fl(thresh * (1 - 2^-21)) * uni)  =>  r < thresh * (1 - 2^-22)  =>  fl(r) <  thresh   (more than an ulp below),
+    // (two roundings cost <= 2^-23 of the 2^-21 margin).  Disjoint boxes (inter = 0, uni > 0) leave through the second
+    // test; near-ties, non-positive unions and NaNs fail both and take the division: the same decision bit for bit.
+    const float hi = __fmul_rn(__fmul_rn(thresh, 1.00000047683715820312f), uni);      // 1 + 2^-21
+    const float lo = __fmul_rn(__fmul_rn(thresh, 0.99999952316284179688f), uni);      // 1 - 2^-21
+    if (inter >= hi && thresh > 0.f && uni > 0.f) return true;
+    if (inter <= lo && thresh > 0.f && uni > 0.f) return false;
+    return __fdiv_rn(inter, uni) >= thresh;
 }
 
 // ------------------------------------------------------------------------------------

@@ -33,6 +33,45 @@ __device__ __forceinline__ int fpn_level(float x1, float y1, float x2, float y2,
 // level), restore[i] = position of i in order[].  Block of kSelThreads.
 __device__ void split_by_level(const int* lvl, int n, int k_min, int k_max, int* order, int* restore,
                                int* level_count, int* warp_sums) {
+    if (n <= kSelThreads && k_max - k_min < 4) {
+        // one tile, <= 4 levels: ONE block scan over four 16-bit counters packed in a 64-bit word instead of one scan per
+        // level (same stable order: position within the level = number of earlier rows of that level)
+        const int t = threadIdx.x;
+        const int L = t < n ? lvl[t] - k_min : -1;
+        const unsigned long long v = L >= 0 ? 1ull << (16 * L) : 0ull;
+        const int lane = t & 31, warp = t >> 5;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        __shared__ unsigned long long wsum[32];
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            wsum[lane] = w;                              // inclusive sums of the warp totals
+        }
+        __syncthreads();
+        const unsigned long long total = wsum[31];
+        const unsigned long long excl = (warp == 0 ? 0ull : wsum[warp - 1]) + inc - v;
+        if (L >= 0) {
+            int base = 0;
+            for (int k = 0; k < L; k++) base += (int)((total >> (16 * k)) & 0xffffull);
+            const int pos = base + (int)((excl >> (16 * L)) & 0xffffull);
+            order[pos] = t;
+            restore[t] = pos;
+        }
+        if (t <= k_max - k_min) level_count[t] = (int)((total >> (16 * t)) & 0xffffull);
+        __syncthreads();
+        return;
+    }
     int base = 0;
     for (int L = k_min; L <= k_max; L++) {
         const int start = base;

@@ -211,8 +211,7 @@ extern "C" int vosd_box_results(const float* scores, const float* boxes, const i
     cls_sort_kernel<<<L.segs, kSelThreads, dyn, stream>>>(scores, boxes, rows, R, K, score_thresh, P, wb, orig, flag, count);
     const int use_mask = nms_thresh > 0.f;
     if (use_mask) {
-        dim3 grid(L.words, L.words, L.segs);
-        nms_mask_kernel<<<grid, 64, 0, stream>>>(wb, count, R, L.words, nms_thresh, mask);
+        nms_mask_kernel<<<nms_mask_grid(L.words, L.segs), 64, 0, stream>>>(wb, count, R, L.words, nms_thresh, mask);
     }
     if (launch_nms_reduce(L.segs, R, L.words, wb, nullptr, count, mask, use_mask, 0, 2, 1, R, nullptr, nullptr, nullptr, orig, flag,
                           stream) != cudaSuccess)

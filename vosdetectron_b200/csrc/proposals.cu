@@ -193,15 +193,18 @@ topk_decode_kernel(const __grid_constant__ RpnParams p, const float* __restrict_
     if (threadIdx.x == 0) ws_count[seg] = base;
 }
 
-// K2.  grid = (col blocks, row blocks, segments), block = 64.  Bit j of mask[i][c] is set
-// when sorted box i suppresses sorted box 64c+j (only j-global > i is ever computed).
+// K2.  grid = (tiles of the upper triangle, 1, segments), block = 64.  Bit j of mask[i][c] is set
+// when sorted box i suppresses sorted box 64c+j (only j-global > i is ever computed).  Only the W (W + 1) / 2 tiles
+// with cb >= rb are launched (nms_mask_grid): a square grid spends half its blocks on a load of count[] and a return.
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ count, int seg_stride,
                 int words_per_row, float thresh, unsigned long long* __restrict__ mask) {
     const int seg = blockIdx.z;
+    int t = blockIdx.x, rb = 0;                        // linear tile index -> (row block, column block >= row block)
+    while (t >= words_per_row - rb) { t -= words_per_row - rb; rb++; }
+    const int cb = rb + t;
     const int n = count[seg];
-    const int rb = blockIdx.y, cb = blockIdx.x;
-    if (cb < rb || rb * 64 >= n || cb * 64 >= n) return;
+    if (cb * 64 >= n) return;                          // (rb <= cb)
     const float4* b = boxes + (size_t)seg * seg_stride;
     __shared__ float4 cbox[64];
     __shared__ float carea[64];
@@ -223,6 +226,8 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ count,
         if (suppresses(a, area, cbox[j], carea[j], thresh)) bits |= 1ull << j;
     mask[((size_t)seg * seg_stride + i) * words_per_row + cb] = bits;
 }
+
+static inline dim3 nms_mask_grid(int words, int segs) { return dim3((unsigned)(words * (words + 1) / 2), 1, (unsigned)segs); }
 
 // K3.  grid = segments, block = 32 (one warp).  Greedy reduce in sorted order, 64 boxes at
 // a time: resolve the chunk against itself sequentially, then OR the rows of its survivors
@@ -409,9 +414,12 @@ nms_reduce_cta_kernel(const float4* __restrict__ boxes, const float* __restrict_
     if (mode == 2) { orig_index += (size_t)seg * seg_stride; keep_flag += (size_t)seg * seg_stride; }   // per-segment flags
     if (use_mask) {
         // only words w >= i / 64 of row i were written by nms_mask_kernel (upper triangle)
-        for (int idx = tid; idx < n * nblk; idx += kNmsCtaThreads) {
-            const int i = idx / nblk, w = idx - i * nblk;
-            sm_mask[idx] = w >= (i >> 6) ? mrow[(size_t)i * words_per_row + w] : 0ull;
+        // thread = (word w of the row, row i0 + k * rows-per-sweep): no division, four independent loads in flight
+        const int w = tid % nblk, i0 = tid / nblk, rps = kNmsCtaThreads / nblk;
+        if (i0 < rps) {
+#pragma unroll 4
+            for (int i = i0; i < n; i += rps)
+                sm_mask[(size_t)i * nblk + w] = w >= (i >> 6) ? mrow[(size_t)i * words_per_row + w] : 0ull;
         }
     }
     __shared__ unsigned long long removed[kNmsCtaMaxWords];
@@ -894,8 +902,7 @@ extern "C" int vosd_generate_proposals(const vosd_rpn_level* levels, int num_lev
     count_launch();
     const int use_mask = nms_thresh > 0.f;
     if (use_mask) {
-        dim3 grid(lay.words, lay.words, lay.S);
-        nms_mask_kernel<<<grid, 64, 0, stream>>>(ws_boxes, ws_count, lay.M, lay.words, nms_thresh, ws_mask);
+        nms_mask_kernel<<<nms_mask_grid(lay.words, lay.S), 64, 0, stream>>>(ws_boxes, ws_count, lay.M, lay.words, nms_thresh, ws_mask);
         count_launch();
     }
     if (launch_nms_reduce(lay.S, lay.M, lay.words, ws_boxes, ws_scores, ws_count, ws_mask, use_mask, use_mask ? post_nms_topN : 0, 0,
@@ -987,8 +994,7 @@ extern "C" int vosd_nms(const float* dets, int n, float thresh, int64_t* keep, i
     if (cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
         return VOSD_ERR_LAUNCH;
     nms_sort_kernel<<<1, kSelThreads, dyn, stream>>>(dets, n, P, boxes, orig, count, flag);
-    dim3 grid(L.words, L.words, 1);
-    nms_mask_kernel<<<grid, 64, 0, stream>>>(boxes, count, n, L.words, thresh, mask);
+    nms_mask_kernel<<<nms_mask_grid(L.words, 1), 64, 0, stream>>>(boxes, count, n, L.words, thresh, mask);
     if (launch_nms_reduce(1, n, L.words, boxes, nullptr, count, mask, 1, 0, 1, 1, n, nullptr, nullptr, nullptr, orig, flag, stream) !=
         cudaSuccess)
         return VOSD_ERR_LAUNCH;

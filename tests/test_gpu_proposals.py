@@ -219,3 +219,33 @@ def test_generate_proposals_op_signature(golden, orc):
         op.forward(_cu(g["scores4"]), bad, torch.from_numpy(g["im_info"]))
     with pytest.raises(NotImplementedError):
         op.forward(torch.from_numpy(g["scores4"]), torch.from_numpy(g["deltas4"]), torch.from_numpy(g["im_info"]))
+
+
+@pytest.mark.parametrize("kind", ["one_bin", "two_bins", "near_zero"])
+def test_topk_select_on_degenerate_score_distributions(synth, orc, kind):
+    """The cluster top-k keeps the keys of the leading digit's threshold bin in a shared-memory candidate buffer and
+    falls back to rescanning when they do not fit.  `one_bin`: every score of a P2 plane (201 600) lies in ONE
+    11-bit bin of the key (fallback path); `two_bins`: the top-1000 cut falls inside a bin holding half of the plane;
+    `near_zero`: the usual RPN picture, almost everything near 0 and a thin foreground tail.  Order and boxes against
+    the oracle."""
+    from vosdetectron_b200 import ops
+    rpn = synth.rpn_outputs(77, synth.COCO_BLOB, 1, levels=(2,))
+    sc = rpn[2][0]
+    n = sc.size
+    rank = np.argsort(np.argsort(sc.ravel())).astype(np.float64)          # 0 .. n-1, the plane's own (tie-free) order
+    if kind == "one_bin":
+        new = 0.90 + 0.04 * (rank + 0.5) / n                               # [0.90, 0.94): inside [0.875, 1.0)
+    elif kind == "two_bins":
+        new = np.where(rank < n // 2, 0.30 + 0.1 * rank / n, 0.76 + 0.2 * rank / n)
+    else:
+        new = np.where(rank < n - 1500, 1e-4 + 1e-3 * rank / n, 0.2 + 0.79 * (rank - (n - 1500)) / 1500.0)
+    new = new.astype(np.float32).reshape(sc.shape)
+    assert len(np.unique(new)) == n                                        # still tie-free in fp32
+    rpn = {2: (new, rpn[2][1])}
+    im_info = np.array([[800, 1344, 1.0]], dtype=np.float32)
+    for pre, post in ((1000, 1000), (6000, 300)):
+        rois, probs, count = ops.generate_proposals_cuda(_levels(orc, rpn, [2]), _cu(im_info), pre, post, 0.7, 0.0)
+        ro, po = orc.generate_proposals(rpn[2][0], rpn[2][1], im_info, orc.fpn_anchors(2), 0.25, pre, post, 0.7, 0)
+        r, p = _split(rois, probs, count, 0, 1)
+        assert np.array_equal(p, po), (kind, pre, len(p), len(po))
+        _assert_rois_close(r, ro)

@@ -6,7 +6,7 @@
 //   K1 topk_decode_kernel : 1 CTA / segment -- radix-select the pre_nms_topN best scores,
 //                           bitonic-sort them, decode + clip + filter the survivors.
 //   K2 nms_mask_kernel    : 64x64 IoU tiles -> suppression bitmask (upper triangle only).
-//   K3 nms_reduce_kernel  : 1 warp / segment -- ordered greedy reduce over 64-box chunks,
+//   K3 nms_reduce_cta_*   : 1 CTA / segment -- ordered greedy reduce over 64-box chunks,
 //                           writes the first post_nms_topN kept boxes.
 #include <math.h>
 #include "common.cuh"
@@ -229,164 +229,15 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ count,
 
 static inline dim3 nms_mask_grid(int words, int segs) { return dim3((unsigned)(words * (words + 1) / 2), 1, (unsigned)segs); }
 
-// K3.  grid = segments, block = 32 (one warp).  Greedy reduce in sorted order, 64 boxes at
-// a time: resolve the chunk against itself sequentially, then OR the rows of its survivors
-// into the running `removed` bitmap.
+// K3: greedy reduce over the bitmask in sorted order, 64 boxes at a time: the chunk is resolved against itself, then
+// the rows of its survivors are OR-ed into the running `removed` bitmap.
 //   mode 0: write [img, box] / score of the first `post` kept boxes (proposal path);
 //   mode 1: set keep_flag[orig_index[pos]] for every kept box (standalone nms);
 //   mode 2: as 1 with orig_index / keep_flag laid out per segment (class-segmented nms, detections.cuh).
 constexpr int kMaxWords = VOSD_MAX_TOPK / 64;
-__global__ void __launch_bounds__(32)
-nms_reduce_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
-                  const int* __restrict__ count, int seg_stride, int words_per_row,
-                  const unsigned long long* __restrict__ mask, int use_mask, int post, int mode,
-                  int num_images, int cap, float* __restrict__ out_rois, float* __restrict__ out_probs,
-                  int* __restrict__ out_count, const int* __restrict__ orig_index,
-                  int* __restrict__ keep_flag) {
-    __shared__ unsigned long long removed[kMaxWords];
-    __shared__ unsigned long long diag[64];
-    const int seg = blockIdx.x, lane = threadIdx.x;
-    const int n = count[seg];
-    const int nblk = (n + 63) / 64;
-    const float4* b = boxes + (size_t)seg * seg_stride;
-    const float* sc = scores ? scores + (size_t)seg * seg_stride : nullptr;
-    const unsigned long long* mrow = mask + (size_t)seg * seg_stride * words_per_row;
-    const int limit = post > 0 ? post : n;
-    const float img = (float)(seg % num_images);
-    if (mode == 2) { orig_index += (size_t)seg * seg_stride; keep_flag += (size_t)seg * seg_stride; }   // per-segment flags
-    for (int w = lane; w < nblk; w += 32) removed[w] = 0;
-    __syncwarp();
-    int kept_total = 0;
-    for (int c = 0; c < nblk && kept_total < limit; c++) {
-        const int i0 = c * 64;
-        const int nin = min(64, n - i0);
-        unsigned long long kept;
-        if (use_mask) {
-            for (int t = lane; t < 64; t += 32)
-                diag[t] = t < nin ? mrow[(size_t)(i0 + t) * words_per_row + c] : 0ull;
-            __syncwarp();
-            unsigned long long alive = ~removed[c];
-            if (nin < 64) alive &= (1ull << nin) - 1ull;
-            kept = 0;
-#pragma unroll 8
-            for (int t = 0; t < 64; t++) {
-                const unsigned long long d = diag[t];
-                if ((alive >> t) & 1ull) { kept |= 1ull << t; alive &= ~d; }
-            }
-            // OR the rows of the survivors into the words of the following chunks
-            for (int w = c + 1 + lane; w < nblk; w += 32) {
-                unsigned long long acc = removed[w];
-                unsigned long long kk = kept;
-                while (kk) {
-                    const int t = __ffsll((long long)kk) - 1;
-                    kk &= kk - 1;
-                    acc |= mrow[(size_t)(i0 + t) * words_per_row + w];
-                }
-                removed[w] = acc;
-            }
-            __syncwarp();
-        } else {
-            kept = nin < 64 ? (1ull << nin) - 1ull : ~0ull;
-        }
-        // emit survivors of this chunk in order
-        for (int t = lane; t < 64; t += 32) {
-            if ((kept >> t) & 1ull) {
-                const int pos = kept_total + __popcll(kept & ((1ull << t) - 1ull));
-                if (pos < limit) {
-                    if (mode == 0) {
-                        const float4 v = b[i0 + t];
-                        float* r = out_rois + ((size_t)seg * cap + pos) * 5;
-                        r[0] = img; r[1] = v.x; r[2] = v.y; r[3] = v.z; r[4] = v.w;
-                        out_probs[(size_t)seg * cap + pos] = sc[i0 + t];
-                    } else {
-                        keep_flag[orig_index[i0 + t]] = 1;
-                    }
-                }
-            }
-        }
-        kept_total += __popcll(kept);
-    }
-    if (lane == 0 && out_count) out_count[seg] = min(kept_total, limit);
-}
-
-// K3, fast path for segments of <= 2048 boxes (<= 32 mask words per row): lane w keeps word w of the
-// running `removed` bitmap in a register.  Per 64-box chunk the warp issues ALL its global loads up
-// front -- the 64 diagonal words and, for every later word, the 64 row words of the chunk -- so the
-// chunk costs one memory round trip instead of one per surviving box; the diagonal is then resolved
-// sequentially from shared memory (warp-uniform), and the survivors' rows are OR-ed from registers.
-__global__ void __launch_bounds__(32)
-nms_reduce_warp_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
-                       const int* __restrict__ count, int seg_stride, int words_per_row,
-                       const unsigned long long* __restrict__ mask, int use_mask, int post, int mode,
-                       int num_images, int cap, float* __restrict__ out_rois, float* __restrict__ out_probs,
-                       int* __restrict__ out_count, const int* __restrict__ orig_index,
-                       int* __restrict__ keep_flag) {
-    __shared__ unsigned long long diag[64];
-    const int seg = blockIdx.x, lane = threadIdx.x;
-    const int n = count[seg];
-    const int nblk = (n + 63) / 64;
-    const float4* b = boxes + (size_t)seg * seg_stride;
-    const float* sc = scores ? scores + (size_t)seg * seg_stride : nullptr;
-    const unsigned long long* mrow = mask + (size_t)seg * seg_stride * words_per_row;
-    const int limit = post > 0 ? post : n;
-    const float img = (float)(seg % num_images);
-    if (mode == 2) { orig_index += (size_t)seg * seg_stride; keep_flag += (size_t)seg * seg_stride; }   // per-segment flags
-    unsigned long long rem = 0;          // removed bits of word `lane`
-    int kept_total = 0;
-    for (int c = 0; c < nblk && kept_total < limit; c++) {
-        const int i0 = c * 64;
-        const int nin = min(64, n - i0);
-        unsigned long long kept;
-        if (use_mask) {
-            // all loads of the chunk in flight together
-            unsigned long long d0 = 0, d1 = 0;
-            if (lane < nin) d0 = mrow[(size_t)(i0 + lane) * words_per_row + c];
-            if (lane + 32 < nin) d1 = mrow[(size_t)(i0 + lane + 32) * words_per_row + c];
-            unsigned long long r[64];
-            const bool mine = lane > c && lane < nblk;
-#pragma unroll
-            for (int t = 0; t < 64; t++)
-                r[t] = (mine && t < nin) ? mrow[(size_t)(i0 + t) * words_per_row + lane] : 0ull;
-            diag[lane] = d0;
-            diag[lane + 32] = d1;
-            __syncwarp();
-            unsigned long long alive = ~__shfl_sync(0xffffffffu, rem, c);
-            if (nin < 64) alive &= (1ull << nin) - 1ull;
-            kept = 0;
-#pragma unroll 16
-            for (int t = 0; t < 64; t++) {
-                const unsigned long long d = diag[t];
-                if ((alive >> t) & 1ull) { kept |= 1ull << t; alive &= ~d; }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int t = 0; t < 64; t++)
-                if ((kept >> t) & 1ull) rem |= r[t];
-        } else {
-            kept = nin < 64 ? (1ull << nin) - 1ull : ~0ull;
-        }
-        for (int t = lane; t < 64; t += 32) {
-            if ((kept >> t) & 1ull) {
-                const int pos = kept_total + __popcll(kept & ((1ull << t) - 1ull));
-                if (pos < limit) {
-                    if (mode == 0) {
-                        const float4 v = b[i0 + t];
-                        float* o = out_rois + ((size_t)seg * cap + pos) * 5;
-                        o[0] = img; o[1] = v.x; o[2] = v.y; o[3] = v.z; o[4] = v.w;
-                        out_probs[(size_t)seg * cap + pos] = sc[i0 + t];
-                    } else {
-                        keep_flag[orig_index[i0 + t]] = 1;
-                    }
-                }
-            }
-        }
-        kept_total += __popcll(kept);
-    }
-    if (lane == 0 && out_count) out_count[seg] = min(kept_total, limit);
-}
 
 // K3, CTA-wide path for segments whose whole bitmask fits shared memory (rows * words * 8 bytes <= 128 KB, i.e. up to
-// 1024 boxes: the TEST-mode RPN segments and the per-class segments of the box head).  The one-warp kernels above are
+// 1024 boxes: the TEST-mode RPN segments and the per-class segments of the box head).  A one-warp reduce (round 1) is
 // bound by the latency of their global loads (~1.5 us per 64-box chunk); here 512 threads first copy the segment's upper
 // triangle into shared memory in one coalesced sweep, warp 0 then resolves chunk after chunk from shared memory (64
 // dependent steps per chunk on the diagonal word, then lanes = later words OR the survivors' rows), and all threads
@@ -477,6 +328,111 @@ nms_reduce_cta_kernel(const float4* __restrict__ boxes, const float* __restrict_
     }
     __syncthreads();
     for (int i = tid; i < n; i += kNmsCtaThreads) {
+        const int c = i >> 6, t = i & 63;
+        const unsigned long long kept = kept_w[c];
+        if ((kept >> t) & 1ull) {
+            const int pos = kept_prefix[c] + __popcll(kept & ((1ull << t) - 1ull));
+            if (pos < limit) {
+                if (mode == 0) {
+                    const float4 v = b[i];
+                    float* o = out_rois + ((size_t)seg * cap + pos) * 5;
+                    o[0] = img; o[1] = v.x; o[2] = v.y; o[3] = v.z; o[4] = v.w;
+                    out_probs[(size_t)seg * cap + pos] = sc[i];
+                } else {
+                    keep_flag[orig_index[i]] = 1;
+                }
+            }
+        }
+    }
+}
+
+// K3, CTA-wide path for LONGER segments (1024 < boxes <= VOSD_MAX_TOPK: TRAIN-mode RPN segments of 2000, the
+// standalone nms): the bitmask stays in global memory (L2), 512 threads share the work a one-warp reduce (round 1) did
+// alone.  Per 64-box chunk: warp 0 resolves the diagonal word (fixpoint, as above) from two words per lane that were
+// requested one chunk earlier; after one barrier every warp ORs the rows of ITS four boxes of the chunk, if they
+// survived, into the shared `removed` bitmap (lanes = later words, coalesced), while warp 0 already requests the next
+// chunk's diagonal words.  Two barriers and about one L2 round trip per chunk instead of ~4.5 us on one warp
+// (2000-box TRAIN segments: 144 -> see DESIGN section 7).  Same greedy order: same result bit for bit.
+__global__ void __launch_bounds__(kNmsCtaThreads)
+nms_reduce_cta_global_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                             const int* __restrict__ count, int seg_stride, int words_per_row,
+                             const unsigned long long* __restrict__ mask, int use_mask, int post, int mode,
+                             int num_images, int cap, float* __restrict__ out_rois, float* __restrict__ out_probs,
+                             int* __restrict__ out_count, const int* __restrict__ orig_index,
+                             int* __restrict__ keep_flag) {
+    __shared__ unsigned long long removed[kMaxWords], kept_w[kMaxWords];
+    __shared__ int kept_prefix[kMaxWords + 1];
+    __shared__ unsigned long long kept_now;
+    __shared__ int kept_sofar;
+    const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = count[seg];
+    const int nblk = (n + 63) / 64;
+    const float4* b = boxes + (size_t)seg * seg_stride;
+    const float* sc = scores ? scores + (size_t)seg * seg_stride : nullptr;
+    const unsigned long long* mrow = mask + (size_t)seg * seg_stride * words_per_row;
+    const int limit = post > 0 ? post : n;
+    const float img = (float)(seg % num_images);
+    if (mode == 2) { orig_index += (size_t)seg * seg_stride; keep_flag += (size_t)seg * seg_stride; }
+    for (int w = tid; w < nblk; w += kNmsCtaThreads) { removed[w] = 0; kept_w[w] = 0; }
+    if (tid == 0) kept_sofar = 0;
+    __syncthreads();
+    // warp 0: diagonal words of boxes `lane` and `lane + 32` of the current chunk (requested one chunk ahead)
+    unsigned long long d0 = 0, d1 = 0;
+    if (use_mask && warp == 0 && nblk > 0) {
+        const int nin0 = min(64, n);
+        d0 = lane < nin0 ? mrow[(size_t)lane * words_per_row] : 0ull;
+        d1 = lane + 32 < nin0 ? mrow[(size_t)(lane + 32) * words_per_row] : 0ull;
+    }
+    int nchunks = 0;
+    for (int c = 0; c < nblk; c++) {
+        const int i0 = c * 64;
+        const int nin = min(64, n - i0);
+        if (kept_sofar >= limit) break;                  // uniform: read after the previous chunk's closing barrier
+        nchunks = c + 1;
+        if (warp == 0) {
+            unsigned long long kept = nin < 64 ? (1ull << nin) - 1ull : ~0ull;
+            if (use_mask) {
+                const unsigned long long alive = ~removed[c] & kept;
+                kept = alive;
+                for (int round = 0; round < 65; round++) {
+                    const unsigned long long sup = (((kept >> lane) & 1ull) ? d0 : 0ull) | (((kept >> (lane + 32)) & 1ull) ? d1 : 0ull);
+                    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)sup);
+                    const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(sup >> 32));
+                    const unsigned long long next = alive & ~(((unsigned long long)hi << 32) | lo);
+                    if (next == kept) break;
+                    kept = next;
+                }
+                if (c + 1 < nblk) {                      // next chunk's diagonal: in flight during the OR phase
+                    const int j0 = i0 + 64, njn = min(64, n - j0);
+                    d0 = lane < njn ? mrow[(size_t)(j0 + lane) * words_per_row + c + 1] : 0ull;
+                    d1 = lane + 32 < njn ? mrow[(size_t)(j0 + lane + 32) * words_per_row + c + 1] : 0ull;
+                }
+            }
+            if (lane == 0) { kept_w[c] = kept; kept_prefix[c] = kept_sofar; kept_now = kept; }
+        }
+        __syncthreads();
+        if (use_mask && c + 1 < nblk) {
+            const unsigned long long kept = kept_now;
+            // warp j owns boxes 4j .. 4j+3 of the chunk; lanes = words c+1+lane, c+33+lane, ...
+            for (int w = c + 1 + lane; w < nblk; w += 32) {
+                unsigned long long acc = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int t = 4 * warp + k;
+                    if ((kept >> t) & 1ull) acc |= mrow[(size_t)(i0 + t) * words_per_row + w];
+                }
+                if (acc) atomicOr(&removed[w], acc);
+            }
+        }
+        if (tid == 0) kept_sofar += __popcll(kept_now);
+        __syncthreads();
+    }
+    if (tid == 0) {
+        kept_prefix[nchunks] = kept_sofar;
+        if (out_count) out_count[seg] = min(kept_sofar, limit);
+    }
+    __syncthreads();
+    for (int i = tid; i < min(n, nchunks * 64); i += kNmsCtaThreads) {
         const int c = i >> 6, t = i & 63;
         const unsigned long long kept = kept_w[c];
         if ((kept >> t) & 1ull) {
@@ -666,12 +622,10 @@ static inline cudaError_t launch_nms_reduce(int segs, int seg_stride, int words,
         if (e != cudaSuccess) return e;
         nms_reduce_cta_kernel<<<segs, kNmsCtaThreads, dyn, stream>>>(boxes, scores, count, seg_stride, words, mask, use_mask, post, mode,
                                                                    num_images, cap, out_rois, out_probs, out_count, orig_index, keep_flag);
-    } else if (words <= 32) {
-        nms_reduce_warp_kernel<<<segs, 32, 0, stream>>>(boxes, scores, count, seg_stride, words, mask, use_mask, post, mode, num_images,
-                                                        cap, out_rois, out_probs, out_count, orig_index, keep_flag);
     } else {
-        nms_reduce_kernel<<<segs, 32, 0, stream>>>(boxes, scores, count, seg_stride, words, mask, use_mask, post, mode, num_images, cap,
-                                                   out_rois, out_probs, out_count, orig_index, keep_flag);
+        nms_reduce_cta_global_kernel<<<segs, kNmsCtaThreads, 0, stream>>>(boxes, scores, count, seg_stride, words, mask, use_mask, post,
+                                                                          mode, num_images, cap, out_rois, out_probs, out_count,
+                                                                          orig_index, keep_flag);
     }
     return cudaSuccess;
 }

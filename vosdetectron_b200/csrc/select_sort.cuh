@@ -101,36 +101,72 @@ __device__ void radix_select(const KeyFn& key_at, int n, int m, SelectShared& sh
     out_prefix = prefix;
 }
 
-// P == blockDim.x == 1024 (TEST-mode top-k and collect): one key per thread in a register; the 40 of the 55 stages
-// whose partner sits in the same warp (j < 32) are two shuffles each, only the 15 wider ones go through shared memory.
-__device__ __forceinline__ void bitonic_sort_desc_1024(uint64_t* keys) {
+// P = K * 1024 keys, blockDim.x == 1024: K keys per thread in registers (element e = thread + 1024 * k).  Stages whose
+// partner sits in the same warp (j < 32) are two shuffles per key, stages with j >= 1024 pair two registers of the same
+// thread, only the 32 <= j < 1024 stages go through shared memory (for P = 1024: 15 of 55 stages).
+template <int K>
+__device__ __forceinline__ void bitonic_sort_desc_regs(uint64_t* keys) {
     const int i = threadIdx.x;
-    uint64_t v = keys[i];
-    for (int k = 2; k <= 1024; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            uint64_t w;
-            if (j >= 32) {
-                __syncthreads();                    // the previous exchange has been read
-                keys[i] = v;
-                __syncthreads();
-                w = keys[i ^ j];
-            } else {
-                w = __shfl_xor_sync(0xffffffffu, v, j);
+    uint64_t v[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = keys[i + 1024 * k];
+    for (int kk = 2; kk <= 1024 * K; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            if (j >= 1024) {
+                // partner register k ^ dk, dk = j / 1024 (unrolled over the possible dk: every index is static)
+#pragma unroll
+                for (int dk = K >> 1; dk >= 1; dk >>= 1) {
+                    if (j != (dk << 10)) continue;
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        if ((k & dk) == 0) {
+                            const int e = i + 1024 * k;
+                            const bool desc = (e & kk) == 0;  // lower element keeps the max when the run is descending
+                            const uint64_t a = v[k], b = v[k | dk];
+                            const bool sw = desc ? (a < b) : (a > b);
+                            v[k] = sw ? b : a;
+                            v[k | dk] = sw ? a : b;
+                        }
+                    }
+                }
+                continue;
             }
-            const bool keep_max = ((i & k) == 0) == ((i & j) == 0);
-            v = keep_max ? (v > w ? v : w) : (v < w ? v : w);
+            uint64_t w[K];
+            if (j >= 32) {
+                __syncthreads();                        // the previous exchange has been read
+#pragma unroll
+                for (int k = 0; k < K; k++) keys[i + 1024 * k] = v[k];
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < K; k++) w[k] = keys[(i ^ j) + 1024 * k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; k++) w[k] = __shfl_xor_sync(0xffffffffu, v[k], j);
+            }
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const int e = i + 1024 * k;
+                const bool keep_max = ((e & kk) == 0) == ((e & j) == 0);
+                v[k] = keep_max ? (v[k] > w[k] ? v[k] : w[k]) : (v[k] < w[k] ? v[k] : w[k]);
+            }
         }
     }
     __syncthreads();
-    keys[i] = v;
+#pragma unroll
+    for (int k = 0; k < K; k++) keys[i + 1024 * k] = v[k];
     __syncthreads();
 }
 
 // In-place bitonic sort of `P` (power of two) keys in shared memory, largest first.
 __device__ __forceinline__ void bitonic_sort_desc(uint64_t* keys, int P) {
-    if (P == 1024 && blockDim.x == 1024) {
-        bitonic_sort_desc_1024(keys);
-        return;
+    if (blockDim.x == 1024) {
+        switch (P) {
+            case 1024: bitonic_sort_desc_regs<1>(keys); return;
+            case 2048: bitonic_sort_desc_regs<2>(keys); return;
+            case 4096: bitonic_sort_desc_regs<4>(keys); return;
+            case 8192: bitonic_sort_desc_regs<8>(keys); return;
+            default: break;
+        }
     }
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {

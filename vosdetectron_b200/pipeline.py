@@ -122,7 +122,7 @@ class RegionPipeline:
 
         The step has two chains that only meet through the heads outside this library: proposals ->
         collect -> box RoIAlign, and mask RoIs -> mask RoIAlign / paste.  The proposal chain is a
-        latency-bound sequence on a few SMs (one cluster per (level, frame) segment, one warp per
+        latency-bound sequence on a few SMs (one cluster per (level, frame) segment, one CTA per
         segment in the NMS reduce), so with ``overlap`` (default: ``self.overlap``) it runs on a second,
         high-priority stream beside the mask chain and both join before the box RoIAlign, which then has
         the GPU to itself."""
@@ -141,8 +141,8 @@ class RegionPipeline:
             return prop, level
 
         if overlap:
-            # The proposal chain goes to a HIGH-PRIORITY second stream: its few CTAs (clusters of 8 per segment,
-            # one warp per segment in the NMS reduce) are placed ahead of the pending CTAs of the mask RoIAlign /
+            # The proposal chain goes to a HIGH-PRIORITY second stream: its few CTAs (clusters of 4 per segment,
+            # one CTA per segment in the NMS reduce) are placed ahead of the pending CTAs of the mask RoIAlign /
             # paste kernels that fill the rest of the GPU from the caller's stream.
             if self._side is None:
                 self._side = torch.cuda.Stream(det_boxes.device, priority=-1)

@@ -816,33 +816,42 @@ def gpu_arm(args, rank, world, local_rank):
     h2d_bytes_e2e = h2d_bytes - h_masks.numel() * h_masks.element_size() + h_masks.numel() // h_masks.shape[2] * h_masks.element_size()
     barrier()
     e2e_steps = max(4, min(args.steps, 12))
-    e0.record()
-    hp.s_h2d.wait_event(e0)
-    e2e_pending = []
-    for _ in range(e2e_steps):
-        slot = hp.submit(host_batch)
+    # The e2e region is PCIe- and host-memory-bound (~0.2 s for 12 steps): a neighbour on the host or the page cache
+    # left by the CPU baseline moves one pass by 20 % (453 vs 550 frames/s on one box, minutes apart), so the region is
+    # timed three times and the MEDIAN pass is reported (all three are in the line)
+
+    def e2e_pass():
+        e0.record()
+        hp.s_h2d.wait_event(e0)
+        e2e_pending = []
+        for _ in range(e2e_steps):
+            slot = hp.submit(host_batch)
+            if world > 1 and fg["g"] is not None:
+                # the sharded clip's exchange is part of the end-to-end step: gather this batch's records + packed masks
+                with torch.cuda.stream(hp.s_cmp):
+                    while len(e2e_pending) >= fg["g"].slots:
+                        fg["g"].finish(e2e_pending.pop(0))
+                    o_ = hp.dev_out[slot]
+                    dets = torch.cat([hp.dev[slot]["det_boxes"], hp.dev[slot]["det_cls"].unsqueeze(-1).float(),
+                                      torch.ones_like(hp.dev[slot]["det_cls"]).unsqueeze(-1).float()], dim=2)
+                    e2e_pending.append(fg["g"].start(dets, o_["masks_packed"]))
         if world > 1 and fg["g"] is not None:
-            # the sharded clip's exchange is part of the end-to-end step: gather this batch's records + packed masks
             with torch.cuda.stream(hp.s_cmp):
-                while len(e2e_pending) >= fg["g"].slots:
+                while e2e_pending:
                     fg["g"].finish(e2e_pending.pop(0))
-                o_ = hp.dev_out[slot]
-                dets = torch.cat([hp.dev[slot]["det_boxes"], hp.dev[slot]["det_cls"].unsqueeze(-1).float(),
-                                  torch.ones_like(hp.dev[slot]["det_cls"]).unsqueeze(-1).float()], dim=2)
-                e2e_pending.append(fg["g"].start(dets, o_["masks_packed"]))
-    if world > 1 and fg["g"] is not None:
-        with torch.cuda.stream(hp.s_cmp):
-            while e2e_pending:
-                fg["g"].finish(e2e_pending.pop(0))
-    for s_ in (hp.s_h2d, hp.s_cmp, hp.s_d2h):
-        torch.cuda.current_stream().wait_stream(s_)
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+        for s_ in (hp.s_h2d, hp.s_cmp, hp.s_d2h):
+            torch.cuda.current_stream().wait_stream(s_)
+        e1.record()
+        barrier()
+        ms_ = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item())
+        return ms_
+
+    e2e_all = [e2e_pass() for _ in range(3)]
+    e2e_ms = float(np.median(e2e_all))
     e2e_value = world * B * e2e_steps / (e2e_ms / 1000.0)
     # ---- the same device-resident step with the FPN maps in the OTHER memory order (single GPU only): the default
     #      line is the reference's NCHW; torch.channels_last maps take the TMA-fed RoIAlign kernel.  Reported as an
@@ -950,6 +959,7 @@ def gpu_arm(args, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes_e2e, "d2h_bytes_per_step": d2h_bytes,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                "passes_ms_per_step": [m_ / e2e_steps for m_ in e2e_all], "reported": "median of 3 passes of `steps` steps",
                 "what": "HostPipeline: pinned host inputs -> H2D (class channel of every detection mask gathered on the host "
                         "inside the timed region) -> step -> D2H of rois, counts and the 1-bit-per-pixel pasted masks"},
         "gpu_launches": int(launches),

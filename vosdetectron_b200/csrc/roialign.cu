@@ -1009,6 +1009,11 @@ namespace vosd {
 // the atomic scatter -- profiles/r01_roialign_bwd_staged_*_ncu.txt -- so it is not the default)
 static int g_force_generic = 0;
 
+// L2 promotion of the row-window kernel's tensor maps: a box row is 48 - 112 bytes per channel plane
+#ifndef VOSD_RW_L2PROMO
+#define VOSD_RW_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+#endif
+
 static int fill_table(LevelTable& t, const float* const* data, const int* h, const int* w,
                       const float* scale, int num_levels) {
     if (num_levels < 1 || num_levels > VOSD_MAX_LEVELS) return VOSD_ERR_UNSUPPORTED;
@@ -1378,7 +1383,7 @@ extern "C" int vosd_roialign_ml_fwd_ws(const float* const* level_data, const int
         for (int v = 0; v < kRwVariants; v++) {
             const cuuint32_t box[3] = {(cuuint32_t)(12 + 8 * v), 1, (cuuint32_t)kSlab};
             if (enc(&maps.m[l][v], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(src), dims, strides, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, VOSD_RW_L2PROMO,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return VOSD_ERR_BAD_SHAPE;
         }

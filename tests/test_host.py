@@ -253,3 +253,57 @@ def test_cffi_level_mirrors_import_and_reject_cpu_tensors():
     with pytest.raises(NotImplementedError):
         fa.flow_align_forward_cuda(f, torch.zeros((1, 2, 8, 8)), torch.zeros_like(f))
     assert isinstance(names, list)
+
+
+def test_rpn_label_host_pieces(orc, golden):
+    """Host side of the RPN label mirror (roi_data/rpn.py, roi_data/data_utils.py): the field of anchors equals the
+    oracle's restatement of get_field_of_anchors (and is cached), the blob names are the reference's (= the keys of the
+    golden produced by the unmodified add_rpn_blobs), the config adapter reads the TRAIN.RPN_* keys, and without a GPU
+    the mirror raises instead of computing anything."""
+    import types
+    from vosdetectron_b200.config import RegionConfig
+    from vosdetectron_b200.roi_data import data_utils, rpn
+    c = RegionConfig()
+    c.train_max_size = 384
+    foas = rpn._fields(c)
+    assert [f.field_size for f in foas] == [96, 48, 24, 12, 6] and all(f.num_cell_anchors == 3 for f in foas)
+    for l, f in zip(range(2, 7), foas):
+        ref, A, field = orc.field_of_anchors(2. ** l, (32 * 2. ** (l - 2),), (0.5, 1, 2), 384)
+        assert (A, field) == (f.num_cell_anchors, f.field_size)
+        assert f.field_of_anchors.dtype == np.float32 and np.array_equal(f.field_of_anchors, ref)
+    assert rpn._fields(c)[0] is foas[0]                                    # cached like the reference's thread-local cache
+    c1 = RegionConfig()
+    c1.fpn_on = c1.multilevel_rpn = False
+    c1.train_max_size, c1.rpn_sizes = 384, (32, 64, 128, 256)
+    (single,) = rpn._fields(c1)
+    ref, A, field = orc.field_of_anchors(16, (32, 64, 128, 256), (0.5, 1, 2), 384)
+    assert A == 12 and field == 24 and np.array_equal(single.field_of_anchors, ref)
+    g = golden("rpn_labels")
+    for tag, cfg_ in (("fpn_", c), ("single_", c1)):
+        names = set(rpn.get_rpn_blob_names(cfg=cfg_)) - {"roidb"}
+        assert names == {k[len(tag):] for k in g.files if k.startswith(tag + "rpn_") or k == tag + "im_info"}
+    assert rpn.get_rpn_blob_names(is_training=False, cfg=c) == ["im_info"]
+    fake = types.SimpleNamespace(
+        TRAIN=types.SimpleNamespace(RPN_PRE_NMS_TOP_N=2000, RPN_POST_NMS_TOP_N=2000, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=0,
+                                    RPN_POSITIVE_OVERLAP=0.6, RPN_NEGATIVE_OVERLAP=0.2, RPN_FG_FRACTION=0.25,
+                                    RPN_BATCH_SIZE_PER_IM=128, RPN_STRADDLE_THRESH=-1, MAX_SIZE=1000),
+        TEST=types.SimpleNamespace(RPN_PRE_NMS_TOP_N=1000, RPN_POST_NMS_TOP_N=1000, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=0,
+                                   SCORE_THRESH=0.05, NMS=0.5, DETECTIONS_PER_IM=100,
+                                   SOFT_NMS=types.SimpleNamespace(ENABLED=False), BBOX_VOTE=types.SimpleNamespace(ENABLED=False)),
+        FPN=types.SimpleNamespace(RPN_MIN_LEVEL=2, RPN_MAX_LEVEL=6, ROI_MIN_LEVEL=2, ROI_MAX_LEVEL=5, ROI_CANONICAL_SCALE=224,
+                                  ROI_CANONICAL_LEVEL=4, RPN_COLLECT_SCALE=1, RPN_ANCHOR_START_SIZE=32, RPN_ASPECT_RATIOS=(0.5, 1, 2),
+                                  FPN_ON=True, MULTILEVEL_RPN=False, COARSEST_STRIDE=64),
+        RPN=types.SimpleNamespace(STRIDE=8, SIZES=(16, 32), ASPECT_RATIOS=(1,)),
+        BBOX_XFORM_CLIP=4.135, MODEL=types.SimpleNamespace(NUM_CLASSES=81, BBOX_REG_WEIGHTS=(10., 10., 5., 5.)),
+        MRCNN=types.SimpleNamespace(RESOLUTION=28, THRESH_BINARIZE=0.5, CLS_SPECIFIC_MASK=True))
+    r = RegionConfig.from_cfg(fake)
+    assert (r.train_rpn_positive_overlap, r.train_rpn_negative_overlap, r.train_rpn_fg_fraction) == (0.6, 0.2, 0.25)
+    assert (r.train_rpn_batch_size_per_im, r.train_rpn_straddle_thresh, r.train_max_size) == (128, -1.0, 1000)
+    assert (r.fpn_on, r.multilevel_rpn, r.fpn_coarsest_stride) == (True, False, 64)
+    assert (r.rpn_stride, r.rpn_sizes, r.rpn_single_aspect_ratios) == (8, (16, 32), (1,))
+    if not torch.cuda.is_available():
+        blobs = {k: [] for k in rpn.get_rpn_blob_names(cfg=c)}
+        roidb = [{"height": 100, "width": 120, "boxes": np.zeros((0, 4), np.float32), "gt_classes": np.zeros(0, np.int32),
+                  "is_crowd": np.zeros(0, bool)}]
+        with pytest.raises(Exception):                                     # no CPU path: nothing is computed on the host
+            rpn.add_rpn_blobs(blobs, [1.0], roidb, cfg=c)

@@ -9,7 +9,7 @@ RNG contract of this repository (vosdetectron_b200/roi_data/rpn.py): `npr.choice
 anchors, ties: lower index first); `npr.randint(n, size=k)` = floor(u[:k] * n) of the image's uniforms.  The generator
 installs exactly that as `rpn.npr` (the function bodies of the reference stay untouched).
 
-Cases: "fpn" two images on a five-level field (TRAIN.MAX_SIZE 384), one of them with a gt box that lies outside every
+Cases: "quirk" (see main), "fpn" two images on a five-level field (TRAIN.MAX_SIZE 384), one of them with a gt box that lies outside every
 inside anchor's reach plus many foreground anchors (both subsamples fire); "nogt" an image without gt boxes; "single"
 the classical single-level RPN (RPN.STRIDE 16, four sizes).
 
@@ -132,6 +132,12 @@ def main():
 
     # ---- no gt boxes: every inside anchor is a background candidate ----
     run_case(rpn, cfg, "nogt_", [entry(180, 260, np.zeros((0, 4), np.float32), np.zeros(0, np.int32))], [1.4], rs, g)
+
+    # ---- the reference's quirks: (a) a gt box outside the image overlaps no inside anchor, so EVERY inside anchor with
+    #      zero overlap to it becomes foreground (`anchor_by_gt_overlap == gt_to_anchor_max` with max 0) and the
+    #      foreground subsample decides; (b) a tiny image has fewer background candidates than num_bg: none is labelled
+    run_case(rpn, cfg, "quirk_", [entry(200, 300, [[40, 40, 120, 100], [900, 900, 960, 950]], [5, 6]),
+                                  entry(48, 64, [[4, 4, 40, 40]], [2])], [1.25, 1.0], rs, g)
 
     # ---- classical single-level RPN ----
     cfg.FPN.FPN_ON, cfg.FPN.MULTILEVEL_RPN = False, False

@@ -138,7 +138,7 @@ def _rpn_roidb(g, tag):
             [g["%subg%d" % (tag, i)] for i in range(n)])
 
 
-@pytest.mark.parametrize("tag,fpn", [("fpn_", True), ("nogt_", True), ("single_", False)])
+@pytest.mark.parametrize("tag,fpn", [("fpn_", True), ("nogt_", True), ("quirk_", True), ("single_", False)])
 def test_add_rpn_blobs_matches_the_reference(golden, tag, fpn):
     """add_rpn_blobs / _get_rpn_blobs against tests/golden/rpn_labels.npz (unmodified reference, RNG contract of
     roi_data/rpn.py): labels, weights and im_info bit-exact; regression targets rtol 1e-6 (logf vs NumPy's log)."""

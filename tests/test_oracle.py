@@ -310,7 +310,8 @@ def _rpn_case(orc, g, tag, fields_spec):
 FPN_FIELDS = [(2. ** l, (32 * 2. ** (l - 2),)) for l in range(2, 7)]
 
 
-@pytest.mark.parametrize("tag,spec", [("fpn_", FPN_FIELDS), ("nogt_", FPN_FIELDS), ("single_", [(16, (32, 64, 128, 256))])])
+@pytest.mark.parametrize("tag,spec", [("fpn_", FPN_FIELDS), ("nogt_", FPN_FIELDS), ("quirk_", FPN_FIELDS),
+                                      ("single_", [(16, (32, 64, 128, 256))])])
 def test_rpn_label_oracle_reproduces_the_reference(orc, golden, tag, spec):
     """_get_rpn_blobs restated in oracle/region_oracle.py against tests/golden/rpn_labels.npz (unmodified reference under
     the RNG contract of vosdetectron_b200/roi_data/rpn.py): every blob bit-exact."""
